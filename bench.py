@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- distinct states/sec of the explicit-state BFS hot path (BASELINE.json metric).
+
+A "step" is one complete breadth-first model-checking job of the workload model (all reachable
+states, invariants checked on every state) on N GPUs.  Workload: the committed compiled form of
+BASELINE config #3 scaled to a single-GPU-sized state space (examples/Paxos, 3 acceptors / 2 values,
+ballots 0..2, invariants Inv1-Inv4; tests/golden/MCPaxos3_b2.tlagz, 185,369 distinct states) --
+configs #4/#5 (raft, SSI) are not lowered to the device yet.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (dominant kernel of the
+step, k_wave), k1_roofline (the fingerprint/probe kernel alone on SURVEY §8d's synthetic batch),
+cpu_baseline, e2e, clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, dev=0):
+        super().__init__(daemon=True)
+        self.dev = dev
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.dev)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference(cm, init, info, threads):
+    """The reference arm: the path's CPU implementation (ORACLE O2, oracle/tlag_cpu.c -- TLC itself needs a JVM,
+    which neither this image nor the reference provides) on all host cores, same model."""
+    from oracle import cpu_engine
+    t0 = time.time()
+    r = cpu_engine.run(cm, init, n_threads=threads, deadlock=info["deadlock"], max_states=1 << 24)
+    dt = r["seconds"]
+    return r, dt, time.time() - t0
+
+
+def k1_microbench(dev, peak):
+    """n = 2^27 candidates x W = 20 words, 50 % duplicates, table 2^28 slots.
+    Algorithmic bytes per candidate = S + 8 + p*8 + 1 = 93 (S = 80, p = 0.5)."""
+    import torch
+    from tla_rust_b200.engine import Engine, ProbeOnlyModel
+    W, n = 20, 1 << 27
+    g = torch.Generator(device=dev).manual_seed(0x5EED)
+    half = torch.randint(-2**31, 2**31 - 1, (n // 2, W), dtype=torch.int32, device=dev, generator=g)
+    perm = torch.randint(0, n // 2, (n // 2,), device=dev, generator=g)
+    states = torch.cat([half, half[perm]])
+    del half, perm
+    flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+    e = Engine(ProbeOnlyModel(W), table_log2=28, device=torch.device(dev).index or 0)
+    times = []
+    for it in range(2 + 5):
+        e.reset_table()
+        ms = e.probe_batch_device(states.data_ptr(), n, flags.data_ptr())
+        if it >= 2:
+            times.append(ms)
+    n_new = int(flags.sum().item())
+    med = float(np.median(times))
+    bytes_per = 80 + 8 + 0.5 * 8 + 1
+    ach = bytes_per * n / (med * 1e-3) / 1e9
+    launches = e.launches()
+    e.close()
+    del states, flags
+    torch.cuda.empty_cache()
+    return {"kernel": "k_probe<4>", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(ach / peak, 4), "traffic": None, "n": n, "W": W, "p_new": n_new / n,
+            "ms_per_launch": round(med, 4), "candidates_per_s": round(n / (med * 1e-3), 1),
+            "bytes_per_candidate": bytes_per}, launches
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="MCPaxos3_b2")
+    ap.add_argument("--no-k1", action="store_true")
+    args = ap.parse_args()
+
+    from tla_rust_b200.compiled import load_compiled
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cm, init, exp, info = load_compiled(os.path.join(ROOT, "tests", "golden", args.workload + ".tlagz"))
+    cfg = {"workload": f"{args.workload}: {info.get('source', '')} (compiled fixture), W={cm.W} words/state, "
+                       f"{exp['o2']['distinct']} distinct / {exp['o2']['generated']} generated states, "
+                       f"{len(cm.invariants)} invariants", "l2": "state store + seen-set rebuilt every step (restart), "
+                                                                 "working set streamed; see DESIGN.md",
+           "parallelism": f"fp-hash-range x{args.gpus}"}
+    threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        for _ in range(max(1, min(args.steps, 2))):
+            r, dt, wall = cpu_reference(cm, init, info, threads)
+            vals.append(r["distinct"] / dt)
+        v = float(np.median(vals))
+        line = {"impl": "reference", "metric": "distinct states/sec", "value": round(v, 1), "unit": "states/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(1e3 * exp["o2"]["distinct"] / v, 3), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": round(v, 1), "unit": "states/s", "cores": threads, "kind": "port",
+                                 "sample": "the whole workload model, one BFS per step (TLC needs a JVM: absent)"},
+                "e2e": {"value": round(v, 1), "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tla_rust_b200.engine import Engine
+    dev = f"cuda:{local_rank}"
+    torch.cuda.set_device(local_rank)
+    peak, peak_src = load_peaks()
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    W = cm.W
+    S = 4 * W
+    h2d = int(cm.code.nbytes + cm.cpool.nbytes + cm.layout.nbytes + init.nbytes)
+    stats = {}
+
+    if not multi:
+        e = Engine(cm, deadlock=info["deadlock"], device=local_rank)
+        e.seed(init)
+        for _ in range(args.warmup):
+            e.restart()
+            r = e.run()
+        assert (r["verdict"], r["generated"], r["distinct"], r["depth"]) == (
+            exp["o2"]["verdict"], exp["o2"]["generated"], exp["o2"]["distinct"], exp["o2"]["depth"]), r
+        if sampler:
+            sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        kern_s = 0.0
+        l0 = e.launches()
+        for _ in range(args.steps):
+            e.restart()
+            r = e.run()
+            kern_s += r["device_seconds"]
+        barrier()
+        dt = time.perf_counter() - t0
+        launches = e.launches() - l0
+        distinct, generated = r["distinct"], r["generated"]
+        # end to end through the C ABI with host buffers: create + seed(H2D) + run + result(D2H) + destroy
+        e.close()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            e2 = Engine(cm, deadlock=info["deadlock"], device=local_rank)
+            e2.seed(init)
+            r2 = e2.run()
+            e2.close()
+        torch.cuda.synchronize()
+        dt_e2e = time.perf_counter() - t1
+        assert r2["distinct"] == distinct
+        stats = dict(kern_s=kern_s)
+    else:
+        from tla_rust_b200.dist import DistributedBFS
+        from tla_rust_b200.fingerprint import fingerprint_words
+        fps = [fingerprint_words(w) for w in init]
+
+        def one():
+            e = Engine(cm, deadlock=info["deadlock"], device=local_rank)
+            d = DistributedBFS(e, cm, rank, world, dev)
+            d.seed(init, fps)
+            out = d.run()
+            ks = out["local"]["device_seconds"]
+            ln = e.launches()
+            e.close()
+            return out, ks, ln, d.comm_ms
+        for _ in range(args.warmup):
+            out, _, _, _ = one()
+        assert (out["generated"], out["distinct"]) == (exp["o2"]["generated"], exp["o2"]["distinct"]), out
+        if sampler:
+            sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        kern_s, launches, comm_ms = 0.0, 0, 0.0
+        for _ in range(args.steps):
+            out, ks, ln, cms = one()
+            kern_s += ks
+            launches += ln
+            comm_ms += cms
+        barrier()
+        dt = time.perf_counter() - t0
+        tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dt = float(tmax.item())
+        distinct, generated = out["distinct"], out["generated"]
+        dt_e2e = dt   # the distributed step already builds engines and seeds from host buffers every step
+        stats = dict(kern_s=kern_s, comm_ms=comm_ms)
+
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    if rank != 0:
+        if multi:
+            dist.destroy_process_group()
+        return
+
+    value = distinct * args.steps / dt
+    # roofline of the dominant kernel (k_wave, fused expand + fingerprint + probe + compaction):
+    # algorithmic bytes per step = S*expanded (frontier read) + 8*generated (slot probe) +
+    #                              discovered*(8 slot write + S state write + 8 parent/meta)   [SURVEY §8d, fused form]
+    bytes_step = S * distinct + 8 * generated + (distinct - len(np.unique(init, axis=0))) * (8 + S + 8)
+    ach = bytes_step * args.steps / max(stats["kern_s"], 1e-9) / 1e9
+    roof = {"kernel": "k_wave (fused expand+fingerprint+probe+compact)", "bound": "hbm", "achieved": round(ach, 3),
+            "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6), "traffic": None, "peak_source": peak_src,
+            "bytes_per_step": int(bytes_step), "kernel_s_per_step": round(stats["kern_s"] / args.steps, 6),
+            "note": "interpreter-bound: the wave kernel executes the Next/invariant bytecode per state; HBM is idle"}
+    k1 = None
+    k1_launches = 0
+    if not args.no_k1 and not multi:
+        try:
+            k1, k1_launches = k1_microbench(dev, peak)
+            k1["peak_source"] = peak_src
+        except Exception as ex:  # noqa: BLE001
+            k1 = {"error": str(ex)}
+    cpu_r, cpu_dt, _ = cpu_reference(cm, init, info, threads)
+    line = {"metric": "distinct states/sec", "value": round(value, 1), "unit": "states/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": cfg, "generated_per_s": round(generated * args.steps / dt, 1),
+            "roofline": roof, "k1_roofline": k1,
+            "cpu_baseline": {"value": round(cpu_r["distinct"] / cpu_dt, 1), "unit": "states/s", "cores": threads,
+                             "kind": "port", "sample": "the whole workload model once (oracle/tlag_cpu.c, all cores)"},
+            "e2e": {"value": round(distinct * args.steps / dt_e2e, 1), "unit": "states/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 96},
+            "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None}
+    if multi:
+        line["comm_ms_per_step"] = round(stats["comm_ms"] / args.steps, 3)
+        dist.destroy_process_group()
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,269 @@
+/* ORACLE O2 (test infrastructure + CPU baseline, NOT product): a plain-C, multi-threaded
+ * CPU execution of the same fixed-width bytecode the CUDA engine runs.
+ *
+ * Restates the BFS loop of TLC's ModelChecker/Worker ([ext] tla2tools.jar, not under
+ * /root/reference): level-synchronous frontier expansion, 64-bit
+ * fingerprint set with CAS insertion, invariants on every expanded state, deadlock =
+ * no successor.  The opcode semantics come from the shared header
+ * tla_rust_b200/csrc/tlag_vm.h (one ISA definition for both sides); the *semantic*
+ * oracle that is independent of the compiler and of that header is oracle/tlc_oracle.py
+ * (pinned by README.md:267-321).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.
+ *
+ * Build: make -C oracle   ->  oracle/libtlag_cpu.so
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <time.h>
+
+#include "../tla_rust_b200/csrc/tlag_vm.h"
+
+#define MAXW 64
+#define MAX_STEPS (1u << 26)
+
+typedef struct {
+  uint32_t W;
+  const uint64_t *code; uint32_t code_len;
+  uint32_t entry_inv, entry_next;
+  const int32_t *cpool; uint32_t cpool_len;
+  const tlag_slot *layout; uint32_t n_slots;
+  uint32_t frame_words, unpacked_words, n_invariants;
+  uint32_t flags;           /* 1 = deadlock check */
+  uint32_t table_log2;
+  uint64_t max_states;
+} cpu_model;
+
+typedef struct {
+  int32_t verdict, detail, detail2, pad;
+  uint64_t state_idx, generated, distinct, depth, init_states;
+  uint64_t fp_xor, fp_sum;
+  double seconds;
+  uint64_t n_levels;
+  uint64_t level_sizes[4096];
+} cpu_result;
+
+typedef struct {
+  cpu_model m;
+  uint32_t *states; uint32_t *parent; uint32_t *meta;
+  uint64_t cap;
+  uint64_t *table; uint64_t mask;
+  uint64_t n_states, generated;
+  uint64_t work, lo, hi;
+  uint64_t viol_inv, viol_assert, viol_trap, viol_deadlock;
+  int overflow, table_full;
+} cpu_engine;
+
+static int seen_insert(uint64_t *table, uint64_t mask, uint64_t fp) {
+  uint64_t i = fp & mask;
+  for (uint64_t probes = 0; probes <= mask; ++probes) {
+    uint64_t cur = __atomic_load_n(&table[i], __ATOMIC_RELAXED);
+    if (cur == fp) return 0;
+    if (cur == 0) {
+      uint64_t exp = 0;
+      if (__atomic_compare_exchange_n(&table[i], &exp, fp, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return 1;
+      if (exp == fp) return 0;
+    }
+    i = (i + 1) & mask;
+  }
+  return -1;
+}
+
+static void atomic_min64(uint64_t *p, uint64_t v) {
+  uint64_t cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (v < cur && !__atomic_compare_exchange_n(p, &cur, v, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+}
+
+static void *worker(void *arg) {
+  cpu_engine *e = (cpu_engine *)arg;
+  const cpu_model *m = &e->m;
+  int32_t *frame = (int32_t *)calloc(m->frame_words + 8, 4);
+  uint32_t succ[MAXW];
+  uint64_t gen = 0;
+  const int W = (int)m->W;
+  for (;;) {
+    uint64_t chunk = __atomic_fetch_add(&e->work, 1, __ATOMIC_RELAXED);
+    uint64_t first = e->lo + chunk * 64;
+    if (first >= e->hi) break;
+    uint64_t last = first + 64 < e->hi ? first + 64 : e->hi;
+    for (uint64_t idx = first; idx < last; ++idx) {
+      tlag_unpack(m->layout, (int)m->n_slots, e->states + idx * W, frame);
+      int trapped = 0;
+      if (m->n_invariants) {
+        uint32_t pc = m->entry_inv;
+        for (;;) {
+          int32_t info = 0, info2 = 0;
+          int ev = tlag_vm_run(m->code, m->cpool, frame, &pc, &info, &info2, MAX_STEPS);
+          if (ev == TLAG_EV_HALT) break;
+          if (ev == TLAG_EV_INVF) { atomic_min64(&e->viol_inv, (idx << 20) | (uint32_t)(info & 0xFFFFF)); continue; }
+          if (ev == TLAG_EV_ASSERT) { atomic_min64(&e->viol_assert, (idx << 20) | (uint32_t)(info & 0xFFFFF)); continue; }
+          atomic_min64(&e->viol_trap, (idx << 20) | ((uint64_t)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) | (uint32_t)(info2 & 0xFFFF));
+          trapped = 1;
+          break;
+        }
+      }
+      uint32_t pc = m->entry_next;
+      unsigned nsucc = 0;
+      while (!trapped) {
+        int32_t info = 0, info2 = 0;
+        int ev = tlag_vm_run(m->code, m->cpool, frame, &pc, &info, &info2, MAX_STEPS);
+        if (ev == TLAG_EV_HALT) break;
+        if (ev == TLAG_EV_GEN) { ++nsucc; ++gen; continue; }
+        if (ev == TLAG_EV_ASSERT) { atomic_min64(&e->viol_assert, (idx << 20) | (uint32_t)(info & 0xFFFFF)); continue; }
+        if (ev == TLAG_EV_INVF) continue;
+        if (ev == TLAG_EV_EMIT) {
+          ++nsucc; ++gen;
+          int ov = tlag_pack(m->layout, (int)m->n_slots, frame + m->unpacked_words, succ, W);
+          if (ov) { atomic_min64(&e->viol_trap, (idx << 20) | (2ULL << 16) | (uint32_t)((ov - 1) & 0xFFFF)); continue; }
+          uint64_t fp = tlag_fingerprint(succ, W);
+          int ins = seen_insert(e->table, e->mask, fp);
+          if (ins < 0) { e->table_full = 1; continue; }
+          if (ins > 0) {
+            uint64_t pos = __atomic_fetch_add(&e->n_states, 1, __ATOMIC_RELAXED);
+            if (pos < e->cap) {
+              memcpy(e->states + pos * W, succ, (size_t)W * 4);
+              e->parent[pos] = (uint32_t)idx;
+              e->meta[pos] = (uint32_t)info << 8;
+            } else e->overflow = 1;
+          }
+          continue;
+        }
+        atomic_min64(&e->viol_trap, (idx << 20) | ((uint64_t)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) | (uint32_t)(info2 & 0xFFFF));
+        trapped = 1;
+      }
+      if (nsucc == 0 && !trapped && (m->flags & 1)) atomic_min64(&e->viol_deadlock, idx << 20);
+    }
+  }
+  __atomic_fetch_add(&e->generated, gen, __ATOMIC_RELAXED);
+  free(frame);
+  return NULL;
+}
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
+/* Full BFS on the host cores.  Returns 0 or a negative error code (-2 memory). */
+int tlagcpu_run(const cpu_model *m, const uint32_t *init, uint64_t n_init, int n_threads,
+                uint64_t stop_after_states, cpu_result *out, uint32_t *states_out, uint64_t states_out_cap) {
+  cpu_engine e;
+  memset(&e, 0, sizeof(e));
+  memset(out, 0, sizeof(*out));
+  e.m = *m;
+  const int W = (int)m->W;
+  e.cap = m->max_states ? m->max_states : (1ULL << 22);
+  unsigned lg = m->table_log2 ? m->table_log2 : 24;
+  while ((1ULL << lg) < e.cap * 2) ++lg;
+  e.states = (uint32_t *)malloc(e.cap * (size_t)W * 4);
+  e.parent = (uint32_t *)malloc(e.cap * 4);
+  e.meta = (uint32_t *)malloc(e.cap * 4);
+  e.table = (uint64_t *)calloc(1ULL << lg, 8);
+  if (!e.states || !e.parent || !e.meta || !e.table) return -2;
+  e.mask = (1ULL << lg) - 1;
+  e.viol_inv = e.viol_assert = e.viol_trap = e.viol_deadlock = ~0ULL;
+  double t0 = now_s();
+  for (uint64_t i = 0; i < n_init; ++i) {
+    uint64_t fp = tlag_fingerprint(init + i * W, W);
+    e.generated++;
+    if (seen_insert(e.table, e.mask, fp) > 0) {
+      memcpy(e.states + e.n_states * W, init + i * W, (size_t)W * 4);
+      e.parent[e.n_states] = 0xFFFFFFFFu;
+      e.meta[e.n_states] = 0xFFFFFF00u;
+      e.n_states++;
+    }
+  }
+  out->init_states = e.n_states;
+  uint64_t lo = 0, hi = e.n_states, level = 1, depth = hi ? 1 : 0;
+  out->level_sizes[0] = hi;
+  out->n_levels = 1;
+  int verdict = 0;
+  if (n_threads < 1) n_threads = 1;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+  while (lo < hi) {
+    e.lo = lo; e.hi = hi; e.work = 0;
+    for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, worker, &e);
+    for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    if (e.overflow || e.table_full) { free(th); free(e.states); free(e.parent); free(e.meta); free(e.table); return -2; }
+    uint64_t best = ~0ULL; int kind = 0;
+    if (e.viol_trap != ~0ULL && (e.viol_trap >> 20) < best) { best = e.viol_trap >> 20; kind = 4; }
+    if (e.viol_assert != ~0ULL && (e.viol_assert >> 20) < best) { best = e.viol_assert >> 20; kind = 2; }
+    if (e.viol_inv != ~0ULL && (e.viol_inv >> 20) < best) { best = e.viol_inv >> 20; kind = 1; }
+    if (e.viol_deadlock != ~0ULL && (e.viol_deadlock >> 20) < best) { best = e.viol_deadlock >> 20; kind = 3; }
+    if (e.n_states > hi) depth = level + 1;
+    if (out->n_levels < 4096) out->level_sizes[out->n_levels++] = e.n_states - hi;
+    lo = hi; hi = e.n_states; level++;
+    if (kind) {
+      verdict = kind; out->state_idx = best;
+      if (kind == 4) { out->detail = (int)((e.viol_trap >> 16) & 15); out->detail2 = (int)(e.viol_trap & 0xFFFF); }
+      else if (kind == 2) out->detail = (int)(e.viol_assert & 0xFFFFF);
+      else if (kind == 1) out->detail = (int)(e.viol_inv & 0xFFFFF);
+      break;
+    }
+    if (stop_after_states && e.n_states >= stop_after_states) break;
+  }
+  free(th);
+  out->seconds = now_s() - t0;
+  out->verdict = verdict;
+  out->generated = e.generated;
+  out->distinct = e.n_states;
+  out->depth = depth;
+  uint64_t x = 0, s = 0;
+  for (uint64_t i = 0; i < e.n_states; ++i) {
+    uint64_t fp = tlag_fingerprint(e.states + i * W, W);
+    x ^= fp; s += fp;
+  }
+  out->fp_xor = x; out->fp_sum = s;
+  if (states_out) {
+    uint64_t n = e.n_states < states_out_cap ? e.n_states : states_out_cap;
+    memcpy(states_out, e.states, n * (size_t)W * 4);
+  }
+  free(e.states); free(e.parent); free(e.meta); free(e.table);
+  return 0;
+}
+
+uint64_t tlagcpu_fingerprint(const uint32_t *w, int W) { return tlag_fingerprint(w, W); }
+
+void tlagcpu_digest(const uint32_t *states, uint64_t n, int W, uint64_t *out2) {
+  uint64_t x = 0, s = 0;
+  for (uint64_t i = 0; i < n; ++i) { uint64_t fp = tlag_fingerprint(states + i * (uint64_t)W, W); x ^= fp; s += fp; }
+  out2[0] = x; out2[1] = s;
+}
+
+/* K1 on the host: fingerprint + probe/insert over a batch, n_threads workers, returns seconds. */
+typedef struct { const uint32_t *states; uint64_t lo, hi; int W; uint64_t *table; uint64_t mask; uint8_t *is_new; } probe_job;
+
+static void *probe_worker(void *arg) {
+  probe_job *j = (probe_job *)arg;
+  for (uint64_t i = j->lo; i < j->hi; ++i) {
+    uint64_t fp = tlag_fingerprint(j->states + i * (uint64_t)j->W, j->W);
+    int ins = seen_insert(j->table, j->mask, fp);
+    j->is_new[i] = (uint8_t)(ins > 0);
+  }
+  return NULL;
+}
+
+double tlagcpu_probe_batch(const uint32_t *states, uint64_t n, int W, unsigned table_log2, int n_threads, uint8_t *is_new) {
+  uint64_t *table = (uint64_t *)calloc(1ULL << table_log2, 8);
+  if (!table) return -1.0;
+  if (n_threads < 1) n_threads = 1;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+  probe_job *jobs = (probe_job *)malloc(sizeof(probe_job) * (size_t)n_threads);
+  double t0 = now_s();
+  for (int t = 0; t < n_threads; ++t) {
+    jobs[t] = (probe_job){states, n * t / n_threads, n * (t + 1) / n_threads, W, table, (1ULL << table_log2) - 1, is_new};
+    pthread_create(&th[t], NULL, probe_worker, &jobs[t]);
+  }
+  for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+  double dt = now_s() - t0;
+  free(th); free(jobs); free(table);
+  return dt;
+}
+
+/* pack / unpack helpers exposed for host-side tests of the layout */
+int tlagcpu_pack(const tlag_slot *lay, int nslots, const int32_t *st, uint32_t *out, int W) { return tlag_pack(lay, nslots, st, out, W); }
+void tlagcpu_unpack(const tlag_slot *lay, int nslots, const uint32_t *in, int32_t *st) { tlag_unpack(lay, nslots, in, st); }

@@ -1,0 +1,114 @@
+"""GPU parity tests (run on the B200 box): the CUDA engine, called through the C ABI, against the
+recorded oracle results of the committed fixtures and against ORACLE O2 run live on the host."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from tla_rust_b200.compiled import load_compiled
+from tla_rust_b200.checker import decode_state, result_from_engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(cm, **kw):
+    from tla_rust_b200.engine import Engine
+    return Engine(cm, **kw)
+
+
+@pytest.mark.parametrize("name", ["atomic_add", "pcal_intro", "pcal_intro_readme_buggy", "MCPaxos", "MCVoting",
+                                  "HourClock", "AsynchInterface", "MCPaxos3", "MCPaxos3_b2"])
+def test_bfs_matches_oracle(name):
+    from oracle import cpu_engine
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
+    e = _engine(cm, deadlock=info["deadlock"])
+    e.seed(init)
+    levels = [int(len(np.unique(init, axis=0)))]
+    while True:
+        ws = e.step()
+        if ws["expanded"]:
+            levels.append(int(ws["discovered"]))
+        if ws["verdict"] != 5:
+            break
+    r = e.result()
+    o2 = exp["o2"]
+    assert r["verdict"] == o2["verdict"], (r, o2)
+    assert (r["generated"], r["distinct"], r["depth"]) == (o2["generated"], o2["distinct"], o2["depth"])
+    assert levels == o2["levels"]
+    if r["verdict"] != 0:
+        assert r["detail"] == o2["detail"]
+    # bit-exact state set: fingerprint digest of everything the GPU stored (checksum of checksums)
+    states = e.read_states(0, r["distinct"])
+    assert cpu_engine.digest(states, cm.W) == (o2["fp_xor"], o2["fp_sum"])
+    if "o1" in exp and exp["o1"]["verdict"] == "ok":
+        assert (r["generated"], r["distinct"], r["depth"]) == (exp["o1"]["generated"], exp["o1"]["distinct"],
+                                                               exp["o1"]["depth"])
+    assert e.launches() >= len(levels)
+    e.close()
+
+
+def test_assert_trace_is_a_shortest_counterexample():
+    """README.md:267-316: the failing assertion is reached after 5 steps from an initial state; the GPU
+    trace must be a valid 6-state behaviour ending in a state with pc = C for a process whose alice < 0."""
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, "pcal_intro_readme_buggy.tlagz"))
+    e = _engine(cm)
+    e.seed(init)
+    r = e.run()
+    assert r["verdict"] == 2
+    states, acts = e.trace(r["state_idx"])
+    res = result_from_engine(cm, r, (states, acts))
+    assert res.error_text == "Failure of assertion at line 16, column 4."
+    assert len(res.trace) == 6 and res.trace[0][1] is None
+    last = res.trace[-1][0]
+    assert last["alice_account"] < 0 and "C" in last["pc"]
+    assert res.trace[0][0]["alice_account"] == 10 and res.trace[0][0]["pc"] == ("Transfer", "Transfer")
+    e.close()
+
+
+@pytest.mark.parametrize("W,n", [(1, 1000), (3, 5000), (4, 100000), (20, 200000), (7, 0), (64, 300)])
+def test_probe_batch_matches_cpu(W, n):
+    """K1 alone through the C ABI: exactly one 'new' flag per distinct state, same set as the CPU oracle;
+    edge cases: empty batch, widest state, ragged (non-vectorisable) widths."""
+    from tla_rust_b200.engine import Engine, ProbeOnlyModel
+    from oracle import cpu_engine
+    rng = np.random.default_rng(1234 + W)
+    base = rng.integers(0, 2**32, size=(max(n // 2, 1), W), dtype=np.uint64).astype(np.uint32)
+    states = np.concatenate([base, base[rng.integers(0, len(base), size=n - len(base))]]) if n else base[:0]
+    e = Engine(ProbeOnlyModel(W), table_log2=20)
+    flags = e.probe_batch(states)
+    assert flags.shape == (n,)
+    if n:
+        cflags, _ = cpu_engine.probe_batch(states, W, 20, 1)
+        uniq, inv = np.unique(states, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        assert int(flags.sum()) == len(uniq) == int(cflags.sum())
+        per = np.bincount(inv, weights=flags, minlength=len(uniq))
+        assert (per == 1).all()
+        # idempotence: probing again finds nothing new
+        assert int(e.probe_batch(states).sum()) == 0
+    e.close()
+
+
+def test_probe_roundtrip_full_size_properties():
+    """BASELINE-size property test (SURVEY §8d synthetic K1 input, scaled to 2^24 here): #new == #distinct,
+    second pass == 0, after reset the same batch is all-new again."""
+    import torch
+    from tla_rust_b200.engine import Engine, ProbeOnlyModel
+    W, n = 20, 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(0x5EED)
+    half = torch.randint(0, 2**31 - 1, (n // 2, W), dtype=torch.int32, device="cuda", generator=g)
+    perm = torch.randint(0, n // 2, (n // 2,), device="cuda", generator=g)
+    states = torch.cat([half, half[perm]])
+    flags = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    e = Engine(ProbeOnlyModel(W), table_log2=26)
+    e.probe_batch_device(states.data_ptr(), n, flags.data_ptr())
+    torch.cuda.synchronize()
+    n_new = int(flags.sum().item())
+    assert n_new == n // 2          # random 80-byte rows: distinct with overwhelming probability
+    e.probe_batch_device(states.data_ptr(), n, flags.data_ptr())
+    assert int(flags.sum().item()) == 0
+    e.reset_table()
+    e.probe_batch_device(states.data_ptr(), n, flags.data_ptr())
+    assert int(flags.sum().item()) == n // 2
+    e.close()

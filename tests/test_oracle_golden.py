@@ -1,0 +1,79 @@
+"""Pins the oracle (oracle/tlc_oracle.py) against the only known-answer transcript the reference
+holds for the hot path: README.md:267-321 (buggy pcal_intro) -- counts, trace, action locations --
+and the verdict-only expectations (README.md:349-352, HourClock = 12 states)."""
+import os
+import tempfile
+
+import pytest
+
+from conftest import REF, needs_reference
+from tla_rust_b200.front.spec import Model
+from tla_rust_b200.front.pcal import translate_file
+from tla_rust_b200.front.report import format_result
+from oracle.tlc_oracle import Oracle
+from test_frontend import README_BUGGY
+
+README_TRACE = [
+    dict(bob_account=10, money=(1, 10), alice_account=10, pc=("Transfer", "Transfer"), account_total=20),
+    dict(bob_account=10, money=(1, 10), alice_account=10, pc=("A", "Transfer"), account_total=20),
+    dict(bob_account=10, money=(1, 10), alice_account=10, pc=("A", "A"), account_total=20),
+    dict(bob_account=10, money=(1, 10), alice_account=9, pc=("B", "A"), account_total=20),
+    dict(bob_account=11, money=(1, 10), alice_account=9, pc=("C", "A"), account_total=20),
+    dict(bob_account=11, money=(1, 10), alice_account=-1, pc=("C", "B"), account_total=20),
+]
+README_ACTIONS = [None, (35, 19, 40, 42), (35, 19, 40, 42), (42, 12, 45, 63), (47, 12, 50, 65), (42, 12, 45, 63)]
+
+
+def _copy(name, edits=(), cfg=None):
+    d = tempfile.mkdtemp(prefix="tlag_t_")
+    src = open(os.path.join(REF, name + ".tla")).read()
+    for a, b in edits:
+        src = src.replace(a, b)
+    p = os.path.join(d, name + ".tla")
+    open(p, "w").write(src)
+    if cfg is not None:
+        open(os.path.join(d, name + ".cfg"), "w").write(cfg)
+    elif os.path.exists(os.path.join(REF, name + ".cfg")):
+        open(os.path.join(d, name + ".cfg"), "w").write(open(os.path.join(REF, name + ".cfg")).read())
+    translate_file(p)
+    return p
+
+
+@needs_reference
+def test_readme_transcript_exact():
+    p = _copy("pcal_intro", README_BUGGY, cfg="SPECIFICATION Spec\n")
+    m = Model(p)
+    r = Oracle(m).run()
+    assert r.verdict == "assert"
+    assert r.error_text == "Failure of assertion at line 16, column 4."
+    assert (r.generated, r.distinct, r.queue, r.depth) == (9097, 6164, 999, 7)      # README.md:319-320
+    assert [st for st, _ in r.trace] == README_TRACE                               # README.md:271-311
+    assert [None if a is None else a[2] for _, a in r.trace] == README_ACTIONS      # README.md:278-306
+    txt = format_result(r, m.vars, m.module_name)
+    assert "State 6: <Action line 42, col 12 to line 45, col 63 of module pcal_intro>" in txt
+    assert txt.rstrip().endswith("The depth of the complete state graph search is 7.")
+    assert "9097 states generated, 6164 distinct states found, 999 states left on queue." in txt
+
+
+@needs_reference
+def test_bundled_specs_no_error():
+    p = _copy("pcal_intro")                       # README.md:349-352 "should produce no errors"
+    r = Oracle(Model(p)).run()
+    assert (r.verdict, r.generated, r.distinct, r.depth, r.init_states) == ("ok", 5850, 3800, 5, 400)
+    p = _copy("atomic_add")
+    r = Oracle(Model(p)).run()
+    assert (r.verdict, r.generated, r.distinct, r.depth) == ("ok", 7, 5, 4)
+    assert os.path.exists(os.path.splitext(p)[0] + ".cfg") and os.path.exists(os.path.splitext(p)[0] + ".old")
+
+
+@needs_reference
+def test_small_corpus_counts():
+    ex = REF + "/examples/SpecifyingSystems/"
+    r = Oracle(Model(ex + "HourClock/HourClock.tla")).run()
+    assert (r.verdict, r.distinct) == ("ok", 12)            # HourClock.tla:4-5
+    r = Oracle(Model(REF + "/examples/Paxos/MCPaxos.tla")).run()
+    assert (r.verdict, r.generated, r.distinct, r.depth) == ("ok", 82, 25, 9)
+    m = Model(REF + "/examples/Paxos/MCConsensus.tla")
+    m.check_deadlock = False
+    r = Oracle(m).run()
+    assert (r.verdict, r.distinct, r.init_states) == ("ok", 4, 4)

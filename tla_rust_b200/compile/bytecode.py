@@ -1,0 +1,217 @@
+"""Fixed-width state-vector bytecode (the ISA shared by the CUDA engine and the CPU
+bytecode oracle; mirrored in csrc/tlag_vm.h -- keep the two tables in sync).
+
+One instruction = 64 bits:  op[0:8] a[8:22] b[22:36] c[36:50] d[50:64].
+Operands a..d are 14-bit frame word indices unless noted; imm28(b,c) = bits 22..49,
+imm28(c,d) = bits 36..63 (signed).  The frame is a per-thread array of int32 words:
+[ current state (unpacked) | primed state (unpacked) | temporaries ].
+"""
+from __future__ import annotations
+
+import numpy as np
+
+OPS = [
+    "HALT", "LI", "LIW", "MOV", "MOVN", "ZERO", "LDC",
+    "ADD", "SUB", "MUL", "DIV", "MOD", "NEG",
+    "LT", "LE", "EQ", "NE", "EQN", "NOT", "AND", "OR",
+    "LDX", "STX", "TBL",
+    "BSET", "BCLR", "BTEST", "BOR", "BAND", "BANDN", "BISZ", "BSUB", "BCNT", "BNEXT", "BFILL",
+    "JMP", "JZ", "JNZ", "JNEG",
+    "TRAP", "EMIT", "GEN", "ASSERTF", "INVF",
+    "ADDI", "MULI", "EQI", "NEI", "LTI", "LEI", "GTI", "GEI", "UCLAMP",
+    "BSETI", "BTESTI", "SHRI", "ANDI",
+]
+OP = {n: i for i, n in enumerate(OPS)}
+
+# operand formats: which fields are registers(r) / imm28 in (b,c) 'I' / imm28 in (c,d) 'J' / small imm 'n'
+FMT = {
+    "HALT": "", "LI": "rI", "LIW": "rI", "MOV": "rr", "MOVN": "rrn", "ZERO": "rn", "LDC": "rIn",
+    "ADD": "rrr", "SUB": "rrr", "MUL": "rrr", "DIV": "rrr", "MOD": "rrr", "NEG": "rr",
+    "LT": "rrr", "LE": "rrr", "EQ": "rrr", "NE": "rrr", "EQN": "rrrn", "NOT": "rr", "AND": "rrr", "OR": "rrr",
+    "LDX": "rrrn", "STX": "rrrn", "TBL": "rIr",
+    "BSET": "rr", "BCLR": "rr", "BTEST": "rrr", "BOR": "rrrn", "BAND": "rrrn", "BANDN": "rrrn",
+    "BISZ": "rrn", "BSUB": "rrrn", "BCNT": "rrn", "BNEXT": "rrrn", "BFILL": "rn",
+    "JMP": "_I", "JZ": "rI", "JNZ": "rI", "JNEG": "rI",
+    "TRAP": "nI", "EMIT": "_I", "GEN": "", "ASSERTF": "_I", "INVF": "_I",
+    "ADDI": "rrJ", "MULI": "rrJ", "EQI": "rrJ", "NEI": "rrJ", "LTI": "rrJ", "LEI": "rrJ", "GTI": "rrJ",
+    "GEI": "rrJ", "UCLAMP": "rI", "BSETI": "rI", "BTESTI": "rrJ", "SHRI": "rrJ", "ANDI": "rrJ",
+}
+
+TRAP_EVAL, TRAP_OVERFLOW, TRAP_CASE, TRAP_CHOOSE, TRAP_ASSIGN = 1, 2, 3, 4, 5
+TRAP_NAMES = {1: "evaluation error (function applied outside its domain / missing record field)",
+              2: "value outside its inferred fixed-width type (capacity overflow)",
+              3: "CASE: no arm is true", 4: "CHOOSE: no element satisfies the predicate",
+              5: "internal: unassigned variable"}
+
+MAXREG = (1 << 14) - 1
+IMM28_MIN, IMM28_MAX = -(1 << 27), (1 << 27) - 1
+
+
+class Label:
+    __slots__ = ("name", "pos")
+    _n = 0
+
+    def __init__(self, hint="L"):
+        Label._n += 1
+        self.name = f"{hint}{Label._n}"
+        self.pos = None
+
+    def __repr__(self):
+        return self.name
+
+
+class AsmError(Exception):
+    pass
+
+
+class Asm:
+    def __init__(self):
+        self.code = []       # list of tuples (op, a, b, c, d) with Label operands allowed / ('label', L)
+        self.cpool = []      # int32 constants
+        self._cp_cache = {}
+
+    def emit(self, op, *args):
+        self.code.append((op,) + tuple(args))
+
+    def label(self, L: Label):
+        self.code.append(("label", L))
+
+    def const_table(self, words):
+        """Intern a table of int32 words in the constant pool; returns its base index."""
+        key = tuple(int(w) for w in words)
+        base = self._cp_cache.get(key)
+        if base is None:
+            base = len(self.cpool)
+            self.cpool.extend(key)
+            self._cp_cache[key] = base
+        return base
+
+    def capture(self):
+        return _Capture(self)
+
+    def splice(self, buf):
+        self.code.extend(buf)
+
+    def assemble(self, entry_points: dict):
+        """Resolve labels -> (uint64 code array, int32 cpool array, {name: pc})."""
+        pos = 0
+        for ins in self.code:
+            if ins[0] == "label":
+                ins[1].pos = pos
+            else:
+                pos += 1
+        out = np.zeros(pos, dtype=np.uint64)
+        i = 0
+        for ins in self.code:
+            if ins[0] == "label":
+                continue
+            out[i] = self._encode(ins)
+            i += 1
+        cp = np.array(self.cpool if self.cpool else [0], dtype=np.int64)
+        cp = ((cp + (1 << 31)) % (1 << 32) - (1 << 31)).astype(np.int32)
+        entries = {k: (v.pos if isinstance(v, Label) else v) for k, v in entry_points.items()}
+        return out, cp, entries
+
+    def _encode(self, ins):
+        name = ins[0]
+        fmt = FMT[name]
+        args = list(ins[1:])
+        a = b = c = d = 0
+        fields = []
+        ai = 0
+        slot = 0  # 0:a 1:b 2:c 3:d
+
+        def val(x):
+            if isinstance(x, Label):
+                if x.pos is None:
+                    raise AsmError(f"unresolved label {x}")
+                return x.pos
+            return int(x)
+
+        regs = [0, 0, 0, 0]
+        for ch in fmt:
+            if ch == "_":
+                slot += 1
+                continue
+            v = val(args[ai])
+            ai += 1
+            if ch in "rn":
+                if not (0 <= v <= MAXREG):
+                    raise AsmError(f"{name}: operand {v} out of 14-bit range")
+                regs[slot] = v
+                slot += 1
+            elif ch == "I":
+                if not (IMM28_MIN <= v <= IMM28_MAX):
+                    raise AsmError(f"{name}: immediate {v} out of 28-bit range")
+                v &= (1 << 28) - 1
+                regs[1] = v & 0x3FFF
+                regs[2] = (v >> 14) & 0x3FFF
+                slot = 3
+            elif ch == "J":
+                if not (IMM28_MIN <= v <= IMM28_MAX):
+                    raise AsmError(f"{name}: immediate {v} out of 28-bit range")
+                v &= (1 << 28) - 1
+                regs[2] = v & 0x3FFF
+                regs[3] = (v >> 14) & 0x3FFF
+                slot = 4
+        if ai != len(args):
+            raise AsmError(f"{name}: expected {ai} operands, got {len(args)}")
+        a, b, c, d = regs
+        return np.uint64(OP[name] | (a << 8) | (b << 22) | (c << 36) | (d << 50))
+
+
+class _Capture:
+    def __init__(self, asm):
+        self.asm = asm
+
+    def __enter__(self):
+        self.saved = self.asm.code
+        self.asm.code = []
+        return self
+
+    def __exit__(self, *exc):
+        self.buf = self.asm.code
+        self.asm.code = self.saved
+        return False
+
+
+def disasm(code, entries=None):
+    inv = {}
+    if entries:
+        for k, v in entries.items():
+            inv.setdefault(v, []).append(k)
+    lines = []
+    for pc, w in enumerate(code):
+        w = int(w)
+        op = w & 0xFF
+        a = (w >> 8) & 0x3FFF
+        b = (w >> 22) & 0x3FFF
+        c = (w >> 36) & 0x3FFF
+        d = (w >> 50) & 0x3FFF
+        name = OPS[op]
+        fmt = FMT[name]
+        regs = [a, b, c, d]
+        outs = []
+        slot = 0
+        for ch in fmt:
+            if ch == "_":
+                slot += 1
+            elif ch in "rn":
+                outs.append(("r" if ch == "r" else "#") + str(regs[slot]))
+                slot += 1
+            elif ch == "I":
+                v = b | (c << 14)
+                if v >= (1 << 27):
+                    v -= 1 << 28
+                outs.append(f"${v}")
+                slot = 3
+            elif ch == "J":
+                v = c | (d << 14)
+                if v >= (1 << 27):
+                    v -= 1 << 28
+                outs.append(f"${v}")
+                slot = 4
+        for nm in inv.get(pc, []):
+            lines.append(f"{nm}:")
+        lines.append(f"{pc:5d}  {name:8s} " + ", ".join(outs))
+    return "\n".join(lines)

@@ -1,0 +1,2389 @@
+"""Lowering of a Model (Next action, invariants, constraints) to fixed-width bytecode.
+
+Pipeline (north_star "lowers each next-state action and invariant
+to a fixed-width state-vector bytecode"):
+  1. variable types from a TypeOK-style definition (or widened shapes of the initial
+     states) -> state layout (compile/types.py)
+  2. Next -> one straight-line program with guards, loops over runtime sets and an
+     EMIT per completed successor (continuation-passing over TLC's conjunct/disjunct
+     evaluation order; constant quantifiers are unrolled, constant subexpressions are
+     folded by the host evaluator)
+  3. invariants / constraints -> predicate programs over the unpacked state.
+"""
+from __future__ import annotations
+
+import re
+
+from ..front.parser import Node, OpDef
+from ..front.eval import Evaluator, Fr, Thunk, Closure, OpVal, AssertFailure, BuiltinOp
+from ..front.values import (EvalError, ModelValue, Fcn, LazySet, LazyFcn, SetNat, SetInt, mk_fcn, sorted_vals,
+                            set_contains, set_iter, to_finite, is_set, is_enumerable, fmt, vkey, fcn_items)
+from .types import (T, TInt, TBool, TAtom, TRec, TTuple, TFun, TSet, TSeq, TBottom, TypeErr, Atoms, Codec, join,
+                    type_of_value, type_of_set, widen_init, is_atom)
+from .bytecode import (Asm, Label, TRAP_EVAL, TRAP_OVERFLOW, TRAP_CASE, TRAP_CHOOSE, IMM28_MAX, IMM28_MIN, MAXREG)
+
+UNROLL_MAX = 24
+UNIV_TABLE_MAX = 1 << 16
+
+
+class CompileError(Exception):
+    pass
+
+
+class Const:
+    __slots__ = ("v",)
+
+    def __init__(self, v):
+        self.v = v
+
+    def __repr__(self):
+        return f"Const({fmt(self.v)})"
+
+
+class Val:
+    __slots__ = ("t", "loc")
+
+    def __init__(self, t, loc):
+        self.t = t
+        self.loc = loc
+
+    def __repr__(self):
+        return f"Val({self.t}@{self.loc})"
+
+
+class Lazy:
+    __slots__ = ("node", "env", "ctx", "base")
+
+    def __init__(self, node, env, ctx, base):
+        self.node, self.env, self.ctx, self.base = node, env, ctx, base
+
+
+class OpC:
+    """Operator value at compile time (definition with parameters, LET operator, LAMBDA)."""
+    __slots__ = ("params", "body", "env", "ctx", "name")
+
+    def __init__(self, params, body, env, ctx, name):
+        self.params, self.body, self.env, self.ctx, self.name = params, body, env, ctx, name
+
+
+_RUNTIME_NODE = Node("runtime", ())
+
+
+class CompiledModel:
+    """Everything the engine needs + what the host needs to decode states."""
+
+    def __init__(self):
+        self.code = None
+        self.cpool = None
+        self.entries = {}
+        self.W = 0
+        self.frame_words = 0
+        self.layout = None       # np.int32 [nslots,3]: frame_off, width, bias
+        self.n_off = 0
+        self.p_off = 0
+        self.state_words_unpacked = 0
+        self.var_types = {}
+        self.var_off = {}
+        self.vars = []
+        self.actions = []        # id -> (name, loc, module)
+        self.invariants = []     # names
+        self.asserts = []        # id -> message
+        self.atoms = None
+        self.codec = None
+        self.warnings = []
+
+
+class Lowering:
+    def __init__(self, model, seq_cap=None, type_hint=None):
+        self.m = model
+        self.ev = model.ev
+        self.ev.disp["runtime"] = self._runtime_node
+        self.ctx = model.ctx
+        self.asm = Asm()
+        self.atoms = Atoms()
+        self.codec = Codec(self.atoms)
+        self.seq_cap = seq_cap
+        self.type_hint = type_hint
+        self.top = 0
+        self.high = 0
+        self.bound = frozenset()
+        self.actions = []
+        self.asserts = []
+        self.warnings = []
+        self._evenv_cache = {}
+        self.hoisted = {}
+        self.def_uses = {}
+        self.def_info = {}
+        self.program = "inv"
+        self.hoist_keys = []
+        self.dry = False
+        self._intern_all_atoms()
+
+    @staticmethod
+    def _runtime_node(n, env, fr):
+        raise EvalError("runtime value")
+
+    # ------------------------------------------------------------------ atoms
+    def _intern_all_atoms(self):
+        strs = set()
+        mvs = set()
+
+        def walk(n):
+            if isinstance(n, Node):
+                if n.k == "str":
+                    strs.add(n.a[0])
+                for x in n.a:
+                    walk(x)
+            elif isinstance(n, (tuple, list)):
+                for x in n:
+                    walk(x)
+            elif isinstance(n, OpDef):
+                walk(n.body)
+
+        def walkv(v):
+            if isinstance(v, ModelValue):
+                mvs.add(v)
+            elif isinstance(v, str):
+                strs.add(v)
+            elif isinstance(v, (frozenset, tuple)):
+                for x in v:
+                    walkv(x)
+            elif isinstance(v, Fcn):
+                for k, x in v.d.items():
+                    walkv(k)
+                    walkv(x)
+
+        for name in self.m.loader.cache:
+            mod = self.m.loader.cache[name]
+            for d in mod.defs.values():
+                walk(d.body)
+            for _, e in mod.assumes:
+                walk(e)
+        for c in [self.ctx] + self.ctx.all_instances:
+            for v in c.consts.values():
+                walkv(v)
+        for s in sorted(strs):
+            self.atoms.id(s)
+        for mv in sorted(mvs, key=lambda x: x.name):
+            self.atoms.id(mv)
+        self.all_strings = sorted(strs)
+        self.all_mvs = sorted(mvs, key=lambda x: x.name)
+
+    # ------------------------------------------------------------- allocation
+    def alloc(self, n):
+        loc = self.top
+        self.top += max(n, 0)
+        if self.top > self.high:
+            self.high = self.top
+        if self.high > MAXREG and not self.dry:
+            raise CompileError("frame exceeds 16K words")
+        return loc
+
+    def mark(self):
+        return self.top
+
+    def release(self, m):
+        self.top = m
+
+    # ------------------------------------------------------------- var types
+    def infer_var_types(self, init_states):
+        m = self.m
+        types = {}
+        hint = self.type_hint
+        cand = [hint] if hint else [n for n in self.ctx.defs
+                                    if re.fullmatch(r"(I?Type(OK|Inv|Invariant|Correct)?)", n)]
+        cand.sort(key=lambda n: (n.startswith("I"), n))
+        for name in cand:
+            d = self.ctx.defs.get(name)
+            if d is None or d[0].params:
+                continue
+            body = d[0].body
+            items = body.a[0] if body.k == "and" else (body,)
+            got = {}
+            for it in items:
+                if it.k == "bin" and it.a[0] in ("\\in", "\\subseteq") and it.a[1].k == "id" \
+                        and it.a[1].a[0] in self.ctx.varset:
+                    v = it.a[1].a[0]
+                    try:
+                        sv = self.ev.eval(it.a[2], {}, Fr(d[1]))
+                        et = type_of_set(sv, self.seq_cap)
+                        got[v] = TSet(et) if it.a[0] == "\\subseteq" else et
+                    except (EvalError, TypeErr) as ex:
+                        self.warnings.append(f"type hint {name}: cannot use conjunct for {v}: {ex}")
+            for v, t in got.items():
+                types.setdefault(v, t)
+            if all(v in types for v in m.vars):
+                break
+        all_atoms = [self.atoms.val(i) for i in range(1, len(self.atoms.vals))]
+        str_atoms = [a for a in all_atoms if isinstance(a, str)]
+        mv_atoms = [a for a in all_atoms if isinstance(a, ModelValue)]
+        for v in m.vars:
+            if v in types:
+                continue
+            t = None
+            for st in init_states:
+                t = join(t, type_of_value(st[v], self.seq_cap))
+            if t is None:
+                raise CompileError(f"cannot infer a type for variable {v}: no initial states")
+            types[v] = self._widen(t, str_atoms, mv_atoms, all_atoms)
+        # initial states must inhabit the types
+        for v in m.vars:
+            for st in init_states[:64]:
+                try:
+                    self.codec.rep(types[v], st[v])
+                except TypeErr as ex:
+                    raise CompileError(f"initial value of {v} does not fit its type {types[v]}: {ex}")
+        return types
+
+    def _widen(self, t, strs, mvs, alla):
+        if isinstance(t, TAtom):
+            has_s = any(isinstance(a, str) for a in t.atoms)
+            has_m = any(isinstance(a, ModelValue) for a in t.atoms)
+            pool = alla if (has_s and has_m) else (strs if has_s else mvs)
+            return TAtom(sorted(pool, key=vkey))
+        if isinstance(t, TInt):
+            return TInt()
+        if isinstance(t, TTuple):
+            return TTuple([self._widen(e, strs, mvs, alla) for e in t.elems])
+        if isinstance(t, TFun):
+            return TFun(t.keys, self._widen(t.elem, strs, mvs, alla))
+        if isinstance(t, TRec):
+            return TRec([{f: self._widen(x, strs, mvs, alla) for f, x in d.items()} for d in t.alt_dicts()])
+        if isinstance(t, TSet):
+            if isinstance(t.elem, TBottom):
+                raise CompileError("cannot infer the element type of an initially-empty set variable; "
+                                   "add a TypeOK-style definition (v \\in S / v \\subseteq S conjuncts)")
+            e = t.elem
+            if isinstance(e, TInt):
+                return t
+            return TSet(self._widen(e, strs, mvs, alla))
+        return t
+
+    # ------------------------------------------------------------ const eval
+    def eval_env(self, env):
+        key = id(env)
+        hit = self._evenv_cache.get(key)
+        if hit is not None and hit[0] is env:
+            return hit[1]
+        out = {}
+        self._evenv_cache[key] = (env, out)   # registered first: LET environments are self-referential
+        for k, v in env.items():
+            if type(v) is Const:
+                out[k] = v.v
+            elif type(v) is Val:
+                out[k] = Thunk(_RUNTIME_NODE, {}, None)
+            elif type(v) is Lazy:
+                if v.base != "N":
+                    out[k] = Thunk(_RUNTIME_NODE, {}, None)
+                else:
+                    out[k] = Thunk(v.node, self.eval_env(v.env), v.ctx)
+            elif type(v) is OpC:
+                out[k] = Closure([p for p, _ in v.params], v.body, self.eval_env(v.env), v.ctx, v.name)
+        self._evenv_cache[key] = (env, out)
+        return out
+
+    def try_const(self, node, env, ctx, base):
+        if base != "N" and node.k not in ("num", "str", "bool"):
+            # primed context: only literals are constant for sure; still try (constants don't read state)
+            pass
+        try:
+            v = self.ev.eval(node, self.eval_env(env), Fr(ctx, None, None))
+        except (EvalError, AssertFailure, RecursionError, TypeErr, TypeError, KeyError, AttributeError,
+                ValueError, IndexError):
+            return None
+        if isinstance(v, (OpVal, Closure, BuiltinOp)):
+            return None
+        if isinstance(v, LazyFcn):
+            v = v.force()
+        return Const(v)
+
+    # ------------------------------------------------------- materialisation
+    def materialize(self, c: Const, t: T) -> Val:
+        try:
+            words = self.codec.rep(t, c.v)
+        except TypeErr as ex:
+            raise CompileError(f"constant {fmt(c.v)} does not fit type {t}: {ex}")
+        loc = self.alloc(t.size)
+        self.load_words(loc, words)
+        return Val(t, loc)
+
+    def load_words(self, loc, words):
+        if len(words) <= 2:
+            for i, w in enumerate(words):
+                self.li(loc + i, w)
+        elif all(w == 0 for w in words):
+            self.asm.emit("ZERO", loc, len(words))
+        else:
+            base = self.asm.const_table(words)
+            i = 0
+            while i < len(words):
+                n = min(len(words) - i, MAXREG)
+                self.asm.emit("LDC", loc + i, base + i, n)
+                i += n
+
+    def li(self, loc, w):
+        w = int(w)
+        if IMM28_MIN <= w <= IMM28_MAX:
+            self.asm.emit("LI", loc, w)
+        else:
+            self.asm.emit("LIW", loc, self.asm.const_table([w]))
+
+    def natural_type(self, v) -> T:
+        t = type_of_value(v, self.seq_cap)
+        return t
+
+    def as_val(self, x, want=None) -> Val:
+        if type(x) is Val:
+            return x
+        t = want if want is not None else self.natural_type(x.v)
+        if want is None and isinstance(t, TSet) and isinstance(t.elem, TBottom):
+            raise CompileError("cannot type the empty set here (no expected type)")
+        return self.materialize(x, t)
+
+    # ------------------------------------------------------------- coercion
+    def coerce(self, x, t: T) -> Val:
+        if type(x) is Const:
+            return self.materialize(x, t)
+        s = x.t
+        if s == t:
+            return x
+        if isinstance(t, TInt) and isinstance(s, TInt):
+            return Val(t, x.loc)
+        if isinstance(t, TAtom) and isinstance(s, TAtom):
+            return Val(t, x.loc)
+        if isinstance(t, TBool) and isinstance(s, TBool):
+            return x
+        if isinstance(t, TRec) and isinstance(s, TRec):
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            if s.tagged:
+                if not t.tagged:
+                    raise CompileError(f"cannot coerce union {s} to record {t}")
+                # map tags through a table
+                tbl = []
+                for alt in s.alts:
+                    tbl.append(t.alt_index(alt))
+                if any(i < 0 for i in tbl):
+                    raise CompileError(f"record alternatives of {s} missing from {t}")
+                self.asm.emit("TBL", dst, self.asm.const_table(tbl), x.loc)
+            else:
+                ai = t.alt_index(s.alts[0])
+                if ai < 0:
+                    raise CompileError(f"record with fields {s.alts[0]} does not fit {t}")
+                if t.tagged:
+                    self.li(dst, ai)
+            for f in s.fnames:
+                if f not in t.fields:
+                    raise CompileError(f"field {f} missing in target record type")
+                sub = self.coerce(Val(s.fields[f], x.loc + s.off[f]), t.fields[f])
+                self.movn(dst + t.off[f], sub.loc, t.fields[f].size)
+            return Val(t, dst)
+        if isinstance(t, TTuple) and isinstance(s, TTuple) and len(t.elems) == len(s.elems):
+            dst = self.alloc(t.size)
+            for te, se, to, so in zip(t.elems, s.elems, t.offs, s.offs):
+                sub = self.coerce(Val(se, x.loc + so), te)
+                self.movn(dst + to, sub.loc, te.size)
+            return Val(t, dst)
+        if isinstance(t, TFun) and isinstance(s, TFun) and t.keys == s.keys:
+            dst = self.alloc(t.size)
+            for j in range(len(t.keys)):
+                sub = self.coerce(Val(s.elem, x.loc + j * s.elem.size), t.elem)
+                self.movn(dst + j * t.elem.size, sub.loc, t.elem.size)
+            return Val(t, dst)
+        if isinstance(t, TFun) and isinstance(s, TTuple) and t.keys == tuple(range(1, len(s.elems) + 1)):
+            dst = self.alloc(t.size)
+            for j in range(len(t.keys)):
+                sub = self.coerce(Val(s.elems[j], x.loc + s.offs[j]), t.elem)
+                self.movn(dst + j * t.elem.size, sub.loc, t.elem.size)
+            return Val(t, dst)
+        if isinstance(t, TSet) and isinstance(s, TSet):
+            if isinstance(s.elem, TBottom):
+                dst = self.alloc(t.size)
+                self.asm.emit("ZERO", dst, t.size)
+                return Val(t, dst)
+            if self._same_universe_prefix(s.elem, t.elem):
+                dst = self.alloc(t.size)
+                self.asm.emit("ZERO", dst, t.size)
+                self.movn(dst, x.loc, s.size)
+                return Val(t, dst)
+            # re-index element by element
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+
+            def body(ev):
+                o = self.ord_in(t.elem, ev)
+                bad = Label("ovf")
+                ok = Label("ok")
+                self.asm.emit("JNEG", o, bad)
+                self.asm.emit("BSET", dst, o)
+                self.asm.emit("JMP", ok)
+                self.asm.label(bad)
+                self.asm.emit("TRAP", TRAP_OVERFLOW, 0)
+                self.asm.label(ok)
+            self.loop_set(x, body)
+            return Val(t, dst)
+        if isinstance(t, TSeq) and isinstance(s, TTuple):
+            if len(s.elems) > t.cap:
+                raise CompileError("tuple longer than sequence capacity")
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            self.li(dst, len(s.elems))
+            for j, (se, so) in enumerate(zip(s.elems, s.offs)):
+                sub = self.coerce(Val(se, x.loc + so), t.elem)
+                self.movn(dst + 1 + j * t.elem.size, sub.loc, t.elem.size)
+            return Val(t, dst)
+        if isinstance(t, TSeq) and isinstance(s, TSeq) and t.elem == s.elem and s.cap <= t.cap:
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            self.movn(dst, x.loc, s.size)
+            return Val(t, dst)
+        raise CompileError(f"cannot coerce {s} to {t}")
+
+    @staticmethod
+    def _same_universe_prefix(a: T, b: T):
+        """True if enumeration of a is a prefix-compatible renumbering-free subset of b (same ordinals)."""
+        if a == b:
+            return True
+        if isinstance(a, TInt) and isinstance(b, TInt) and a.lo is not None and b.lo is not None:
+            return a.lo == b.lo and a.hi <= b.hi
+        if isinstance(a, TAtom) and isinstance(b, TAtom):
+            return b.atoms[:len(a.atoms)] == a.atoms
+        return False
+
+    def movn(self, dst, src, n):
+        if dst == src or n == 0:
+            return
+        if n == 1:
+            self.asm.emit("MOV", dst, src)
+        else:
+            self.asm.emit("MOVN", dst, src, n)
+
+    # --------------------------------------------------------------- ordinals
+    def ord_in(self, E: T, v) -> int:
+        """Emit code computing the ordinal of v within E (or -1 when outside); returns the reg."""
+        if type(v) is Const:
+            o = self.codec.ord_of(E, v.v)
+            r = self.alloc(1)
+            if isinstance(E, TSet):
+                self.li(r, o if o < (1 << 31) else o - (1 << 32))
+            else:
+                self.li(r, o)
+            return r
+        s = v.t
+        r = self.alloc(1)
+        if isinstance(E, TInt):
+            if not isinstance(s, TInt):
+                self.li(r, -1)
+                return r
+            if E.lo is None:
+                raise CompileError("ordinal of an unbounded integer type")
+            if E.lo != 0:
+                self.asm.emit("ADDI", r, v.loc, -E.lo)
+            else:
+                self.asm.emit("MOV", r, v.loc)
+            self.asm.emit("UCLAMP", r, E.card())
+            return r
+        if isinstance(E, TBool):
+            if not isinstance(s, TBool):
+                self.li(r, -1)
+            else:
+                self.asm.emit("MOV", r, v.loc)
+            return r
+        if isinstance(E, TAtom):
+            if not isinstance(s, TAtom):
+                self.li(r, -1)
+                return r
+            tbl = [-1] * len(self.atoms.vals)
+            for i, a in enumerate(E.atoms):
+                tbl[self.atoms.id(a)] = i
+            self.asm.emit("TBL", r, self.asm.const_table(tbl), v.loc)
+            return r
+        if isinstance(E, TRec):
+            if not isinstance(s, TRec):
+                self.li(r, -1)
+                return r
+            bad = Label("obad")
+            end = Label("oend")
+            if not s.tagged:
+                self._ord_rec_alt(E, s, s.alts[0], v, r, bad)
+                self.asm.emit("JMP", end)
+            else:
+                for j, alt in enumerate(s.alts):
+                    nxt = Label("oalt")
+                    t1 = self.alloc(1)
+                    self.asm.emit("EQI", t1, v.loc, j)
+                    self.asm.emit("JZ", t1, nxt)
+                    self._ord_rec_alt(E, s, alt, v, r, bad)
+                    self.asm.emit("JMP", end)
+                    self.asm.label(nxt)
+            self.asm.label(bad)
+            self.li(r, -1)
+            self.asm.label(end)
+            return r
+        if isinstance(E, TTuple):
+            if not (isinstance(s, TTuple) and len(s.elems) == len(E.elems)):
+                self.li(r, -1)
+                return r
+            bad = Label("obad")
+            end = Label("oend")
+            self.li(r, 0)
+            for ee, se, so in zip(E.elems, s.elems, s.offs):
+                o = self.ord_in(ee, Val(se, v.loc + so))
+                self.asm.emit("JNEG", o, bad)
+                self.asm.emit("MULI", r, r, ee.card())
+                self.asm.emit("ADD", r, r, o)
+            self.asm.emit("JMP", end)
+            self.asm.label(bad)
+            self.li(r, -1)
+            self.asm.label(end)
+            return r
+        if isinstance(E, TSet):
+            if not isinstance(s, TSet):
+                self.li(r, -1)
+                return r
+            if E.nbits > 31:
+                raise CompileError("set-of-sets universe too large")
+            cv = self.coerce(v, E)
+            self.asm.emit("MOV", r, cv.loc)
+            return r
+        if isinstance(E, TFun):
+            if not (isinstance(s, TFun) and s.keys == E.keys):
+                self.li(r, -1)
+                return r
+            bad = Label("obad")
+            end = Label("oend")
+            self.li(r, 0)
+            for j in range(len(E.keys)):
+                o = self.ord_in(E.elem, Val(s.elem, v.loc + j * s.elem.size))
+                self.asm.emit("JNEG", o, bad)
+                self.asm.emit("MULI", r, r, E.elem.card())
+                self.asm.emit("ADD", r, r, o)
+            self.asm.emit("JMP", end)
+            self.asm.label(bad)
+            self.li(r, -1)
+            self.asm.label(end)
+            return r
+        raise CompileError(f"ord_in: unsupported universe type {E}")
+
+    def _ord_rec_alt(self, E: TRec, s: TRec, alt, v: Val, r, bad):
+        ai = E.alt_index(alt)
+        if ai < 0:
+            self.asm.emit("JMP", bad)
+            return
+        self.li(r, 0)
+        for f in E.alts[ai]:
+            ft = E.alt_types[ai][f]
+            o = self.ord_in(ft, Val(s.fields[f], v.loc + s.off[f]))
+            self.asm.emit("JNEG", o, bad)
+            self.asm.emit("MULI", r, r, ft.card())
+            self.asm.emit("ADD", r, r, o)
+        base = E.alt_base(ai)
+        if base:
+            self.asm.emit("ADDI", r, r, base)
+
+    def unord(self, E: T, oreg, dst=None) -> Val:
+        """Decode ordinal in oreg to a frame value of type E."""
+        if dst is None:
+            dst = self.alloc(E.size)
+        if isinstance(E, TInt):
+            self.asm.emit("ADDI", dst, oreg, E.lo)
+            return Val(E, dst)
+        if isinstance(E, TBool):
+            self.asm.emit("MOV", dst, oreg)
+            return Val(E, dst)
+        if isinstance(E, TAtom):
+            self.asm.emit("TBL", dst, self.asm.const_table([self.atoms.id(a) for a in E.atoms]), oreg)
+            return Val(E, dst)
+        if isinstance(E, TSet) and E.nbits <= 31:
+            self.asm.emit("MOV", dst, oreg)
+            return Val(E, dst)
+        n = E.card()
+        if n > UNIV_TABLE_MAX:
+            raise CompileError(f"universe of {n} elements too large for table decoding")
+        key = ("univ", E)
+        tabs = self._univ_tables(E)
+        for w in range(E.size):
+            self.asm.emit("TBL", dst + w, tabs[w], oreg)
+        return Val(E, dst)
+
+    def _univ_tables(self, E):
+        cache = self.__dict__.setdefault("_univ_cache", {})
+        if E in cache:
+            return cache[E]
+        vals = self.codec.enum(E)
+        reps = [self.codec.rep(E, v) for v in vals]
+        tabs = []
+        for w in range(E.size):
+            tabs.append(self.asm.const_table([r[w] for r in reps]))
+        cache[E] = tabs
+        return tabs
+
+    # ------------------------------------------------------------------ loops
+    def loop_set(self, sv: Val, body, elem_dst=None):
+        """for x in (runtime bitset sv): body(Val elem).  body may emit jumps to its own labels."""
+        E = sv.t.elem
+        if isinstance(E, TBottom):
+            return
+        idx = self.alloc(1)
+        xloc = self.alloc(E.size) if elem_dst is None else elem_dst
+        self.li(idx, -1)
+        top = Label("loop")
+        done = Label("done")
+        self.asm.label(top)
+        self.asm.emit("BNEXT", idx, sv.loc, idx, sv.t.nbits)
+        self.asm.emit("JNEG", idx, done)
+        self.unord(E, idx, xloc)
+        body(Val(E, xloc))
+        self.asm.emit("JMP", top)
+        self.asm.label(done)
+
+    def set_elements(self, node, env, ctx, base):
+        """Classify a quantifier / comprehension domain: ('const', [values]) | ('val', Val) |
+        ('range', lo, hi) with runtime bounds."""
+        c = self.try_const(node, env, ctx, base)
+        if c is not None:
+            if not is_set(c.v):
+                raise CompileError(f"quantifier domain is not a set: {fmt(c.v)}")
+            return ("const", list(set_iter(c.v)))
+        if node.k == "bin" and node.a[0] == "..":
+            lo = self.cx(node.a[1], env, ctx, base)
+            hi = self.cx(node.a[2], env, ctx, base)
+            return ("range", lo, hi)
+        if node.k == "domain":
+            f = self.cx(node.a[0], env, ctx, base)
+            if type(f) is Val and isinstance(f.t, TSeq):
+                return ("range", Const(1), Val(TInt(0, f.t.cap), f.loc))
+            if type(f) is Val and isinstance(f.t, TFun):
+                return ("const", list(f.t.keys))
+            if type(f) is Val and isinstance(f.t, TTuple):
+                return ("const", list(range(1, len(f.t.elems) + 1)))
+        v = self.cx(node, env, ctx, base)
+        if type(v) is Const:
+            return ("const", list(set_iter(v.v)))
+        if not isinstance(v.t, TSet):
+            raise CompileError(f"quantifier domain has non-set type {v.t}")
+        return ("val", v)
+
+    def bind(self, env, pat, x):
+        env2 = dict(env)
+        if isinstance(pat, str):
+            env2[pat] = x
+            return env2
+        names = pat[1]
+        if type(x) is Const:
+            if not isinstance(x.v, tuple) or len(x.v) != len(names):
+                raise CompileError("tuple pattern mismatch")
+            for nm, xv in zip(names, x.v):
+                env2[nm] = Const(xv)
+        else:
+            if not isinstance(x.t, TTuple) or len(x.t.elems) != len(names):
+                raise CompileError("tuple pattern mismatch")
+            for nm, te, to in zip(names, x.t.elems, x.t.offs):
+                env2[nm] = Val(te, x.loc + to)
+        return env2
+
+    def for_each(self, bounds, env, ctx, base, body, i=0):
+        """Emit nested iteration over quantifier bounds; body(env2) emits the per-combination code."""
+        if i == len(bounds):
+            body(env)
+            return
+        pat, sn = bounds[i]
+        if sn is None:
+            raise CompileError("unbounded quantifier")
+        kind = self.set_elements(sn, env, ctx, base)
+        if kind[0] == "const":
+            vals = kind[1]
+            if len(vals) <= UNROLL_MAX or not vals:
+                for v in vals:
+                    self.for_each(bounds, self.bind(env, pat, Const(v)), ctx, base, body, i + 1)
+                return
+            # long constant domain: iterate a table of representations
+            t = None
+            for v in vals:
+                t = join(t, type_of_value(v, self.seq_cap))
+            reps = []
+            for v in vals:
+                reps += self.codec.rep(t, v)
+            tbase = self.asm.const_table(reps)
+            cnt = self.alloc(1)
+            off = self.alloc(1)
+            xloc = self.alloc(t.size)
+            self.li(cnt, 0)
+            top, done = Label("cl"), Label("cd")
+            self.asm.label(top)
+            tmp = self.alloc(1)
+            self.asm.emit("LTI", tmp, cnt, len(vals))
+            self.asm.emit("JZ", tmp, done)
+            self.asm.emit("MULI", off, cnt, t.size)
+            for w in range(t.size):
+                self.asm.emit("TBL", xloc + w, tbase + w, off)
+            self.asm.emit("ADDI", cnt, cnt, 1)
+            self.for_each(bounds, self.bind(env, pat, Val(t, xloc)), ctx, base, body, i + 1)
+            self.asm.emit("JMP", top)
+            self.asm.label(done)
+            return
+        if kind[0] == "range":
+            lo = self.as_val(kind[1], TInt())
+            hi = self.as_val(kind[2], TInt())
+            tl = lo.t if isinstance(lo.t, TInt) else TInt()
+            th = hi.t if isinstance(hi.t, TInt) else TInt()
+            xt = TInt(tl.lo, th.hi) if (tl.lo is not None and th.hi is not None) else TInt()
+            x = self.alloc(1)
+            hi_s = self.alloc(1)
+            self.asm.emit("MOV", hi_s, hi.loc)
+            self.asm.emit("ADDI", x, lo.loc, -1)
+            top, done = Label("rl"), Label("rd")
+            self.asm.label(top)
+            self.asm.emit("ADDI", x, x, 1)
+            tmp = self.alloc(1)
+            self.asm.emit("LE", tmp, x, hi_s)
+            self.asm.emit("JZ", tmp, done)
+            self.for_each(bounds, self.bind(env, pat, Val(xt, x)), ctx, base, body, i + 1)
+            self.asm.emit("JMP", top)
+            self.asm.label(done)
+            return
+        sv = kind[1]
+        self.loop_set(sv, lambda xv: self.for_each(bounds, self.bind(env, pat, xv), ctx, base, body, i + 1))
+
+    # --------------------------------------------------------- name resolution
+    def resolve(self, name, env, ctx):
+        """-> ('env', x) | ('var', name) | ('def', OpDef, dctx) | ('subst', node, octx) | ('const', v) |
+        ('builtin', b)"""
+        if name in env:
+            return ("env", env[name])
+        sb = ctx.substs.get(name)
+        if sb is not None:
+            return ("subst", sb[0], sb[1])
+        if name in ctx.varset:
+            return ("var", name)
+        if name in ctx.consts:
+            return ("const", ctx.consts[name])
+        d = ctx.defs.get(name)
+        if d is not None:
+            return ("def", d[0], d[1])
+        b = self.ev.builtins.get(name)
+        if b is not None:
+            return ("builtin", b)
+        raise CompileError(f"unknown identifier {name}")
+
+    def var_val(self, name, base) -> Val:
+        if base == "P":
+            if name not in self.bound:
+                raise CompileError(f"primed variable {name}' is read before it is assigned")
+            return Val(self.var_types[name], self.p_off[name])
+        return Val(self.var_types[name], self.n_off[name])
+
+    def bind_args(self, params, args, env, ctx, base):
+        env2 = {}
+        for (pn, ar), a in zip(params, args):
+            if ar > 0:
+                env2[pn] = self.op_value(a, env, ctx)
+            else:
+                c = self.try_const(a, env, ctx, base) if a.k in ("num", "str", "bool", "id") else None
+                env2[pn] = c if c is not None else Lazy(a, env, ctx, base)
+        return env2
+
+    def op_value(self, a, env, ctx) -> OpC:
+        if a.k == "lambda":
+            return OpC([(p, 0) for p in a.a[0]], a.a[1], env, ctx, "LAMBDA")
+        if a.k == "id":
+            r = self.resolve(a.a[0], env, ctx)
+            if r[0] == "env" and type(r[1]) is OpC:
+                return r[1]
+            if r[0] == "def":
+                return OpC(r[1].params, r[1].body, {}, r[2], r[1].name)
+        raise CompileError(f"operator argument expected at line {a.line}")
+
+    def let_env(self, defs, env, ctx, base):
+        env2 = dict(env)
+        for d in defs:
+            if d.params:
+                env2[d.name] = OpC(d.params, d.body, env2, ctx, d.name)
+            else:
+                env2[d.name] = Lazy(d.body, env2, ctx, base)
+        return env2
+
+    # ------------------------------------------------------------ expressions
+    def cx(self, n: Node, env, ctx, base="N", want=None):
+        """Compile expression n in value context -> Const | Val."""
+        c = self.try_const(n, env, ctx, base)
+        if c is not None:
+            return c
+        k = n.k
+        m = getattr(self, "x_" + k, None)
+        if m is None:
+            raise CompileError(f"unsupported construct `{k}` at line {n.line} col {n.col}")
+        return m(n, env, ctx, base, want)
+
+    def x_id(self, n, env, ctx, base, want):
+        r = self.resolve(n.a[0], env, ctx)
+        if r[0] == "env":
+            x = r[1]
+            if type(x) is Lazy:
+                save = self.bound
+                return self.cx(x.node, x.env, x.ctx, x.base if x.base == "P" else base, want)
+            if type(x) is OpC:
+                raise CompileError(f"operator {n.a[0]} used as a value")
+            return x
+        if r[0] == "var":
+            return self.var_val(r[1], base)
+        if r[0] == "subst":
+            return self.cx(r[1], {}, r[2], base, want)
+        if r[0] == "const":
+            return Const(r[1])
+        if r[0] == "def":
+            if r[1].params:
+                raise CompileError(f"operator {n.a[0]} used without arguments")
+            key = (n.a[0], id(r[2]), base, self.program)
+            hv = self.hoisted.get(key)
+            if hv is not None:
+                return hv
+            self.def_uses[key] = self.def_uses.get(key, 0) + 1
+            self.def_info[key] = (r[1], r[2])
+            return self.cx(r[1].body, {}, r[2], base, want)
+        raise CompileError(f"cannot compile identifier {n.a[0]}")
+
+    def x_prime(self, n, env, ctx, base, want):
+        return self.cx(n.a[0], env, ctx, "P", want)
+
+    def x_at(self, n, env, ctx, base, want):
+        if "@" not in env:
+            raise CompileError("@ outside EXCEPT")
+        return env["@"]
+
+    def x_app(self, n, env, ctx, base, want):
+        name, args = n.a
+        r = self.resolve(name, env, ctx)
+        if r[0] == "env" and type(r[1]) is OpC:
+            op = r[1]
+            env2 = dict(op.env)
+            env2.update(self.bind_args(op.params, args, env, ctx, base))
+            return self.cx(op.body, env2, op.ctx, base, want)
+        if r[0] == "def":
+            d = r[1]
+            if len(d.params) != len(args):
+                raise CompileError(f"arity mismatch calling {name}")
+            return self.cx(d.body, self.bind_args(d.params, args, env, ctx, base), r[2], base, want)
+        if r[0] == "builtin":
+            return self.builtin(name, args, n, env, ctx, base, want)
+        raise CompileError(f"cannot apply {name} at line {n.line}")
+
+    def x_sel(self, n, env, ctx, base, want):
+        r = self.ev.resolve_sel(n.a[0], self.eval_env(env), Fr(ctx))
+        if r[0] == "def":
+            _, od, dctx, args = r
+            return self.cx(od.body, self.bind_args(od.params, args, env, ctx, base), dctx, base, want)
+        if r[0] == "name":
+            _, name, c2, args = r
+            return self.cx(Node("id", (name,)), {}, c2, base, want)
+        _, node, dctx, (od, args) = r
+        return self.cx(node, self.bind_args(od.params, args, env, ctx, base), dctx, base, want)
+
+    def x_let(self, n, env, ctx, base, want):
+        return self.cx(n.a[1], self.let_env(n.a[0], env, ctx, base), ctx, base, want)
+
+    # booleans in value context
+    def _bool_value(self, n, env, ctx, base, want):
+        dst = self.alloc(1)
+        lt, lf, end = Label("bt"), Label("bf"), Label("be")
+        self.cc(n, env, ctx, base, lt, lf)
+        self.asm.label(lt)
+        self.li(dst, 1)
+        self.asm.emit("JMP", end)
+        self.asm.label(lf)
+        self.li(dst, 0)
+        self.asm.label(end)
+        return Val(TBool(), dst)
+
+    x_and = x_or = x_not = x_forall = x_exists = _bool_value
+
+    def x_bin(self, n, env, ctx, base, want):
+        op, ln, rn = n.a
+        if op in ("=", "#", "<", ">", "<=", ">=", "\\in", "\\notin", "\\subseteq", "=>", "<=>", "\\subset",
+                  "\\supseteq"):
+            return self._bool_value(n, env, ctx, base, want)
+        if op in ("+", "-", "*", "\\div", "%"):
+            a = self.cx(ln, env, ctx, base)
+            b = self.cx(rn, env, ctx, base)
+            ta = self._int_t(a)
+            tb = self._int_t(b)
+            rt = self._arith_type(op, ta, tb)
+            dst = self.alloc(1)
+            if type(b) is Const and op in ("+", "-") and IMM28_MIN < b.v < IMM28_MAX:
+                av = self.as_val(a, TInt())
+                self.asm.emit("ADDI", dst, av.loc, b.v if op == "+" else -b.v)
+            elif type(b) is Const and op == "*" and IMM28_MIN < b.v < IMM28_MAX:
+                av = self.as_val(a, TInt())
+                self.asm.emit("MULI", dst, av.loc, b.v)
+            else:
+                av = self.as_val(a, TInt())
+                bv = self.as_val(b, TInt())
+                self.asm.emit({"+": "ADD", "-": "SUB", "*": "MUL", "\\div": "DIV", "%": "MOD"}[op],
+                              dst, av.loc, bv.loc)
+            return Val(rt, dst)
+        if op in ("\\cup", "\\cap", "\\"):
+            a = self.cx(ln, env, ctx, base, want)
+            b = self.cx(rn, env, ctx, base, want if want is not None else (a.t if type(a) is Val else None))
+            if type(a) is Const and type(b) is Val and want is None:
+                a2 = a
+                t = b.t
+            t = want
+            if t is None:
+                ta = a.t if type(a) is Val else self.natural_type(a.v)
+                tb = b.t if type(b) is Val else self.natural_type(b.v)
+                t = join(ta, tb)
+            if not isinstance(t, TSet):
+                raise CompileError(f"set operator {op} on non-set type {t}")
+            av = self.coerce(a, t)
+            bv = self.coerce(b, t)
+            dst = self.alloc(t.size)
+            self.asm.emit({"\\cup": "BOR", "\\cap": "BAND", "\\": "BANDN"}[op], dst, av.loc, bv.loc, t.size)
+            return Val(t, dst)
+        if op == "..":
+            a = self.cx(ln, env, ctx, base)
+            b = self.cx(rn, env, ctx, base)
+            ta, tb = self._int_t(a), self._int_t(b)
+            if ta.lo is None or tb.hi is None:
+                raise CompileError("a..b with unbounded runtime bounds used as a value")
+            t = want if isinstance(want, TSet) else TSet(TInt(ta.lo, tb.hi))
+            E = t.elem
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            av, bv = self.as_val(a, TInt()), self.as_val(b, TInt())
+            x = self.alloc(1)
+            tmp = self.alloc(1)
+            top, done = Label("rg"), Label("rgd")
+            self.asm.emit("MOV", x, av.loc)
+            self.asm.label(top)
+            self.asm.emit("LE", tmp, x, bv.loc)
+            self.asm.emit("JZ", tmp, done)
+            o = self.ord_in(E, Val(TInt(E.lo, E.hi), x))
+            ok = Label("rok")
+            self.asm.emit("JNEG", o, ok)
+            self.asm.emit("BSET", dst, o)
+            self.asm.label(ok)
+            self.asm.emit("ADDI", x, x, 1)
+            self.asm.emit("JMP", top)
+            self.asm.label(done)
+            return Val(t, dst)
+        if op == "\\o":
+            return self.seq_concat(ln, rn, env, ctx, base, want)
+        if op in ctx.defs or op in env:
+            r = self.resolve(op, env, ctx)
+            if r[0] == "def":
+                return self.cx(r[1].body, self.bind_args(r[1].params, (ln, rn), env, ctx, base), r[2], base, want)
+        raise CompileError(f"unsupported operator {op} at line {n.line}")
+
+    def _int_t(self, x) -> TInt:
+        if type(x) is Const:
+            if type(x.v) is not int:
+                raise CompileError(f"integer expected, got {fmt(x.v)}")
+            return TInt(x.v, x.v)
+        if not isinstance(x.t, TInt):
+            raise CompileError(f"integer expected, got type {x.t}")
+        return x.t
+
+    @staticmethod
+    def _arith_type(op, a: TInt, b: TInt) -> TInt:
+        if a.lo is None or b.lo is None:
+            return TInt()
+        if op == "+":
+            lo, hi = a.lo + b.lo, a.hi + b.hi
+        elif op == "-":
+            lo, hi = a.lo - b.hi, a.hi - b.lo
+        elif op == "*":
+            c = [a.lo * b.lo, a.lo * b.hi, a.hi * b.lo, a.hi * b.hi]
+            lo, hi = min(c), max(c)
+        elif op == "%":
+            lo, hi = 0, max(b.hi - 1, 0)
+        else:
+            m = max(abs(a.lo), abs(a.hi))
+            lo, hi = -m, m
+        if lo < -(1 << 30) or hi > (1 << 30):
+            return TInt()
+        return TInt(lo, hi)
+
+    def x_neg(self, n, env, ctx, base, want):
+        a = self.as_val(self.cx(n.a[0], env, ctx, base), TInt())
+        dst = self.alloc(1)
+        self.asm.emit("NEG", dst, a.loc)
+        t = a.t
+        return Val(TInt(-t.hi, -t.lo) if t.lo is not None else TInt(), dst)
+
+    def x_if(self, n, env, ctx, base, want):
+        c, a, b = n.a
+        cc_ = self.try_const(c, env, ctx, base)
+        if cc_ is not None:
+            return self.cx(a if cc_.v else b, env, ctx, base, want)
+        lt, lf, end = Label("it"), Label("if"), Label("ie")
+        if want is not None:
+            dst = self.alloc(want.size)
+            self.cc(c, env, ctx, base, lt, lf)
+            self.asm.label(lt)
+            va = self.coerce(self.cx(a, env, ctx, base, want), want)
+            self.movn(dst, va.loc, want.size)
+            self.asm.emit("JMP", end)
+            self.asm.label(lf)
+            vb = self.coerce(self.cx(b, env, ctx, base, want), want)
+            self.movn(dst, vb.loc, want.size)
+            self.asm.label(end)
+            return Val(want, dst)
+        with self.asm.capture() as ca:
+            va = self.cx(a, env, ctx, base)
+        with self.asm.capture() as cb:
+            vb = self.cx(b, env, ctx, base)
+        ta = va.t if type(va) is Val else self.natural_type(va.v)
+        tb = vb.t if type(vb) is Val else self.natural_type(vb.v)
+        t = join(ta, tb)
+        dst = self.alloc(t.size)
+        self.cc(c, env, ctx, base, lt, lf)
+        self.asm.label(lt)
+        self.asm.splice(ca.buf)
+        va2 = self.coerce(va, t)
+        self.movn(dst, va2.loc, t.size)
+        self.asm.emit("JMP", end)
+        self.asm.label(lf)
+        self.asm.splice(cb.buf)
+        vb2 = self.coerce(vb, t)
+        self.movn(dst, vb2.loc, t.size)
+        self.asm.label(end)
+        return Val(t, dst)
+
+    def x_case(self, n, env, ctx, base, want):
+        arms, other = n.a
+        node = other
+        if node is None:
+            node = Node("app", ("__trap_case", ()), n.line, n.col)
+        for c, e in reversed(arms):
+            node = Node("if", (c, e, node), n.line, n.col)
+        return self.cx(node, env, ctx, base, want)
+
+    def x_tuple(self, n, env, ctx, base, want):
+        items = [self.cx(x, env, ctx, base) for x in n.a[0]]
+        wants = None
+        if isinstance(want, TTuple) and len(want.elems) == len(items):
+            wants = want.elems
+        elif isinstance(want, TSeq):
+            wants = [want.elem] * len(items)
+        elif isinstance(want, TFun) and want.keys == tuple(range(1, len(items) + 1)):
+            wants = [want.elem] * len(items)
+        vals = [self.as_val(x, wants[i] if wants else None) for i, x in enumerate(items)]
+        if wants:
+            vals = [self.coerce(v, w) for v, w in zip(vals, wants)]
+        t = TTuple([v.t for v in vals])
+        dst = self.alloc(t.size)
+        for v, o in zip(vals, t.offs):
+            self.movn(dst + o, v.loc, v.t.size)
+        r = Val(t, dst)
+        if isinstance(want, (TSeq, TFun)):
+            return self.coerce(r, want)
+        return r
+
+    def x_record(self, n, env, ctx, base, want):
+        pairs = n.a[0]
+        names = [f for f, _ in pairs]
+        wf = want.fields if isinstance(want, TRec) else {}
+        vals = {}
+        for f, e in pairs:
+            x = self.cx(e, env, ctx, base, wf.get(f))
+            vals[f] = self.as_val(x, wf.get(f))
+        t = TRec([names], {f: vals[f].t for f in names})
+        dst = self.alloc(t.size)
+        for f in names:
+            self.movn(dst + t.off[f], vals[f].loc, vals[f].t.size)
+        r = Val(t, dst)
+        if isinstance(want, TRec) and want != t:
+            return self.coerce(r, want)
+        return r
+
+    def x_dot(self, n, env, ctx, base, want):
+        r = self.cx(n.a[0], env, ctx, base)
+        f = n.a[1]
+        if type(r) is Const:
+            return Const(r.v.d[f])
+        if not isinstance(r.t, TRec) or f not in r.t.fields:
+            raise CompileError(f"no field {f} in type {r.t} (line {n.line})")
+        t = r.t
+        if t.tagged:
+            mask = 0
+            for j, alt in enumerate(t.alts):
+                if f in alt:
+                    mask |= 1 << j
+            if mask != (1 << len(t.alts)) - 1:
+                mreg = self.alloc(1)
+                tst = self.alloc(1)
+                ok = Label("fok")
+                self.li(mreg, mask)
+                self.asm.emit("BTEST", tst, mreg, r.loc)
+                self.asm.emit("JNZ", tst, ok)
+                self.asm.emit("TRAP", TRAP_EVAL, n.line)
+                self.asm.label(ok)
+        return Val(t.fields[f], r.loc + t.off[f])
+
+    def x_setenum(self, n, env, ctx, base, want):
+        items = [self.cx(x, env, ctx, base, want.elem if isinstance(want, TSet) else None) for x in n.a[0]]
+        if isinstance(want, TSet):
+            t = want
+        else:
+            et = TBottom()
+            for x in items:
+                et = join(et, x.t if type(x) is Val else self.natural_type(x.v))
+            t = TSet(self._enumerable(et))
+        dst = self.alloc(t.size)
+        self.asm.emit("ZERO", dst, t.size)
+        for x in items:
+            self._set_add(dst, t, x, n)
+        return Val(t, dst)
+
+    def _enumerable(self, t):
+        if isinstance(t, TInt) and t.lo is None:
+            raise CompileError("set of unbounded integers needs a bounded element type (TypeOK)")
+        return t
+
+    def _set_add(self, dst, t: TSet, x, n=None):
+        o = self.ord_in(t.elem, x if type(x) is Const else x)
+        bad, ok = Label("sb"), Label("so")
+        self.asm.emit("JNEG", o, bad)
+        self.asm.emit("BSET", dst, o)
+        self.asm.emit("JMP", ok)
+        self.asm.label(bad)
+        self.asm.emit("TRAP", TRAP_OVERFLOW, n.line if n is not None else 0)
+        self.asm.label(ok)
+
+    def x_setfilter(self, n, env, ctx, base, want):
+        (pat, sn), pred = n.a
+        kind = self.set_elements(sn, env, ctx, base)
+        if kind[0] == "val":
+            sv = kind[1]
+            t = sv.t
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            idx = self.alloc(1)
+            xloc = self.alloc(t.elem.size)
+            self.li(idx, -1)
+            top, done = Label("fl"), Label("fd")
+            self.asm.label(top)
+            self.asm.emit("BNEXT", idx, sv.loc, idx, t.nbits)
+            self.asm.emit("JNEG", idx, done)
+            self.unord(t.elem, idx, xloc)
+            yes = Label("fy")
+            self.cc(pred, self.bind(env, pat, Val(t.elem, xloc)), ctx, base, yes, top)
+            self.asm.label(yes)
+            self.asm.emit("BSET", dst, idx)
+            self.asm.emit("JMP", top)
+            self.asm.label(done)
+            r = Val(t, dst)
+            return self.coerce(r, want) if isinstance(want, TSet) and want != t else r
+        if kind[0] == "const":
+            vals = kind[1]
+            if isinstance(want, TSet):
+                t = want
+            else:
+                et = TBottom()
+                for v in vals:
+                    et = join(et, type_of_value(v, self.seq_cap))
+                t = TSet(self._enumerable(et))
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            for v in vals:
+                o = self.codec.ord_of(t.elem, v)
+                if o < 0:
+                    continue
+                yes, no = Label("cy"), Label("cn")
+                self.cc(pred, self.bind(env, pat, Const(v)), ctx, base, yes, no)
+                self.asm.label(yes)
+                self.asm.emit("BSETI", dst, o)
+                self.asm.label(no)
+            return Val(t, dst)
+        raise CompileError("set filter over a runtime integer range is not supported")
+
+    def x_setmap(self, n, env, ctx, base, want):
+        e, bounds = n.a
+        t = want if isinstance(want, TSet) else None
+        if t is None:
+            # infer element type by a dry run
+            with self.asm.capture():
+                save_top = self.top
+                holder = []
+
+                def probe(env2):
+                    x = self.cx(e, env2, ctx, base)
+                    holder.append(x.t if type(x) is Val else self.natural_type(x.v))
+                self.for_each(bounds, env, ctx, base, probe)
+                self.top = save_top
+            et = TBottom()
+            for x in holder:
+                et = join(et, x)
+            t = TSet(self._enumerable(et))
+        dst = self.alloc(t.size)
+        self.asm.emit("ZERO", dst, t.size)
+
+        def body(env2):
+            x = self.cx(e, env2, ctx, base, t.elem)
+            self._set_add(dst, t, x, n)
+        self.for_each(bounds, env, ctx, base, body)
+        return Val(t, dst)
+
+    def x_fcn(self, n, env, ctx, base, want):
+        bounds, body = n.a
+        if len(bounds) != 1:
+            raise CompileError("multi-argument function constructors are not supported")
+        pat, sn = bounds[0]
+        kind = self.set_elements(sn, env, ctx, base)
+        if kind[0] != "const":
+            raise CompileError("function constructor over a runtime domain is not supported")
+        keys = sorted(kind[1], key=vkey)
+        we = None
+        if isinstance(want, TFun) and want.keys == tuple(keys):
+            we = want.elem
+        elif isinstance(want, TTuple) and tuple(keys) == tuple(range(1, len(want.elems) + 1)):
+            we = None
+        items = []
+        for i, kv in enumerate(keys):
+            w = we if we is not None else (want.elems[i] if isinstance(want, TTuple) and i < len(want.elems) else None)
+            x = self.cx(body, self.bind(env, pat, Const(kv)), ctx, base, w)
+            items.append(self.as_val(x, w))
+        if isinstance(want, TTuple) and tuple(keys) == tuple(range(1, len(want.elems) + 1)):
+            vals = [self.coerce(v, w) for v, w in zip(items, want.elems)]
+            dst = self.alloc(want.size)
+            for v, o in zip(vals, want.offs):
+                self.movn(dst + o, v.loc, v.t.size)
+            return Val(want, dst)
+        et = we
+        if et is None:
+            et = TBottom()
+            for v in items:
+                et = join(et, v.t)
+        n1 = len(keys)
+        if n1 > 0 and all(type(kk) is int for kk in keys) and keys[0] == 1 and keys[-1] == n1 and we is None:
+            t = TTuple([et] * n1)
+        else:
+            t = TFun(keys, et)
+        dst = self.alloc(t.size)
+        for j, v in enumerate(items):
+            cv = self.coerce(v, et)
+            self.movn(dst + j * et.size, cv.loc, et.size)
+        return Val(t, dst)
+
+    def key_index(self, ft: T, kx, n):
+        """Index of key kx in function-like type ft: returns ('static', j) or ('dyn', reg)."""
+        if isinstance(ft, TFun):
+            if type(kx) is Const:
+                j = ft.kindex.get(kx.v)
+                if j is None:
+                    return ("none", None)
+                return ("static", j)
+            keys = ft.keys
+            if all(type(kk) is int for kk in keys) and list(keys) == list(range(keys[0], keys[0] + len(keys))):
+                o = self.ord_in(TInt(keys[0], keys[-1]), kx)
+            elif all(is_atom(kk) for kk in keys):
+                o = self.ord_in(TAtom(keys), kx)
+            else:
+                raise CompileError("function with non-scalar keys indexed by a runtime value")
+            return ("dyn", o)
+        if isinstance(ft, TTuple):
+            if type(kx) is Const:
+                if type(kx.v) is int and 1 <= kx.v <= len(ft.elems):
+                    return ("static", kx.v - 1)
+                return ("none", None)
+            if len(set(ft.elems)) > 1:
+                raise CompileError("heterogeneous tuple indexed by a runtime value")
+            o = self.ord_in(TInt(1, len(ft.elems)), kx)
+            return ("dyn", o)
+        if isinstance(ft, TSeq):
+            kv = self.as_val(kx, TInt())
+            o = self.alloc(1)
+            self.asm.emit("ADDI", o, kv.loc, -1)
+            # (unsigned)(i-1) < len  else -1
+            t1 = self.alloc(1)
+            ok, bad, end = Label("sk"), Label("sb"), Label("se")
+            self.asm.emit("JNEG", o, bad)
+            self.asm.emit("LT", t1, o, None)  # patched below
+            raise CompileError("internal")  # replaced by seq_index
+        raise CompileError(f"value of type {ft} is not a function")
+
+    def x_fapp(self, n, env, ctx, base, want):
+        fn, args = n.a
+        f = self.cx(fn, env, ctx, base)
+        if len(args) == 1:
+            kx = self.cx(args[0], env, ctx, base)
+        else:
+            kx = self.cx(Node("tuple", (tuple(args),), n.line, n.col), env, ctx, base)
+        if type(f) is Const:
+            if type(kx) is Const:
+                from ..front.values import fcn_apply
+                return Const(fcn_apply(f.v, kx.v))
+            f = self.as_val(f)
+        ft = f.t
+        if isinstance(ft, TSeq):
+            return self.seq_index(f, kx, n)
+        if isinstance(ft, TSet) or not isinstance(ft, (TFun, TTuple)):
+            raise CompileError(f"applying a non-function of type {ft} at line {n.line}")
+        ki = self.key_index(ft, kx, n)
+        if ki[0] == "none":
+            self.asm.emit("TRAP", TRAP_EVAL, n.line)
+            et = ft.elem if isinstance(ft, TFun) else ft.elems[0]
+            return Val(et, f.loc)
+        if ki[0] == "static":
+            j = ki[1]
+            if isinstance(ft, TFun):
+                return Val(ft.elem, f.loc + j * ft.elem.size)
+            return Val(ft.elems[j], f.loc + ft.offs[j])
+        o = ki[1]
+        et = ft.elem if isinstance(ft, TFun) else ft.elems[0]
+        ok = Label("ak")
+        self.asm.emit("JNEG", o, Label("dummy")) if False else None
+        bad = Label("ab")
+        self.asm.emit("JNEG", o, bad)
+        dst = self.alloc(et.size)
+        self.asm.emit("LDX", dst, f.loc, o, et.size)
+        self.asm.emit("JMP", ok)
+        self.asm.label(bad)
+        self.asm.emit("TRAP", TRAP_EVAL, n.line)
+        self.asm.label(ok)
+        return Val(et, dst)
+
+    def x_except(self, n, env, ctx, base, want):
+        fn, ups = n.a
+        f = self.cx(fn, env, ctx, base, want)
+        f = self.as_val(f, want)
+        if want is not None and f.t != want:
+            f = self.coerce(f, want)
+        dst = self.alloc(f.t.size)
+        self.movn(dst, f.loc, f.t.size)
+        cur = Val(f.t, dst)
+        for path, valnode in ups:
+            self._except_path(cur, path, 0, valnode, env, ctx, base, n)
+        return cur
+
+    def _except_path(self, cur: Val, path, i, valnode, env, ctx, base, n):
+        """Update cur (a writable Val) in place at path[i:]."""
+        if i == len(path):
+            env2 = dict(env)
+            env2["@"] = cur
+            x = self.cx(valnode, env2, ctx, base, cur.t)
+            xv = self.coerce(x, cur.t)
+            self.movn(cur.loc, xv.loc, cur.t.size)
+            return
+        kind, p = path[i]
+        t = cur.t
+        if kind == "fld":
+            if not isinstance(t, TRec) or p not in t.fields:
+                raise CompileError(f"EXCEPT !.{p} on type {t}")
+            self._except_path(Val(t.fields[p], cur.loc + t.off[p]), path, i + 1, valnode, env, ctx, base, n)
+            return
+        if len(p) == 1:
+            kx = self.cx(p[0], env, ctx, base)
+        else:
+            kx = self.cx(Node("tuple", (tuple(p),)), env, ctx, base)
+        if isinstance(t, TSeq):
+            et = t.elem
+            o = self.seq_index_reg(cur, kx, n, trap=False)
+            skip = Label("xs")
+            self.asm.emit("JNEG", o, skip)
+            tmp = self.alloc(et.size)
+            self.asm.emit("LDX", tmp, cur.loc + 1, o, et.size)
+            self._except_path(Val(et, tmp), path, i + 1, valnode, env, ctx, base, n)
+            self.asm.emit("STX", cur.loc + 1, o, tmp, et.size)
+            self.asm.label(skip)
+            return
+        if not isinstance(t, (TFun, TTuple)):
+            raise CompileError(f"EXCEPT on non-function type {t}")
+        ki = self.key_index(t, kx, n)
+        if ki[0] == "none":
+            return
+        if ki[0] == "static":
+            j = ki[1]
+            if isinstance(t, TFun):
+                sub = Val(t.elem, cur.loc + j * t.elem.size)
+            else:
+                sub = Val(t.elems[j], cur.loc + t.offs[j])
+            self._except_path(sub, path, i + 1, valnode, env, ctx, base, n)
+            return
+        o = ki[1]
+        et = t.elem if isinstance(t, TFun) else t.elems[0]
+        skip = Label("xs")
+        self.asm.emit("JNEG", o, skip)
+        tmp = self.alloc(et.size)
+        self.asm.emit("LDX", tmp, cur.loc, o, et.size)
+        self._except_path(Val(et, tmp), path, i + 1, valnode, env, ctx, base, n)
+        self.asm.emit("STX", cur.loc, o, tmp, et.size)
+        self.asm.label(skip)
+
+    def _copy(self, v: Val):
+        loc = self.alloc(v.t.size)
+        self.movn(loc, v.loc, v.t.size)
+        return loc
+
+    def x_choose(self, n, env, ctx, base, want):
+        pat, sn, body = n.a
+        if sn is None:
+            raise CompileError("unbounded CHOOSE")
+        kind = self.set_elements(sn, env, ctx, base)
+        if kind[0] == "const":
+            t = want
+            if t is None:
+                t = TBottom()
+                for v in kind[1]:
+                    t = join(t, type_of_value(v, self.seq_cap))
+        elif kind[0] == "val":
+            t = kind[1].t.elem
+        else:
+            t = TInt()
+        dst = self.alloc(t.size)
+        end = Label("che")
+
+        def each(env2):
+            x = env2[pat] if isinstance(pat, str) else None
+            yes, no = Label("chy"), Label("chn")
+            self.cc(body, env2, ctx, base, yes, no)
+            self.asm.label(yes)
+            if x is None:
+                raise CompileError("CHOOSE with tuple pattern is not supported")
+            xv = self.coerce(x, t) if type(x) is Val else self.materialize(x, t)
+            self.movn(dst, xv.loc, t.size)
+            self.asm.emit("JMP", end)
+            self.asm.label(no)
+        self.for_each([(pat, sn)], env, ctx, base, each)
+        self.asm.emit("TRAP", TRAP_CHOOSE, n.line)
+        self.asm.label(end)
+        return Val(t, dst)
+
+    def x_domain(self, n, env, ctx, base, want):
+        f = self.cx(n.a[0], env, ctx, base)
+        if type(f) is Val and isinstance(f.t, TFun):
+            return Const(frozenset(f.t.keys))
+        if type(f) is Val and isinstance(f.t, TTuple):
+            return Const(frozenset(range(1, len(f.t.elems) + 1)))
+        if type(f) is Val and isinstance(f.t, TSeq):
+            t = TSet(TInt(1, f.t.cap))
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            self.asm.emit("BFILL", dst, 0)  # placeholder, filled below via loop
+            # bits 0..len-1
+            i = self.alloc(1)
+            tmp = self.alloc(1)
+            top, done = Label("dl"), Label("dd")
+            self.li(i, 0)
+            self.asm.label(top)
+            self.asm.emit("LT", tmp, i, f.loc)
+            self.asm.emit("JZ", tmp, done)
+            self.asm.emit("BSET", dst, i)
+            self.asm.emit("ADDI", i, i, 1)
+            self.asm.emit("JMP", top)
+            self.asm.label(done)
+            return Val(t, dst)
+        raise CompileError("DOMAIN of unsupported value")
+
+    # ---------------------------------------------------------------- builtins
+    def builtin(self, name, args, n, env, ctx, base, want):
+        if name == "Cardinality":
+            s = self.cx(args[0], env, ctx, base)
+            sv = self.as_val(s)
+            dst = self.alloc(1)
+            self.asm.emit("BCNT", dst, sv.loc, sv.t.size)
+            return Val(TInt(0, sv.t.nbits), dst)
+        if name == "Len":
+            s = self.cx(args[0], env, ctx, base)
+            if type(s) is Val and isinstance(s.t, TSeq):
+                return Val(TInt(0, s.t.cap), s.loc)
+            if type(s) is Val and isinstance(s.t, TTuple):
+                return Const(len(s.t.elems))
+            raise CompileError("Len of unsupported value")
+        if name in ("Append", "Head", "Tail", "SubSeq", "SelectSeq"):
+            return self.seq_builtin(name, args, n, env, ctx, base, want)
+        if name in ("Assert", "Print", "PrintT"):
+            return self._bool_value(n, env, ctx, base, want)
+        if name == "IsFiniteSet":
+            return Const(True)
+        raise CompileError(f"builtin {name} is not supported on the device")
+
+    # --------------------------------------------------------------- sequences
+    def _as_seq(self, x, want=None) -> Val:
+        if type(x) is Const:
+            if want is None:
+                raise CompileError("constant sequence without an expected type")
+            return self.materialize(x, want)
+        if isinstance(x.t, TSeq):
+            return x
+        if isinstance(x.t, TTuple):
+            if isinstance(want, TSeq):
+                return self.coerce(x, want)
+            et = TBottom()
+            for e in x.t.elems:
+                et = join(et, e)
+            cap = max(len(x.t.elems), self.seq_cap or len(x.t.elems))
+            return self.coerce(x, TSeq(et, cap))
+        raise CompileError(f"sequence expected, got {x.t}")
+
+    def seq_index_reg(self, s: Val, kx, n, trap=True):
+        kv = self.as_val(kx, TInt())
+        o = self.alloc(1)
+        t1 = self.alloc(1)
+        ok, bad = Label("sik"), Label("sib")
+        self.asm.emit("ADDI", o, kv.loc, -1)
+        self.asm.emit("JNEG", o, bad)
+        self.asm.emit("LT", t1, o, s.loc)
+        self.asm.emit("JNZ", t1, ok)
+        self.asm.label(bad)
+        if trap:
+            self.asm.emit("TRAP", TRAP_EVAL, n.line)
+        self.li(o, -1)
+        self.asm.label(ok)
+        return o
+
+    def seq_index(self, s: Val, kx, n):
+        o = self.seq_index_reg(s, kx, n)
+        et = s.t.elem
+        dst = self.alloc(et.size)
+        self.asm.emit("LDX", dst, s.loc + 1, o, et.size)
+        return Val(et, dst)
+
+    def seq_builtin(self, name, args, n, env, ctx, base, want):
+        if name == "Append":
+            s = self._as_seq(self.cx(args[0], env, ctx, base, want), want if isinstance(want, TSeq) else None)
+            t = want if isinstance(want, TSeq) else s.t
+            s = self.coerce(s, t)
+            e = self.coerce(self.cx(args[1], env, ctx, base, t.elem), t.elem)
+            dst = self.alloc(t.size)
+            self.movn(dst, s.loc, t.size)
+            t1 = self.alloc(1)
+            ok = Label("apk")
+            self.asm.emit("LTI", t1, dst, t.cap)
+            self.asm.emit("JNZ", t1, ok)
+            self.asm.emit("TRAP", TRAP_OVERFLOW, n.line)
+            self.asm.label(ok)
+            self.asm.emit("STX", dst + 1, dst, e.loc, t.elem.size)
+            self.asm.emit("ADDI", dst, dst, 1)
+            return Val(t, dst)
+        if name == "Head":
+            s = self._as_seq(self.cx(args[0], env, ctx, base))
+            return self.seq_index(s, Const(1), n)
+        if name == "Tail":
+            s = self._as_seq(self.cx(args[0], env, ctx, base, want), want if isinstance(want, TSeq) else None)
+            t = s.t
+            es = t.elem.size
+            dst = self.alloc(t.size)
+            ok = Label("tlk")
+            t1 = self.alloc(1)
+            self.asm.emit("GTI", t1, s.loc, 0)
+            self.asm.emit("JNZ", t1, ok)
+            self.asm.emit("TRAP", TRAP_EVAL, n.line)
+            self.asm.label(ok)
+            self.asm.emit("ZERO", dst, t.size)
+            self.asm.emit("ADDI", dst, s.loc, -1)
+            if t.cap > 1:
+                self.movn(dst + 1, s.loc + 1 + es, (t.cap - 1) * es)
+            r = Val(t, dst)
+            return r
+        raise CompileError(f"sequence operator {name} is not supported on the device yet")
+
+    def seq_concat(self, ln, rn, env, ctx, base, want):
+        a = self._as_seq(self.cx(ln, env, ctx, base, want), want if isinstance(want, TSeq) else None)
+        t = want if isinstance(want, TSeq) else a.t
+        a = self.coerce(a, t)
+        bx = self.cx(rn, env, ctx, base, t)
+        b = self.coerce(self._as_seq(bx, t), t)
+        es = t.elem.size
+        dst = self.alloc(t.size)
+        self.movn(dst, a.loc, t.size)
+        i = self.alloc(1)
+        t1 = self.alloc(1)
+        tmp = self.alloc(es)
+        top, done, ok = Label("ccl"), Label("ccd"), Label("cck")
+        self.li(i, 0)
+        self.asm.label(top)
+        self.asm.emit("LT", t1, i, b.loc)
+        self.asm.emit("JZ", t1, done)
+        self.asm.emit("LTI", t1, dst, t.cap)
+        self.asm.emit("JNZ", t1, ok)
+        self.asm.emit("TRAP", TRAP_OVERFLOW, 0)
+        self.asm.label(ok)
+        self.asm.emit("LDX", tmp, b.loc + 1, i, es)
+        self.asm.emit("STX", dst + 1, dst, tmp, es)
+        self.asm.emit("ADDI", dst, dst, 1)
+        self.asm.emit("ADDI", i, i, 1)
+        self.asm.emit("JMP", top)
+        self.asm.label(done)
+        return Val(t, dst)
+
+    # ------------------------------------------------------------- conditions
+    def cc(self, n: Node, env, ctx, base, lt: Label, lf: Label):
+        """Compile n in control context: jump to lt if TRUE else lf.  Falls through to neither.
+        All temporaries are dead once control has left, so the frame is released on exit."""
+        mk = self.mark()
+        try:
+            self._cc(n, env, ctx, base, lt, lf)
+        finally:
+            self.release(mk)
+
+    def _cc(self, n: Node, env, ctx, base, lt: Label, lf: Label):
+        c = self.try_const(n, env, ctx, base)
+        if c is not None:
+            if c.v is True:
+                self.asm.emit("JMP", lt)
+            elif c.v is False:
+                self.asm.emit("JMP", lf)
+            else:
+                raise CompileError(f"BOOLEAN expected at line {n.line}, got {fmt(c.v)}")
+            return
+        k = n.k
+        if k == "and":
+            items = n.a[0]
+            for x in items[:-1]:
+                nxt = Label("an")
+                self.cc(x, env, ctx, base, nxt, lf)
+                self.asm.label(nxt)
+            self.cc(items[-1], env, ctx, base, lt, lf)
+            return
+        if k == "or":
+            items = n.a[0]
+            for x in items[:-1]:
+                nxt = Label("on")
+                self.cc(x, env, ctx, base, lt, nxt)
+                self.asm.label(nxt)
+            self.cc(items[-1], env, ctx, base, lt, lf)
+            return
+        if k == "not":
+            self.cc(n.a[0], env, ctx, base, lf, lt)
+            return
+        if k == "if":
+            c1 = self.try_const(n.a[0], env, ctx, base)
+            if c1 is not None:
+                self.cc(n.a[1] if c1.v else n.a[2], env, ctx, base, lt, lf)
+                return
+            a, b = Label("cit"), Label("cif")
+            self.cc(n.a[0], env, ctx, base, a, b)
+            self.asm.label(a)
+            self.cc(n.a[1], env, ctx, base, lt, lf)
+            self.asm.label(b)
+            self.cc(n.a[2], env, ctx, base, lt, lf)
+            return
+        if k == "case":
+            arms, other = n.a
+            node = other if other is not None else Node("app", ("__trap_case", ()), n.line, n.col)
+            for c2, e in reversed(arms):
+                node = Node("if", (c2, e, node), n.line, n.col)
+            self.cc(node, env, ctx, base, lt, lf)
+            return
+        if k == "let":
+            self.cc(n.a[1], self.let_env(n.a[0], env, ctx, base), ctx, base, lt, lf)
+            return
+        if k == "prime":
+            self.cc(n.a[0], env, ctx, "P", lt, lf)
+            return
+        if k == "forall" or k == "exists":
+            bounds, body = n.a
+            is_all = k == "forall"
+
+            def each(env2):
+                nxt = Label("qn")
+                if is_all:
+                    self.cc(body, env2, ctx, base, nxt, lf)
+                else:
+                    self.cc(body, env2, ctx, base, lt, nxt)
+                self.asm.label(nxt)
+            self.for_each(bounds, env, ctx, base, each)
+            self.asm.emit("JMP", lt if is_all else lf)
+            return
+        if k == "bin":
+            op, ln, rn = n.a
+            if op == "=>":
+                nxt = Label("im")
+                self.cc(ln, env, ctx, base, nxt, lt)
+                self.asm.label(nxt)
+                self.cc(rn, env, ctx, base, lt, lf)
+                return
+            if op == "<=>":
+                a = self.as_val(self.cx(ln, env, ctx, base), TBool())
+                b = self.as_val(self.cx(rn, env, ctx, base), TBool())
+                t1 = self.alloc(1)
+                self.asm.emit("EQ", t1, a.loc, b.loc)
+                self.asm.emit("JNZ", t1, lt)
+                self.asm.emit("JMP", lf)
+                return
+            if op in ("=", "#"):
+                self.cc_eq(ln, rn, env, ctx, base, lt if op == "=" else lf, lf if op == "=" else lt, n)
+                return
+            if op in ("<", ">", "<=", ">="):
+                a = self.cx(ln, env, ctx, base)
+                b = self.cx(rn, env, ctx, base)
+                self._int_t(a)
+                self._int_t(b)
+                t1 = self.alloc(1)
+                if type(b) is Const and IMM28_MIN < b.v < IMM28_MAX:
+                    av = self.as_val(a, TInt())
+                    self.asm.emit({"<": "LTI", ">": "GTI", "<=": "LEI", ">=": "GEI"}[op], t1, av.loc, b.v)
+                else:
+                    av, bv = self.as_val(a, TInt()), self.as_val(b, TInt())
+                    if op == "<":
+                        self.asm.emit("LT", t1, av.loc, bv.loc)
+                    elif op == "<=":
+                        self.asm.emit("LE", t1, av.loc, bv.loc)
+                    elif op == ">":
+                        self.asm.emit("LT", t1, bv.loc, av.loc)
+                    else:
+                        self.asm.emit("LE", t1, bv.loc, av.loc)
+                self.asm.emit("JNZ", t1, lt)
+                self.asm.emit("JMP", lf)
+                return
+            if op in ("\\in", "\\notin"):
+                self.cc_in(ln, rn, env, ctx, base, lt if op == "\\in" else lf, lf if op == "\\in" else lt, n)
+                return
+            if op in ("\\subseteq", "\\supseteq"):
+                if op == "\\supseteq":
+                    ln, rn = rn, ln
+                self.cc_subseteq(ln, rn, env, ctx, base, lt, lf, n)
+                return
+        if k == "app" and n.a[0] == "Assert":
+            r = self.resolve("Assert", env, ctx)
+            if r[0] == "builtin":
+                cond, msg = n.a[1]
+                ok, bad = Label("ask"), Label("asb")
+                self.cc(cond, env, ctx, base, ok, bad)
+                self.asm.label(bad)
+                mc = self.try_const(msg, env, ctx, base)
+                self.asserts.append((mc.v if mc is not None else "<non-constant message>", n.loc()))
+                self.asm.emit("ASSERTF", len(self.asserts) - 1)
+                self.asm.emit("JMP", lf)
+                self.asm.label(ok)
+                self.asm.emit("JMP", lt)
+                return
+        if k == "app" and n.a[0] in ("Print", "PrintT") and self.resolve(n.a[0], env, ctx)[0] == "builtin":
+            # printing from the device is not supported; the value of Print(out, v) is v / TRUE
+            if n.a[0] == "PrintT":
+                self.asm.emit("JMP", lt)
+            else:
+                self.cc(n.a[1][1], env, ctx, base, lt, lf)
+            return
+        if k == "app" and n.a[0] == "__trap_case":
+            self.asm.emit("TRAP", TRAP_CASE, n.line)
+            self.asm.emit("JMP", lf)
+            return
+        if k in ("id", "app", "sel"):
+            # expand user operators in control context (keeps short-circuiting)
+            tgt = self._expand(n, env, ctx, base)
+            if tgt is not None:
+                node2, env2, ctx2, base2 = tgt
+                self.cc(node2, env2, ctx2, base2, lt, lf)
+                return
+        v = self.cx(n, env, ctx, base)
+        if type(v) is Const:
+            self.asm.emit("JMP", lt if v.v is True else lf)
+            return
+        if not isinstance(v.t, TBool):
+            raise CompileError(f"BOOLEAN expected at line {n.line} col {n.col}, got {v.t}")
+        self.asm.emit("JNZ", v.loc, lt)
+        self.asm.emit("JMP", lf)
+
+    def _expand(self, n, env, ctx, base):
+        """If n is a reference to a user operator / LET definition return (body, env, ctx, base)."""
+        if n.k == "sel":
+            r = self.ev.resolve_sel(n.a[0], self.eval_env(env), Fr(ctx))
+            if r[0] == "def":
+                _, od, dctx, args = r
+                return (od.body, self.bind_args(od.params, args, env, ctx, base), dctx, base)
+            if r[0] == "expr":
+                _, node, dctx, (od, args) = r
+                return (node, self.bind_args(od.params, args, env, ctx, base), dctx, base)
+            return None
+        name = n.a[0]
+        args = n.a[1] if n.k == "app" else ()
+        try:
+            r = self.resolve(name, env, ctx)
+        except CompileError:
+            return None
+        if r[0] == "env":
+            x = r[1]
+            if type(x) is Lazy and not args:
+                return (x.node, x.env, x.ctx, x.base if x.base == "P" else base)
+            if type(x) is OpC:
+                env2 = dict(x.env)
+                env2.update(self.bind_args(x.params, args, env, ctx, base))
+                return (x.body, env2, x.ctx, base)
+            return None
+        if r[0] == "def":
+            d = r[1]
+            if len(d.params) != len(args):
+                raise CompileError(f"arity mismatch calling {name}")
+            return (d.body, self.bind_args(d.params, args, env, ctx, base), r[2], base)
+        if r[0] == "subst" and not args:
+            return (r[1], {}, r[2], base)
+        return None
+
+    def cc_eq(self, ln, rn, env, ctx, base, lt, lf, n):
+        a = self.cx(ln, env, ctx, base)
+        b = self.cx(rn, env, ctx, base, a.t if type(a) is Val else None)
+        if type(a) is Const and type(b) is Val:
+            a, b = b, a
+        if type(a) is Const:
+            from ..front.values import values_equal
+            self.asm.emit("JMP", lt if values_equal(a.v, b.v) else lf)
+            return
+        t1 = self.alloc(1)
+        if type(b) is Const:
+            if a.t.scalar:
+                if isinstance(a.t, TInt) and type(b.v) is int and IMM28_MIN < b.v < IMM28_MAX:
+                    self.asm.emit("EQI", t1, a.loc, b.v)
+                elif isinstance(a.t, TAtom) and is_atom(b.v):
+                    self.asm.emit("EQI", t1, a.loc, self.atoms.id(b.v))
+                elif isinstance(a.t, TBool) and type(b.v) is bool:
+                    self.asm.emit("EQI", t1, a.loc, int(b.v))
+                else:
+                    self.asm.emit("JMP", lf)
+                    return
+                self.asm.emit("JNZ", t1, lt)
+                self.asm.emit("JMP", lf)
+                return
+            if isinstance(a.t, TSet) and isinstance(b.v, frozenset) and len(b.v) == 0:
+                self.asm.emit("BISZ", t1, a.loc, a.t.size)
+                self.asm.emit("JNZ", t1, lt)
+                self.asm.emit("JMP", lf)
+                return
+            try:
+                tj = join(a.t, self.natural_type(b.v))
+            except TypeErr:
+                self.asm.emit("JMP", lf)
+                return
+            av = self.coerce(a, tj)
+            bv = self.materialize(b, tj)
+        else:
+            try:
+                tj = join(a.t, b.t)
+            except TypeErr:
+                self.asm.emit("JMP", lf)
+                return
+            av = self.coerce(a, tj)
+            bv = self.coerce(b, tj)
+        if tj.size == 1:
+            self.asm.emit("EQ", t1, av.loc, bv.loc)
+        else:
+            self.asm.emit("EQN", t1, av.loc, bv.loc, tj.size)
+        self.asm.emit("JNZ", t1, lt)
+        self.asm.emit("JMP", lf)
+
+    def cc_in(self, en, sn, env, ctx, base, lt, lf, n):
+        # structural set expressions first (avoid materialising big sets)
+        sc = self.try_const(sn, env, ctx, base)
+        if sc is None:
+            if sn.k == "subset":
+                self.cc_subseteq(en, sn.a[0], env, ctx, base, lt, lf, n)
+                return
+            if sn.k == "bin" and sn.a[0] == "\\cup":
+                nxt = Label("iu")
+                self.cc_in(en, sn.a[1], env, ctx, base, lt, nxt, n)
+                self.asm.label(nxt)
+                self.cc_in(en, sn.a[2], env, ctx, base, lt, lf, n)
+                return
+            if sn.k == "bin" and sn.a[0] == "\\cap":
+                nxt = Label("ic")
+                self.cc_in(en, sn.a[1], env, ctx, base, nxt, lf, n)
+                self.asm.label(nxt)
+                self.cc_in(en, sn.a[2], env, ctx, base, lt, lf, n)
+                return
+            if sn.k == "bin" and sn.a[0] == "\\":
+                nxt = Label("id")
+                self.cc_in(en, sn.a[1], env, ctx, base, nxt, lf, n)
+                self.asm.label(nxt)
+                self.cc_in(en, sn.a[2], env, ctx, base, lf, lt, n)
+                return
+            if sn.k == "bin" and sn.a[0] == "..":
+                e = self.as_val(self.cx(en, env, ctx, base), TInt())
+                lo = self.as_val(self.cx(sn.a[1], env, ctx, base), TInt())
+                hi = self.as_val(self.cx(sn.a[2], env, ctx, base), TInt())
+                t1 = self.alloc(1)
+                self.asm.emit("LE", t1, lo.loc, e.loc)
+                self.asm.emit("JZ", t1, lf)
+                self.asm.emit("LE", t1, e.loc, hi.loc)
+                self.asm.emit("JNZ", t1, lt)
+                self.asm.emit("JMP", lf)
+                return
+            if sn.k == "setfilter":
+                (pat, s2), pred = sn.a
+                nxt = Label("isf")
+                self.cc_in(en, s2, env, ctx, base, nxt, lf, n)
+                self.asm.label(nxt)
+                e = self.cx(en, env, ctx, base)
+                self.cc(pred, self.bind(env, pat, e), ctx, base, lt, lf)
+                return
+            if sn.k in ("id", "app", "sel"):
+                tgt = self._expand(sn, env, ctx, base)
+                if tgt is not None and tgt[0].k in ("subset", "bin", "setfilter", "funcset", "recset"):
+                    # re-dispatch on the definition body with its own environment
+                    node2, env2, ctx2, base2 = tgt
+                    e = self.cx(en, env, ctx, base)
+                    env3 = dict(env2)
+                    env3["__in_lhs"] = e
+                    self.cc_in(Node("id", ("__in_lhs",)), node2, env3, ctx2, base2, lt, lf, n)
+                    return
+        e = self.cx(en, env, ctx, base)
+        if sc is not None:
+            s = sc.v
+            if not is_set(s):
+                raise CompileError(f"\\in applied to a non-set at line {n.line}")
+            if type(e) is Const:
+                self.asm.emit("JMP", lt if set_contains(s, e.v) else lf)
+                return
+            self._in_const_set(e, s, lt, lf, n)
+            return
+        sv = self.cx(sn, env, ctx, base)
+        if type(sv) is Const:
+            self._in_const_set(self.as_val(e), sv.v, lt, lf, n)
+            return
+        if not isinstance(sv.t, TSet):
+            raise CompileError(f"\\in applied to non-set type {sv.t}")
+        if isinstance(sv.t.elem, TBottom):
+            self.asm.emit("JMP", lf)
+            return
+        o = self.ord_in(sv.t.elem, e)
+        t1 = self.alloc(1)
+        self.asm.emit("JNEG", o, lf)
+        self.asm.emit("BTEST", t1, sv.loc, o)
+        self.asm.emit("JNZ", t1, lt)
+        self.asm.emit("JMP", lf)
+
+    def _in_const_set(self, e: Val, s, lt, lf, n):
+        from ..front.values import SetFuncs, SetSubset, SetRecs, SetTimes, SetUnionLazy
+        t = e.t
+        # structural membership in lazy set values (never enumerate [S -> T], SUBSET S, ...)
+        if isinstance(s, SetUnionLazy):
+            nxt = Label("mu")
+            self._in_const_set(e, s.a, lt, nxt, n)
+            self.asm.label(nxt)
+            self._in_const_set(e, s.b, lt, lf, n)
+            return
+        if isinstance(s, SetFuncs) and isinstance(t, (TFun, TTuple)):
+            dom = tuple(sorted_vals(to_finite(s.dom)))
+            keys = t.keys if isinstance(t, TFun) else tuple(range(1, len(t.elems) + 1))
+            if dom != tuple(keys):
+                self.asm.emit("JMP", lf)
+                return
+            for j in range(len(keys)):
+                sub = Val(t.elem, e.loc + j * t.elem.size) if isinstance(t, TFun) else Val(t.elems[j], e.loc + t.offs[j])
+                nxt = Label("mf")
+                self._in_const_set(sub, s.rng, nxt, lf, n)
+                self.asm.label(nxt)
+            self.asm.emit("JMP", lt)
+            return
+        if isinstance(s, SetSubset) and isinstance(t, TSet):
+            if isinstance(t.elem, TBottom):
+                self.asm.emit("JMP", lt)
+                return
+            vals = self.codec.enum(t.elem)
+            words = [0] * t.size
+            for i, v in enumerate(vals):
+                if set_contains(s.s, v):
+                    words[i >> 5] |= 1 << (i & 31)
+            words = [w - (1 << 32) if w >= (1 << 31) else w for w in words]
+            mloc = self.alloc(t.size)
+            self.load_words(mloc, words)
+            t2 = self.alloc(1)
+            self.asm.emit("BSUB", t2, e.loc, mloc, t.size)
+            self.asm.emit("JNZ", t2, lt)
+            self.asm.emit("JMP", lf)
+            return
+        if isinstance(s, SetRecs) and isinstance(t, TRec) and not t.tagged:
+            names = tuple(sorted(f for f, _ in s.fields))
+            if names != t.alts[0]:
+                self.asm.emit("JMP", lf)
+                return
+            for f, fs in s.fields:
+                nxt = Label("mr")
+                self._in_const_set(Val(t.fields[f], e.loc + t.off[f]), fs, nxt, lf, n)
+                self.asm.label(nxt)
+            self.asm.emit("JMP", lt)
+            return
+        if isinstance(s, SetTimes) and isinstance(t, TTuple) and len(s.sets) == len(t.elems):
+            for j, ss in enumerate(s.sets):
+                nxt = Label("mt")
+                self._in_const_set(Val(t.elems[j], e.loc + t.offs[j]), ss, nxt, lf, n)
+                self.asm.label(nxt)
+            self.asm.emit("JMP", lt)
+            return
+        t1 = self.alloc(1)
+        if isinstance(t, TInt) and t.lo is None:
+            if isinstance(s, SetNat):
+                self.asm.emit("GEI", t1, e.loc, 0)
+                self.asm.emit("JNZ", t1, lt)
+                self.asm.emit("JMP", lf)
+                return
+            if isinstance(s, SetInt):
+                self.asm.emit("JMP", lt)
+                return
+            if isinstance(s, frozenset):
+                ints = sorted(x for x in s if type(x) is int)
+                if ints and ints == list(range(ints[0], ints[-1] + 1)):
+                    self.asm.emit("GEI", t1, e.loc, ints[0])
+                    self.asm.emit("JZ", t1, lf)
+                    self.asm.emit("LEI", t1, e.loc, ints[-1])
+                    self.asm.emit("JNZ", t1, lt)
+                    self.asm.emit("JMP", lf)
+                    return
+                for x in ints:
+                    self.asm.emit("EQI", t1, e.loc, x)
+                    self.asm.emit("JNZ", t1, lt)
+                self.asm.emit("JMP", lf)
+                return
+            raise CompileError("membership of an unbounded integer in a lazy set")
+        # enumerable element type: constant bitmask over its universe
+        try:
+            n_u = t.card()
+        except TypeErr as ex:
+            raise CompileError(str(ex))
+        if n_u > 8192:
+            raise CompileError("membership test over a universe larger than 8192 values")
+        vals = self.codec.enum(t)
+        words = [0] * ((n_u + 31) // 32)
+        anyb = False
+        for i, v in enumerate(vals):
+            if set_contains(s, v):
+                words[i >> 5] |= 1 << (i & 31)
+                anyb = True
+        if not anyb:
+            self.asm.emit("JMP", lf)
+            return
+        words = [w - (1 << 32) if w >= (1 << 31) else w for w in words]
+        mloc = self.alloc(len(words))
+        self.load_words(mloc, words)
+        o = self.ord_in(t, e)
+        self.asm.emit("JNEG", o, lf)
+        self.asm.emit("BTEST", t1, mloc, o)
+        self.asm.emit("JNZ", t1, lt)
+        self.asm.emit("JMP", lf)
+
+    def cc_subseteq(self, ln, rn, env, ctx, base, lt, lf, n):
+        a = self.cx(ln, env, ctx, base)
+        if type(a) is Const:
+            vals = list(set_iter(a.v))
+            for v in vals:
+                nxt = Label("ss")
+                env2 = dict(env)
+                env2["__ss_elem"] = Const(v)
+                self.cc_in(Node("id", ("__ss_elem",)), rn, env2, ctx, base, nxt, lf, n)
+                self.asm.label(nxt)
+            self.asm.emit("JMP", lt)
+            return
+        if not isinstance(a.t, TSet):
+            raise CompileError(f"\\subseteq on non-set type {a.t}")
+        rc = self.try_const(rn, env, ctx, base)
+        if rc is not None and not is_enumerable(rc.v):
+            # e.g.  S \subseteq Nat : check element-wise
+            def each(x):
+                nxt = Label("se")
+                self._in_const_set(x, rc.v, nxt, lf, n)
+                self.asm.label(nxt)
+            self.loop_set(a, each)
+            self.asm.emit("JMP", lt)
+            return
+        b = self.cx(rn, env, ctx, base, a.t)
+        try:
+            bv = self.coerce(b, a.t) if type(b) is Const or b.t != a.t else b
+            av = a
+        except CompileError:
+            tj = join(a.t, b.t if type(b) is Val else self.natural_type(b.v))
+            av, bv = self.coerce(a, tj), self.coerce(b, tj)
+        t1 = self.alloc(1)
+        self.asm.emit("BSUB", t1, av.loc, bv.loc, av.t.size)
+        self.asm.emit("JNZ", t1, lt)
+        self.asm.emit("JMP", lf)
+
+    # ----------------------------------------------------------------- actions
+    def ca(self, n, env, ctx, bound, k, act):
+        """Compile action n; `k(bound)` emits the continuation for each satisfying branch.
+        Control falls through after all alternatives are exhausted."""
+        self.bound = bound
+        kind = n.k
+        if kind == "and":
+            items = n.a[0]
+            if len(items) > 1 and act is not None and act[0] == "split":
+                act = ("fixed",) + act[1:]
+
+            def chain(i, b):
+                if i == len(items):
+                    k(b, act)
+                    return
+                self.ca(items[i], env, ctx, b, lambda b2, _a: chain(i + 1, b2), act)
+            chain(0, bound)
+            return
+        if kind == "or":
+            for x in n.a[0]:
+                self.bound = bound
+                m = self.mark()
+                self.ca(x, env, ctx, bound, k, act)
+                self.release(m)
+            return
+        if kind == "exists":
+            bounds, body = n.a
+
+            def each(env2):
+                m = self.mark()
+                self.bound = bound
+                self.ca(body, env2, ctx, bound, k, act)
+                self.release(m)
+            self.for_each(bounds, env, ctx, "N", each)
+            return
+        if kind == "if":
+            c1 = self.try_const(n.a[0], env, ctx, "N")
+            if c1 is not None:
+                self.ca(n.a[1] if c1.v else n.a[2], env, ctx, bound, k, act)
+                return
+            lt, lf, end = Label("at"), Label("af"), Label("ae")
+            m = self.mark()
+            self.cc(n.a[0], env, ctx, "N", lt, lf)
+            self.release(m)
+            self.asm.label(lt)
+            self.ca(n.a[1], env, ctx, bound, k, act)
+            self.asm.emit("JMP", end)
+            self.asm.label(lf)
+            self.ca(n.a[2], env, ctx, bound, k, act)
+            self.asm.label(end)
+            return
+        if kind == "case":
+            arms, other = n.a
+            node = other if other is not None else Node("bool", (False,), n.line, n.col)
+            for c2, e in reversed(arms):
+                node = Node("if", (c2, e, node), n.line, n.col)
+            self.ca(node, env, ctx, bound, k, act)
+            return
+        if kind == "let":
+            self.ca(n.a[1], self.let_env(n.a[0], env, ctx, "N"), ctx, bound, k, act)
+            return
+        if kind in ("id", "app", "sel"):
+            is_assert = kind == "app" and n.a[0] == "Assert"
+            tgt = None if is_assert else self._expand(n, env, ctx, "N")
+            if tgt is not None:
+                node2, env2, ctx2, _ = tgt
+                act2 = act
+                if (act is None or act[0] == "split") and kind != "sel":
+                    r = self.resolve(n.a[0], env, ctx)
+                    if r[0] == "def":
+                        act2 = ("split", r[1].name, r[1].body.loc(), r[2].name)
+                self.ca(node2, env2, ctx2, bound, k, act2)
+                return
+        if kind == "bin" and n.a[0] in ("=", "\\in"):
+            tv = self._assign_target(n.a[1], env, ctx, bound)
+            if tv is not None:
+                t = self.var_types[tv]
+                if n.a[0] == "=":
+                    m = self.mark()
+                    x = self.cx(n.a[2], env, ctx, "N", t)
+                    xv = self.coerce(x, t)
+                    self.movn(self.p_off[tv], xv.loc, t.size)
+                    self.release(m)
+                    b2 = bound | {tv}
+                    self.bound = b2
+                    k(b2, act)
+                    return
+                # x' \in S : one alternative per element
+                def each(env2):
+                    m = self.mark()
+                    x = env2["__asg"]
+                    xv = self.coerce(x, t)
+                    self.movn(self.p_off[tv], xv.loc, t.size)
+                    self.release(m)
+                    b2 = bound | {tv}
+                    self.bound = b2
+                    k(b2, act)
+                self.for_each([("__asg", n.a[2])], env, ctx, "N", each)
+                return
+        if kind == "unchanged":
+            names = []
+            if self._unchanged_vars(n.a[0], env, ctx, names):
+                b2 = set(bound)
+                end = Label("ue")
+                for v in names:
+                    t = self.var_types[v]
+                    if v in b2:
+                        t1 = self.alloc(1)
+                        if t.size == 1:
+                            self.asm.emit("EQ", t1, self.p_off[v], self.n_off[v])
+                        else:
+                            self.asm.emit("EQN", t1, self.p_off[v], self.n_off[v], t.size)
+                        self.asm.emit("JZ", t1, end)
+                    else:
+                        self.movn(self.p_off[v], self.n_off[v], t.size)
+                        b2.add(v)
+                b2 = frozenset(b2)
+                self.bound = b2
+                k(b2, act)
+                self.asm.label(end)
+                return
+        # guard
+        lt, lf = Label("gt"), Label("gf")
+        m = self.mark()
+        self.bound = bound
+        self.cc(n, env, ctx, "N", lt, lf)
+        self.release(m)
+        self.asm.label(lt)
+        k(bound, act)
+        self.asm.label(lf)
+
+    def _assign_target(self, ln, env, ctx, bound):
+        if ln.k == "id" and ln.a[0] in env and type(env[ln.a[0]]) is Lazy:
+            lz = env[ln.a[0]]
+            return self._assign_target(lz.node, lz.env, lz.ctx, bound)
+        if ln.k == "prime" and ln.a[0].k == "id":
+            v = ln.a[0].a[0]
+            if v in ctx.varset and v not in env and v not in ctx.substs and v not in bound \
+                    and v in self.var_types:
+                return v
+        return None
+
+    def _unchanged_vars(self, e, env, ctx, out):
+        if e.k == "id":
+            nm = e.a[0]
+            if nm in env:
+                return False
+            if nm in ctx.varset and nm not in ctx.substs:
+                out.append(nm)
+                return True
+            d = ctx.defs.get(nm)
+            if d is not None and not d[0].params:
+                return self._unchanged_vars(d[0].body, {}, d[1], out)
+            return False
+        if e.k == "tuple":
+            return all(self._unchanged_vars(x, env, ctx, out) for x in e.a[0])
+        return False
+
+    # ------------------------------------------------------------------ driver
+    def compile(self, init_states) -> CompiledModel:
+        """Two passes: a dry pass counts how often each zero-arity state-level definition
+        (e.g. Paxos.tla:185 `votes`) is expanded; definitions used more than once and free of
+        traps are then evaluated once per state in the program prologue (hoisted)."""
+        self.var_types = self.infer_var_types(init_states)
+        self.dry = True
+        try:
+            self._compile_pass()
+        except CompileError:
+            self.dry = False
+            raise
+        keys = [k for k, c in self.def_uses.items() if c >= 2]
+        info = dict(self.def_info)
+        # reset the assembler state
+        self.dry = False
+        self.asm = Asm()
+        self.actions, self.asserts = [], []
+        self.hoisted, self.def_uses, self.def_info = {}, {}, {}
+        self._evenv_cache = {}
+        self.__dict__.pop("_univ_cache", None)
+        self.hoist_keys = [(k, info[k]) for k in keys]
+        return self._compile_pass()
+
+    def _hoist_prologue(self, program):
+        for key, (od, dctx) in self.hoist_keys:
+            name, _, base, prog = key
+            if prog != program or base != "N":
+                continue
+            with self.asm.capture() as cap:
+                save_top = self.top
+                try:
+                    v = self.cx(od.body, {}, dctx, "N")
+                except CompileError:
+                    v = None
+                if v is None or type(v) is Const or any(i[0] in ("TRAP", "ASSERTF") for i in cap.asm.code):
+                    self.top = save_top
+                    v = None
+            if v is None:
+                continue
+            self.asm.splice(cap.buf)
+            self.hoisted[key] = v
+
+    def _compile_pass(self) -> CompiledModel:
+        m = self.m
+        self.n_off, self.p_off = {}, {}
+        off = 0
+        for v in m.vars:
+            self.n_off[v] = off
+            off += self.var_types[v].size
+        usz = off
+        for v in m.vars:
+            self.p_off[v] = usz + self.n_off[v]
+        self.top = self.high = 2 * usz
+        entries = {}
+        # ---- invariants (evaluated on the state being expanded) ----
+        linv = Label("inv")
+        self.asm.label(linv)
+        entries["inv"] = linv
+        self.program = "inv"
+        self._hoist_prologue("inv")
+        for i, (nm, node, c) in enumerate(m.invariants):
+            ok, bad = Label("iok"), Label("ibad")
+            mk = self.mark()
+            self.bound = frozenset()
+            self.cc(node, {}, c, "N", ok, bad)
+            self.release(mk)
+            self.asm.label(bad)
+            self.asm.emit("INVF", i)
+            self.asm.label(ok)
+        self.asm.emit("HALT")
+        # ---- next ----
+        lnext = Label("next")
+        self.asm.label(lnext)
+        entries["next"] = lnext
+        self.program = "next"
+        inv_top = self.top
+        self._hoist_prologue("next")
+        allv = frozenset(m.vars)
+
+        def emit_k(b, act):
+            missing = [v for v in m.vars if v not in b]
+            if missing:
+                raise CompileError(f"action {act[1] if act else 'Next'} does not assign {missing}")
+            aid = self._action_id(act)
+            if m.constraints or m.action_constraints:
+                ok, bad, end = Label("cok"), Label("cbad"), Label("cend")
+                mk = self.mark()
+                self.bound = allv
+                conj = [Node("prime", (Node("id", (nm,)),)) for nm, _, _ in m.constraints]
+                conj += [Node("id", (nm,)) for nm, _, _ in m.action_constraints]
+                self.cc(Node("and", (tuple(conj),)), {}, self.ctx, "N", ok, bad)
+                self.release(mk)
+                self.asm.label(bad)
+                self.asm.emit("GEN")
+                self.asm.emit("JMP", end)
+                self.asm.label(ok)
+                self.asm.emit("EMIT", aid)
+                self.asm.label(end)
+            else:
+                self.asm.emit("EMIT", aid)
+        if m.next_node is None:
+            raise CompileError("no next-state action")
+        self.ca(m.next_node, {}, m.next_ctx, frozenset(), emit_k, None)
+        self.asm.emit("HALT")
+        code, cpool, ent = self.asm.assemble(entries)
+        cm = CompiledModel()
+        cm.code, cm.cpool, cm.entries = code, cpool, ent
+        cm.frame_words = self.high + 4
+        cm.var_types = self.var_types
+        cm.var_off = dict(self.n_off)
+        cm.vars = list(m.vars)
+        cm.n_off, cm.p_off = 0, usz
+        cm.state_words_unpacked = usz
+        cm.actions = list(self.actions)
+        cm.asserts = list(self.asserts)
+        cm.invariants = [nm for nm, _, _ in m.invariants]
+        cm.atoms, cm.codec = self.atoms, self.codec
+        cm.warnings = self.warnings
+        # packed layout
+        lay = []
+        aw = self.atoms.width()
+        for v in m.vars:
+            for (fo, w, bias) in self.codec.layout(self.var_types[v], self.n_off[v]):
+                lay.append((fo, aw if w < 0 else w, bias))
+        import numpy as np
+        cm.layout = np.array(lay, dtype=np.int32).reshape(-1, 3)
+        bits = int(cm.layout[:, 1].sum())
+        cm.W = max(1, (bits + 31) // 32)
+        cm.state_bits = bits
+        return cm
+
+    def _action_id(self, act):
+        if act is None:
+            key = ("Next", (0, 0, 0, 0), self.m.module_name)
+        else:
+            key = (act[1], act[2], act[3])
+        for i, a in enumerate(self.actions):
+            if a == key:
+                return i
+        self.actions.append(key)
+        return len(self.actions) - 1

@@ -1,0 +1,824 @@
+// tlag_engine.cu -- sm_100a BFS engine behind include/tlag.h.
+//
+// One wave (BFS level) = one launch of k_wave: a persistent grid pulls 32-state chunks of
+// the frontier; each thread unpacks its state, runs the invariant program, then the
+// next-state program.  Every EMIT event is handled warp-synchronously: pack -> 64-bit
+// fingerprint -> open-addressed seen-set probe/insert (atomicCAS on 8-byte slots in HBM)
+// -> __ballot_sync compaction of the newly discovered states into the tail of the state
+// store (which doubles as the BFS queue: the next frontier is the slice appended by this
+// wave).  Successor states never round-trip through HBM before the probe (SURVEY.md §8d:
+// the fused form of K2->K1->K3->K4).  No tensor cores: integer / hash work only.
+//
+// Replaces TLC's Worker loop + StateQueue, action evaluator, FPSet and invariant checker
+// (all external to /root/reference, which only fixes the CLI contract
+// Makefile:6-7 and the output format README.md:267-321).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+
+#include "../../include/tlag.h"
+#include "tlag_vm.h"
+
+#define TLAG_MAXW 64
+#define TLAG_BLOCK 128
+#define TLAG_MAX_STEPS (1u << 26)
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                       \
+      return TLAG_ECUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+struct Counters {
+  unsigned long long n_states;      // tail of the state store
+  unsigned long long generated;
+  unsigned long long work;          // chunk dispenser
+  unsigned long long viol_inv;      // min key: idx<<20 | detail
+  unsigned long long viol_assert;
+  unsigned long long viol_trap;     // idx<<20 | code<<16 | line
+  unsigned long long viol_deadlock;
+  unsigned long long store_overflow;
+  unsigned long long table_full;
+  unsigned long long route_overflow;
+  unsigned long long send_count[16];
+};
+
+struct DevParams {
+  const uint64_t* code; uint32_t code_len; int code_in_smem;
+  const int32_t* cpool;
+  const tlag_slot* layout; int n_slots;
+  uint32_t entry_inv, entry_next;
+  uint32_t n_off, p_off;
+  int W;
+  uint32_t* states; uint32_t* parent; uint32_t* meta;
+  unsigned long long cap_states;
+  unsigned long long* table; unsigned long long mask;
+  Counters* ctr;
+  uint32_t flags;
+  int n_inv;
+  // route mode
+  uint32_t* send; unsigned long long region_cap; int n_ranks; int rank;
+};
+
+struct tlag_engine {
+  tlag_model m;
+  std::vector<uint64_t> h_code;
+  std::vector<uint32_t> h_init;     // retained initial states (for tlag_restart)
+  DevParams p;
+  uint64_t* d_code = nullptr; int32_t* d_cpool = nullptr; tlag_slot* d_layout = nullptr;
+  uint32_t* d_states = nullptr; uint32_t* d_parent = nullptr; uint32_t* d_meta = nullptr;
+  unsigned long long* d_table = nullptr; unsigned table_log2 = 0;
+  Counters* d_ctr = nullptr;
+  uint64_t cap_states = 0;
+  uint64_t lo = 0, hi = 0;          // current frontier [lo,hi)
+  uint64_t level = 0;               // level of the frontier (1 = initial states)
+  uint64_t init_states = 0;
+  uint64_t generated = 0;
+  uint64_t depth = 0;
+  int verdict = TLAG_V_RUNNING; int detail = 0, detail2 = 0; uint64_t viol_idx = 0;
+  double dev_seconds = 0;
+  uint64_t launches = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  int frame_class = 0;
+  bool restarting = false;
+  std::string err;
+  uint32_t* d_scratch = nullptr; uint64_t scratch_words = 0; uint8_t* d_flags = nullptr; uint64_t flags_cap = 0;
+};
+
+// ------------------------------------------------------------------ seen-set
+// returns 1 if fp was inserted by this call, 0 if already present, -1 if the table is full
+__device__ __forceinline__ int seen_insert(unsigned long long* table, unsigned long long mask,
+                                           unsigned long long fp) {
+  unsigned long long i = fp & mask;
+  for (unsigned long long probes = 0; probes <= mask; ++probes) {
+    unsigned long long cur = table[i];
+    if (cur == fp) return 0;
+    if (cur == 0ULL) {
+      unsigned long long old = atomicCAS(&table[i], 0ULL, fp);
+      if (old == 0ULL) return 1;
+      if (old == fp) return 0;
+    }
+    i = (i + 1) & mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+__device__ __forceinline__ void report_min(unsigned long long* slot, unsigned long long key) {
+  atomicMin(slot, key);
+}
+
+// ------------------------------------------------------------------ wave kernel
+// MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
+template <int FRAME, int MODE>
+__global__ void __launch_bounds__(TLAG_BLOCK) k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
+  extern __shared__ uint64_t s_code[];
+  const uint64_t* code = p.code;
+  if (p.code_in_smem) {
+    for (uint32_t i = threadIdx.x; i < p.code_len; i += blockDim.x) s_code[i] = p.code[i];
+    __syncthreads();
+    code = s_code;
+  }
+  int32_t frame[FRAME];
+  uint32_t succ[TLAG_MAXW];
+  const unsigned lane = threadIdx.x & 31;
+  const int W = p.W;
+  unsigned long long gen_local = 0;
+
+  for (;;) {
+    unsigned long long chunk = 0;
+    if (lane == 0) chunk = atomicAdd(&p.ctr->work, 1ULL);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    const unsigned long long first = lo + chunk * 32ULL;
+    if (first >= hi) break;
+    const unsigned long long idx = first + lane;
+    const bool active = idx < hi;
+    if (active) {
+      const uint32_t* src = p.states + idx * (unsigned long long)W;
+      for (int i = 0; i < W; ++i) succ[i] = src[i];
+      tlag_unpack(p.layout, p.n_slots, succ, frame + p.n_off);
+    }
+    bool dead = !active;   // thread has nothing (more) to do
+    bool trapped = false;
+    // ---- invariants on the state being expanded --------------------------------
+    if (active && p.n_inv > 0) {
+      uint32_t pc = p.entry_inv;
+      for (;;) {
+        int32_t info = 0, info2 = 0;
+        int ev = tlag_vm_run(code, p.cpool, frame, &pc, &info, &info2, TLAG_MAX_STEPS);
+        if (ev == TLAG_EV_HALT) break;
+        if (ev == TLAG_EV_INVF) { report_min(&p.ctr->viol_inv, (idx << 20) | (unsigned)(info & 0xFFFFF)); continue; }
+        if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); continue; }
+        // trap / runaway
+        report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) |
+                                          (unsigned)(info2 & 0xFFFF));
+        dead = true; trapped = true;
+        break;
+      }
+    }
+    // ---- successors -------------------------------------------------------------
+    uint32_t pc = p.entry_next;
+    unsigned nsucc = 0;
+    for (;;) {
+      int32_t act = 0;
+      bool has = false;
+      while (!dead) {
+        int32_t info = 0, info2 = 0;
+        int ev = tlag_vm_run(code, p.cpool, frame, &pc, &info, &info2, TLAG_MAX_STEPS);
+        if (ev == TLAG_EV_EMIT) { has = true; act = info; ++nsucc; ++gen_local; break; }
+        if (ev == TLAG_EV_GEN) { ++nsucc; ++gen_local; continue; }
+        if (ev == TLAG_EV_HALT) { dead = true; break; }
+        if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); continue; }
+        if (ev == TLAG_EV_INVF) { continue; }
+        report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) |
+                                          (unsigned)(info2 & 0xFFFF));
+        dead = true; trapped = true;
+        break;
+      }
+      if (!__any_sync(0xffffffffu, has)) break;
+      unsigned long long fp = 0;
+      if (has) {
+        int ov = tlag_pack(p.layout, p.n_slots, frame + p.p_off, succ, W);
+        if (ov) {
+          report_min(&p.ctr->viol_trap, (idx << 20) | (2ULL << 16) | (unsigned)((ov - 1) & 0xFFFF));
+          has = false;
+        } else {
+          fp = tlag_fingerprint(succ, W);
+        }
+      }
+      if (MODE == 0) {
+        int ins = has ? seen_insert(p.table, p.mask, fp) : 0;
+        if (ins < 0) { atomicExch(&p.ctr->table_full, 1ULL); ins = 0; }
+        const bool isnew = ins > 0;
+        const unsigned m = __ballot_sync(0xffffffffu, isnew);
+        if (m) {
+          const int leader = __ffs((int)m) - 1;
+          unsigned long long base = 0;
+          if ((int)lane == leader) base = atomicAdd(&p.ctr->n_states, (unsigned long long)__popc(m));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (isnew) {
+            const unsigned long long pos = base + (unsigned long long)__popc(m & lanemask_lt());
+            if (pos < p.cap_states) {
+              uint32_t* dst = p.states + pos * (unsigned long long)W;
+              for (int i = 0; i < W; ++i) dst[i] = succ[i];
+              p.parent[pos] = (uint32_t)idx;
+              p.meta[pos] = ((uint32_t)act << 8) | (uint32_t)(p.rank & 0xFF);
+            } else {
+              atomicExch(&p.ctr->store_overflow, 1ULL);
+            }
+          }
+        }
+      } else {
+        // route: owner = high bits of the fingerprint scaled to n_ranks (hash-range partition)
+        int owner = has ? (int)__umul64hi(fp, (unsigned long long)p.n_ranks) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, owner);
+        if (has) {
+          const int leader = __ffs((int)peers) - 1;
+          unsigned long long base = 0;
+          if ((int)lane == leader) base = atomicAdd(&p.ctr->send_count[owner], (unsigned long long)__popc(peers));
+          base = __shfl_sync(peers, base, leader);
+          const unsigned long long pos = base + (unsigned long long)__popc(peers & lanemask_lt());
+          if (pos < p.region_cap) {
+            uint32_t* dst = p.send + ((unsigned long long)owner * p.region_cap + pos) * (unsigned long long)(W + 2);
+            for (int i = 0; i < W; ++i) dst[i] = succ[i];
+            dst[W] = (uint32_t)idx;
+            dst[W + 1] = ((uint32_t)act << 8) | (uint32_t)(p.rank & 0xFF);
+          } else {
+            atomicExch(&p.ctr->route_overflow, 1ULL);
+          }
+        }
+      }
+    }
+    if (active && nsucc == 0 && !trapped && (p.flags & TLAG_F_DEADLOCK_CHECK)) {
+      // a trapped thread is not a deadlock
+      report_min(&p.ctr->viol_deadlock, idx << 20);
+    }
+  }
+  // generated counter: warp reduce then one atomic
+  for (int o = 16; o > 0; o >>= 1) gen_local += __shfl_down_sync(0xffffffffu, gen_local, o);
+  if (lane == 0 && gen_local) atomicAdd(&p.ctr->generated, gen_local);
+}
+
+// ------------------------------------------------------------------ K1 alone: fingerprint + probe/insert
+// One thread per candidate state; W words loaded with the widest aligned vector the layout allows.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_probe(const uint32_t* __restrict__ states, unsigned long long n, int W,
+                                               unsigned long long* table, unsigned long long mask,
+                                               uint8_t* __restrict__ is_new, Counters* ctr) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[TLAG_MAXW];
+  const uint32_t* src = states + i * (unsigned long long)W;
+  if (VEC == 4) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll 4
+    for (int k = 0; k < W / 4; ++k) {
+      uint4 v = __ldg(s4 + k);
+      w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    }
+  } else if (VEC == 2) {
+    const uint2* s2 = reinterpret_cast<const uint2*>(src);
+    for (int k = 0; k < W / 2; ++k) { uint2 v = __ldg(s2 + k); w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+  } else {
+    for (int k = 0; k < W; ++k) w[k] = __ldg(src + k);
+  }
+  const unsigned long long fp = tlag_fingerprint(w, W);
+  int ins = seen_insert(table, mask, fp);
+  if (ins < 0) { atomicExch(&ctr->table_full, 1ULL); ins = 0; }
+  is_new[i] = (uint8_t)ins;
+}
+
+// insert routed records (W state words + parent + meta) into this rank's shard
+__global__ void __launch_bounds__(256) k_insert_records(DevParams p, const uint32_t* __restrict__ rec,
+                                                        unsigned long long n) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31;
+  const int W = p.W;
+  uint32_t w[TLAG_MAXW];
+  bool has = i < n;
+  unsigned long long fp = 0;
+  const uint32_t* src = rec + i * (unsigned long long)(W + 2);
+  if (has) {
+    for (int k = 0; k < W; ++k) w[k] = src[k];
+    fp = tlag_fingerprint(w, W);
+  }
+  int ins = has ? seen_insert(p.table, p.mask, fp) : 0;
+  if (ins < 0) { atomicExch(&p.ctr->table_full, 1ULL); ins = 0; }
+  const bool isnew = ins > 0;
+  const unsigned m = __ballot_sync(0xffffffffu, isnew);
+  if (m) {
+    const int leader = __ffs((int)m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(&p.ctr->n_states, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (isnew) {
+      const unsigned long long pos = base + (unsigned long long)__popc(m & lanemask_lt());
+      if (pos < p.cap_states) {
+        uint32_t* dst = p.states + pos * (unsigned long long)W;
+        for (int k = 0; k < W; ++k) dst[k] = w[k];
+        p.parent[pos] = src[W];
+        p.meta[pos] = src[W + 1];
+      } else {
+        atomicExch(&p.ctr->store_overflow, 1ULL);
+      }
+    }
+  }
+}
+
+// rebuild the table from the state store after growing it
+__global__ void k_rehash(DevParams p, unsigned long long n) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[TLAG_MAXW];
+  for (int k = 0; k < p.W; ++k) w[k] = p.states[i * (unsigned long long)p.W + k];
+  seen_insert(p.table, p.mask, tlag_fingerprint(w, p.W));
+}
+
+// ------------------------------------------------------------------ host side
+static const int kFrameClasses[] = {64, 128, 256, 512, 1024, 2048, 4096};
+
+template <int MODE>
+static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
+  const uint64_t n = hi - lo;
+  uint64_t chunks = (n + 31) / 32;
+  uint64_t blocks = (chunks + (TLAG_BLOCK / 32) - 1) / (TLAG_BLOCK / 32);
+  const uint64_t maxb = (uint64_t)e->sm_count * 8;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks == 0) blocks = 1;
+  size_t smem = e->p.code_in_smem ? (size_t)e->p.code_len * 8 : 0;
+  void (*fn)(DevParams, unsigned long long, unsigned long long) = nullptr;
+  switch (e->frame_class) {
+    case 0: fn = k_wave<64, MODE>; break;
+    case 1: fn = k_wave<128, MODE>; break;
+    case 2: fn = k_wave<256, MODE>; break;
+    case 3: fn = k_wave<512, MODE>; break;
+    case 4: fn = k_wave<1024, MODE>; break;
+    case 5: fn = k_wave<2048, MODE>; break;
+    default: fn = k_wave<4096, MODE>; break;
+  }
+  if (smem > 48 * 1024) {
+    cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (r != cudaSuccess) return r;
+  }
+  fn<<<(unsigned)blocks, TLAG_BLOCK, smem, e->stream>>>(e->p, lo, hi);
+  e->launches++;
+  return cudaGetLastError();
+}
+
+static int alloc_table(tlag_engine* e, unsigned log2) {
+  if (e->d_table) cudaFree(e->d_table);
+  e->d_table = nullptr;
+  const uint64_t slots = 1ULL << log2;
+  CK(cudaMalloc(&e->d_table, slots * 8));
+  CK(cudaMemsetAsync(e->d_table, 0, slots * 8, e->stream));
+  e->table_log2 = log2;
+  e->p.table = e->d_table;
+  e->p.mask = slots - 1;
+  return TLAG_OK;
+}
+
+static int grow_table_if_needed(tlag_engine* e, uint64_t expected_states) {
+  const uint64_t slots = 1ULL << e->table_log2;
+  if (expected_states * 2 <= slots) return TLAG_OK;
+  unsigned log2 = e->table_log2;
+  while ((1ULL << log2) < expected_states * 4) ++log2;
+  Counters hc;
+  CK(cudaMemcpyAsync(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  int r = alloc_table(e, log2);
+  if (r) return r;
+  const uint64_t n = hc.n_states;
+  if (n) {
+    k_rehash<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->p, n);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  return TLAG_OK;
+}
+
+static int grow_store_if_needed(tlag_engine* e, uint64_t need) {
+  if (need <= e->cap_states) return TLAG_OK;
+  uint64_t ncap = e->cap_states;
+  while (ncap < need) ncap *= 2;
+  if (e->m.max_states && ncap > e->m.max_states) ncap = e->m.max_states;
+  if (ncap <= e->cap_states) return TLAG_OK;   // at the configured limit; overflow is detected by the kernel
+  size_t freeb = 0, totalb = 0;
+  cudaMemGetInfo(&freeb, &totalb);
+  const uint64_t per = (uint64_t)e->m.words_per_state * 4 + 8;
+  if ((ncap - 0) * per > freeb * 9 / 10) {
+    ncap = e->cap_states + (freeb * 8 / 10) / per;
+    if (ncap <= e->cap_states) return TLAG_OK;
+  }
+  uint32_t *ns = nullptr, *np = nullptr, *nm = nullptr;
+  CK(cudaMalloc(&ns, ncap * (uint64_t)e->m.words_per_state * 4));
+  CK(cudaMalloc(&np, ncap * 4));
+  CK(cudaMalloc(&nm, ncap * 4));
+  Counters hc;
+  CK(cudaMemcpyAsync(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const uint64_t n = hc.n_states;
+  CK(cudaMemcpyAsync(ns, e->d_states, n * (uint64_t)e->m.words_per_state * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(np, e->d_parent, n * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(nm, e->d_meta, n * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(e->d_states); cudaFree(e->d_parent); cudaFree(e->d_meta);
+  e->d_states = ns; e->d_parent = np; e->d_meta = nm;
+  e->cap_states = ncap;
+  e->p.states = ns; e->p.parent = np; e->p.meta = nm; e->p.cap_states = ncap;
+  return TLAG_OK;
+}
+
+extern "C" const char* tlag_version(void) { return "tlag 0.1 (sm_100a)"; }
+
+extern "C" const char* tlag_last_error(const tlag_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+extern "C" uint64_t tlag_kernel_launches(const tlag_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
+  if (!m || !out) return TLAG_EINVAL;
+  *out = nullptr;
+  tlag_engine* e = new tlag_engine();
+  *out = e;   // returned even on failure so that tlag_last_error works; caller destroys it
+  e->m = *m;
+  if (m->words_per_state == 0 || m->words_per_state > TLAG_MAXW) { e->err = "words_per_state out of range (1..64)"; return TLAG_EINVAL; }
+  if (m->frame_words > 4096) { e->err = "frame_words > 4096 not supported"; return TLAG_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { e->err = "no CUDA device available"; return TLAG_ECUDA; }
+  CK(cudaSetDevice(m->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, m->device));
+  e->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&e->ev0));
+  CK(cudaEventCreate(&e->ev1));
+  e->frame_class = 6;
+  for (int i = 0; i < 7; ++i) if ((int)m->frame_words <= kFrameClasses[i]) { e->frame_class = i; break; }
+  // program image
+  CK(cudaMalloc(&e->d_code, (size_t)(m->code_len ? m->code_len : 1) * 8));
+  CK(cudaMemcpy(e->d_code, m->code, (size_t)m->code_len * 8, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&e->d_cpool, (size_t)(m->cpool_len ? m->cpool_len : 1) * 4));
+  CK(cudaMemcpy(e->d_cpool, m->cpool, (size_t)m->cpool_len * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&e->d_layout, (size_t)(m->n_slots ? m->n_slots : 1) * sizeof(tlag_slot)));
+  CK(cudaMemcpy(e->d_layout, m->layout, (size_t)m->n_slots * sizeof(tlag_slot), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&e->d_ctr, sizeof(Counters)));
+  Counters hc;
+  memset(&hc, 0, sizeof(hc));
+  hc.viol_inv = hc.viol_assert = hc.viol_trap = hc.viol_deadlock = ~0ULL;
+  CK(cudaMemcpy(e->d_ctr, &hc, sizeof(hc), cudaMemcpyHostToDevice));
+  // state store
+  uint64_t cap = m->max_states ? m->max_states : (1ULL << 20);
+  if (cap < 1024) cap = 1024;
+  if (!m->max_states) cap = 1ULL << 20;
+  else if (cap > (1ULL << 22)) cap = 1ULL << 22;   // start modest, grow on demand up to max_states
+  e->cap_states = cap;
+  CK(cudaMalloc(&e->d_states, cap * (uint64_t)m->words_per_state * 4));
+  CK(cudaMalloc(&e->d_parent, cap * 4));
+  CK(cudaMalloc(&e->d_meta, cap * 4));
+  memset(&e->p, 0, sizeof(e->p));
+  e->p.code = e->d_code; e->p.code_len = m->code_len;
+  e->p.code_in_smem = ((size_t)m->code_len * 8 <= 200 * 1024) ? 1 : 0;
+  e->p.cpool = e->d_cpool; e->p.layout = e->d_layout; e->p.n_slots = (int)m->n_slots;
+  e->p.entry_inv = m->entry_inv; e->p.entry_next = m->entry_next;
+  e->p.n_off = 0; e->p.p_off = m->unpacked_words; e->p.W = (int)m->words_per_state;
+  e->p.states = e->d_states; e->p.parent = e->d_parent; e->p.meta = e->d_meta; e->p.cap_states = cap;
+  e->p.ctr = e->d_ctr; e->p.flags = m->flags; e->p.n_inv = (int)m->n_invariants;
+  e->p.n_ranks = 1; e->p.rank = 0;
+  unsigned log2 = m->table_slots_log2 ? m->table_slots_log2 : 22;
+  int r = alloc_table(e, log2);
+  if (r) return r;
+  CK(cudaStreamSynchronize(e->stream));
+  return TLAG_OK;
+}
+
+extern "C" void tlag_destroy(tlag_engine* e) {
+  if (!e) return;
+  cudaFree(e->d_code); cudaFree(e->d_cpool); cudaFree(e->d_layout); cudaFree(e->d_states);
+  cudaFree(e->d_parent); cudaFree(e->d_meta); cudaFree(e->d_table); cudaFree(e->d_ctr);
+  cudaFree(e->d_scratch); cudaFree(e->d_flags);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+static int ensure_scratch(tlag_engine* e, uint64_t words, uint64_t flags) {
+  if (words > e->scratch_words) {
+    cudaFree(e->d_scratch); e->d_scratch = nullptr; e->scratch_words = 0;
+    CK(cudaMalloc(&e->d_scratch, words * 4));
+    e->scratch_words = words;
+  }
+  if (flags > e->flags_cap) {
+    cudaFree(e->d_flags); e->d_flags = nullptr; e->flags_cap = 0;
+    CK(cudaMalloc(&e->d_flags, flags));
+    e->flags_cap = flags;
+  }
+  return TLAG_OK;
+}
+
+static int launch_probe(tlag_engine* e, const uint32_t* d_states, uint64_t n, uint8_t* d_is_new) {
+  const int W = (int)e->m.words_per_state;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (n == 0) return TLAG_OK;
+  const bool a16 = ((uintptr_t)d_states % 16) == 0, a8 = ((uintptr_t)d_states % 8) == 0;
+  if (W % 4 == 0 && a16) k_probe<4><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
+  else if (W % 2 == 0 && a8) k_probe<2><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
+  else k_probe<1><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
+  e->launches++;
+  CK(cudaGetLastError());
+  return TLAG_OK;
+}
+
+extern "C" int tlag_probe_batch_device(tlag_engine* e, uint64_t d_states, uint64_t n, uint64_t d_is_new, float* kernel_ms) {
+  if (!e) return TLAG_EINVAL;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  int r = launch_probe(e, (const uint32_t*)(uintptr_t)d_states, n, (uint8_t*)(uintptr_t)d_is_new);
+  if (r) return r;
+  CK(cudaEventRecord(e->ev1, e->stream));
+  CK(cudaEventSynchronize(e->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  if (kernel_ms) *kernel_ms = ms;
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (hc.table_full) { e->err = "seen-set table is full"; return TLAG_ENOMEM; }
+  return TLAG_OK;
+}
+
+extern "C" int tlag_probe_batch(tlag_engine* e, const uint32_t* states, uint64_t n, uint8_t* is_new) {
+  if (!e || (!states && n) || (!is_new && n)) return TLAG_EINVAL;
+  if (n == 0) return TLAG_OK;
+  const uint64_t W = e->m.words_per_state;
+  int r = ensure_scratch(e, n * W, n);
+  if (r) return r;
+  CK(cudaMemcpyAsync(e->d_scratch, states, n * W * 4, cudaMemcpyHostToDevice, e->stream));
+  r = launch_probe(e, e->d_scratch, n, e->d_flags);
+  if (r) return r;
+  CK(cudaMemcpyAsync(is_new, e->d_flags, n, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (hc.table_full) { e->err = "seen-set table is full"; return TLAG_ENOMEM; }
+  return TLAG_OK;
+}
+
+extern "C" int tlag_reset_table(tlag_engine* e) {
+  if (!e) return TLAG_EINVAL;
+  CK(cudaMemsetAsync(e->d_table, 0, (1ULL << e->table_log2) * 8, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TLAG_OK;
+}
+
+extern "C" int tlag_seed(tlag_engine* e, const uint32_t* states, uint64_t n) {
+  if (!e || (!states && n)) return TLAG_EINVAL;
+  if (e->level != 0) { e->err = "tlag_seed after the search started"; return TLAG_ESTATE; }
+  const uint64_t W = e->m.words_per_state;
+  int r = grow_store_if_needed(e, e->hi + n + 1024);
+  if (r) return r;
+  r = grow_table_if_needed(e, e->hi + n);
+  if (r) return r;
+  if (n) {
+    // records: W words + parent(-1) + meta(action -1)
+    std::vector<uint32_t> rec(n * (W + 2));
+    for (uint64_t i = 0; i < n; ++i) {
+      memcpy(&rec[i * (W + 2)], states + i * W, W * 4);
+      rec[i * (W + 2) + W] = 0xFFFFFFFFu;
+      rec[i * (W + 2) + W + 1] = 0xFFFFFF00u;
+    }
+    r = ensure_scratch(e, n * (W + 2), 0);
+    if (r) return r;
+    CK(cudaMemcpyAsync(e->d_scratch, rec.data(), rec.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    k_insert_records<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->p, e->d_scratch, n);
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  e->generated += n;
+  e->hi = hc.n_states;
+  e->init_states = hc.n_states;
+  if (n && !e->restarting) e->h_init.insert(e->h_init.end(), states, states + n * W);
+  return TLAG_OK;
+}
+
+// Forget everything discovered and start again from the retained initial states (bench loops).
+extern "C" int tlag_restart(tlag_engine* e) {
+  if (!e) return TLAG_EINVAL;
+  Counters hc;
+  memset(&hc, 0, sizeof(hc));
+  hc.viol_inv = hc.viol_assert = hc.viol_trap = hc.viol_deadlock = ~0ULL;
+  CK(cudaMemcpyAsync(e->d_ctr, &hc, sizeof(hc), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemsetAsync(e->d_table, 0, (1ULL << e->table_log2) * 8, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->lo = e->hi = 0; e->level = 0; e->init_states = 0; e->generated = 0; e->depth = 0;
+  e->verdict = TLAG_V_RUNNING; e->detail = e->detail2 = 0; e->viol_idx = 0; e->dev_seconds = 0;
+  e->restarting = true;
+  const uint64_t W = e->m.words_per_state;
+  int r = tlag_seed(e, e->h_init.data(), e->h_init.size() / W);
+  e->restarting = false;
+  return r;
+}
+
+static void fill_result(tlag_engine* e, tlag_result* out, uint64_t n_states) {
+  memset(out, 0, sizeof(*out));
+  out->verdict = e->verdict;
+  out->detail = e->detail;
+  out->detail2 = e->detail2;
+  out->state_idx = e->viol_idx;
+  out->generated = e->generated;
+  out->distinct = n_states;
+  out->queue_left = (e->verdict == TLAG_V_OK) ? 0 : (n_states - e->hi) + 0;
+  out->depth = e->depth;
+  out->init_states = e->init_states;
+  const double n = (double)n_states, g = (double)e->generated;
+  out->fp_collision_estimate = n * (g > n ? g - n : 0.0) / 18446744073709551616.0;
+  out->device_seconds = e->dev_seconds;
+}
+
+// decode violation counters after a wave; sets e->verdict if something was found
+static void collect_violations(tlag_engine* e, const Counters& hc) {
+  unsigned long long best = ~0ULL; int kind = 0;
+  if (hc.viol_trap != ~0ULL && (hc.viol_trap >> 20) < best) { best = hc.viol_trap >> 20; kind = TLAG_V_EVAL_ERROR; }
+  if (hc.viol_assert != ~0ULL && (hc.viol_assert >> 20) < best) { best = hc.viol_assert >> 20; kind = TLAG_V_ASSERT; }
+  if (hc.viol_inv != ~0ULL && (hc.viol_inv >> 20) < best) { best = hc.viol_inv >> 20; kind = TLAG_V_INVARIANT; }
+  if (hc.viol_deadlock != ~0ULL && (hc.viol_deadlock >> 20) < best) { best = hc.viol_deadlock >> 20; kind = TLAG_V_DEADLOCK; }
+  if (!kind) return;
+  e->verdict = kind;
+  e->viol_idx = best;
+  if (kind == TLAG_V_EVAL_ERROR) { e->detail = (int)((hc.viol_trap >> 16) & 15); e->detail2 = (int)(hc.viol_trap & 0xFFFF); }
+  else if (kind == TLAG_V_ASSERT) e->detail = (int)(hc.viol_assert & 0xFFFFF);
+  else if (kind == TLAG_V_INVARIANT) e->detail = (int)(hc.viol_inv & 0xFFFFF);
+}
+
+extern "C" int tlag_step(tlag_engine* e, tlag_wave_stats* out) {
+  if (!e) return TLAG_EINVAL;
+  if (out) memset(out, 0, sizeof(*out));
+  if (e->level == 0) { e->level = 1; e->lo = 0; e->depth = e->hi > 0 ? 1 : 0; }
+  if (e->verdict != TLAG_V_RUNNING) { if (out) out->verdict = e->verdict; return TLAG_OK; }
+  const uint64_t lo = e->lo, hi = e->hi;
+  if (lo >= hi) { e->verdict = TLAG_V_OK; if (out) out->verdict = e->verdict; return TLAG_OK; }
+  int r = grow_store_if_needed(e, hi + (hi - lo) * 4 + 4096);
+  if (r) return r;
+  r = grow_table_if_needed(e, hi + (hi - lo) * 2);
+  if (r) return r;
+  CK(cudaMemsetAsync(&e->d_ctr->work, 0, 8, e->stream));
+  CK(cudaEventRecord(e->ev0, e->stream));
+  cudaError_t ce = launch_wave<0>(e, lo, hi);
+  if (ce != cudaSuccess) { e->err = std::string("k_wave launch: ") + cudaGetErrorString(ce); return TLAG_ECUDA; }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  Counters hc;
+  CK(cudaMemcpyAsync(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->dev_seconds += ms * 1e-3;
+  if (hc.store_overflow) { e->err = "state store overflow: raise max_states"; return TLAG_ENOMEM; }
+  if (hc.table_full) { e->err = "seen-set table full"; return TLAG_ENOMEM; }
+  const uint64_t gen_wave = hc.generated;
+  e->generated += gen_wave;
+  CK(cudaMemsetAsync(&e->d_ctr->generated, 0, 8, e->stream));
+  const uint64_t n_states = hc.n_states;
+  collect_violations(e, hc);
+  if (out) {
+    out->level = e->level; out->expanded = hi - lo; out->generated = gen_wave;
+    out->discovered = n_states - hi; out->distinct_total = n_states; out->generated_total = e->generated;
+    out->kernel_ms = ms;
+  }
+  if (n_states > hi) e->depth = e->level + 1;
+  e->lo = hi; e->hi = n_states; e->level += 1;
+  if (e->verdict == TLAG_V_RUNNING && e->lo >= e->hi) e->verdict = TLAG_V_OK;
+  if (e->verdict != TLAG_V_RUNNING && e->verdict != TLAG_V_OK && (e->m.flags & TLAG_F_KEEP_GOING)) {
+    // keep exploring: remember the first violation only
+  }
+  if (out) out->verdict = e->verdict;
+  return TLAG_OK;
+}
+
+extern "C" int tlag_result_now(tlag_engine* e, tlag_result* out) {
+  if (!e || !out) return TLAG_EINVAL;
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  fill_result(e, out, hc.n_states);
+  return TLAG_OK;
+}
+
+extern "C" int tlag_run(tlag_engine* e, tlag_result* out) {
+  if (!e || !out) return TLAG_EINVAL;
+  tlag_wave_stats ws;
+  for (;;) {
+    int r = tlag_step(e, &ws);
+    if (r) return r;
+    if (ws.verdict != TLAG_V_RUNNING) break;
+  }
+  return tlag_result_now(e, out);
+}
+
+extern "C" int tlag_read_states(tlag_engine* e, uint64_t first, uint64_t n, uint32_t* states_out) {
+  if (!e || (!states_out && n)) return TLAG_EINVAL;
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (first + n > hc.n_states) { e->err = "tlag_read_states: range beyond the state store"; return TLAG_EINVAL; }
+  const uint64_t W = e->m.words_per_state;
+  CK(cudaMemcpy(states_out, e->d_states + first * W, n * W * 4, cudaMemcpyDeviceToHost));
+  return TLAG_OK;
+}
+
+extern "C" int tlag_trace(tlag_engine* e, uint64_t state_idx, uint32_t* states_out, int32_t* actions_out, uint32_t* len_inout) {
+  if (!e || !len_inout) return TLAG_EINVAL;
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (state_idx >= hc.n_states) { e->err = "tlag_trace: no such state"; return TLAG_EINVAL; }
+  const uint64_t W = e->m.words_per_state;
+  std::vector<uint64_t> chain;
+  std::vector<int32_t> acts;
+  uint64_t cur = state_idx;
+  for (;;) {
+    uint32_t par = 0, meta = 0;
+    CK(cudaMemcpy(&par, e->d_parent + cur, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&meta, e->d_meta + cur, 4, cudaMemcpyDeviceToHost));
+    chain.push_back(cur);
+    acts.push_back(par == 0xFFFFFFFFu ? -1 : (int32_t)(meta >> 8));
+    if (par == 0xFFFFFFFFu) break;
+    cur = par;
+    if (chain.size() > (1u << 24)) { e->err = "tlag_trace: parent chain too long"; return TLAG_ESTATE; }
+  }
+  const uint32_t len = (uint32_t)chain.size();
+  if (len > *len_inout) { *len_inout = len; e->err = "tlag_trace: buffer too small"; return TLAG_EINVAL; }
+  for (uint32_t i = 0; i < len; ++i) {
+    const uint64_t s = chain[len - 1 - i];
+    if (states_out) CK(cudaMemcpy(states_out + (uint64_t)i * W, e->d_states + s * W, W * 4, cudaMemcpyDeviceToHost));
+    if (actions_out) actions_out[i] = acts[len - 1 - i];
+  }
+  *len_inout = len;
+  return TLAG_OK;
+}
+
+// ---- multi-GPU building blocks -----------------------------------------------------
+extern "C" int tlag_expand_route(tlag_engine* e, uint32_t n_ranks, uint64_t d_send, uint64_t cap_records,
+                                 uint64_t* counts, tlag_wave_stats* out) {
+  if (!e || !counts || n_ranks == 0 || n_ranks > 16) return TLAG_EINVAL;
+  if (out) memset(out, 0, sizeof(*out));
+  if (e->level == 0) { e->level = 1; e->lo = 0; e->depth = 1; }
+  const uint64_t lo = e->lo, hi = e->hi;
+  e->p.n_ranks = (int)n_ranks;
+  e->p.send = (uint32_t*)(uintptr_t)d_send;
+  e->p.region_cap = cap_records / n_ranks;
+  CK(cudaMemsetAsync(&e->d_ctr->work, 0, 8, e->stream));
+  CK(cudaMemsetAsync(e->d_ctr->send_count, 0, sizeof(unsigned long long) * 16, e->stream));
+  CK(cudaEventRecord(e->ev0, e->stream));
+  if (hi > lo) {
+    cudaError_t ce = launch_wave<1>(e, lo, hi);
+    if (ce != cudaSuccess) { e->err = std::string("k_wave<route> launch: ") + cudaGetErrorString(ce); return TLAG_ECUDA; }
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  Counters hc;
+  CK(cudaMemcpyAsync(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->dev_seconds += ms * 1e-3;
+  if (hc.route_overflow) { e->err = "send buffer overflow in tlag_expand_route"; return TLAG_EOVERFLOW; }
+  e->generated += hc.generated;
+  CK(cudaMemsetAsync(&e->d_ctr->generated, 0, 8, e->stream));
+  for (uint32_t r = 0; r < n_ranks; ++r) counts[r] = hc.send_count[r];
+  collect_violations(e, hc);
+  if (out) {
+    out->level = e->level; out->expanded = hi - lo; out->generated = hc.generated;
+    out->distinct_total = hc.n_states; out->generated_total = e->generated; out->kernel_ms = ms;
+    out->verdict = e->verdict;
+  }
+  return TLAG_OK;
+}
+
+extern "C" int tlag_insert_records(tlag_engine* e, uint64_t d_recv, uint64_t n_records, uint32_t, uint64_t* n_new) {
+  if (!e) return TLAG_EINVAL;
+  Counters hc;
+  CK(cudaMemcpyAsync(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const uint64_t before = hc.n_states;
+  int r = grow_store_if_needed(e, before + n_records + 1024);
+  if (r) return r;
+  r = grow_table_if_needed(e, before + n_records);
+  if (r) return r;
+  if (n_records) {
+    CK(cudaEventRecord(e->ev0, e->stream));
+    k_insert_records<<<(unsigned)((n_records + 255) / 256), 256, 0, e->stream>>>(e->p, (const uint32_t*)(uintptr_t)d_recv, n_records);
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaEventSynchronize(e->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->dev_seconds += ms * 1e-3;
+  }
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (hc.store_overflow) { e->err = "state store overflow: raise max_states"; return TLAG_ENOMEM; }
+  if (hc.table_full) { e->err = "seen-set table full"; return TLAG_ENOMEM; }
+  if (n_new) *n_new = hc.n_states - before;
+  return TLAG_OK;
+}
+
+extern "C" int tlag_advance_level(tlag_engine* e, tlag_wave_stats* out) {
+  if (!e) return TLAG_EINVAL;
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  const uint64_t n_states = hc.n_states;
+  if (out) { memset(out, 0, sizeof(*out)); out->level = e->level; out->discovered = n_states - e->hi; out->distinct_total = n_states; out->generated_total = e->generated; out->verdict = e->verdict; }
+  if (n_states > e->hi) e->depth = e->level + 1;
+  e->lo = e->hi; e->hi = n_states; e->level += 1;
+  return TLAG_OK;
+}

@@ -1,0 +1,222 @@
+// tlag_vm.h -- bytecode VM core, state pack/unpack and the 64-bit fingerprint.
+//
+// One definition of the ISA semantics, compiled by nvcc into the CUDA engine
+// (tlag_engine.cu) and by gcc into the CPU bytecode oracle (oracle/tlag_cpu.c, test
+// infrastructure).  The opcode order MUST match tla_rust_b200/compile/bytecode.py:OPS.
+//
+// Replaces (all [ext] TLC components, none present under /root/reference):
+//   next-state action evaluator  -> tlag_vm_run over the Next program
+//   invariant checker            -> tlag_vm_run over the invariant program
+//   64-bit state fingerprint     -> tlag_fingerprint (own hash; TLC's FP64 polynomial is
+//                                   not observable through any reference artefact)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TLAG_HD __host__ __device__ __forceinline__
+#else
+#define TLAG_HD static inline
+#endif
+
+enum {
+  OP_HALT = 0, OP_LI, OP_LIW, OP_MOV, OP_MOVN, OP_ZERO, OP_LDC,
+  OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_MOD, OP_NEG,
+  OP_LT, OP_LE, OP_EQ, OP_NE, OP_EQN, OP_NOT, OP_AND, OP_OR,
+  OP_LDX, OP_STX, OP_TBL,
+  OP_BSET, OP_BCLR, OP_BTEST, OP_BOR, OP_BAND, OP_BANDN, OP_BISZ, OP_BSUB, OP_BCNT, OP_BNEXT, OP_BFILL,
+  OP_JMP, OP_JZ, OP_JNZ, OP_JNEG,
+  OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
+  OP_ADDI, OP_MULI, OP_EQI, OP_NEI, OP_LTI, OP_LEI, OP_GTI, OP_GEI, OP_UCLAMP,
+  OP_BSETI, OP_BTESTI, OP_SHRI, OP_ANDI,
+  OP__COUNT
+};
+
+// events returned by tlag_vm_run
+#define TLAG_EV_HALT 0
+#define TLAG_EV_EMIT 1
+#define TLAG_EV_GEN 2
+#define TLAG_EV_TRAP 3
+#define TLAG_EV_ASSERT 4
+#define TLAG_EV_INVF 5
+#define TLAG_EV_STEPS 6   /* instruction budget exhausted (runaway program) */
+
+typedef struct { int32_t off, width, bias; } tlag_slot;
+
+TLAG_HD int32_t tlag_imm28(uint32_t v) { return (int32_t)(v << 4) >> 4; }
+
+TLAG_HD int32_t tlag_cp(const int32_t* cpool, int32_t i) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(cpool + i);
+#else
+  return cpool[i];
+#endif
+}
+
+TLAG_HD int tlag_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+
+TLAG_HD int tlag_ffs(uint32_t x) {  /* 1-based index of lowest set bit, 0 if none */
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x);
+#else
+  return __builtin_ffs((int)x);
+#endif
+}
+
+// Runs from *pc until the next event.  `code` may live in shared memory on the device.
+// info receives the event payload (action id / trap code / assert id / invariant index),
+// info2 the secondary payload (trap source line).
+TLAG_HD int tlag_vm_run(const uint64_t* code, const int32_t* cpool, int32_t* f, uint32_t* pc_io,
+                        int32_t* info, int32_t* info2, uint32_t max_steps) {
+  uint32_t pc = *pc_io;
+  for (uint32_t steps = 0; steps < max_steps; ++steps) {
+    const uint64_t w = code[pc++];
+    const uint32_t op = (uint32_t)(w & 0xFF);
+    const uint32_t a = (uint32_t)(w >> 8) & 0x3FFF;
+    const uint32_t b = (uint32_t)(w >> 22) & 0x3FFF;
+    const uint32_t c = (uint32_t)(w >> 36) & 0x3FFF;
+    const uint32_t d = (uint32_t)(w >> 50) & 0x3FFF;
+    const int32_t immI = tlag_imm28((uint32_t)(w >> 22) & 0xFFFFFFF);
+    const int32_t immJ = tlag_imm28((uint32_t)(w >> 36) & 0xFFFFFFF);
+    switch (op) {
+      case OP_HALT: *pc_io = pc - 1; return TLAG_EV_HALT;
+      case OP_LI: f[a] = immI; break;
+      case OP_LIW: f[a] = tlag_cp(cpool, immI); break;
+      case OP_MOV: f[a] = f[b]; break;
+      case OP_MOVN:
+        if (a <= b) { for (uint32_t i = 0; i < c; ++i) f[a + i] = f[b + i]; }
+        else { for (uint32_t i = c; i-- > 0;) f[a + i] = f[b + i]; }
+        break;
+      case OP_ZERO: for (uint32_t i = 0; i < b; ++i) f[a + i] = 0; break;
+      case OP_LDC: for (uint32_t i = 0; i < d; ++i) f[a + i] = tlag_cp(cpool, immI + (int32_t)i); break;
+      case OP_ADD: f[a] = (int32_t)((uint32_t)f[b] + (uint32_t)f[c]); break;
+      case OP_SUB: f[a] = (int32_t)((uint32_t)f[b] - (uint32_t)f[c]); break;
+      case OP_MUL: f[a] = (int32_t)((uint32_t)f[b] * (uint32_t)f[c]); break;
+      case OP_DIV: {  // TLA+ \div: floor division (Integers.tla)
+        int32_t x = f[b], y = f[c];
+        if (y == 0) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
+        int32_t q = x / y; if ((x % y != 0) && ((x < 0) != (y < 0))) --q; f[a] = q; break; }
+      case OP_MOD: {  // TLA+ %: result in 0..y-1
+        int32_t x = f[b], y = f[c];
+        if (y <= 0) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
+        int32_t r = x % y; if (r < 0) r += y; f[a] = r; break; }
+      case OP_NEG: f[a] = -f[b]; break;
+      case OP_LT: f[a] = f[b] < f[c]; break;
+      case OP_LE: f[a] = f[b] <= f[c]; break;
+      case OP_EQ: f[a] = f[b] == f[c]; break;
+      case OP_NE: f[a] = f[b] != f[c]; break;
+      case OP_EQN: { int32_t e = 1; for (uint32_t i = 0; i < d; ++i) e &= (f[b + i] == f[c + i]); f[a] = e; break; }
+      case OP_NOT: f[a] = !f[b]; break;
+      case OP_AND: f[a] = (f[b] != 0) & (f[c] != 0); break;
+      case OP_OR: f[a] = (f[b] != 0) | (f[c] != 0); break;
+      case OP_LDX: { uint32_t base = b + (uint32_t)f[c] * d; for (uint32_t i = 0; i < d; ++i) f[a + i] = f[base + i]; break; }
+      case OP_STX: { uint32_t base = a + (uint32_t)f[b] * d; for (uint32_t i = 0; i < d; ++i) f[base + i] = f[c + i]; break; }
+      case OP_TBL: f[a] = tlag_cp(cpool, immI + f[d]); break;
+      case OP_BSET: { uint32_t i = (uint32_t)f[b]; f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break; }
+      case OP_BCLR: { uint32_t i = (uint32_t)f[b]; f[a + (i >> 5)] &= ~(int32_t)(1u << (i & 31)); break; }
+      case OP_BTEST: { uint32_t i = (uint32_t)f[c]; f[a] = (int32_t)(((uint32_t)f[b + (i >> 5)] >> (i & 31)) & 1u); break; }
+      case OP_BOR: for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] | f[c + i]; break;
+      case OP_BAND: for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] & f[c + i]; break;
+      case OP_BANDN: for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] & ~f[c + i]; break;
+      case OP_BISZ: { int32_t z = 1; for (uint32_t i = 0; i < c; ++i) z &= (f[b + i] == 0); f[a] = z; break; }
+      case OP_BSUB: { int32_t z = 1; for (uint32_t i = 0; i < d; ++i) z &= ((f[b + i] & ~f[c + i]) == 0); f[a] = z; break; }
+      case OP_BCNT: { int32_t n = 0; for (uint32_t i = 0; i < c; ++i) n += tlag_popc((uint32_t)f[b + i]); f[a] = n; break; }
+      case OP_BNEXT: {  // a = smallest set bit index > f[c] (f[c] = -1 to start) within d bits, else -1
+        int32_t cur = f[c] + 1; int32_t res = -1;
+        uint32_t nb = d;
+        while ((uint32_t)cur < nb) {
+          uint32_t word = (uint32_t)f[b + ((uint32_t)cur >> 5)] >> ((uint32_t)cur & 31);
+          if (word) { int32_t cand = cur + tlag_ffs(word) - 1; if ((uint32_t)cand < nb) res = cand; break; }
+          cur = (int32_t)(((uint32_t)cur | 31u) + 1u);
+        }
+        f[a] = res; break; }
+      case OP_BFILL: for (uint32_t i = 0; i < b; ++i) f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break;
+      case OP_JMP: pc = (uint32_t)immI; break;
+      case OP_JZ: if (f[a] == 0) pc = (uint32_t)immI; break;
+      case OP_JNZ: if (f[a] != 0) pc = (uint32_t)immI; break;
+      case OP_JNEG: if (f[a] < 0) pc = (uint32_t)immI; break;
+      case OP_TRAP: *info = (int32_t)a; *info2 = immI; *pc_io = pc; return TLAG_EV_TRAP;
+      case OP_EMIT: *info = immI; *pc_io = pc; return TLAG_EV_EMIT;
+      case OP_GEN: *pc_io = pc; return TLAG_EV_GEN;
+      case OP_ASSERTF: *info = immI; *pc_io = pc; return TLAG_EV_ASSERT;
+      case OP_INVF: *info = immI; *pc_io = pc; return TLAG_EV_INVF;
+      case OP_ADDI: f[a] = (int32_t)((uint32_t)f[b] + (uint32_t)immJ); break;
+      case OP_MULI: f[a] = (int32_t)((uint32_t)f[b] * (uint32_t)immJ); break;
+      case OP_EQI: f[a] = f[b] == immJ; break;
+      case OP_NEI: f[a] = f[b] != immJ; break;
+      case OP_LTI: f[a] = f[b] < immJ; break;
+      case OP_LEI: f[a] = f[b] <= immJ; break;
+      case OP_GTI: f[a] = f[b] > immJ; break;
+      case OP_GEI: f[a] = f[b] >= immJ; break;
+      case OP_UCLAMP: if ((uint32_t)f[a] >= (uint32_t)immI) f[a] = -1; break;
+      case OP_BSETI: { uint32_t i = (uint32_t)immI; f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break; }
+      case OP_BTESTI: { uint32_t i = (uint32_t)immJ; f[a] = (int32_t)(((uint32_t)f[b + (i >> 5)] >> (i & 31)) & 1u); break; }
+      case OP_SHRI: f[a] = (int32_t)((uint32_t)f[b] >> (immJ & 31)); break;
+      case OP_ANDI: f[a] = f[b] & immJ; break;
+      default: *info = 99; *info2 = (int32_t)op; *pc_io = pc; return TLAG_EV_TRAP;
+    }
+  }
+  *pc_io = pc;
+  return TLAG_EV_STEPS;
+}
+
+// ---- packed state <-> frame ----------------------------------------------------
+// Slots are laid out LSB-first in a little-endian bit stream of W 32-bit words.
+// Returns 0, or 1+slot index when a value does not fit its slot (overflow trap).
+TLAG_HD int tlag_pack(const tlag_slot* lay, int nslots, const int32_t* st, uint32_t* out, int W) {
+  for (int i = 0; i < W; ++i) out[i] = 0;
+  uint32_t bitpos = 0;
+  for (int s = 0; s < nslots; ++s) {
+    const int32_t width = lay[s].width;
+    uint32_t v = (uint32_t)(st[lay[s].off] - lay[s].bias);
+    if (width < 32 && (v >> width) != 0) return 1 + s;
+    const uint32_t wi = bitpos >> 5, sh = bitpos & 31;
+    out[wi] |= v << sh;
+    if (sh + (uint32_t)width > 32) out[wi + 1] |= v >> (32 - sh);
+    bitpos += (uint32_t)width;
+  }
+  return 0;
+}
+
+TLAG_HD void tlag_unpack(const tlag_slot* lay, int nslots, const uint32_t* in, int32_t* st) {
+  uint32_t bitpos = 0;
+  for (int s = 0; s < nslots; ++s) {
+    const int32_t width = lay[s].width;
+    const uint32_t wi = bitpos >> 5, sh = bitpos & 31;
+    uint32_t v = in[wi] >> sh;
+    if (sh + (uint32_t)width > 32) v |= in[wi + 1] << (32 - sh);
+    if (width < 32) v &= (1u << width) - 1u;
+    st[lay[s].off] = (int32_t)v + lay[s].bias;
+    bitpos += (uint32_t)width;
+  }
+}
+
+// ---- 64-bit fingerprint of a packed state --------------------------------------
+TLAG_HD uint64_t tlag_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+TLAG_HD uint64_t tlag_fmix64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  return k;
+}
+
+TLAG_HD uint64_t tlag_fingerprint(const uint32_t* w, int W) {
+  uint64_t h = 0x9E3779B97F4A7C15ULL ^ ((uint64_t)W * 0xD6E8FEB86659FD93ULL);
+  int i = 0;
+  for (; i + 1 < W; i += 2) {
+    uint64_t k = (uint64_t)w[i] | ((uint64_t)w[i + 1] << 32);
+    k *= 0x87c37b91114253d5ULL; k = tlag_rotl64(k, 31); k *= 0x4cf5ad432745937fULL;
+    h ^= k; h = tlag_rotl64(h, 27) * 5 + 0x52dce729ULL;
+  }
+  if (i < W) {
+    uint64_t k = (uint64_t)w[i];
+    k *= 0x87c37b91114253d5ULL; k = tlag_rotl64(k, 31); k *= 0x4cf5ad432745937fULL;
+    h ^= k;
+  }
+  h = tlag_fmix64(h ^ (uint64_t)W);
+  return h ? h : 1ULL;   // 0 is the empty-slot marker of the seen-set
+}

@@ -1,0 +1,216 @@
+"""ctypes binding of the C-ABI engine library (include/tlag.h, csrc/libtlag.so).
+
+The product path has no CPU fallback: if the CUDA extension is missing or no GPU is
+visible, construction fails loudly (EngineUnavailable)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtlag.so")
+_LIB = None
+
+F_DEADLOCK_CHECK = 1
+F_KEEP_GOING = 2
+V_OK, V_INVARIANT, V_ASSERT, V_DEADLOCK, V_EVAL_ERROR, V_RUNNING = 0, 1, 2, 3, 4, 5
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class TlagModel(C.Structure):
+    _fields_ = [("words_per_state", C.c_uint32), ("code", C.c_void_p), ("code_len", C.c_uint32),
+                ("entry_inv", C.c_uint32), ("entry_next", C.c_uint32),
+                ("cpool", C.c_void_p), ("cpool_len", C.c_uint32),
+                ("layout", C.c_void_p), ("n_slots", C.c_uint32),
+                ("frame_words", C.c_uint32), ("unpacked_words", C.c_uint32),
+                ("n_invariants", C.c_uint32), ("n_actions", C.c_uint32),
+                ("table_slots_log2", C.c_uint32), ("max_states", C.c_uint64),
+                ("flags", C.c_uint32), ("device", C.c_int32)]
+
+
+class WaveStats(C.Structure):
+    _fields_ = [("level", C.c_uint64), ("expanded", C.c_uint64), ("generated", C.c_uint64),
+                ("discovered", C.c_uint64), ("distinct_total", C.c_uint64), ("generated_total", C.c_uint64),
+                ("kernel_ms", C.c_float), ("verdict", C.c_int32)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class TlagResult(C.Structure):
+    _fields_ = [("verdict", C.c_int32), ("detail", C.c_int32), ("detail2", C.c_int32), ("reserved", C.c_int32),
+                ("state_idx", C.c_uint64), ("generated", C.c_uint64), ("distinct", C.c_uint64),
+                ("queue_left", C.c_uint64), ("depth", C.c_uint64), ("init_states", C.c_uint64),
+                ("fp_collision_estimate", C.c_double), ("device_seconds", C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+EXPORTS = ["tlag_create", "tlag_seed", "tlag_step", "tlag_run", "tlag_result_now", "tlag_trace",
+           "tlag_read_states", "tlag_probe_batch", "tlag_probe_batch_device", "tlag_reset_table", "tlag_restart",
+           "tlag_kernel_launches", "tlag_destroy", "tlag_last_error", "tlag_version",
+           "tlag_expand_route", "tlag_insert_records", "tlag_advance_level"]
+
+
+def build_library(verbose=False):
+    """nvcc cross-compiles for sm_100a without a GPU (driver `build()` check)."""
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")] + ([] if verbose else ["-s"]))
+
+
+def load_library():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineUnavailable(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                    f"(the product has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.tlag_last_error.restype = C.c_char_p
+        L.tlag_version.restype = C.c_char_p
+        L.tlag_kernel_launches.restype = C.c_uint64
+        L.tlag_destroy.restype = None
+        for fn in EXPORTS:
+            getattr(L, fn)
+        _LIB = L
+    return _LIB
+
+
+class Engine:
+    """One BFS engine instance on one GPU (mirrors tlag_engine)."""
+
+    def __init__(self, cm, deadlock=True, device=0, table_log2=0, max_states=0, keep_going=False):
+        self.L = load_library()
+        self.cm = cm
+        self._code = np.ascontiguousarray(cm.code, dtype=np.uint64)
+        self._cpool = np.ascontiguousarray(cm.cpool, dtype=np.int32)
+        self._layout = np.ascontiguousarray(cm.layout, dtype=np.int32)
+        flags = (F_DEADLOCK_CHECK if deadlock else 0) | (F_KEEP_GOING if keep_going else 0)
+        m = TlagModel(cm.W, self._code.ctypes.data, len(self._code), cm.entries["inv"], cm.entries["next"],
+                      self._cpool.ctypes.data, len(self._cpool), self._layout.ctypes.data, self._layout.shape[0],
+                      cm.frame_words, cm.state_words_unpacked, len(cm.invariants), len(cm.actions),
+                      table_log2, max_states, flags, device)
+        self.h = C.c_void_p()
+        rc = self.L.tlag_create(C.byref(m), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.tlag_last_error(self.h).decode() if self.h else "tlag_create failed"
+            if self.h:
+                self.L.tlag_destroy(self.h)
+                self.h = None
+            if rc == -3:
+                raise EngineUnavailable(f"CUDA engine unavailable: {msg}")
+            raise EngineError(f"tlag_create: {msg}")
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what}: rc={rc}: {self.L.tlag_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tlag_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed(self, init_words: np.ndarray):
+        a = np.ascontiguousarray(init_words, dtype=np.uint32).reshape(-1, self.cm.W)
+        self._ck(self.L.tlag_seed(self.h, a.ctypes.data_as(C.c_void_p), C.c_uint64(a.shape[0])), "tlag_seed")
+
+    def step(self) -> dict:
+        ws = WaveStats()
+        self._ck(self.L.tlag_step(self.h, C.byref(ws)), "tlag_step")
+        return ws.as_dict()
+
+    def run(self) -> dict:
+        r = TlagResult()
+        self._ck(self.L.tlag_run(self.h, C.byref(r)), "tlag_run")
+        return r.as_dict()
+
+    def result(self) -> dict:
+        r = TlagResult()
+        self._ck(self.L.tlag_result_now(self.h, C.byref(r)), "tlag_result_now")
+        return r.as_dict()
+
+    def trace(self, state_idx: int, cap=4096):
+        W = self.cm.W
+        states = np.zeros((cap, W), dtype=np.uint32)
+        acts = np.zeros(cap, dtype=np.int32)
+        n = C.c_uint32(cap)
+        self._ck(self.L.tlag_trace(self.h, C.c_uint64(state_idx), states.ctypes.data_as(C.c_void_p),
+                                   acts.ctypes.data_as(C.c_void_p), C.byref(n)), "tlag_trace")
+        return states[:n.value].copy(), acts[:n.value].copy()
+
+    def read_states(self, first: int, n: int) -> np.ndarray:
+        out = np.zeros((n, self.cm.W), dtype=np.uint32)
+        self._ck(self.L.tlag_read_states(self.h, C.c_uint64(first), C.c_uint64(n), out.ctypes.data_as(C.c_void_p)),
+                 "tlag_read_states")
+        return out
+
+    def probe_batch(self, states: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(states, dtype=np.uint32).reshape(-1, self.cm.W)
+        flags = np.zeros(a.shape[0], dtype=np.uint8)
+        self._ck(self.L.tlag_probe_batch(self.h, a.ctypes.data_as(C.c_void_p), C.c_uint64(a.shape[0]),
+                                         flags.ctypes.data_as(C.c_void_p)), "tlag_probe_batch")
+        return flags
+
+    def probe_batch_device(self, d_states_ptr: int, n: int, d_flags_ptr: int) -> float:
+        ms = C.c_float()
+        self._ck(self.L.tlag_probe_batch_device(self.h, C.c_uint64(d_states_ptr), C.c_uint64(n),
+                                                C.c_uint64(d_flags_ptr), C.byref(ms)), "tlag_probe_batch_device")
+        return ms.value
+
+    def reset_table(self):
+        self._ck(self.L.tlag_reset_table(self.h), "tlag_reset_table")
+
+    def restart(self):
+        self._ck(self.L.tlag_restart(self.h), "tlag_restart")
+
+    def launches(self) -> int:
+        return int(self.L.tlag_kernel_launches(self.h))
+
+    # multi-GPU building blocks
+    def expand_route(self, n_ranks, d_send_ptr, cap_records):
+        counts = (C.c_uint64 * n_ranks)()
+        ws = WaveStats()
+        self._ck(self.L.tlag_expand_route(self.h, C.c_uint32(n_ranks), C.c_uint64(d_send_ptr),
+                                          C.c_uint64(cap_records), counts, C.byref(ws)), "tlag_expand_route")
+        return [int(c) for c in counts], ws.as_dict()
+
+    def insert_records(self, d_recv_ptr, n_records) -> int:
+        nn = C.c_uint64()
+        self._ck(self.L.tlag_insert_records(self.h, C.c_uint64(d_recv_ptr), C.c_uint64(n_records), C.c_uint32(0),
+                                            C.byref(nn)), "tlag_insert_records")
+        return int(nn.value)
+
+    def advance_level(self) -> dict:
+        ws = WaveStats()
+        self._ck(self.L.tlag_advance_level(self.h, C.byref(ws)), "tlag_advance_level")
+        return ws.as_dict()
+
+
+class ProbeOnlyModel:
+    """Minimal stand-in CompiledModel for K1-only use (tlag_probe_batch on W-word states)."""
+
+    def __init__(self, W):
+        self.W = W
+        self.code = np.zeros(2, dtype=np.uint64)  # HALT, HALT
+        self.cpool = np.zeros(1, dtype=np.int32)
+        self.layout = np.array([[i, 32, 0] for i in range(W)], dtype=np.int32)
+        self.entries = {"inv": 0, "next": 1}
+        self.frame_words = 2 * W + 4
+        self.state_words_unpacked = W
+        self.invariants = []
+        self.actions = []

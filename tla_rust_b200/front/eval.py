@@ -200,6 +200,8 @@ class Evaluator:
         v = env.get("@", _MISSING)
         if v is _MISSING:
             raise EvalError("@ used outside EXCEPT")
+        if type(v) is Thunk:
+            return self.force(v, fr)
         return v
 
     def resolve_callable(self, name, env, fr, n=None):
@@ -873,8 +875,13 @@ class Evaluator:
                 cal = OpVal(*ctx.defs[name])
             if cal is not None and not (type(cal) is OpVal and cal.d.name in ("Assert",)):
                 fr = self._fr(ctx, s, asg, target)
-                argv = [self.eval_arg(a, env, fr) for a in args]
+                # call-by-name for action parameters so that `Send(p, d, memInt, memInt')`
+                # (CachingMemory/MCInternalMemory.tla:15-29) can bind memInt' inside the callee
+                argv = [Thunk(a, env, ctx) if a.k in ("prime", "id", "fapp", "app", "dot") else
+                        self.eval_arg(a, env, fr) for a in args]
                 if type(cal) is OpVal:
+                    argv = [self.force(a, fr) if type(a) is Thunk and pa[1] > 0 else a
+                            for a, pa in zip(argv, cal.d.params)] if len(argv) == len(cal.d.params) else argv
                     d = cal.d
                     if len(d.params) != len(argv):
                         raise EvalError(f"operator {d.name} arity mismatch at line {n.line}")
@@ -953,6 +960,10 @@ class Evaluator:
             yield from self._seq(items, i + 1, env, ctx, s, a2, target, act)
 
     def _assign_target(self, ln, ctx, asg, target, env):
+        if ln.k == "id":
+            th = env.get(ln.a[0])
+            if type(th) is Thunk and not th.done and th.body.k in ("prime", "id"):
+                return self._assign_target(th.body, th.ctx, asg, target, th.env)
         if target == "next":
             if ln.k == "prime" and ln.a[0].k == "id":
                 v = ln.a[0].a[0]
