@@ -4,7 +4,7 @@
 A "step" is one complete breadth-first model-checking job of the workload model (all reachable
 states, invariants checked on every state) on N GPUs.  Workload: the committed compiled form of
 BASELINE config #3 scaled to a single-GPU-sized state space (examples/Paxos, 3 acceptors / 2 values,
-ballots 0..2, invariants Inv1-Inv4; tests/golden/MCPaxos3_b2.tlagz, 185,369 distinct states) --
+ballots 0..3, invariants Inv1-Inv4; tests/golden/MCPaxos3_b3.tlagz, 8,220,065 distinct states) --
 configs #4/#5 (raft, SSI) are not lowered to the device yet.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
@@ -76,7 +76,7 @@ def cpu_reference(cm, init, info, threads):
     which neither this image nor the reference provides) on all host cores, same model."""
     from oracle import cpu_engine
     t0 = time.time()
-    r = cpu_engine.run(cm, init, n_threads=threads, deadlock=info["deadlock"], max_states=1 << 24)
+    r = cpu_engine.run(cm, init, n_threads=threads, deadlock=info["deadlock"], max_states=1 << 26)
     dt = r["seconds"]
     return r, dt, time.time() - t0
 
@@ -120,7 +120,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default="MCPaxos3_b2")
+    ap.add_argument("--workload", default="MCPaxos3_b3")
     ap.add_argument("--no-k1", action="store_true")
     args = ap.parse_args()
 

@@ -267,3 +267,128 @@ double tlagcpu_probe_batch(const uint32_t *states, uint64_t n, int W, unsigned t
 /* pack / unpack helpers exposed for host-side tests of the layout */
 int tlagcpu_pack(const tlag_slot *lay, int nslots, const int32_t *st, uint32_t *out, int W) { return tlag_pack(lay, nslots, st, out, W); }
 void tlagcpu_unpack(const tlag_slot *lay, int nslots, const uint32_t *in, int32_t *st) { tlag_unpack(lay, nslots, in, st); }
+
+/* ---- stateful shard engine: the CPU stand-in for tlag_expand_route / tlag_insert_records /
+ * tlag_advance_level, used by the world_size-2 gloo tests of the multi-GPU host logic. ---------- */
+typedef struct {
+  cpu_engine e;
+  uint64_t lo, hi, level, depth, init_states;
+  int verdict, detail;
+} cpu_shard;
+
+cpu_shard *tlagcpu_shard_create(const cpu_model *m) {
+  cpu_shard *s = (cpu_shard *)calloc(1, sizeof(cpu_shard));
+  s->e.m = *m;
+  s->e.cap = m->max_states ? m->max_states : (1ULL << 20);
+  unsigned lg = 8;
+  while ((1ULL << lg) < s->e.cap * 2) ++lg;
+  s->e.states = (uint32_t *)malloc(s->e.cap * (size_t)m->W * 4);
+  s->e.parent = (uint32_t *)malloc(s->e.cap * 4);
+  s->e.meta = (uint32_t *)malloc(s->e.cap * 4);
+  s->e.table = (uint64_t *)calloc(1ULL << lg, 8);
+  s->e.mask = (1ULL << lg) - 1;
+  s->e.viol_inv = s->e.viol_assert = s->e.viol_trap = s->e.viol_deadlock = ~0ULL;
+  return s;
+}
+
+void tlagcpu_shard_destroy(cpu_shard *s) {
+  if (!s) return;
+  free(s->e.states); free(s->e.parent); free(s->e.meta); free(s->e.table); free(s);
+}
+
+/* records: W words + parent + meta */
+uint64_t tlagcpu_shard_insert(cpu_shard *s, const uint32_t *rec, uint64_t n) {
+  const int W = (int)s->e.m.W;
+  uint64_t n_new = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t *r = rec + i * (uint64_t)(W + 2);
+    uint64_t fp = tlag_fingerprint(r, W);
+    if (seen_insert(s->e.table, s->e.mask, fp) > 0) {
+      uint64_t pos = s->e.n_states++;
+      memcpy(s->e.states + pos * W, r, (size_t)W * 4);
+      s->e.parent[pos] = r[W]; s->e.meta[pos] = r[W + 1];
+      ++n_new;
+    }
+  }
+  return n_new;
+}
+
+void tlagcpu_shard_seed(cpu_shard *s, const uint32_t *init, uint64_t n) {
+  const int W = (int)s->e.m.W;
+  uint32_t rec[MAXW + 2];
+  for (uint64_t i = 0; i < n; ++i) {
+    memcpy(rec, init + i * W, (size_t)W * 4);
+    rec[W] = 0xFFFFFFFFu; rec[W + 1] = 0xFFFFFF00u;
+    tlagcpu_shard_insert(s, rec, 1);
+  }
+  s->e.generated += n;
+  s->hi = s->e.n_states;
+  s->init_states = s->e.n_states;
+}
+
+/* expand frontier [lo,hi): successors bucketed by owner = floor(fp * n_ranks / 2^64) into
+ * send[owner * region_cap ...]; counts[r] records per rank.  Returns verdict kind (0 none). */
+int tlagcpu_shard_expand_route(cpu_shard *s, uint32_t n_ranks, uint32_t *send, uint64_t cap_records, uint64_t *counts,
+                               uint64_t *generated_out) {
+  const cpu_model *m = &s->e.m;
+  const int W = (int)m->W;
+  const uint64_t region = cap_records / n_ranks;
+  int32_t *frame = (int32_t *)calloc(m->frame_words + 8, 4);
+  uint32_t succ[MAXW];
+  uint64_t gen = 0;
+  if (s->level == 0) { s->level = 1; s->lo = 0; s->depth = s->hi ? 1 : 0; }
+  for (uint32_t r = 0; r < n_ranks; ++r) counts[r] = 0;
+  int kind = 0;
+  for (uint64_t idx = s->lo; idx < s->hi; ++idx) {
+    tlag_unpack(m->layout, (int)m->n_slots, s->e.states + idx * W, frame);
+    if (m->n_invariants) {
+      uint32_t pc = m->entry_inv;
+      for (;;) {
+        int32_t info = 0, info2 = 0;
+        int ev = tlag_vm_run(m->code, m->cpool, frame, &pc, &info, &info2, MAX_STEPS);
+        if (ev == TLAG_EV_HALT) break;
+        if (ev == TLAG_EV_INVF) { if (!kind) { kind = 1; s->detail = info; } continue; }
+        if (!kind) kind = 4;
+        break;
+      }
+    }
+    uint32_t pc = m->entry_next;
+    unsigned nsucc = 0;
+    for (;;) {
+      int32_t info = 0, info2 = 0;
+      int ev = tlag_vm_run(m->code, m->cpool, frame, &pc, &info, &info2, MAX_STEPS);
+      if (ev == TLAG_EV_HALT) break;
+      if (ev == TLAG_EV_GEN) { ++nsucc; ++gen; continue; }
+      if (ev == TLAG_EV_ASSERT) { if (!kind) { kind = 2; s->detail = info; } continue; }
+      if (ev == TLAG_EV_EMIT) {
+        ++nsucc; ++gen;
+        if (tlag_pack(m->layout, (int)m->n_slots, frame + m->unpacked_words, succ, W)) { if (!kind) kind = 4; continue; }
+        uint64_t fp = tlag_fingerprint(succ, W);
+        uint32_t owner = (uint32_t)(((unsigned __int128)fp * n_ranks) >> 64);
+        if (counts[owner] >= region) { free(frame); return -5; }
+        uint32_t *dst = send + (owner * region + counts[owner]) * (uint64_t)(W + 2);
+        memcpy(dst, succ, (size_t)W * 4);
+        dst[W] = (uint32_t)idx; dst[W + 1] = (uint32_t)info << 8;
+        counts[owner]++;
+        continue;
+      }
+      if (!kind) kind = 4;
+      break;
+    }
+    if (nsucc == 0 && (m->flags & 1) && !kind) kind = 3;
+  }
+  free(frame);
+  s->e.generated += gen;
+  if (generated_out) *generated_out = gen;
+  if (kind && !s->verdict) s->verdict = kind;
+  return kind;
+}
+
+void tlagcpu_shard_advance(cpu_shard *s) {
+  if (s->e.n_states > s->hi) s->depth = s->level + 1;
+  s->lo = s->hi; s->hi = s->e.n_states; s->level += 1;
+}
+
+void tlagcpu_shard_result(cpu_shard *s, uint64_t *out4) {
+  out4[0] = s->e.generated; out4[1] = s->e.n_states; out4[2] = s->depth; out4[3] = (uint64_t)s->verdict;
+}

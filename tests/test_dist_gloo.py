@@ -1,0 +1,105 @@
+"""Multi-GPU host logic on CPU: world_size-2 `gloo` run of the distributed BFS driver
+(tla_rust_b200/dist.py) with the CPU shard engine of the oracle library standing in for the CUDA
+engine's tlag_expand_route / tlag_insert_records / tlag_advance_level.  The partitioned search must
+reproduce the single-process counts exactly."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN, ROOT
+
+
+class CpuShardEngine:
+    """Same surface as tla_rust_b200.engine.Engine for the calls DistributedBFS makes."""
+
+    def __init__(self, cm, deadlock=True):
+        from oracle import cpu_engine
+        self.L = cpu_engine.lib()
+        self.cm = cm
+        self._code = np.ascontiguousarray(cm.code, dtype=np.uint64)
+        self._cpool = np.ascontiguousarray(cm.cpool, dtype=np.int32)
+        self._layout = np.ascontiguousarray(cm.layout, dtype=np.int32)
+        m = cpu_engine.CpuModel(cm.W, self._code.ctypes.data, len(self._code), cm.entries["inv"], cm.entries["next"],
+                                self._cpool.ctypes.data, len(self._cpool), self._layout.ctypes.data,
+                                self._layout.shape[0], cm.frame_words, cm.state_words_unpacked, len(cm.invariants),
+                                1 if deadlock else 0, 0, 1 << 20)
+        self.L.tlagcpu_shard_create.restype = C.c_void_p
+        self.L.tlagcpu_shard_insert.restype = C.c_uint64
+        self.h = C.c_void_p(self.L.tlagcpu_shard_create(C.byref(m)))
+
+    def seed(self, init):
+        a = np.ascontiguousarray(init, dtype=np.uint32).reshape(-1, self.cm.W)
+        self.L.tlagcpu_shard_seed(self.h, a.ctypes.data_as(C.c_void_p), C.c_uint64(a.shape[0]))
+
+    def expand_route(self, n_ranks, send_ptr, cap_records):
+        counts = (C.c_uint64 * n_ranks)()
+        gen = C.c_uint64()
+        kind = self.L.tlagcpu_shard_expand_route(self.h, C.c_uint32(n_ranks), C.c_void_p(send_ptr),
+                                                 C.c_uint64(cap_records), counts, C.byref(gen))
+        assert kind >= 0
+        return [int(c) for c in counts], {"verdict": kind if kind else 5, "generated": int(gen.value)}
+
+    def insert_records(self, recv_ptr, n):
+        return int(self.L.tlagcpu_shard_insert(self.h, C.c_void_p(recv_ptr), C.c_uint64(n)))
+
+    def advance_level(self):
+        self.L.tlagcpu_shard_advance(self.h)
+        return {}
+
+    def result(self):
+        out = (C.c_uint64 * 4)()
+        self.L.tlagcpu_shard_result(self.h, out)
+        return {"generated": int(out[0]), "distinct": int(out[1]), "depth": int(out[2]), "verdict": int(out[3]),
+                "device_seconds": 0.0}
+
+    def close(self):
+        self.L.tlagcpu_shard_destroy(self.h)
+
+
+def _worker(rank, world, port, name, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, ROOT)
+    from tla_rust_b200.compiled import load_compiled
+    from tla_rust_b200.dist import DistributedBFS
+    from tla_rust_b200.fingerprint import fingerprint_words
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
+    e = CpuShardEngine(cm, deadlock=info["deadlock"])
+    d = DistributedBFS(e, cm, rank, world, "cpu", cap_records=1 << 16)
+    d.seed(init, [fingerprint_words(w) for w in init])
+    out = d.run()
+    if rank == 0:
+        q.put((out["verdict"], out["generated"], out["distinct"], out["depth"], out["local"]["distinct"]))
+    e.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["pcal_intro", "MCPaxos3"])
+def test_two_rank_partitioned_bfs_matches_single(name):
+    from tla_rust_b200.compiled import load_compiled
+    _, _, exp, _ = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    res = q.get(timeout=10)
+    verdict, generated, distinct, depth, local = res
+    o2 = exp["o2"]
+    assert (verdict, generated, distinct, depth) == (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"])
+    assert 0 < local < distinct            # the state space really was sharded

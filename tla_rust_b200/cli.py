@@ -1,0 +1,130 @@
+"""Command-line front ends replacing the two external commands the reference's Makefile shells out to
+(Makefile:3-7): `pcal2tla FILE.tla...` and `tlc FILE.tla...` (several files per invocation, FILE.cfg
+looked up next to FILE.tla, TLC-format report on stdout, non-zero exit status on any error so that
+`make` stops).  The search itself runs on the GPU through the C ABI; there is no CPU backend."""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+from .front.spec import Model, SpecError
+from .front.parser import ParseError
+from .front.lexer import LexError
+from .front.values import EvalError
+from .front.pcal import translate_file, PcalError
+from .front.report import format_result, OK
+from .compile.lower import CompileError
+from .compile.types import TypeErr
+
+
+def pcal2tla_main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    files = [a for a in argv if not a.startswith("-")]
+    nocfg = "-nocfg" in argv
+    if not files:
+        print("usage: pcal2tla [-nocfg] FILE.tla ...", file=sys.stderr)
+        return 2
+    rc = 0
+    for f in files:
+        if not f.endswith(".tla"):
+            f += ".tla"
+        try:
+            had = translate_file(f, write_cfg=not nocfg)
+            if had:
+                print(f"pcal2tla: translated {f}")
+            else:
+                print(f"pcal2tla: no PlusCal algorithm in {f}; file unchanged")
+        except (PcalError, LexError, OSError) as ex:
+            print(f"pcal2tla: {f}: {ex}", file=sys.stderr)
+            rc = 1
+    return rc
+
+
+def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq_cap=None, verbose=True):
+    from .checker import compile_model, encode_states, result_from_engine
+    from .engine import Engine
+    t0 = time.time()
+    m = Model(path, cfg_path=cfg_path)
+    m.ev.out = out
+    for w in m.warnings:
+        print(f"Warning: {w}", file=out)
+    m.check_assumes()
+    if m.next_node is None and not m.init_nodes:
+        print("Model checking completed. No error has been found.", file=out)
+        print("  (the module has no behaviour specification; only its assumptions were checked)", file=out)
+        return 0
+    if m.symmetry:
+        print(f"Warning: SYMMETRY {m.symmetry} is ignored (states are not reduced; the verdict is unaffected)", file=out)
+    if m.properties:
+        print(f"Warning: PROPERTY {' '.join(m.properties)} is not checked (safety search only)", file=out)
+    init = m.initial_states()
+    cm = compile_model(m, init, seq_cap=seq_cap)
+    for w in cm.warnings:
+        print(f"Warning: {w}", file=out)
+    iw = encode_states(cm, init)
+    e = Engine(cm, deadlock=deadlock and m.check_deadlock, device=device)
+    e.seed(iw)
+    r0 = e.result()
+    print(f"Finished computing initial states: {r0['distinct']} distinct state"
+          f"{'s' if r0['distinct'] != 1 else ''} generated.", file=out)
+    while True:
+        ws = e.step()
+        if ws["verdict"] != 5:
+            break
+        if verbose and ws["expanded"]:
+            print(f"Progress({ws['level']}): {ws['generated_total']} states generated, {ws['distinct_total']} distinct "
+                  f"states found, {ws['discovered']} states left on queue.", file=out)
+    r = e.result()
+    trace = None
+    if r["verdict"] != 0:
+        trace = e.trace(r["state_idx"])
+    res = result_from_engine(cm, r, trace)
+    print(format_result(res, m.vars, m.module_name), file=out)
+    print(f"Finished in {time.time() - t0:.2f}s ({r['device_seconds']:.4f}s in GPU wave kernels, "
+          f"{e.launches()} kernel launches).", file=out)
+    e.close()
+    return 0 if res.verdict == OK else 12
+
+
+def tlc_main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    files, deadlock, cfg, dev = [], True, None, 0
+    i = 0
+    while i < len(argv):
+        a = argv[i]
+        if a == "-deadlock":
+            deadlock = False
+        elif a == "-config":
+            i += 1
+            cfg = argv[i]
+        elif a in ("-workers", "-gpus", "-device", "-fpmem", "-depth", "-coverage", "-checkpoint"):
+            i += 1
+            if a == "-device":
+                dev = int(argv[i])
+        elif a.startswith("-"):
+            pass
+        else:
+            files.append(a)
+        i += 1
+    if not files:
+        print("usage: tlc [-deadlock] [-config FILE.cfg] FILE.tla ...", file=sys.stderr)
+        return 2
+    rc = 0
+    for f in files:
+        if not f.endswith(".tla"):
+            f += ".tla"
+        print(f"Parsing file {os.path.abspath(f)}")
+        try:
+            r = check_file(f, deadlock=deadlock, cfg_path=cfg, device=dev)
+        except (SpecError, ParseError, LexError, EvalError, CompileError, TypeErr) as ex:
+            print(f"Error: {type(ex).__name__}: {ex}")
+            r = 150
+        if r != 0:
+            rc = r
+            break      # `make` semantics: TLC exits non-zero at the first failing module
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(tlc_main())

@@ -19,7 +19,7 @@ OPS = [
     "JMP", "JZ", "JNZ", "JNEG",
     "TRAP", "EMIT", "GEN", "ASSERTF", "INVF",
     "ADDI", "MULI", "EQI", "NEI", "LTI", "LEI", "GTI", "GEI", "UCLAMP",
-    "BSETI", "BTESTI", "SHRI", "ANDI",
+    "BSETI", "BTESTI", "SHRI", "ANDI", "TBLT",
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 
@@ -34,7 +34,7 @@ FMT = {
     "JMP": "_I", "JZ": "rI", "JNZ": "rI", "JNEG": "rI",
     "TRAP": "nI", "EMIT": "_I", "GEN": "", "ASSERTF": "_I", "INVF": "_I",
     "ADDI": "rrJ", "MULI": "rrJ", "EQI": "rrJ", "NEI": "rrJ", "LTI": "rrJ", "LEI": "rrJ", "GTI": "rrJ",
-    "GEI": "rrJ", "UCLAMP": "rI", "BSETI": "rI", "BTESTI": "rrJ", "SHRI": "rrJ", "ANDI": "rrJ",
+    "GEI": "rrJ", "UCLAMP": "rI", "BSETI": "rI", "BTESTI": "rrJ", "SHRI": "rrJ", "ANDI": "rrJ", "TBLT": "rIr",
 }
 
 TRAP_EVAL, TRAP_OVERFLOW, TRAP_CASE, TRAP_CHOOSE, TRAP_ASSIGN = 1, 2, 3, 4, 5
@@ -69,9 +69,13 @@ class Asm:
         self.code = []       # list of tuples (op, a, b, c, d) with Label operands allowed / ('label', L)
         self.cpool = []      # int32 constants
         self._cp_cache = {}
+        self.cur_line = 0    # source line of the construct being lowered (debug / profiling info)
+        self.lines = {}      # id(instruction tuple) -> line
 
     def emit(self, op, *args):
-        self.code.append((op,) + tuple(args))
+        ins = (op,) + tuple(args)
+        self.code.append(ins)
+        self.lines[id(ins)] = self.cur_line
 
     def label(self, L: Label):
         self.code.append(("label", L))
@@ -101,11 +105,13 @@ class Asm:
             else:
                 pos += 1
         out = np.zeros(pos, dtype=np.uint64)
+        self.line_table = np.zeros(pos, dtype=np.int32)
         i = 0
         for ins in self.code:
             if ins[0] == "label":
                 continue
             out[i] = self._encode(ins)
+            self.line_table[i] = self.lines.get(id(ins), 0)
             i += 1
         cp = np.array(self.cpool if self.cpool else [0], dtype=np.int64)
         cp = ((cp + (1 << 31)) % (1 << 32) - (1 << 31)).astype(np.int32)

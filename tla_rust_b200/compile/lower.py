@@ -51,6 +51,34 @@ class Val:
         return f"Val({self.t}@{self.loc})"
 
 
+class MVal(Val):
+    """A set value known to be a subset of a compile-time mask (`alive` = admissible ordinals)."""
+    __slots__ = ("alive",)
+
+    def __init__(self, t, loc, alive):
+        self.t, self.loc, self.alive = t, loc, alive
+
+
+class OVal(Val):
+    """Element of an enumerable composite type known only by its ordinal (loop variable over a
+    bitset universe).  Fields are decoded on demand with one table lookup each; touching `.loc`
+    materialises the whole value (fresh temporaries every time, so it is valid on any path)."""
+    __slots__ = ("lw", "oreg", "alive")
+
+    def __init__(self, lw, t, oreg, alive=None):
+        self.lw = lw
+        self.t = t
+        self.oreg = oreg
+        self.alive = alive
+
+    @property
+    def loc(self):
+        return self.lw.unord(self.t, self.oreg).loc
+
+    def __repr__(self):
+        return f"OVal({self.t}#{self.oreg})"
+
+
 class Lazy:
     __slots__ = ("node", "env", "ctx", "base")
 
@@ -270,7 +298,7 @@ class Lowering:
         for k, v in env.items():
             if type(v) is Const:
                 out[k] = v.v
-            elif type(v) is Val:
+            elif isinstance(v, Val):
                 out[k] = Thunk(_RUNTIME_NODE, {}, None)
             elif type(v) is Lazy:
                 if v.base != "N":
@@ -333,7 +361,7 @@ class Lowering:
         return t
 
     def as_val(self, x, want=None) -> Val:
-        if type(x) is Val:
+        if isinstance(x, Val):
             return x
         t = want if want is not None else self.natural_type(x.v)
         if want is None and isinstance(t, TSet) and isinstance(t.elem, TBottom):
@@ -469,6 +497,8 @@ class Lowering:
             else:
                 self.li(r, o)
             return r
+        if type(v) is OVal and v.t == E:
+            return v.oreg
         s = v.t
         r = self.alloc(1)
         if isinstance(E, TInt):
@@ -606,6 +636,27 @@ class Lowering:
             self.asm.emit("TBL", dst + w, tabs[w], oreg)
         return Val(E, dst)
 
+    def _field_tables(self, E: TRec, f):
+        """Per-word column tables of field f over the enumeration of E; ordinals whose alternative
+        lacks f hold INT32_MIN in word 0 (TBLT traps on it, like TLC's missing-field error)."""
+        cache = self.__dict__.setdefault("_field_cache", {})
+        key = (E, f)
+        if key in cache:
+            return cache[key]
+        vals = self.codec.enum(E)
+        ft = E.fields[f]
+        cols = [[] for _ in range(ft.size)]
+        for v in vals:
+            if f in v.d:
+                r = self.codec.rep(ft, v.d[f])
+            else:
+                r = [-(1 << 31)] + [0] * (ft.size - 1)
+            for w in range(ft.size):
+                cols[w].append(r[w])
+        tabs = [self.asm.const_table(c) for c in cols]
+        cache[key] = tabs
+        return tabs
+
     def _univ_tables(self, E):
         cache = self.__dict__.setdefault("_univ_cache", {})
         if E in cache:
@@ -625,15 +676,19 @@ class Lowering:
         if isinstance(E, TBottom):
             return
         idx = self.alloc(1)
-        xloc = self.alloc(E.size) if elem_dst is None else elem_dst
+        lazy = elem_dst is None and isinstance(E, (TRec, TTuple)) and E.card() <= UNIV_TABLE_MAX
+        xloc = None if lazy else (self.alloc(E.size) if elem_dst is None else elem_dst)
         self.li(idx, -1)
         top = Label("loop")
         done = Label("done")
         self.asm.label(top)
         self.asm.emit("BNEXT", idx, sv.loc, idx, sv.t.nbits)
         self.asm.emit("JNEG", idx, done)
-        self.unord(E, idx, xloc)
-        body(Val(E, xloc))
+        if lazy:
+            body(OVal(self, E, idx, getattr(sv, "alive", None)))
+        else:
+            self.unord(E, idx, xloc)
+            body(Val(E, xloc))
         self.asm.emit("JMP", top)
         self.asm.label(done)
 
@@ -651,11 +706,11 @@ class Lowering:
             return ("range", lo, hi)
         if node.k == "domain":
             f = self.cx(node.a[0], env, ctx, base)
-            if type(f) is Val and isinstance(f.t, TSeq):
+            if isinstance(f, Val) and isinstance(f.t, TSeq):
                 return ("range", Const(1), Val(TInt(0, f.t.cap), f.loc))
-            if type(f) is Val and isinstance(f.t, TFun):
+            if isinstance(f, Val) and isinstance(f.t, TFun):
                 return ("const", list(f.t.keys))
-            if type(f) is Val and isinstance(f.t, TTuple):
+            if isinstance(f, Val) and isinstance(f.t, TTuple):
                 return ("const", list(range(1, len(f.t.elems) + 1)))
         v = self.cx(node, env, ctx, base)
         if type(v) is Const:
@@ -678,8 +733,9 @@ class Lowering:
         else:
             if not isinstance(x.t, TTuple) or len(x.t.elems) != len(names):
                 raise CompileError("tuple pattern mismatch")
+            base = x.loc
             for nm, te, to in zip(names, x.t.elems, x.t.offs):
-                env2[nm] = Val(te, x.loc + to)
+                env2[nm] = Val(te, base + to)
         return env2
 
     def for_each(self, bounds, env, ctx, base, body, i=0):
@@ -810,6 +866,8 @@ class Lowering:
         if c is not None:
             return c
         k = n.k
+        if n.line:
+            self.asm.cur_line = n.line
         m = getattr(self, "x_" + k, None)
         if m is None:
             raise CompileError(f"unsupported construct `{k}` at line {n.line} col {n.col}")
@@ -923,14 +981,14 @@ class Lowering:
             return Val(rt, dst)
         if op in ("\\cup", "\\cap", "\\"):
             a = self.cx(ln, env, ctx, base, want)
-            b = self.cx(rn, env, ctx, base, want if want is not None else (a.t if type(a) is Val else None))
-            if type(a) is Const and type(b) is Val and want is None:
+            b = self.cx(rn, env, ctx, base, want if want is not None else (a.t if isinstance(a, Val) else None))
+            if type(a) is Const and isinstance(b, Val) and want is None:
                 a2 = a
                 t = b.t
             t = want
             if t is None:
-                ta = a.t if type(a) is Val else self.natural_type(a.v)
-                tb = b.t if type(b) is Val else self.natural_type(b.v)
+                ta = a.t if isinstance(a, Val) else self.natural_type(a.v)
+                tb = b.t if isinstance(b, Val) else self.natural_type(b.v)
                 t = join(ta, tb)
             if not isinstance(t, TSet):
                 raise CompileError(f"set operator {op} on non-set type {t}")
@@ -1032,8 +1090,8 @@ class Lowering:
             va = self.cx(a, env, ctx, base)
         with self.asm.capture() as cb:
             vb = self.cx(b, env, ctx, base)
-        ta = va.t if type(va) is Val else self.natural_type(va.v)
-        tb = vb.t if type(vb) is Val else self.natural_type(vb.v)
+        ta = va.t if isinstance(va, Val) else self.natural_type(va.v)
+        tb = vb.t if isinstance(vb, Val) else self.natural_type(vb.v)
         t = join(ta, tb)
         dst = self.alloc(t.size)
         self.cc(c, env, ctx, base, lt, lf)
@@ -1104,6 +1162,17 @@ class Lowering:
         if not isinstance(r.t, TRec) or f not in r.t.fields:
             raise CompileError(f"no field {f} in type {r.t} (line {n.line})")
         t = r.t
+        if type(r) is OVal:
+            ft = t.fields[f]
+            tabs = self._field_tables(t, f)
+            dst = self.alloc(ft.size)
+            partial = any(f not in alt for alt in t.alts)
+            if partial and r.alive is not None:
+                vals = self._enum_cached(t)
+                partial = any(f not in vals[o].d for o in r.alive)
+            for w in range(ft.size):
+                self.asm.emit("TBLT" if (partial and w == 0) else "TBL", dst + w, tabs[w], r.oreg)
+            return Val(ft, dst)
         if t.tagged:
             mask = 0
             for j, alt in enumerate(t.alts):
@@ -1127,7 +1196,7 @@ class Lowering:
         else:
             et = TBottom()
             for x in items:
-                et = join(et, x.t if type(x) is Val else self.natural_type(x.v))
+                et = join(et, x.t if isinstance(x, Val) else self.natural_type(x.v))
             t = TSet(self._enumerable(et))
         dst = self.alloc(t.size)
         self.asm.emit("ZERO", dst, t.size)
@@ -1156,23 +1225,25 @@ class Lowering:
         if kind[0] == "val":
             sv = kind[1]
             t = sv.t
-            dst = self.alloc(t.size)
-            self.asm.emit("ZERO", dst, t.size)
-            idx = self.alloc(1)
-            xloc = self.alloc(t.elem.size)
-            self.li(idx, -1)
-            top, done = Label("fl"), Label("fd")
-            self.asm.label(top)
-            self.asm.emit("BNEXT", idx, sv.loc, idx, t.nbits)
-            self.asm.emit("JNEG", idx, done)
-            self.unord(t.elem, idx, xloc)
-            yes = Label("fy")
-            self.cc(pred, self.bind(env, pat, Val(t.elem, xloc)), ctx, base, yes, top)
-            self.asm.label(yes)
-            self.asm.emit("BSET", dst, idx)
-            self.asm.emit("JMP", top)
-            self.asm.label(done)
-            r = Val(t, dst)
+            if isinstance(t.elem, TBottom):
+                return sv
+            sv2, rest = self.narrow(sv, pat, self.flat_and(pred), env, ctx, base)
+            if not rest:
+                r = sv2
+            else:
+                pred2 = rest[0] if len(rest) == 1 else Node("and", (tuple(rest),), pred.line, pred.col)
+                dst = self.alloc(t.size)
+                self.asm.emit("ZERO", dst, t.size)
+
+                def each(xv):
+                    yes, no = Label("fy"), Label("fn")
+                    self.cc(pred2, self.bind(env, pat, xv), ctx, base, yes, no)
+                    self.asm.label(yes)
+                    o = self.ord_in(t.elem, xv)
+                    self.asm.emit("BSET", dst, o)
+                    self.asm.label(no)
+                self.loop_set(sv2, each)
+                r = Val(t, dst)
             return self.coerce(r, want) if isinstance(want, TSet) and want != t else r
         if kind[0] == "const":
             vals = kind[1]
@@ -1208,7 +1279,7 @@ class Lowering:
 
                 def probe(env2):
                     x = self.cx(e, env2, ctx, base)
-                    holder.append(x.t if type(x) is Val else self.natural_type(x.v))
+                    holder.append(x.t if isinstance(x, Val) else self.natural_type(x.v))
                 self.for_each(bounds, env, ctx, base, probe)
                 self.top = save_top
             et = TBottom()
@@ -1326,11 +1397,20 @@ class Lowering:
             return Val(et, f.loc)
         if ki[0] == "static":
             j = ki[1]
+            if type(f) is OVal and isinstance(ft, TTuple):
+                tabs = self._univ_tables(ft)
+                et_ = ft.elems[j]
+                dst = self.alloc(et_.size)
+                for w in range(et_.size):
+                    self.asm.emit("TBL", dst + w, tabs[ft.offs[j] + w], f.oreg)
+                return Val(et_, dst)
             if isinstance(ft, TFun):
                 return Val(ft.elem, f.loc + j * ft.elem.size)
             return Val(ft.elems[j], f.loc + ft.offs[j])
         o = ki[1]
         et = ft.elem if isinstance(ft, TFun) else ft.elems[0]
+        if type(f) is OVal:
+            f = Val(ft, f.loc)
         ok = Label("ak")
         self.asm.emit("JNEG", o, Label("dummy")) if False else None
         bad = Label("ab")
@@ -1440,7 +1520,7 @@ class Lowering:
             self.asm.label(yes)
             if x is None:
                 raise CompileError("CHOOSE with tuple pattern is not supported")
-            xv = self.coerce(x, t) if type(x) is Val else self.materialize(x, t)
+            xv = self.coerce(x, t) if isinstance(x, Val) else self.materialize(x, t)
             self.movn(dst, xv.loc, t.size)
             self.asm.emit("JMP", end)
             self.asm.label(no)
@@ -1451,11 +1531,11 @@ class Lowering:
 
     def x_domain(self, n, env, ctx, base, want):
         f = self.cx(n.a[0], env, ctx, base)
-        if type(f) is Val and isinstance(f.t, TFun):
+        if isinstance(f, Val) and isinstance(f.t, TFun):
             return Const(frozenset(f.t.keys))
-        if type(f) is Val and isinstance(f.t, TTuple):
+        if isinstance(f, Val) and isinstance(f.t, TTuple):
             return Const(frozenset(range(1, len(f.t.elems) + 1)))
-        if type(f) is Val and isinstance(f.t, TSeq):
+        if isinstance(f, Val) and isinstance(f.t, TSeq):
             t = TSet(TInt(1, f.t.cap))
             dst = self.alloc(t.size)
             self.asm.emit("ZERO", dst, t.size)
@@ -1485,9 +1565,9 @@ class Lowering:
             return Val(TInt(0, sv.t.nbits), dst)
         if name == "Len":
             s = self.cx(args[0], env, ctx, base)
-            if type(s) is Val and isinstance(s.t, TSeq):
+            if isinstance(s, Val) and isinstance(s.t, TSeq):
                 return Val(TInt(0, s.t.cap), s.loc)
-            if type(s) is Val and isinstance(s.t, TTuple):
+            if isinstance(s, Val) and isinstance(s.t, TTuple):
                 return Const(len(s.t.elems))
             raise CompileError("Len of unsupported value")
         if name in ("Append", "Head", "Tail", "SubSeq", "SelectSeq"):
@@ -1607,6 +1687,109 @@ class Lowering:
         self.asm.label(done)
         return Val(t, dst)
 
+    # ------------------------------------------- compile-time masks over set universes
+    @staticmethod
+    def flat_and(n):
+        if n.k == "and":
+            out = []
+            for x in n.a[0]:
+                out += Lowering.flat_and(x)
+            return out
+        return [n]
+
+    def elem_truth(self, E, pat, c, env, ctx, base, alive):
+        """Evaluate predicate c at compile time for every universe ordinal in `alive` (element bound
+        to `pat`).  Returns the list of ordinals where it is TRUE, or None if c depends on run-time
+        values (or fails to evaluate) for any of them."""
+        vals = self._enum_cached(E)
+        keep = []
+        for o in alive:
+            env2 = dict(env)
+            env2[pat] = Const(vals[o])
+            r = self.try_const(c, env2, ctx, base)
+            if r is None or type(r.v) is not bool:
+                return None
+            if r.v:
+                keep.append(o)
+        return keep
+
+    def _enum_cached(self, E):
+        cache = self.__dict__.setdefault("_enum_cache", {})
+        v = cache.get(E)
+        if v is None:
+            v = cache[E] = self.codec.enum(E)
+        return v
+
+    def mask_words(self, E, ordinals, invert=False):
+        n = E.card()
+        words = [0] * max(1, (n + 31) // 32)
+        s = set(ordinals)
+        for o in range(n):
+            if (o in s) != invert:
+                words[o >> 5] |= 1 << (o & 31)
+        return [w - (1 << 32) if w >= (1 << 31) else w for w in words]
+
+    def narrow(self, sv: Val, pat, items, env, ctx, base):
+        """Fold the element-only conjuncts of `items` (predicates over the bound element and constants,
+        e.g. m.type = "1b" /\\ m.bal = b with b unrolled) into a constant bitmask over the universe:
+        returns (sv AND mask, remaining conjuncts).  Conjuncts are tried in order on the elements that
+        survive the earlier ones, so guards like `m.type = "1b" /\\ m.acc \\in Q` keep their meaning."""
+        E = sv.t.elem
+        if not isinstance(pat, str) or isinstance(E, TBottom) or E.card() > 4096:
+            return sv, items
+        alive = list(getattr(sv, "alive", None) or range(E.card()))
+        rest, masked = [], False
+        for c in items:
+            keep = self.elem_truth(E, pat, c, env, ctx, base, alive)
+            if keep is None:
+                rest.append(c)
+            else:
+                alive, masked = keep, True
+        if not masked:
+            return sv, items
+        mloc = self.alloc(sv.t.size)
+        self.load_words(mloc, self.mask_words(E, alive))
+        dst = self.alloc(sv.t.size)
+        self.asm.emit("BAND", dst, sv.loc, mloc, sv.t.size)
+        return MVal(sv.t, dst, alive), rest
+
+    def forall_val(self, sv: Val, pat, P, env, ctx, base, lf):
+        """Emit code for  \\A pat \\in sv : P  -- jumps to lf when violated, falls through when it holds."""
+        E = sv.t.elem
+        if P.k == "and" and len(P.a[0]) > 1:
+            for x in P.a[0]:
+                self.forall_val(sv, pat, x, env, ctx, base, lf)
+            return
+        if P.k == "and":
+            P = P.a[0][0]
+        if P.k == "bin" and P.a[0] == "=>":
+            sv2, rest = self.narrow(sv, pat, self.flat_and(P.a[1]), env, ctx, base)
+            if sv2 is not sv:
+                if rest:
+                    ante = rest[0] if len(rest) == 1 else Node("and", (tuple(rest),), P.line, P.col)
+                    P2 = Node("bin", ("=>", ante, P.a[2]), P.line, P.col)
+                    self._forall_loop(sv2, pat, P2, env, ctx, base, lf)
+                else:
+                    self.forall_val(sv2, pat, P.a[2], env, ctx, base, lf)
+                return
+        if E.card() <= 4096:
+            keep = self.elem_truth(E, pat, P, env, ctx, base, list(range(E.card())))
+            if keep is not None:
+                mloc = self.alloc(sv.t.size)
+                self.load_words(mloc, self.mask_words(E, keep))
+                t1 = self.alloc(1)
+                self.asm.emit("BSUB", t1, sv.loc, mloc, sv.t.size)
+                self.asm.emit("JZ", t1, lf)
+                return
+        self._forall_loop(sv, pat, P, env, ctx, base, lf)
+
+    def _forall_loop(self, sv, pat, P, env, ctx, base, lf):
+        def each(xv):
+            nxt = Label("fa")
+            self.cc(P, self.bind(env, pat, xv), ctx, base, nxt, lf)
+            self.asm.label(nxt)
+        self.loop_set(sv, each)
+
     # ------------------------------------------------------------- conditions
     def cc(self, n: Node, env, ctx, base, lt: Label, lf: Label):
         """Compile n in control context: jump to lt if TRUE else lf.  Falls through to neither.
@@ -1618,6 +1801,8 @@ class Lowering:
             self.release(mk)
 
     def _cc(self, n: Node, env, ctx, base, lt: Label, lf: Label):
+        if n.line:
+            self.asm.cur_line = n.line
         c = self.try_const(n, env, ctx, base)
         if c is not None:
             if c.v is True:
@@ -1675,6 +1860,30 @@ class Lowering:
         if k == "forall" or k == "exists":
             bounds, body = n.a
             is_all = k == "forall"
+            if len(bounds) == 1 and isinstance(bounds[0][0], str) and bounds[0][1] is not None:
+                kind = self.set_elements(bounds[0][1], env, ctx, base)
+                if kind[0] == "val" and not isinstance(kind[1].t.elem, TBottom):
+                    pat, sv = bounds[0][0], kind[1]
+                    if is_all:
+                        self.forall_val(sv, pat, body, env, ctx, base, lf)
+                        self.asm.emit("JMP", lt)
+                    else:
+                        sv2, rest = self.narrow(sv, pat, self.flat_and(body), env, ctx, base)
+                        if not rest:
+                            t1 = self.alloc(1)
+                            self.asm.emit("BISZ", t1, sv2.loc, sv2.t.size)
+                            self.asm.emit("JZ", t1, lt)
+                            self.asm.emit("JMP", lf)
+                        else:
+                            body2 = rest[0] if len(rest) == 1 else Node("and", (tuple(rest),), body.line, body.col)
+
+                            def each1(xv):
+                                nxt = Label("qn")
+                                self.cc(body2, self.bind(env, pat, xv), ctx, base, lt, nxt)
+                                self.asm.label(nxt)
+                            self.loop_set(sv2, each1)
+                            self.asm.emit("JMP", lf)
+                    return
 
             def each(env2):
                 nxt = Label("qn")
@@ -1813,8 +2022,8 @@ class Lowering:
 
     def cc_eq(self, ln, rn, env, ctx, base, lt, lf, n):
         a = self.cx(ln, env, ctx, base)
-        b = self.cx(rn, env, ctx, base, a.t if type(a) is Val else None)
-        if type(a) is Const and type(b) is Val:
+        b = self.cx(rn, env, ctx, base, a.t if isinstance(a, Val) else None)
+        if type(a) is Const and isinstance(b, Val):
             a, b = b, a
         if type(a) is Const:
             from ..front.values import values_equal
@@ -2080,7 +2289,7 @@ class Lowering:
             bv = self.coerce(b, a.t) if type(b) is Const or b.t != a.t else b
             av = a
         except CompileError:
-            tj = join(a.t, b.t if type(b) is Val else self.natural_type(b.v))
+            tj = join(a.t, b.t if isinstance(b, Val) else self.natural_type(b.v))
             av, bv = self.coerce(a, tj), self.coerce(b, tj)
         t1 = self.alloc(1)
         self.asm.emit("BSUB", t1, av.loc, bv.loc, av.t.size)
@@ -2114,6 +2323,21 @@ class Lowering:
             return
         if kind == "exists":
             bounds, body = n.a
+            if len(bounds) == 1 and isinstance(bounds[0][0], str) and bounds[0][1] is not None:
+                sk = self.set_elements(bounds[0][1], env, ctx, "N")
+                if sk[0] == "val" and not isinstance(sk[1].t.elem, TBottom):
+                    pat = bounds[0][0]
+                    sv2, rest = self.narrow(sk[1], pat, self.flat_and(body), env, ctx, "N")
+                    body2 = Node("bool", (True,)) if not rest else (
+                        rest[0] if len(rest) == 1 else Node("and", (tuple(rest),), body.line, body.col))
+
+                    def each1(xv):
+                        m = self.mark()
+                        self.bound = bound
+                        self.ca(body2, self.bind(env, pat, xv), ctx, bound, k, act)
+                        self.release(m)
+                    self.loop_set(sv2, each1)
+                    return
 
             def each(env2):
                 m = self.mark()
@@ -2266,6 +2490,7 @@ class Lowering:
         self.hoisted, self.def_uses, self.def_info = {}, {}, {}
         self._evenv_cache = {}
         self.__dict__.pop("_univ_cache", None)
+        self.__dict__.pop("_field_cache", None)
         self.hoist_keys = [(k, info[k]) for k in keys]
         return self._compile_pass()
 
@@ -2280,7 +2505,8 @@ class Lowering:
                     v = self.cx(od.body, {}, dctx, "N")
                 except CompileError:
                     v = None
-                if v is None or type(v) is Const or any(i[0] in ("TRAP", "ASSERTF") for i in cap.asm.code):
+                if v is None or type(v) is Const or any(
+                        (i[0] == "TRAP" and i[1] != TRAP_OVERFLOW) or i[0] in ("ASSERTF", "TBLT") for i in cap.asm.code):
                     self.top = save_top
                     v = None
             if v is None:
@@ -2353,6 +2579,7 @@ class Lowering:
         code, cpool, ent = self.asm.assemble(entries)
         cm = CompiledModel()
         cm.code, cm.cpool, cm.entries = code, cpool, ent
+        cm.line_table = self.asm.line_table
         cm.frame_words = self.high + 4
         cm.var_types = self.var_types
         cm.var_off = dict(self.n_off)

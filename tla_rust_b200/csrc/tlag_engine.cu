@@ -24,7 +24,7 @@
 #include "tlag_vm.h"
 
 #define TLAG_MAXW 64
-#define TLAG_BLOCK 128
+#define TLAG_BLOCK 512
 #define TLAG_MAX_STEPS (1u << 26)
 
 #define CK(call)                                                                         \
@@ -336,8 +336,6 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   const uint64_t n = hi - lo;
   uint64_t chunks = (n + 31) / 32;
   uint64_t blocks = (chunks + (TLAG_BLOCK / 32) - 1) / (TLAG_BLOCK / 32);
-  const uint64_t maxb = (uint64_t)e->sm_count * 8;
-  if (blocks > maxb) blocks = maxb;
   if (blocks == 0) blocks = 1;
   size_t smem = e->p.code_in_smem ? (size_t)e->p.code_len * 8 : 0;
   void (*fn)(DevParams, unsigned long long, unsigned long long) = nullptr;
@@ -354,6 +352,10 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
     cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (r != cudaSuccess) return r;
   }
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TLAG_BLOCK, smem) != cudaSuccess || occ < 1) occ = 1;
+  const uint64_t maxb = (uint64_t)e->sm_count * (uint64_t)occ;   // persistent grid: one resident wave of CTAs
+  if (blocks > maxb) blocks = maxb;
   fn<<<(unsigned)blocks, TLAG_BLOCK, smem, e->stream>>>(e->p, lo, hi);
   e->launches++;
   return cudaGetLastError();

@@ -27,7 +27,7 @@ enum {
   OP_JMP, OP_JZ, OP_JNZ, OP_JNEG,
   OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
   OP_ADDI, OP_MULI, OP_EQI, OP_NEI, OP_LTI, OP_LEI, OP_GTI, OP_GEI, OP_UCLAMP,
-  OP_BSETI, OP_BTESTI, OP_SHRI, OP_ANDI,
+  OP_BSETI, OP_BTESTI, OP_SHRI, OP_ANDI, OP_TBLT,
   OP__COUNT
 };
 
@@ -158,6 +158,10 @@ TLAG_HD int tlag_vm_run(const uint64_t* code, const int32_t* cpool, int32_t* f, 
       case OP_BTESTI: { uint32_t i = (uint32_t)immJ; f[a] = (int32_t)(((uint32_t)f[b + (i >> 5)] >> (i & 31)) & 1u); break; }
       case OP_SHRI: f[a] = (int32_t)((uint32_t)f[b] >> (immJ & 31)); break;
       case OP_ANDI: f[a] = f[b] & immJ; break;
+      case OP_TBLT: {  // table lookup that traps on the "field absent" sentinel
+        int32_t v = tlag_cp(cpool, immI + f[d]);
+        if (v == (int32_t)0x80000000) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
+        f[a] = v; break; }
       default: *info = 99; *info2 = (int32_t)op; *pc_io = pc; return TLAG_EV_TRAP;
     }
   }

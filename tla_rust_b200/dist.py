@@ -12,6 +12,25 @@ import torch
 import torch.distributed as dist
 
 
+def _all_to_all(outs, ins, rank):
+    """all_to_all over NCCL; point-to-point emulation on backends without it (gloo, CPU tests)."""
+    if dist.get_backend() == "nccl":
+        dist.all_to_all(outs, ins)
+        return
+    outs[rank].copy_(ins[rank])
+    ops = []
+    for r in range(len(ins)):
+        if r == rank:
+            continue
+        if ins[r].numel():
+            ops.append(dist.P2POp(dist.isend, ins[r], r))
+        if outs[r].numel():
+            ops.append(dist.P2POp(dist.irecv, outs[r], r))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
 class DistributedBFS:
     def __init__(self, engine, cm, rank, world, device, cap_records=1 << 22):
         self.e, self.cm, self.rank, self.world, self.device = engine, cm, rank, world, device
@@ -33,14 +52,19 @@ class DistributedBFS:
         e, world, rw = self.e, self.world, self.rec_words
         region = self.cap_records // world
         levels = 0
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        on_gpu = str(self.device).startswith("cuda")
+        if on_gpu:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         verdict = 5
         while levels < max_levels:
             counts, ws = e.expand_route(world, self.send.data_ptr(), self.cap_records)
             cnt = torch.tensor(counts, dtype=torch.int64, device=self.device)
             rcnt = torch.empty_like(cnt)
-            ev0.record()
-            dist.all_to_all_single(rcnt, cnt)
+            if on_gpu:
+                ev0.record()
+            rl = [torch.empty(1, dtype=torch.int64, device=self.device) for _ in range(world)]
+            _all_to_all(rl, [cnt[r:r + 1].clone() for r in range(world)], self.rank)
+            rcnt = torch.cat(rl)
             rc = rcnt.tolist()
             tot = sum(rc)
             if tot > self.cap_records:
@@ -50,10 +74,11 @@ class DistributedBFS:
             for r in range(world):
                 outs.append(self.recv[o * rw:(o + rc[r]) * rw])
                 o += rc[r]
-            dist.all_to_all(outs, ins)
-            ev1.record()
-            torch.cuda.synchronize()
-            self.comm_ms += ev0.elapsed_time(ev1)
+            _all_to_all(outs, ins, self.rank)
+            if on_gpu:
+                ev1.record()
+                torch.cuda.synchronize()
+                self.comm_ms += ev0.elapsed_time(ev1)
             n_new = e.insert_records(self.recv.data_ptr(), tot)
             adv = e.advance_level()
             flag = torch.tensor([n_new, ws["verdict"] if ws["verdict"] not in (0, 5) else 0, ws["generated"]],
