@@ -178,7 +178,7 @@ def main():
     if not multi:
         e = Engine(cm, deadlock=info["deadlock"], device=local_rank)
         e.seed(init)
-        for _ in range(args.warmup):
+        for _ in range(max(args.warmup, 1)):
             e.restart()
             r = e.run()
         assert (r["verdict"], r["generated"], r["distinct"], r["depth"]) == (
@@ -224,7 +224,7 @@ def main():
             ln = e.launches()
             e.close()
             return out, ks, ln, d.comm_ms
-        for _ in range(args.warmup):
+        for _ in range(max(args.warmup, 1)):
             out, _, _, _ = one()
         assert (out["generated"], out["distinct"]) == (exp["o2"]["generated"], exp["o2"]["distinct"]), out
         if sampler:

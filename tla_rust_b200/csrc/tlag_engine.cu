@@ -123,6 +123,31 @@ __device__ __forceinline__ void report_min(unsigned long long* slot, unsigned lo
 }
 
 // ------------------------------------------------------------------ wave kernel
+// Warp-scheduled interpreter.  A SIMT interpreter that lets every lane follow its own pc pays a
+// divergent fetch/decode/dispatch per distinct opcode per step.  Here the warp executes, at every
+// step, the ONE instruction at the minimum pc among its running lanes (REDUX min), for exactly the
+// lanes that are at that pc: fetch (shared-memory broadcast), decode and dispatch are warp-uniform,
+// frame accesses use the same word index in every lane (coalesced local memory), and lanes that
+// took different branches re-join as soon as the laggards catch up (forward progress is by
+// construction: the lowest pc always advances).
+enum { L_RUN = 0, L_EMIT = 1, L_DONE = 2, L_STOP = 3 };
+
+__device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ code, const int32_t* __restrict__ cpool,
+                                        int32_t* frame, uint32_t& pc, int& st, int& ev_out, int32_t& info,
+                                        int32_t& info2) {
+  for (uint32_t steps = 0;; ++steps) {
+    const uint32_t mypc = (st == L_RUN) ? pc : 0xFFFFFFFFu;
+    const uint32_t pcm = __reduce_min_sync(0xffffffffu, mypc);
+    if (pcm == 0xFFFFFFFFu) break;
+    const uint64_t w = code[pcm];
+    if (mypc == pcm) {
+      const int ev = tlag_vm_exec(w, cpool, frame, &pc, &info, &info2);
+      if (ev >= 0) { ev_out = ev; st = L_STOP; }
+    }
+    if (steps > TLAG_MAX_STEPS && st == L_RUN) { ev_out = TLAG_EV_STEPS; st = L_STOP; }
+  }
+}
+
 // MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
 template <int FRAME, int MODE>
 __global__ void __launch_bounds__(TLAG_BLOCK) k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
@@ -152,44 +177,52 @@ __global__ void __launch_bounds__(TLAG_BLOCK) k_wave(DevParams p, unsigned long 
       for (int i = 0; i < W; ++i) succ[i] = src[i];
       tlag_unpack(p.layout, p.n_slots, succ, frame + p.n_off);
     }
-    bool dead = !active;   // thread has nothing (more) to do
     bool trapped = false;
+    int st, ev = 0;
+    int32_t info = 0, info2 = 0;
+    uint32_t pc;
     // ---- invariants on the state being expanded --------------------------------
-    if (active && p.n_inv > 0) {
-      uint32_t pc = p.entry_inv;
+    if (p.n_inv > 0) {
+      pc = p.entry_inv;
+      st = active ? L_RUN : L_DONE;
       for (;;) {
-        int32_t info = 0, info2 = 0;
-        int ev = tlag_vm_run(code, p.cpool, frame, &pc, &info, &info2, TLAG_MAX_STEPS);
-        if (ev == TLAG_EV_HALT) break;
-        if (ev == TLAG_EV_INVF) { report_min(&p.ctr->viol_inv, (idx << 20) | (unsigned)(info & 0xFFFFF)); continue; }
-        if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); continue; }
-        // trap / runaway
-        report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) |
-                                          (unsigned)(info2 & 0xFFFF));
-        dead = true; trapped = true;
-        break;
+        warp_vm(code, p.cpool, frame, pc, st, ev, info, info2);
+        if (st == L_STOP) {
+          if (ev == TLAG_EV_HALT) st = L_DONE;
+          else if (ev == TLAG_EV_INVF) { report_min(&p.ctr->viol_inv, (idx << 20) | (unsigned)(info & 0xFFFFF)); st = L_RUN; }
+          else if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); st = L_RUN; }
+          else {
+            report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) |
+                                              (unsigned)(info2 & 0xFFFF));
+            st = L_DONE; trapped = true;
+          }
+        }
+        if (!__any_sync(0xffffffffu, st == L_RUN)) break;
       }
     }
     // ---- successors -------------------------------------------------------------
-    uint32_t pc = p.entry_next;
+    pc = p.entry_next;
+    st = (active && !trapped) ? L_RUN : L_DONE;
     unsigned nsucc = 0;
     for (;;) {
+      warp_vm(code, p.cpool, frame, pc, st, ev, info, info2);
       int32_t act = 0;
-      bool has = false;
-      while (!dead) {
-        int32_t info = 0, info2 = 0;
-        int ev = tlag_vm_run(code, p.cpool, frame, &pc, &info, &info2, TLAG_MAX_STEPS);
-        if (ev == TLAG_EV_EMIT) { has = true; act = info; ++nsucc; ++gen_local; break; }
-        if (ev == TLAG_EV_GEN) { ++nsucc; ++gen_local; continue; }
-        if (ev == TLAG_EV_HALT) { dead = true; break; }
-        if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); continue; }
-        if (ev == TLAG_EV_INVF) { continue; }
-        report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) |
-                                          (unsigned)(info2 & 0xFFFF));
-        dead = true; trapped = true;
-        break;
+      if (st == L_STOP) {
+        if (ev == TLAG_EV_EMIT) { st = L_EMIT; ++nsucc; ++gen_local; }
+        else if (ev == TLAG_EV_GEN) { ++nsucc; ++gen_local; st = L_RUN; }
+        else if (ev == TLAG_EV_HALT) st = L_DONE;
+        else if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); st = L_RUN; }
+        else if (ev == TLAG_EV_INVF) st = L_RUN;
+        else {
+          report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) |
+                                            (unsigned)(info2 & 0xFFFF));
+          st = L_DONE; trapped = true;
+        }
       }
-      if (!__any_sync(0xffffffffu, has)) break;
+      if (__any_sync(0xffffffffu, st == L_RUN)) continue;      // resume the lanes that only reported
+      bool has = (st == L_EMIT);
+      if (!__any_sync(0xffffffffu, has)) break;                 // every lane is done
+      act = info;
       unsigned long long fp = 0;
       if (has) {
         int ov = tlag_pack(p.layout, p.n_slots, frame + p.p_off, succ, W);
@@ -242,9 +275,9 @@ __global__ void __launch_bounds__(TLAG_BLOCK) k_wave(DevParams p, unsigned long 
           }
         }
       }
+      if (st == L_EMIT) st = L_RUN;
     }
     if (active && nsucc == 0 && !trapped && (p.flags & TLAG_F_DEADLOCK_CHECK)) {
-      // a trapped thread is not a deadlock
       report_min(&p.ctr->viol_deadlock, idx << 20);
     }
   }
@@ -261,25 +294,71 @@ __global__ void __launch_bounds__(256) k_probe(const uint32_t* __restrict__ stat
                                                uint8_t* __restrict__ is_new, Counters* ctr) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t w[TLAG_MAXW];
   const uint32_t* src = states + i * (unsigned long long)W;
+  uint64_t h = tlag_fp_init(W);
   if (VEC == 4) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
-#pragma unroll 4
-    for (int k = 0; k < W / 4; ++k) {
-      uint4 v = __ldg(s4 + k);
-      w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+    const int n4 = W / 4;
+#pragma unroll 5
+    for (int k = 0; k < n4; ++k) {
+      const uint4 v = __ldg(s4 + k);
+      h = tlag_fp_pair(h, v.x, v.y);
+      h = tlag_fp_pair(h, v.z, v.w);
     }
   } else if (VEC == 2) {
     const uint2* s2 = reinterpret_cast<const uint2*>(src);
-    for (int k = 0; k < W / 2; ++k) { uint2 v = __ldg(s2 + k); w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+    for (int k = 0; k < W / 2; ++k) { const uint2 v = __ldg(s2 + k); h = tlag_fp_pair(h, v.x, v.y); }
   } else {
-    for (int k = 0; k < W; ++k) w[k] = __ldg(src + k);
+    int k = 0;
+    for (; k + 1 < W; k += 2) h = tlag_fp_pair(h, __ldg(src + k), __ldg(src + k + 1));
+    if (k < W) h = tlag_fp_tail(h, __ldg(src + k));
   }
-  const unsigned long long fp = tlag_fingerprint(w, W);
+  const unsigned long long fp = tlag_fp_final(h, W);
   int ins = seen_insert(table, mask, fp);
   if (ins < 0) { atomicExch(&ctr->table_full, 1ULL); ins = 0; }
   is_new[i] = (uint8_t)ins;
+}
+
+// K1, coalesced form: a CTA of 256 threads owns 256 consecutive candidates = one contiguous span of
+// 256*W words.  The span is fetched with fully coalesced 128-bit loads (every 32-byte sector is read
+// exactly once; ncu on the strided v0 showed 2.4x DRAM read amplification from L1 thrash), staged in
+// shared memory with an odd row stride (W|1 words -> conflict-free), then each thread fingerprints its
+// own row and probes the table.
+__global__ void __launch_bounds__(256) k_probe_staged(const uint32_t* __restrict__ states, unsigned long long n, int W,
+                                                      unsigned long long* table, unsigned long long mask,
+                                                      uint8_t* __restrict__ is_new, Counters* ctr) {
+  extern __shared__ uint32_t s_rows[];
+  const int stride = W | 1;
+  const unsigned long long base = (unsigned long long)blockIdx.x * 256ULL;
+  const unsigned nst = (unsigned)((n - base) < 256ULL ? (n - base) : 256ULL);
+  const uint32_t* g = states + base * (unsigned long long)W;
+  const unsigned total = nst * (unsigned)W;          // words in this CTA's span
+  const unsigned total4 = total >> 2;
+  const uint4* g4 = reinterpret_cast<const uint4*>(g);
+  for (unsigned i = threadIdx.x; i < total4; i += 256) {
+    const uint4 v = __ldcs(g4 + i);                  // streaming: each word is used once
+    unsigned wi = i << 2;
+    unsigned row = wi / (unsigned)W, col = wi - row * (unsigned)W;
+    s_rows[row * stride + col] = v.x; if (++col == (unsigned)W) { col = 0; ++row; }
+    s_rows[row * stride + col] = v.y; if (++col == (unsigned)W) { col = 0; ++row; }
+    s_rows[row * stride + col] = v.z; if (++col == (unsigned)W) { col = 0; ++row; }
+    s_rows[row * stride + col] = v.w;
+  }
+  for (unsigned wi = (total4 << 2) + threadIdx.x; wi < total; wi += 256) {   // ragged tail (< 4 words)
+    const unsigned row = wi / (unsigned)W, col = wi - row * (unsigned)W;
+    s_rows[row * stride + col] = g[wi];
+  }
+  __syncthreads();
+  if (threadIdx.x >= nst) return;
+  const uint32_t* r = s_rows + threadIdx.x * stride;
+  uint64_t h = tlag_fp_init(W);
+  int k = 0;
+  for (; k + 1 < W; k += 2) h = tlag_fp_pair(h, r[k], r[k + 1]);
+  if (k < W) h = tlag_fp_tail(h, r[k]);
+  const unsigned long long fp = tlag_fp_final(h, W);
+  int ins = seen_insert(table, mask, fp);
+  if (ins < 0) { atomicExch(&ctr->table_full, 1ULL); ins = 0; }
+  is_new[base + threadIdx.x] = (uint8_t)ins;
 }
 
 // insert routed records (W state words + parent + meta) into this rank's shard
@@ -516,7 +595,10 @@ static int launch_probe(tlag_engine* e, const uint32_t* d_states, uint64_t n, ui
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (n == 0) return TLAG_OK;
   const bool a16 = ((uintptr_t)d_states % 16) == 0, a8 = ((uintptr_t)d_states % 8) == 0;
-  if (W % 4 == 0 && a16) k_probe<4><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
+  if (a16 && W >= 2) {
+    const size_t smem = (size_t)256 * (size_t)(W | 1) * 4;
+    k_probe_staged<<<blocks, 256, smem, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
+  } else if (W % 4 == 0 && a16) k_probe<4><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
   else if (W % 2 == 0 && a8) k_probe<2><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
   else k_probe<1><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
   e->launches++;

@@ -68,14 +68,15 @@ TLAG_HD int tlag_ffs(uint32_t x) {  /* 1-based index of lowest set bit, 0 if non
 #endif
 }
 
-// Runs from *pc until the next event.  `code` may live in shared memory on the device.
-// info receives the event payload (action id / trap code / assert id / invariant index),
-// info2 the secondary payload (trap source line).
-TLAG_HD int tlag_vm_run(const uint64_t* code, const int32_t* cpool, int32_t* f, uint32_t* pc_io,
-                        int32_t* info, int32_t* info2, uint32_t max_steps) {
-  uint32_t pc = *pc_io;
-  for (uint32_t steps = 0; steps < max_steps; ++steps) {
-    const uint64_t w = code[pc++];
+// Executes ONE instruction word `w` (fetched from code[*pc_io]) for the calling thread: updates the
+// frame and *pc_io; returns -1 to continue or a TLAG_EV_* event.  info receives the event payload
+// (action id / trap code / assert id / invariant index), info2 the secondary payload (source line).
+// The scalar interpreter (tlag_vm_run) and the warp-scheduled interpreter of the CUDA engine both
+// call this, so the ISA semantics have a single definition.
+TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uint32_t* pc_io,
+                         int32_t* info, int32_t* info2) {
+  uint32_t pc = *pc_io + 1;
+  {
     const uint32_t op = (uint32_t)(w & 0xFF);
     const uint32_t a = (uint32_t)(w >> 8) & 0x3FFF;
     const uint32_t b = (uint32_t)(w >> 22) & 0x3FFF;
@@ -166,6 +167,16 @@ TLAG_HD int tlag_vm_run(const uint64_t* code, const int32_t* cpool, int32_t* f, 
     }
   }
   *pc_io = pc;
+  return -1;
+}
+
+// Runs from *pc until the next event.  `code` may live in shared memory on the device.
+TLAG_HD int tlag_vm_run(const uint64_t* code, const int32_t* cpool, int32_t* f, uint32_t* pc_io,
+                        int32_t* info, int32_t* info2, uint32_t max_steps) {
+  for (uint32_t steps = 0; steps < max_steps; ++steps) {
+    const int ev = tlag_vm_exec(code[*pc_io], cpool, f, pc_io, info, info2);
+    if (ev >= 0) return ev;
+  }
   return TLAG_EV_STEPS;
 }
 
@@ -208,19 +219,31 @@ TLAG_HD uint64_t tlag_fmix64(uint64_t k) {
   return k;
 }
 
-TLAG_HD uint64_t tlag_fingerprint(const uint32_t* w, int W) {
-  uint64_t h = 0x9E3779B97F4A7C15ULL ^ ((uint64_t)W * 0xD6E8FEB86659FD93ULL);
-  int i = 0;
-  for (; i + 1 < W; i += 2) {
-    uint64_t k = (uint64_t)w[i] | ((uint64_t)w[i + 1] << 32);
-    k *= 0x87c37b91114253d5ULL; k = tlag_rotl64(k, 31); k *= 0x4cf5ad432745937fULL;
-    h ^= k; h = tlag_rotl64(h, 27) * 5 + 0x52dce729ULL;
-  }
-  if (i < W) {
-    uint64_t k = (uint64_t)w[i];
-    k *= 0x87c37b91114253d5ULL; k = tlag_rotl64(k, 31); k *= 0x4cf5ad432745937fULL;
-    h ^= k;
-  }
+// incremental form (lets the probe kernel hash straight out of its vector loads)
+TLAG_HD uint64_t tlag_fp_init(int W) { return 0x9E3779B97F4A7C15ULL ^ ((uint64_t)W * 0xD6E8FEB86659FD93ULL); }
+
+TLAG_HD uint64_t tlag_fp_pair(uint64_t h, uint32_t lo, uint32_t hi) {
+  uint64_t k = (uint64_t)lo | ((uint64_t)hi << 32);
+  k *= 0x87c37b91114253d5ULL; k = tlag_rotl64(k, 31); k *= 0x4cf5ad432745937fULL;
+  h ^= k;
+  return tlag_rotl64(h, 27) * 5 + 0x52dce729ULL;
+}
+
+TLAG_HD uint64_t tlag_fp_tail(uint64_t h, uint32_t w) {
+  uint64_t k = (uint64_t)w;
+  k *= 0x87c37b91114253d5ULL; k = tlag_rotl64(k, 31); k *= 0x4cf5ad432745937fULL;
+  return h ^ k;
+}
+
+TLAG_HD uint64_t tlag_fp_final(uint64_t h, int W) {
   h = tlag_fmix64(h ^ (uint64_t)W);
   return h ? h : 1ULL;   // 0 is the empty-slot marker of the seen-set
+}
+
+TLAG_HD uint64_t tlag_fingerprint(const uint32_t* w, int W) {
+  uint64_t h = tlag_fp_init(W);
+  int i = 0;
+  for (; i + 1 < W; i += 2) h = tlag_fp_pair(h, w[i], w[i + 1]);
+  if (i < W) h = tlag_fp_tail(h, w[i]);
+  return tlag_fp_final(h, W);
 }
