@@ -71,12 +71,13 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference(cm, init, info, threads):
+def cpu_reference(cm, init, info, threads, expect_distinct=0):
     """The reference arm: the path's CPU implementation (ORACLE O2, oracle/tlag_cpu.c -- TLC itself needs a JVM,
     which neither this image nor the reference provides) on all host cores, same model."""
     from oracle import cpu_engine
     t0 = time.time()
-    r = cpu_engine.run(cm, init, n_threads=threads, deadlock=info["deadlock"], max_states=1 << 26)
+    cap = max(1 << 16, int(expect_distinct * 1.25) + 4096) if expect_distinct else 1 << 26   # right-sized store/table
+    r = cpu_engine.run(cm, init, n_threads=threads, deadlock=info["deadlock"], max_states=cap)
     dt = r["seconds"]
     return r, dt, time.time() - t0
 
@@ -141,7 +142,7 @@ def main():
             return
         vals = []
         for _ in range(max(1, min(args.steps, 2))):
-            r, dt, wall = cpu_reference(cm, init, info, threads)
+            r, dt, wall = cpu_reference(cm, init, info, threads, exp["o2"]["distinct"])
             vals.append(r["distinct"] / dt)
         v = float(np.median(vals))
         line = {"impl": "reference", "metric": "distinct states/sec", "value": round(v, 1), "unit": "states/s",
@@ -272,7 +273,7 @@ def main():
             k1["peak_source"] = peak_src
         except Exception as ex:  # noqa: BLE001
             k1 = {"error": str(ex)}
-    cpu_r, cpu_dt, _ = cpu_reference(cm, init, info, threads)
+    cpu_r, cpu_dt, _ = cpu_reference(cm, init, info, threads, exp["o2"]["distinct"])
     line = {"metric": "distinct states/sec", "value": round(value, 1), "unit": "states/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",

@@ -20,6 +20,8 @@ OPS = [
     "TRAP", "EMIT", "GEN", "ASSERTF", "INVF",
     "ADDI", "MULI", "EQI", "NEI", "LTI", "LEI", "GTI", "GEI", "UCLAMP",
     "BSETI", "BTESTI", "SHRI", "ANDI", "TBLT",
+    # fused compare-and-branch (target = imm28 in (c,d))
+    "JEQ", "JNE", "JLT", "JGE", "JEQI", "JNEI", "JLTI", "JGEI", "JBT", "JBF", "JBTI", "JBFI", "JGEZ",
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 
@@ -35,7 +37,16 @@ FMT = {
     "TRAP": "nI", "EMIT": "_I", "GEN": "", "ASSERTF": "_I", "INVF": "_I",
     "ADDI": "rrJ", "MULI": "rrJ", "EQI": "rrJ", "NEI": "rrJ", "LTI": "rrJ", "LEI": "rrJ", "GTI": "rrJ",
     "GEI": "rrJ", "UCLAMP": "rI", "BSETI": "rI", "BTESTI": "rrJ", "SHRI": "rrJ", "ANDI": "rrJ", "TBLT": "rIr",
+    "JEQ": "rrJ", "JNE": "rrJ", "JLT": "rrJ", "JGE": "rrJ",
+    "JEQI": "rkJ", "JNEI": "rkJ", "JLTI": "rkJ", "JGEI": "rkJ",
+    "JBT": "rrJ", "JBF": "rrJ", "JBTI": "rnJ", "JBFI": "rnJ", "JGEZ": "rI",
 }
+
+INVERSE = {"JZ": "JNZ", "JEQ": "JNE", "JLT": "JGE", "JEQI": "JNEI", "JLTI": "JGEI", "JBT": "JBF", "JBTI": "JBFI",
+           "JNEG": "JGEZ"}
+INVERSE.update({v: k for k, v in list(INVERSE.items())})
+COND_JUMPS = set(INVERSE)
+IMM14_MIN, IMM14_MAX = -(1 << 13), (1 << 13) - 1
 
 TRAP_EVAL, TRAP_OVERFLOW, TRAP_CASE, TRAP_CHOOSE, TRAP_ASSIGN = 1, 2, 3, 4, 5
 TRAP_NAMES = {1: "evaluation error (function applied outside its domain / missing record field)",
@@ -98,6 +109,7 @@ class Asm:
 
     def assemble(self, entry_points: dict):
         """Resolve labels -> (uint64 code array, int32 cpool array, {name: pc})."""
+        self.peephole()
         pos = 0
         for ins in self.code:
             if ins[0] == "label":
@@ -117,6 +129,129 @@ class Asm:
         cp = ((cp + (1 << 31)) % (1 << 32) - (1 << 31)).astype(np.int32)
         entries = {k: (v.pos if isinstance(v, Label) else v) for k, v in entry_points.items()}
         return out, cp, entries
+
+    def peephole(self):
+        """Branch clean-up on the symbolic code: drop `JMP L` when L is the next instruction, turn
+        `Jcc L1; JMP L2; L1:` into `J!cc L2`, thread jumps through `L: JMP L'`."""
+        def jump_target(ins):
+            if ins[0] == "JMP":
+                return ins[1]
+            if ins[0] in COND_JUMPS:
+                return ins[-1]
+            return None
+
+        self.fuse_compare_branch()
+        for _ in range(4):
+            code = self.code
+            # label -> first real instruction after it (for threading)
+            nxt_real = {}
+            pending = []
+            for ins in code:
+                if ins[0] == "label":
+                    pending.append(ins[1])
+                else:
+                    for L in pending:
+                        nxt_real[id(L)] = ins
+                    pending = []
+            out = []
+            changed = False
+            i, n = 0, len(code)
+            while i < n:
+                ins = code[i]
+                if ins[0] == "label":
+                    out.append(ins)
+                    i += 1
+                    continue
+                tgt = jump_target(ins)
+                if tgt is not None:
+                    # thread through unconditional jumps
+                    hops = 0
+                    t2 = nxt_real.get(id(tgt))
+                    while t2 is not None and t2[0] == "JMP" and t2[1] is not tgt and hops < 8:
+                        tgt = t2[1]
+                        t2 = nxt_real.get(id(tgt))
+                        hops += 1
+                    if hops:
+                        new = ins[:-1] + (tgt,) if ins[0] != "JMP" else ("JMP", tgt)
+                        self.lines[id(new)] = self.lines.get(id(ins), 0)
+                        ins = new
+                        changed = True
+                    # labels immediately following
+                    j = i + 1
+                    following = []
+                    while j < n and code[j][0] == "label":
+                        following.append(code[j][1])
+                        j += 1
+                    if ins[0] == "JMP" and any(L is tgt for L in following):
+                        changed = True
+                        i += 1
+                        continue
+                    if ins[0] in COND_JUMPS and i + 1 < n and code[i + 1][0] == "JMP":
+                        k = i + 2
+                        foll2 = []
+                        while k < n and code[k][0] == "label":
+                            foll2.append(code[k][1])
+                            k += 1
+                        if any(L is tgt for L in foll2):
+                            new = (INVERSE[ins[0]],) + ins[1:-1] + (code[i + 1][1],)
+                            self.lines[id(new)] = self.lines.get(id(ins), 0)
+                            out.append(new)
+                            changed = True
+                            i += 2
+                            continue
+                out.append(ins)
+                i += 1
+            self.code = out
+            if not changed:
+                break
+
+    def fuse_compare_branch(self):
+        """`CMP t, x, y ; JNZ/JZ t, L`  ->  one fused compare-and-branch.  Every compare the lowering
+        emits writes a freshly allocated temporary that is consumed only by the jump that follows."""
+        out = []
+        code = self.code
+        i, n = 0, len(code)
+        fits = lambda v: isinstance(v, int) and IMM14_MIN <= v <= IMM14_MAX
+        while i < n:
+            a = code[i]
+            b = code[i + 1] if i + 1 < n else None
+            new = None
+            if b is not None and b[0] in ("JNZ", "JZ") and a[0] != "label" and len(a) >= 2 and b[1] == a[1]:
+                t_ = b[0] == "JNZ"
+                L = b[2]
+                op = a[0]
+                if op == "EQ":
+                    new = ("JEQ" if t_ else "JNE", a[2], a[3], L)
+                elif op == "NE":
+                    new = ("JNE" if t_ else "JEQ", a[2], a[3], L)
+                elif op == "LT":
+                    new = ("JLT" if t_ else "JGE", a[2], a[3], L)
+                elif op == "LE":
+                    new = ("JGE" if t_ else "JLT", a[3], a[2], L)
+                elif op == "EQI" and fits(a[3]):
+                    new = ("JEQI" if t_ else "JNEI", a[2], a[3], L)
+                elif op == "NEI" and fits(a[3]):
+                    new = ("JNEI" if t_ else "JEQI", a[2], a[3], L)
+                elif op == "LTI" and fits(a[3]):
+                    new = ("JLTI" if t_ else "JGEI", a[2], a[3], L)
+                elif op == "GEI" and fits(a[3]):
+                    new = ("JGEI" if t_ else "JLTI", a[2], a[3], L)
+                elif op == "LEI" and fits(a[3] + 1):
+                    new = ("JLTI" if t_ else "JGEI", a[2], a[3] + 1, L)
+                elif op == "GTI" and fits(a[3] + 1):
+                    new = ("JGEI" if t_ else "JLTI", a[2], a[3] + 1, L)
+                elif op == "BTEST":
+                    new = ("JBT" if t_ else "JBF", a[2], a[3], L)
+                elif op == "BTESTI" and isinstance(a[3], int) and 0 <= a[3] <= MAXREG:
+                    new = ("JBTI" if t_ else "JBFI", a[2], a[3], L)
+            if new is not None:
+                self.lines[id(new)] = self.lines.get(id(a), 0)
+                out.append(new)
+                i += 2
+            else:
+                out.append(a)
+                i += 1
+        self.code = out
 
     def _encode(self, ins):
         name = ins[0]
@@ -145,6 +280,11 @@ class Asm:
                 if not (0 <= v <= MAXREG):
                     raise AsmError(f"{name}: operand {v} out of 14-bit range")
                 regs[slot] = v
+                slot += 1
+            elif ch == "k":
+                if not (-(1 << 13) <= v < (1 << 13)):
+                    raise AsmError(f"{name}: immediate {v} out of signed 14-bit range")
+                regs[slot] = v & 0x3FFF
                 slot += 1
             elif ch == "I":
                 if not (IMM28_MIN <= v <= IMM28_MAX):
@@ -204,6 +344,10 @@ def disasm(code, entries=None):
                 slot += 1
             elif ch in "rn":
                 outs.append(("r" if ch == "r" else "#") + str(regs[slot]))
+                slot += 1
+            elif ch == "k":
+                v = regs[slot]
+                outs.append("$" + str(v - (1 << 14) if v >= (1 << 13) else v))
                 slot += 1
             elif ch == "I":
                 v = b | (c << 14)

@@ -2144,10 +2144,18 @@ class Lowering:
         if isinstance(sv.t.elem, TBottom):
             self.asm.emit("JMP", lf)
             return
-        o = self.ord_in(sv.t.elem, e)
         t1 = self.alloc(1)
-        self.asm.emit("JNEG", o, lf)
-        self.asm.emit("BTEST", t1, sv.loc, o)
+        if type(e) is Const:
+            oc = self.codec.ord_of(sv.t.elem, e.v)
+            if oc < 0:
+                self.asm.emit("JMP", lf)
+                return
+            self.asm.emit("BTESTI", t1, sv.loc, oc)
+        else:
+            o = self.ord_in(sv.t.elem, e)
+            if not (type(e) is OVal and e.t == sv.t.elem):
+                self.asm.emit("JNEG", o, lf)
+            self.asm.emit("BTEST", t1, sv.loc, o)
         self.asm.emit("JNZ", t1, lt)
         self.asm.emit("JMP", lf)
 

@@ -28,6 +28,7 @@ enum {
   OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
   OP_ADDI, OP_MULI, OP_EQI, OP_NEI, OP_LTI, OP_LEI, OP_GTI, OP_GEI, OP_UCLAMP,
   OP_BSETI, OP_BTESTI, OP_SHRI, OP_ANDI, OP_TBLT,
+  OP_JEQ, OP_JNE, OP_JLT, OP_JGE, OP_JEQI, OP_JNEI, OP_JLTI, OP_JGEI, OP_JBT, OP_JBF, OP_JBTI, OP_JBFI, OP_JGEZ,
   OP__COUNT
 };
 
@@ -163,6 +164,20 @@ TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uin
         int32_t v = tlag_cp(cpool, immI + f[d]);
         if (v == (int32_t)0x80000000) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
         f[a] = v; break; }
+      // fused compare-and-branch: target = immJ; b is a register or a signed 14-bit immediate
+      case OP_JEQ: if (f[a] == f[b]) pc = (uint32_t)immJ; break;
+      case OP_JNE: if (f[a] != f[b]) pc = (uint32_t)immJ; break;
+      case OP_JLT: if (f[a] < f[b]) pc = (uint32_t)immJ; break;
+      case OP_JGE: if (f[a] >= f[b]) pc = (uint32_t)immJ; break;
+      case OP_JEQI: if (f[a] == ((int32_t)(b << 18) >> 18)) pc = (uint32_t)immJ; break;
+      case OP_JNEI: if (f[a] != ((int32_t)(b << 18) >> 18)) pc = (uint32_t)immJ; break;
+      case OP_JLTI: if (f[a] < ((int32_t)(b << 18) >> 18)) pc = (uint32_t)immJ; break;
+      case OP_JGEI: if (f[a] >= ((int32_t)(b << 18) >> 18)) pc = (uint32_t)immJ; break;
+      case OP_JBT: { uint32_t i = (uint32_t)f[b]; if (((uint32_t)f[a + (i >> 5)] >> (i & 31)) & 1u) pc = (uint32_t)immJ; break; }
+      case OP_JBF: { uint32_t i = (uint32_t)f[b]; if (!(((uint32_t)f[a + (i >> 5)] >> (i & 31)) & 1u)) pc = (uint32_t)immJ; break; }
+      case OP_JBTI: if (((uint32_t)f[a + (b >> 5)] >> (b & 31)) & 1u) pc = (uint32_t)immJ; break;
+      case OP_JBFI: if (!(((uint32_t)f[a + (b >> 5)] >> (b & 31)) & 1u)) pc = (uint32_t)immJ; break;
+      case OP_JGEZ: if (f[a] >= 0) pc = (uint32_t)immI; break;
       default: *info = 99; *info2 = (int32_t)op; *pc_io = pc; return TLAG_EV_TRAP;
     }
   }
