@@ -120,6 +120,9 @@ def tlc_main(argv=None):
         except (SpecError, ParseError, LexError, EvalError, CompileError, TypeErr) as ex:
             print(f"Error: {type(ex).__name__}: {ex}")
             r = 150
+        except Exception as ex:  # noqa: BLE001 -- e.g. EngineUnavailable: no CUDA device (there is no CPU backend)
+            print(f"Error: {type(ex).__name__}: {ex}")
+            r = 255
         if r != 0:
             rc = r
             break      # `make` semantics: TLC exits non-zero at the first failing module

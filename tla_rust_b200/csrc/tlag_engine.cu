@@ -520,6 +520,9 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { e->err = "no CUDA device available"; return TLAG_ECUDA; }
   CK(cudaSetDevice(m->device));
+  // Seen-set probes are random 8-byte accesses: ncu showed every probe pulling a full 128-byte line
+  // from DRAM (4 sectors) with the default L2 fetch granularity; 32 B makes a probe cost one sector.
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, m->device));
   e->sm_count = prop.multiProcessorCount;
@@ -597,6 +600,7 @@ static int launch_probe(tlag_engine* e, const uint32_t* d_states, uint64_t n, ui
   const bool a16 = ((uintptr_t)d_states % 16) == 0, a8 = ((uintptr_t)d_states % 8) == 0;
   if (a16 && W >= 2) {
     const size_t smem = (size_t)256 * (size_t)(W | 1) * 4;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_probe_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_probe_staged<<<blocks, 256, smem, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
   } else if (W % 4 == 0 && a16) k_probe<4><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
   else if (W % 2 == 0 && a8) k_probe<2><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);

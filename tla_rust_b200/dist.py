@@ -57,7 +57,16 @@ class DistributedBFS:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         verdict = 5
         while levels < max_levels:
-            counts, ws = e.expand_route(world, self.send.data_ptr(), self.cap_records)
+            while True:
+                try:
+                    counts, ws = e.expand_route(world, self.send.data_ptr(), self.cap_records)
+                    break
+                except Exception as ex:  # noqa: BLE001 -- send regions too small for this level: grow and redo
+                    if "overflow" not in str(ex) or self.cap_records >= (1 << 30):
+                        raise
+                    self.cap_records *= 4
+                    self.send = torch.empty(self.cap_records * rw, dtype=torch.int32, device=self.device)
+                    region = self.cap_records // world
             cnt = torch.tensor(counts, dtype=torch.int64, device=self.device)
             rcnt = torch.empty_like(cnt)
             if on_gpu:
@@ -67,8 +76,8 @@ class DistributedBFS:
             rcnt = torch.cat(rl)
             rc = rcnt.tolist()
             tot = sum(rc)
-            if tot > self.cap_records:
-                raise RuntimeError("receive buffer too small")
+            if tot * rw > self.recv.numel():
+                self.recv = torch.empty(int(tot * 1.5) * rw, dtype=torch.int32, device=self.device)
             ins = [self.send[r * region * rw:(r * region + counts[r]) * rw] for r in range(world)]
             outs, o = [], 0
             for r in range(world):
