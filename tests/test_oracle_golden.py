@@ -77,3 +77,19 @@ def test_small_corpus_counts():
     m.check_deadlock = False
     r = Oracle(m).run()
     assert (r.verdict, r.distinct, r.init_states) == ("ok", 4, 4)
+
+
+@needs_reference
+def test_oracle_handles_raft_and_ssi_at_small_bounds():
+    """BASELINE configs #4/#5 (raft.tla, serializableSnapshotIsolation.tla) through the front end and O1 at reduced
+    bounds.  The reference holds no counts for them (parity unpinned at the TLC boundary); these pin
+    the oracle against itself: RECURSIVE operators, LAMBDA arguments, CHOOSE, bags as functions (raft.tla:117-135),
+    @@ / :>, SelectSeq, CONSTRAINT semantics."""
+    from conftest import ROOT
+    m = Model(ROOT + "/models/MCssi.tla", extra_dirs=[REF + "/examples"])
+    r = Oracle(m).run()
+    assert (r.verdict, r.generated, r.distinct, r.depth) == ("ok", 945, 569, 9)
+    m = Model(ROOT + "/models/MCraft.tla", extra_dirs=[REF + "/examples"])
+    m.check_deadlock = False
+    r = Oracle(m).run()
+    assert (r.verdict, r.generated, r.distinct, r.depth) == ("ok", 6185, 694, 12)

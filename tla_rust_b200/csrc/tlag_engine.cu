@@ -98,15 +98,13 @@ struct tlag_engine {
 // returns 1 if fp was inserted by this call, 0 if already present, -1 if the table is full
 __device__ __forceinline__ int seen_insert(unsigned long long* table, unsigned long long mask,
                                            unsigned long long fp) {
+  // One L2 round trip per probe: the CAS itself is the read (at load <= 0.5 the first slot is almost
+  // always either empty or the duplicate); ncu showed the read-then-CAS form latency-bound.
   unsigned long long i = fp & mask;
   for (unsigned long long probes = 0; probes <= mask; ++probes) {
-    unsigned long long cur = table[i];
-    if (cur == fp) return 0;
-    if (cur == 0ULL) {
-      unsigned long long old = atomicCAS(&table[i], 0ULL, fp);
-      if (old == 0ULL) return 1;
-      if (old == fp) return 0;
-    }
+    const unsigned long long old = atomicCAS(&table[i], 0ULL, fp);
+    if (old == 0ULL) return 1;
+    if (old == fp) return 0;
     i = (i + 1) & mask;
   }
   return -1;
@@ -149,8 +147,8 @@ __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ code, const
 }
 
 // MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
-template <int FRAME, int MODE>
-__global__ void __launch_bounds__(TLAG_BLOCK) k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
+template <int FRAME, int MODE, int MINB>
+__global__ void __launch_bounds__(TLAG_BLOCK, MINB) k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
   extern __shared__ uint64_t s_code[];
   const uint64_t* code = p.code;
   if (p.code_in_smem) {
@@ -418,14 +416,15 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   if (blocks == 0) blocks = 1;
   size_t smem = e->p.code_in_smem ? (size_t)e->p.code_len * 8 : 0;
   void (*fn)(DevParams, unsigned long long, unsigned long long) = nullptr;
+  static const bool dense = getenv("TLAG_WAVE_MINB4") != nullptr;   // A/B knob: 4 CTAs/SM (32 regs) vs 3 (40 regs)
   switch (e->frame_class) {
-    case 0: fn = k_wave<64, MODE>; break;
-    case 1: fn = k_wave<128, MODE>; break;
-    case 2: fn = k_wave<256, MODE>; break;
-    case 3: fn = k_wave<512, MODE>; break;
-    case 4: fn = k_wave<1024, MODE>; break;
-    case 5: fn = k_wave<2048, MODE>; break;
-    default: fn = k_wave<4096, MODE>; break;
+    case 0: fn = dense ? k_wave<64, MODE, 4> : k_wave<64, MODE, 3>; break;
+    case 1: fn = dense ? k_wave<128, MODE, 4> : k_wave<128, MODE, 3>; break;
+    case 2: fn = dense ? k_wave<256, MODE, 4> : k_wave<256, MODE, 3>; break;
+    case 3: fn = k_wave<512, MODE, 2>; break;
+    case 4: fn = k_wave<1024, MODE, 1>; break;
+    case 5: fn = k_wave<2048, MODE, 1>; break;
+    default: fn = k_wave<4096, MODE, 1>; break;
   }
   if (smem > 48 * 1024) {
     cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
