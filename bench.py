@@ -124,6 +124,9 @@ def main():
     ap.add_argument("--workload", default="MCPaxos3_b3")
     ap.add_argument("--no-k1", action="store_true")
     args = ap.parse_args()
+    if os.environ.get("TLAG_BENCH_WATCHDOG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["TLAG_BENCH_WATCHDOG"]), exit=True)
 
     from tla_rust_b200.compiled import load_compiled
     rank = int(os.environ.get("RANK", "0"))

@@ -29,7 +29,7 @@ from collections import deque
 
 from tla_rust_b200.front.eval import AssertFailure, Fr
 from tla_rust_b200.front.values import EvalError
-from tla_rust_b200.front.report import (CheckResult, OK, INVARIANT, ASSERT, DEADLOCK, EVAL_ERROR)
+from tla_rust_b200.front.report import (CheckResult, OK, INVARIANT, ASSERT, DEADLOCK, EVAL_ERROR, PROPERTY)
 
 
 class Oracle:
@@ -55,6 +55,20 @@ class Oracle:
         for nm, node, ctx in self.m.invariants:
             if self.ev.eval(node, {}, Fr(ctx, st, None)) is not True:
                 return nm
+        return None
+
+    def check_refinements(self, s, t):
+        """[Next2]_v2 on the transition s -> t for every refinement PROPERTY (safety part)."""
+        from tla_rust_b200.front.values import values_equal
+        for nm, _, nxt, sub, ctx in self.m.refinements:
+            if nxt is None:
+                continue
+            fr = Fr(ctx, s, t)
+            if self.ev.eval(nxt, {}, fr) is True:
+                continue
+            if values_equal(self.ev.eval(sub, {}, fr), self.ev.eval(sub, {}, Fr(ctx, t, None))):
+                continue
+            return nm
         return None
 
     def in_model(self, st):
@@ -115,6 +129,12 @@ class Oracle:
             parent.append((-1, None))
             level.append(1)
             maxlevel = 1
+            pbad = self.m.check_refinement_init(st)
+            if pbad is not None:
+                res.invariant = pbad
+                res.error_text = f"Property {pbad} is violated by the initial state"
+                res.trace = trace_to(idx)
+                return finish(PROPERTY)
             if bad is not None:
                 res.invariant = bad
                 res.trace = trace_to(idx)
@@ -132,6 +152,12 @@ class Oracle:
                 for t, act in self.successors(st):
                     nsucc += 1
                     res.generated += 1
+                    if self.m.refinements:
+                        pbad = self.check_refinements(st, t)
+                        if pbad is not None:
+                            res.invariant = pbad
+                            res.trace = trace_to(cur, (t, act))
+                            return finish(PROPERTY)
                     in_model = self.in_model(t) and self.in_actions(st, t)
                     k = self.key(t)
                     is_seen = False

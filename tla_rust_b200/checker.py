@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 
 from .front.spec import Model
-from .front.report import CheckResult, OK, INVARIANT, ASSERT, DEADLOCK, EVAL_ERROR
+from .front.report import CheckResult, OK, INVARIANT, ASSERT, DEADLOCK, EVAL_ERROR, PROPERTY
 from .compile.lower import Lowering, CompiledModel, CompileError
 from .compile.bytecode import TRAP_NAMES
 
@@ -90,6 +90,9 @@ def result_from_engine(cm: CompiledModel, res: dict, trace=None) -> CheckResult:
         r.invariant = cm.invariants[res["detail"]]
     elif r.verdict == ASSERT:
         r.error_text = cm.asserts[res["detail"]][0]
+        if r.error_text.startswith("\x00property:"):
+            r.verdict = PROPERTY
+            r.invariant = r.error_text.split(":", 1)[1]
     elif r.verdict == EVAL_ERROR:
         r.error_text = f"{TRAP_NAMES.get(res['detail'], 'trap ' + str(res['detail']))} (source line {res['detail2']})"
     if trace is not None:

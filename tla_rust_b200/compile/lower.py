@@ -1857,6 +1857,9 @@ class Lowering:
         if k == "prime":
             self.cc(n.a[0], env, ctx, "P", lt, lf)
             return
+        if k == "unchanged":
+            self.cc_eq(Node("prime", (n.a[0],), n.line, n.col), n.a[0], env, ctx, base, lt, lf, n)
+            return
         if k == "forall" or k == "exists":
             bounds, body = n.a
             is_all = k == "forall"
@@ -2564,6 +2567,21 @@ class Lowering:
             if missing:
                 raise CompileError(f"action {act[1] if act else 'Next'} does not assign {missing}")
             aid = self._action_id(act)
+            # refinement PROPERTYs: every transition must satisfy [Next2]_v2 (checked like TLC's action
+            # properties, on every generated successor); a violation is reported through ASSERTF
+            for nm, _inits, nxt2, sub2, c2 in getattr(m, "refinements", []):
+                if nxt2 is None:
+                    continue
+                ok, bad = Label("pok"), Label("pbad")
+                mk = self.mark()
+                self.bound = allv
+                step = Node("or", ((nxt2, Node("unchanged", (sub2,))),))
+                self.cc(step, {}, c2, "N", ok, bad)
+                self.release(mk)
+                self.asm.label(bad)
+                self.asserts.append(("\x00property:" + nm, nxt2.loc()))
+                self.asm.emit("ASSERTF", len(self.asserts) - 1)
+                self.asm.label(ok)
             if m.constraints or m.action_constraints:
                 ok, bad, end = Label("cok"), Label("cbad"), Label("cend")
                 mk = self.mark()

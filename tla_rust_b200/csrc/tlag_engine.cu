@@ -98,13 +98,17 @@ struct tlag_engine {
 // returns 1 if fp was inserted by this call, 0 if already present, -1 if the table is full
 __device__ __forceinline__ int seen_insert(unsigned long long* table, unsigned long long mask,
                                            unsigned long long fp) {
-  // One L2 round trip per probe: the CAS itself is the read (at load <= 0.5 the first slot is almost
-  // always either empty or the duplicate); ncu showed the read-then-CAS form latency-bound.
+  // read first, CAS only on an empty slot: measured 6.1 ms vs 7.9 ms for a CAS-first probe on the
+  // 2^27-candidate K1 batch (atomics are throughput-limited at L2; duplicates need no atomic at all)
   unsigned long long i = fp & mask;
   for (unsigned long long probes = 0; probes <= mask; ++probes) {
-    const unsigned long long old = atomicCAS(&table[i], 0ULL, fp);
-    if (old == 0ULL) return 1;
-    if (old == fp) return 0;
+    const unsigned long long cur = __ldcv(&table[i]);
+    if (cur == fp) return 0;
+    if (cur == 0ULL) {
+      const unsigned long long old = atomicCAS(&table[i], 0ULL, fp);
+      if (old == 0ULL) return 1;
+      if (old == fp) return 0;
+    }
     i = (i + 1) & mask;
   }
   return -1;
@@ -322,13 +326,15 @@ __global__ void __launch_bounds__(256) k_probe(const uint32_t* __restrict__ stat
 // exactly once; ncu on the strided v0 showed 2.4x DRAM read amplification from L1 thrash), staged in
 // shared memory with an odd row stride (W|1 words -> conflict-free), then each thread fingerprints its
 // own row and probes the table.
+#define TLAG_PROBE_ROWS 2   /* rows per thread: two independent probes in flight per thread */
 __global__ void __launch_bounds__(256) k_probe_staged(const uint32_t* __restrict__ states, unsigned long long n, int W,
                                                       unsigned long long* table, unsigned long long mask,
                                                       uint8_t* __restrict__ is_new, Counters* ctr) {
   extern __shared__ uint32_t s_rows[];
   const int stride = W | 1;
-  const unsigned long long base = (unsigned long long)blockIdx.x * 256ULL;
-  const unsigned nst = (unsigned)((n - base) < 256ULL ? (n - base) : 256ULL);
+  const unsigned ROWS = 256 * TLAG_PROBE_ROWS;
+  const unsigned long long base = (unsigned long long)blockIdx.x * ROWS;
+  const unsigned nst = (unsigned)((n - base) < (unsigned long long)ROWS ? (n - base) : (unsigned long long)ROWS);
   const uint32_t* g = states + base * (unsigned long long)W;
   const unsigned total = nst * (unsigned)W;          // words in this CTA's span
   const unsigned total4 = total >> 2;
@@ -347,16 +353,39 @@ __global__ void __launch_bounds__(256) k_probe_staged(const uint32_t* __restrict
     s_rows[row * stride + col] = g[wi];
   }
   __syncthreads();
-  if (threadIdx.x >= nst) return;
-  const uint32_t* r = s_rows + threadIdx.x * stride;
-  uint64_t h = tlag_fp_init(W);
-  int k = 0;
-  for (; k + 1 < W; k += 2) h = tlag_fp_pair(h, r[k], r[k + 1]);
-  if (k < W) h = tlag_fp_tail(h, r[k]);
-  const unsigned long long fp = tlag_fp_final(h, W);
-  int ins = seen_insert(table, mask, fp);
-  if (ins < 0) { atomicExch(&ctr->table_full, 1ULL); ins = 0; }
-  is_new[base + threadIdx.x] = (uint8_t)ins;
+  unsigned long long fp[TLAG_PROBE_ROWS];
+  unsigned long long slot[TLAG_PROBE_ROWS];
+  unsigned long long cur[TLAG_PROBE_ROWS];
+  bool live[TLAG_PROBE_ROWS];
+#pragma unroll
+  for (int q = 0; q < TLAG_PROBE_ROWS; ++q) {
+    const unsigned row = threadIdx.x + 256u * q;
+    live[q] = row < nst;
+    const uint32_t* r = s_rows + (live[q] ? row : 0) * stride;
+    uint64_t h = tlag_fp_init(W);
+    int k = 0;
+    for (; k + 1 < W; k += 2) h = tlag_fp_pair(h, r[k], r[k + 1]);
+    if (k < W) h = tlag_fp_tail(h, r[k]);
+    fp[q] = tlag_fp_final(h, W);
+    slot[q] = fp[q] & mask;
+  }
+  // first probe of every row issued back to back (independent loads in flight), then resolved
+#pragma unroll
+  for (int q = 0; q < TLAG_PROBE_ROWS; ++q) cur[q] = live[q] ? __ldcv(&table[slot[q]]) : 0ULL;
+#pragma unroll
+  for (int q = 0; q < TLAG_PROBE_ROWS; ++q) {
+    if (!live[q]) continue;
+    int ins;
+    if (cur[q] == fp[q]) ins = 0;
+    else if (cur[q] == 0ULL) {
+      const unsigned long long old = atomicCAS(&table[slot[q]], 0ULL, fp[q]);
+      ins = (old == 0ULL) ? 1 : (old == fp[q] ? 0 : seen_insert(table, mask, fp[q]));
+    } else {
+      ins = seen_insert(table, mask, fp[q]);        // collision chain: generic path from the home slot
+    }
+    if (ins < 0) { atomicExch(&ctr->table_full, 1ULL); ins = 0; }
+    is_new[base + threadIdx.x + 256u * q] = (uint8_t)ins;
+  }
 }
 
 // insert routed records (W state words + parent + meta) into this rank's shard
@@ -416,7 +445,7 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   if (blocks == 0) blocks = 1;
   size_t smem = e->p.code_in_smem ? (size_t)e->p.code_len * 8 : 0;
   void (*fn)(DevParams, unsigned long long, unsigned long long) = nullptr;
-  static const bool dense = getenv("TLAG_WAVE_MINB4") != nullptr;   // A/B knob: 4 CTAs/SM (32 regs) vs 3 (40 regs)
+  static const bool dense = getenv("TLAG_WAVE_MINB3") == nullptr;   // 4 CTAs/SM (32 regs; measured +4.5 %) unless TLAG_WAVE_MINB3 is set
   switch (e->frame_class) {
     case 0: fn = dense ? k_wave<64, MODE, 4> : k_wave<64, MODE, 3>; break;
     case 1: fn = dense ? k_wave<128, MODE, 4> : k_wave<128, MODE, 3>; break;
@@ -598,9 +627,10 @@ static int launch_probe(tlag_engine* e, const uint32_t* d_states, uint64_t n, ui
   if (n == 0) return TLAG_OK;
   const bool a16 = ((uintptr_t)d_states % 16) == 0, a8 = ((uintptr_t)d_states % 8) == 0;
   if (a16 && W >= 2) {
-    const size_t smem = (size_t)256 * (size_t)(W | 1) * 4;
+    const size_t smem = (size_t)256 * TLAG_PROBE_ROWS * (size_t)(W | 1) * 4;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_probe_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_probe_staged<<<blocks, 256, smem, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
+    const unsigned sblocks = (unsigned)((n + 256 * TLAG_PROBE_ROWS - 1) / (256 * TLAG_PROBE_ROWS));
+    k_probe_staged<<<sblocks, 256, smem, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
   } else if (W % 4 == 0 && a16) k_probe<4><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
   else if (W % 2 == 0 && a8) k_probe<2><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
   else k_probe<1><<<blocks, 256, 0, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);

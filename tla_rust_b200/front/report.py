@@ -4,7 +4,7 @@ from __future__ import annotations
 
 from .values import fmt
 
-OK, INVARIANT, ASSERT, DEADLOCK, EVAL_ERROR = "ok", "invariant", "assert", "deadlock", "eval_error"
+OK, INVARIANT, ASSERT, DEADLOCK, EVAL_ERROR, PROPERTY = "ok", "invariant", "assert", "deadlock", "eval_error", "property"
 
 
 class CheckResult:
@@ -67,6 +67,8 @@ def format_result(res: CheckResult, var_order, module):
             out.append(f"Error: Invariant {res.invariant} is violated.")
         elif res.verdict == DEADLOCK:
             out.append("Error: Deadlock reached.")
+        elif res.verdict == PROPERTY:
+            out.append(f"Error: Action property {res.invariant} is violated.")
         else:
             out.append(f"Error: {res.error_text}")
         out.append(format_trace(res, var_order, module))

@@ -344,8 +344,19 @@ class Model:
         for nm in cfg.action_constraints:
             d, c = self._def(nm)
             self.action_constraints.append((nm, d.body, c))
-        # PROPERTYs: safety part  Init2 /\ [][Next2]_v2  -> refinement obligations (oracle / "next" row)
+        # PROPERTYs: the safety part  Init2 /\ [][Next2]_v2  becomes a refinement obligation: Init => Init2 and
+        # every transition satisfies [Next2]_v2 (MCPaxos.cfg:12, MCVoting.cfg:9, HourClock2.cfg:9); the
+        # liveness part (fairness, <>, ~>) is out of scope and ignored with a warning.
         self.properties = list(cfg.properties)
+        self.refinements = []
+        for nm in cfg.properties:
+            d, c = self._def(nm)
+            acc = {"init": [], "next": None, "sub": None, "ctx": None, "live": False}
+            self._split_prop(d.body, c, acc)
+            if acc["live"]:
+                self.warnings.append(f"PROPERTY {nm}: temporal (liveness) conjuncts are not checked")
+            if acc["next"] is not None or acc["init"]:
+                self.refinements.append((nm, acc["init"], acc["next"], acc["sub"], acc["ctx"]))
         self.symmetry = cfg.symmetry
         self.check_deadlock = True if cfg.check_deadlock is None else cfg.check_deadlock
 
@@ -376,6 +387,37 @@ class Model:
             self.fairness_ignored = True
             return
         self.init_nodes.append((n, ctx))
+
+    def _split_prop(self, n, ctx, acc):
+        if n.k == "and":
+            for x in n.a[0]:
+                self._split_prop(x, ctx, acc)
+            return
+        if n.k == "box" and n.a[0].k == "abox":
+            acc["next"], acc["sub"], acc["ctx"] = n.a[0].a[0], n.a[0].a[1], ctx
+            return
+        if n.k == "id":
+            d = ctx.defs.get(n.a[0])
+            if d is not None and not d[0].params and _has_temporal(d[0].body, d[1]):
+                self._split_prop(d[0].body, d[1], acc)
+                return
+        if n.k == "sel":
+            r = self.ev.resolve_sel(n.a[0], {}, Fr(ctx))
+            if r[0] == "def" and _has_temporal(r[1].body, r[2]):
+                self._split_prop(r[1].body, r[2], acc)
+                return
+        if _has_temporal(n, ctx):
+            acc["live"] = True
+            return
+        acc["init"].append((n, ctx))
+
+    def check_refinement_init(self, st):
+        """Init => Init2 for every refinement PROPERTY; returns the name of a violated property or None."""
+        for nm, inits, _, _, _ in self.refinements:
+            for node, c in inits:
+                if self.ev.eval(node, {}, Fr(c, st, None)) is not True:
+                    return nm
+        return None
 
     # -- evaluation helpers ------------------------------------------------------
     def check_assumes(self):
