@@ -91,6 +91,9 @@ int  tlag_result_now(tlag_engine *e, tlag_result *out);        /* counters so fa
 int  tlag_trace(tlag_engine *e, uint64_t state_idx, uint32_t *states_out, int32_t *actions_out,
                 uint32_t *len_inout);
 int  tlag_read_states(tlag_engine *e, uint64_t first, uint64_t n, uint32_t *states_out);
+/* Checksum of checksums over every stored state: XOR and SUM (mod 2^64) of the 64-bit fingerprints
+ * (size-independent parity property for state spaces too large to read back). */
+int  tlag_digest(tlag_engine *e, uint64_t *xor_out, uint64_t *sum_out);
 /* K1 alone (fingerprint + seen-set probe/insert) on caller-provided HOST states: unit tests
  * and the e2e leg of the roofline bench.  is_new[i] = 1 iff state i was not in the set. */
 int  tlag_probe_batch(tlag_engine *e, const uint32_t *states, uint64_t n, uint8_t *is_new);
@@ -110,8 +113,10 @@ const char *tlag_version(void);
 /* Expand the current frontier WITHOUT inserting: successor records (W state words + parent
  * index + action id, record = W+2 u32) are bucketed by owner rank = fingerprint >> (64-log2 R)
  * ... into d_send (device, capacity cap_records), counts[r] records per rank (host out). */
-int  tlag_expand_route(tlag_engine *e, uint32_t n_ranks, uint64_t d_send, uint64_t cap_records,
-                       uint64_t *counts, tlag_wave_stats *out);
+int  tlag_frontier(tlag_engine *e, uint64_t *first_idx, uint64_t *count);   /* current frontier slice */
+/* `first`/`count` select a sub-range of the frontier (chunked exchange with bounded buffers). */
+int  tlag_expand_route(tlag_engine *e, uint32_t n_ranks, uint64_t first, uint64_t count, uint64_t d_send,
+                       uint64_t cap_records, uint64_t *counts, tlag_wave_stats *out);
 /* Insert received records (device buffer) into this rank's seen-set shard / state store. */
 int  tlag_insert_records(tlag_engine *e, uint64_t d_recv, uint64_t n_records, uint32_t src_rank_unused,
                          uint64_t *n_new);

@@ -328,8 +328,13 @@ void tlagcpu_shard_seed(cpu_shard *s, const uint32_t *init, uint64_t n) {
 
 /* expand frontier [lo,hi): successors bucketed by owner = floor(fp * n_ranks / 2^64) into
  * send[owner * region_cap ...]; counts[r] records per rank.  Returns verdict kind (0 none). */
-int tlagcpu_shard_expand_route(cpu_shard *s, uint32_t n_ranks, uint32_t *send, uint64_t cap_records, uint64_t *counts,
-                               uint64_t *generated_out) {
+void tlagcpu_shard_frontier(cpu_shard *s, uint64_t *out2) {
+  if (s->level == 0) { s->level = 1; s->lo = 0; s->depth = s->hi ? 1 : 0; }
+  out2[0] = s->lo; out2[1] = s->hi - s->lo;
+}
+
+int tlagcpu_shard_expand_route(cpu_shard *s, uint32_t n_ranks, uint64_t first, uint64_t count, uint32_t *send,
+                               uint64_t cap_records, uint64_t *counts, uint64_t *generated_out) {
   const cpu_model *m = &s->e.m;
   const int W = (int)m->W;
   const uint64_t region = cap_records / n_ranks;
@@ -339,7 +344,10 @@ int tlagcpu_shard_expand_route(cpu_shard *s, uint32_t n_ranks, uint32_t *send, u
   if (s->level == 0) { s->level = 1; s->lo = 0; s->depth = s->hi ? 1 : 0; }
   for (uint32_t r = 0; r < n_ranks; ++r) counts[r] = 0;
   int kind = 0;
-  for (uint64_t idx = s->lo; idx < s->hi; ++idx) {
+  uint64_t c_lo = s->lo + first, c_hi = c_lo + count;
+  if (c_lo > s->hi) c_lo = s->hi;
+  if (c_hi > s->hi) c_hi = s->hi;
+  for (uint64_t idx = c_lo; idx < c_hi; ++idx) {
     tlag_unpack(m->layout, (int)m->n_slots, s->e.states + idx * W, frame);
     if (m->n_invariants) {
       uint32_t pc = m->entry_inv;

@@ -37,11 +37,16 @@ class CpuShardEngine:
         a = np.ascontiguousarray(init, dtype=np.uint32).reshape(-1, self.cm.W)
         self.L.tlagcpu_shard_seed(self.h, a.ctypes.data_as(C.c_void_p), C.c_uint64(a.shape[0]))
 
-    def expand_route(self, n_ranks, send_ptr, cap_records):
+    def frontier(self):
+        out = (C.c_uint64 * 2)()
+        self.L.tlagcpu_shard_frontier(self.h, out)
+        return int(out[0]), int(out[1])
+
+    def expand_route(self, n_ranks, first, count, send_ptr, cap_records):
         counts = (C.c_uint64 * n_ranks)()
         gen = C.c_uint64()
-        kind = self.L.tlagcpu_shard_expand_route(self.h, C.c_uint32(n_ranks), C.c_void_p(send_ptr),
-                                                 C.c_uint64(cap_records), counts, C.byref(gen))
+        kind = self.L.tlagcpu_shard_expand_route(self.h, C.c_uint32(n_ranks), C.c_uint64(first), C.c_uint64(count),
+                                                 C.c_void_p(send_ptr), C.c_uint64(cap_records), counts, C.byref(gen))
         assert kind >= 0
         return [int(c) for c in counts], {"verdict": kind if kind else 5, "generated": int(gen.value)}
 
@@ -73,7 +78,7 @@ def _worker(rank, world, port, name, q):
     from tla_rust_b200.fingerprint import fingerprint_words
     cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
     e = CpuShardEngine(cm, deadlock=info["deadlock"])
-    d = DistributedBFS(e, cm, rank, world, "cpu", cap_records=1 << 16)
+    d = DistributedBFS(e, cm, rank, world, "cpu", cap_records=1 << 16, chunk_states=500)
     d.seed(init, [fingerprint_words(w) for w in init])
     out = d.run()
     if rank == 0:

@@ -18,7 +18,7 @@ def _engine(cm, **kw):
 
 
 @pytest.mark.parametrize("name", ["atomic_add", "pcal_intro", "pcal_intro_readme_buggy", "MCPaxos", "MCVoting",
-                                  "HourClock", "AsynchInterface", "MCPaxos3", "MCPaxos3_b2", "MCPaxos3_b3"])
+                                  "HourClock", "AsynchInterface", "MCPaxos3", "MCPaxos3_b2", "MCPaxos3_b3", "MCPaxos3_b4"])
 def test_bfs_matches_oracle(name):
     from oracle import cpu_engine
     cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
@@ -38,9 +38,12 @@ def test_bfs_matches_oracle(name):
     assert levels == o2["levels"]
     if r["verdict"] == 2:   # which Assert site is hit first depends on the (parallel) discovery order
         assert cm.asserts[r["detail"]][0] == cm.asserts[o2["detail"]][0]
-    # bit-exact state set: fingerprint digest of everything the GPU stored (checksum of checksums)
-    states = e.read_states(0, r["distinct"])
-    assert cpu_engine.digest(states, cm.W) == (o2["fp_xor"], o2["fp_sum"])
+    # bit-exact state set: fingerprint digest of everything the GPU stored (checksum of checksums);
+    # MCPaxos3_b4 is the BASELINE-size case (352,133,865 states): digest computed on the device
+    assert e.digest() == (o2["fp_xor"], o2["fp_sum"])
+    if r["distinct"] <= 1 << 20:
+        states = e.read_states(0, r["distinct"])
+        assert cpu_engine.digest(states, cm.W) == (o2["fp_xor"], o2["fp_sum"])
     if "o1" in exp and exp["o1"]["verdict"] == "ok":
         assert (r["generated"], r["distinct"], r["depth"]) == (exp["o1"]["generated"], exp["o1"]["distinct"],
                                                                exp["o1"]["depth"])

@@ -90,6 +90,7 @@ struct tlag_engine {
   int sm_count = 148;
   int frame_class = 0;
   bool restarting = false;
+  double growth_hint = 4.0;
   std::string err;
   uint32_t* d_scratch = nullptr; uint64_t scratch_words = 0; uint8_t* d_flags = nullptr; uint64_t flags_cap = 0;
 };
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(256) k_probe(const uint32_t* __restrict__ stat
 // exactly once; ncu on the strided v0 showed 2.4x DRAM read amplification from L1 thrash), staged in
 // shared memory with an odd row stride (W|1 words -> conflict-free), then each thread fingerprints its
 // own row and probes the table.
-#define TLAG_PROBE_ROWS 2   /* rows per thread: two independent probes in flight per thread */
+#define TLAG_PROBE_ROWS 1   /* rows per thread: two independent probes in flight per thread */
 __global__ void __launch_bounds__(256) k_probe_staged(const uint32_t* __restrict__ states, unsigned long long n, int W,
                                                       unsigned long long* table, unsigned long long mask,
                                                       uint8_t* __restrict__ is_new, Counters* ctr) {
@@ -423,6 +424,20 @@ __global__ void __launch_bounds__(256) k_insert_records(DevParams p, const uint3
       }
     }
   }
+}
+
+// checksum of checksums over the state store: XOR and SUM (mod 2^64) of all fingerprints
+__global__ void k_digest(DevParams p, unsigned long long n, unsigned long long* out2) {
+  unsigned long long x = 0, sm = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    uint32_t w[TLAG_MAXW];
+    for (int k = 0; k < p.W; ++k) w[k] = p.states[i * (unsigned long long)p.W + k];
+    const unsigned long long fp = tlag_fingerprint(w, p.W);
+    x ^= fp; sm += fp;
+  }
+  for (int o = 16; o > 0; o >>= 1) { x ^= __shfl_down_sync(0xffffffffu, x, o); sm += __shfl_down_sync(0xffffffffu, sm, o); }
+  if ((threadIdx.x & 31) == 0) { atomicXor(&out2[0], x); atomicAdd(&out2[1], sm); }
 }
 
 // rebuild the table from the state store after growing it
@@ -768,7 +783,7 @@ extern "C" int tlag_step(tlag_engine* e, tlag_wave_stats* out) {
   if (e->verdict != TLAG_V_RUNNING) { if (out) out->verdict = e->verdict; return TLAG_OK; }
   const uint64_t lo = e->lo, hi = e->hi;
   if (lo >= hi) { e->verdict = TLAG_V_OK; if (out) out->verdict = e->verdict; return TLAG_OK; }
-  int r = grow_store_if_needed(e, hi + (hi - lo) * 4 + 4096);
+  int r = grow_store_if_needed(e, hi + (uint64_t)((double)(hi - lo) * e->growth_hint) + 4096);
   if (r) return r;
   r = grow_table_if_needed(e, hi + (hi - lo) * 2);
   if (r) return r;
@@ -796,6 +811,10 @@ extern "C" int tlag_step(tlag_engine* e, tlag_wave_stats* out) {
     out->kernel_ms = ms;
   }
   if (n_states > hi) e->depth = e->level + 1;
+  {  // head-room for the next level: twice the observed discovered/expanded ratio, at least 4x
+    const double ratio = (double)(n_states - hi) / (double)(hi - lo);
+    e->growth_hint = ratio * 2.0 > 4.0 ? ratio * 2.0 : 4.0;
+  }
   e->lo = hi; e->hi = n_states; e->level += 1;
   if (e->verdict == TLAG_V_RUNNING && e->lo >= e->hi) e->verdict = TLAG_V_OK;
   if (e->verdict != TLAG_V_RUNNING && e->verdict != TLAG_V_OK && (e->m.flags & TLAG_F_KEEP_GOING)) {
@@ -834,6 +853,26 @@ extern "C" int tlag_read_states(tlag_engine* e, uint64_t first, uint64_t n, uint
   return TLAG_OK;
 }
 
+extern "C" int tlag_digest(tlag_engine* e, uint64_t* xor_out, uint64_t* sum_out) {
+  if (!e || !xor_out || !sum_out) return TLAG_EINVAL;
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  unsigned long long* d2 = nullptr;
+  CK(cudaMalloc(&d2, 16));
+  CK(cudaMemsetAsync(d2, 0, 16, e->stream));
+  if (hc.n_states) {
+    k_digest<<<e->sm_count * 8, 256, 0, e->stream>>>(e->p, hc.n_states, d2);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  unsigned long long h2[2];
+  CK(cudaMemcpyAsync(h2, d2, 16, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(d2);
+  *xor_out = h2[0]; *sum_out = h2[1];
+  return TLAG_OK;
+}
+
 extern "C" int tlag_trace(tlag_engine* e, uint64_t state_idx, uint32_t* states_out, int32_t* actions_out, uint32_t* len_inout) {
   if (!e || !len_inout) return TLAG_EINVAL;
   Counters hc;
@@ -865,17 +904,29 @@ extern "C" int tlag_trace(tlag_engine* e, uint64_t state_idx, uint32_t* states_o
 }
 
 // ---- multi-GPU building blocks -----------------------------------------------------
-extern "C" int tlag_expand_route(tlag_engine* e, uint32_t n_ranks, uint64_t d_send, uint64_t cap_records,
-                                 uint64_t* counts, tlag_wave_stats* out) {
+extern "C" int tlag_frontier(tlag_engine* e, uint64_t* first_idx, uint64_t* count) {
+  if (!e) return TLAG_EINVAL;
+  if (e->level == 0) { e->level = 1; e->lo = 0; e->depth = e->hi > 0 ? 1 : 0; }
+  if (first_idx) *first_idx = e->lo;
+  if (count) *count = e->hi - e->lo;
+  return TLAG_OK;
+}
+
+extern "C" int tlag_expand_route(tlag_engine* e, uint32_t n_ranks, uint64_t first, uint64_t count, uint64_t d_send,
+                                 uint64_t cap_records, uint64_t* counts, tlag_wave_stats* out) {
   if (!e || !counts || n_ranks == 0 || n_ranks > 16) return TLAG_EINVAL;
   if (out) memset(out, 0, sizeof(*out));
   if (e->level == 0) { e->level = 1; e->lo = 0; e->depth = 1; }
-  const uint64_t lo = e->lo, hi = e->hi;
+  uint64_t lo = e->lo + first, hi = lo + count;
+  if (lo > e->hi) lo = e->hi;
+  if (hi > e->hi) hi = e->hi;
   e->p.n_ranks = (int)n_ranks;
   e->p.send = (uint32_t*)(uintptr_t)d_send;
   e->p.region_cap = cap_records / n_ranks;
   CK(cudaMemsetAsync(&e->d_ctr->work, 0, 8, e->stream));
   CK(cudaMemsetAsync(e->d_ctr->send_count, 0, sizeof(unsigned long long) * 16, e->stream));
+  CK(cudaMemsetAsync(&e->d_ctr->route_overflow, 0, 8, e->stream));   // a failed attempt may be retried with
+  CK(cudaMemsetAsync(&e->d_ctr->generated, 0, 8, e->stream));        // larger regions: start from clean counters
   CK(cudaEventRecord(e->ev0, e->stream));
   if (hi > lo) {
     cudaError_t ce = launch_wave<1>(e, lo, hi);

@@ -1,10 +1,10 @@
 """Multi-GPU BFS: one process per GPU, fingerprint space hash-range
-partitioned across ranks.  Per BFS level each rank expands its frontier shard
-(tlag_expand_route: successors bucketed by owner = high bits of the fingerprint), the
-buckets are exchanged with ONE all-to-all over NCCL/NVLink, and every owner inserts what it
-received into its seen-set shard / state store (tlag_insert_records) -- the received states
-are that rank's share of the next frontier, so the frontier stays balanced by the hash.
-A 3-word all-reduce decides termination.  torch.distributed is plumbing only."""
+partitioned across ranks.  Per BFS level each rank expands its frontier shard in chunks
+(tlag_expand_route: successors bucketed by owner = high bits of the fingerprint), each
+chunk's buckets are exchanged with ONE all-to-all over NCCL/NVLink, and every owner inserts
+what it received into its seen-set shard / state store (tlag_insert_records) -- the received
+states are that rank's share of the next frontier, so the frontier stays balanced by the hash.
+A 3-word all-reduce per level decides termination.  torch.distributed is plumbing only."""
 from __future__ import annotations
 
 import numpy as np
@@ -32,13 +32,15 @@ def _all_to_all(outs, ins, rank):
 
 
 class DistributedBFS:
-    def __init__(self, engine, cm, rank, world, device, cap_records=1 << 22):
+    def __init__(self, engine, cm, rank, world, device, cap_records=1 << 24, chunk_states=1 << 21):
         self.e, self.cm, self.rank, self.world, self.device = engine, cm, rank, world, device
         self.rec_words = cm.W + 2
-        self.cap_records = cap_records
+        self.cap_records = cap_records          # send-buffer capacity in records (all destinations together)
+        self.chunk_states = chunk_states        # frontier states expanded per exchange
         self.send = torch.empty(cap_records * self.rec_words, dtype=torch.int32, device=device)
         self.recv = torch.empty(cap_records * self.rec_words, dtype=torch.int32, device=device)
         self.comm_ms = 0.0
+        self.exchanges = 0
 
     def seed(self, init_words: np.ndarray, fingerprints):
         """Every rank sees all initial states and keeps those it owns (owner = umulhi(fp, world))."""
@@ -48,54 +50,67 @@ class DistributedBFS:
         self.e.seed(mine)
         self.n_init_total = len(init_words)
 
-    def run(self, max_levels=1 << 20):
+    def _exchange_chunk(self, first, count, on_gpu, ev):
         e, world, rw = self.e, self.world, self.rec_words
+        while True:
+            try:
+                counts, ws = e.expand_route(world, first, count, self.send.data_ptr(), self.cap_records)
+                break
+            except Exception as ex:  # noqa: BLE001 -- send regions too small for this chunk: grow and redo
+                if "overflow" not in str(ex) or self.cap_records >= (1 << 30):
+                    raise
+                self.cap_records *= 2
+                self.send = torch.empty(self.cap_records * rw, dtype=torch.int32, device=self.device)
         region = self.cap_records // world
+        cnt = torch.tensor(counts, dtype=torch.int64, device=self.device)
+        if on_gpu:
+            ev[0].record()
+        rl = [torch.empty(1, dtype=torch.int64, device=self.device) for _ in range(world)]
+        _all_to_all(rl, [cnt[r:r + 1].clone() for r in range(world)], self.rank)
+        rc = torch.cat(rl).tolist()
+        tot = sum(rc)
+        if tot * rw > self.recv.numel():
+            self.recv = torch.empty(int(tot * 1.5) * rw, dtype=torch.int32, device=self.device)
+        ins = [self.send[r * region * rw:(r * region + counts[r]) * rw] for r in range(world)]
+        outs, o = [], 0
+        for r in range(world):
+            outs.append(self.recv[o * rw:(o + rc[r]) * rw])
+            o += rc[r]
+        _all_to_all(outs, ins, self.rank)
+        if on_gpu:
+            ev[1].record()
+            torch.cuda.synchronize()
+            self.comm_ms += ev[0].elapsed_time(ev[1])
+        self.exchanges += 1
+        n_new = e.insert_records(self.recv.data_ptr(), tot)
+        return n_new, ws
+
+    def run(self, max_levels=1 << 20):
+        e = self.e
         levels = 0
         on_gpu = str(self.device).startswith("cuda")
-        if on_gpu:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if on_gpu else None
         verdict = 5
         while levels < max_levels:
-            while True:
-                try:
-                    counts, ws = e.expand_route(world, self.send.data_ptr(), self.cap_records)
-                    break
-                except Exception as ex:  # noqa: BLE001 -- send regions too small for this level: grow and redo
-                    if "overflow" not in str(ex) or self.cap_records >= (1 << 30):
-                        raise
-                    self.cap_records *= 4
-                    self.send = torch.empty(self.cap_records * rw, dtype=torch.int32, device=self.device)
-                    region = self.cap_records // world
-            cnt = torch.tensor(counts, dtype=torch.int64, device=self.device)
-            rcnt = torch.empty_like(cnt)
-            if on_gpu:
-                ev0.record()
-            rl = [torch.empty(1, dtype=torch.int64, device=self.device) for _ in range(world)]
-            _all_to_all(rl, [cnt[r:r + 1].clone() for r in range(world)], self.rank)
-            rcnt = torch.cat(rl)
-            rc = rcnt.tolist()
-            tot = sum(rc)
-            if tot * rw > self.recv.numel():
-                self.recv = torch.empty(int(tot * 1.5) * rw, dtype=torch.int32, device=self.device)
-            ins = [self.send[r * region * rw:(r * region + counts[r]) * rw] for r in range(world)]
-            outs, o = [], 0
-            for r in range(world):
-                outs.append(self.recv[o * rw:(o + rc[r]) * rw])
-                o += rc[r]
-            _all_to_all(outs, ins, self.rank)
-            if on_gpu:
-                ev1.record()
-                torch.cuda.synchronize()
-                self.comm_ms += ev0.elapsed_time(ev1)
-            n_new = e.insert_records(self.recv.data_ptr(), tot)
-            adv = e.advance_level()
-            flag = torch.tensor([n_new, ws["verdict"] if ws["verdict"] not in (0, 5) else 0, ws["generated"]],
-                                dtype=torch.int64, device=self.device)
+            _, fr = e.frontier()
+            nch = torch.tensor([(fr + self.chunk_states - 1) // self.chunk_states], dtype=torch.int64,
+                               device=self.device)
+            dist.all_reduce(nch, op=dist.ReduceOp.MAX)
+            n_new, gen, bad = 0, 0, 0
+            for c in range(int(nch.item())):
+                first = c * self.chunk_states
+                count = max(0, min(self.chunk_states, fr - first))
+                nn, ws = self._exchange_chunk(first, count, on_gpu, ev)
+                n_new += nn
+                gen += ws["generated"]
+                if ws["verdict"] not in (0, 5):
+                    bad = ws["verdict"]
+            e.advance_level()
+            flag = torch.tensor([n_new, bad, gen], dtype=torch.int64, device=self.device)
             dist.all_reduce(flag, op=dist.ReduceOp.SUM)
             levels += 1
             if flag[1].item() != 0:
-                verdict = ws["verdict"]
+                verdict = bad or 1
                 break
             if flag[0].item() == 0:
                 verdict = 0

@@ -58,9 +58,9 @@ class TlagResult(C.Structure):
 
 
 EXPORTS = ["tlag_create", "tlag_seed", "tlag_step", "tlag_run", "tlag_result_now", "tlag_trace",
-           "tlag_read_states", "tlag_probe_batch", "tlag_probe_batch_device", "tlag_reset_table", "tlag_restart",
+           "tlag_read_states", "tlag_digest", "tlag_probe_batch", "tlag_probe_batch_device", "tlag_reset_table", "tlag_restart",
            "tlag_kernel_launches", "tlag_destroy", "tlag_last_error", "tlag_version",
-           "tlag_expand_route", "tlag_insert_records", "tlag_advance_level"]
+           "tlag_frontier", "tlag_expand_route", "tlag_insert_records", "tlag_advance_level"]
 
 
 def build_library(verbose=False):
@@ -159,6 +159,11 @@ class Engine:
                  "tlag_read_states")
         return out
 
+    def digest(self):
+        x, s_ = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.tlag_digest(self.h, C.byref(x), C.byref(s_)), "tlag_digest")
+        return int(x.value), int(s_.value)
+
     def probe_batch(self, states: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(states, dtype=np.uint32).reshape(-1, self.cm.W)
         flags = np.zeros(a.shape[0], dtype=np.uint8)
@@ -182,11 +187,17 @@ class Engine:
         return int(self.L.tlag_kernel_launches(self.h))
 
     # multi-GPU building blocks
-    def expand_route(self, n_ranks, d_send_ptr, cap_records):
+    def frontier(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.tlag_frontier(self.h, C.byref(a), C.byref(b)), "tlag_frontier")
+        return int(a.value), int(b.value)
+
+    def expand_route(self, n_ranks, first, count, d_send_ptr, cap_records):
         counts = (C.c_uint64 * n_ranks)()
         ws = WaveStats()
-        self._ck(self.L.tlag_expand_route(self.h, C.c_uint32(n_ranks), C.c_uint64(d_send_ptr),
-                                          C.c_uint64(cap_records), counts, C.byref(ws)), "tlag_expand_route")
+        self._ck(self.L.tlag_expand_route(self.h, C.c_uint32(n_ranks), C.c_uint64(first), C.c_uint64(count),
+                                          C.c_uint64(d_send_ptr), C.c_uint64(cap_records), counts, C.byref(ws)),
+                 "tlag_expand_route")
         return [int(c) for c in counts], ws.as_dict()
 
     def insert_records(self, d_recv_ptr, n_records) -> int:
