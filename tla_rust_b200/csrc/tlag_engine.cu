@@ -134,33 +134,38 @@ __device__ __forceinline__ void report_min(unsigned long long* slot, unsigned lo
 // took different branches re-join as soon as the laggards catch up (forward progress is by
 // construction: the lowest pc always advances).
 enum { L_RUN = 0, L_EMIT = 1, L_DONE = 2, L_STOP = 3 };
+#define TLAG_PC_PARKED 0xFFFFFFFFu
 
-__device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ code, const int32_t* __restrict__ cpool,
-                                        int32_t* frame, uint32_t& pc, int& st, int& ev_out, int32_t& info,
-                                        int32_t& info2) {
-  for (uint32_t steps = 0;; ++steps) {
-    const uint32_t mypc = (st == L_RUN) ? pc : 0xFFFFFFFFu;
-    const uint32_t pcm = __reduce_min_sync(0xffffffffu, mypc);
-    if (pcm == 0xFFFFFFFFu) break;
-    const uint64_t w = code[pcm];
-    if (mypc == pcm) {
+// A lane that is not running parks its pc at TLAG_PC_PARKED (so it never wins the min) and keeps the
+// pc to resume from in `rpc`.  Per step: one REDUX min, one shared-memory broadcast fetch, uniform
+// decode/dispatch; only lanes whose pc equals the minimum execute.  (v1 of this loop spent 41 of ~73
+// SASS instructions per step on bookkeeping and fetched the instruction with a generic per-lane load:
+// profiles/r1_k_wave_warpsched_b2_ncu.txt.)
+template <bool SMEM>
+__device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, const uint64_t* scode,
+                                        const int32_t* __restrict__ cpool, int32_t* frame, uint32_t& pc,
+                                        uint32_t& rpc, int& ev_out, int32_t& info, int32_t& info2) {
+  for (;;) {
+    const uint32_t pcm = __reduce_min_sync(0xffffffffu, pc);
+    if (pcm == TLAG_PC_PARKED) break;
+    const uint64_t w = SMEM ? scode[pcm] : __ldg(gcode + pcm);
+    if (pc == pcm) {
       const int ev = tlag_vm_exec(w, cpool, frame, &pc, &info, &info2);
-      if (ev >= 0) { ev_out = ev; st = L_STOP; }
+      if (ev >= 0) { ev_out = ev; rpc = pc; pc = TLAG_PC_PARKED; }
     }
-    if (steps > TLAG_MAX_STEPS && st == L_RUN) { ev_out = TLAG_EV_STEPS; st = L_STOP; }
   }
 }
 
 // MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
-template <int FRAME, int MODE, int MINB>
-__global__ void __launch_bounds__(TLAG_BLOCK, MINB) k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
+template <int FRAME, int MODE, bool SMEM>
+__global__ void __launch_bounds__(TLAG_BLOCK, (FRAME <= 256 ? 4 : (FRAME <= 512 ? 2 : 1)))
+k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
   extern __shared__ uint64_t s_code[];
-  const uint64_t* code = p.code;
-  if (p.code_in_smem) {
+  if (SMEM) {
     for (uint32_t i = threadIdx.x; i < p.code_len; i += blockDim.x) s_code[i] = p.code[i];
     __syncthreads();
-    code = s_code;
   }
+  const uint64_t* code = p.code;
   int32_t frame[FRAME];
   uint32_t succ[TLAG_MAXW];
   const unsigned lane = threadIdx.x & 31;
@@ -183,46 +188,44 @@ __global__ void __launch_bounds__(TLAG_BLOCK, MINB) k_wave(DevParams p, unsigned
     bool trapped = false;
     int st, ev = 0;
     int32_t info = 0, info2 = 0;
-    uint32_t pc;
+    uint32_t pc, rpc = 0;
     // ---- invariants on the state being expanded --------------------------------
     if (p.n_inv > 0) {
-      pc = p.entry_inv;
+      pc = active ? p.entry_inv : TLAG_PC_PARKED;
       st = active ? L_RUN : L_DONE;
       for (;;) {
-        warp_vm(code, p.cpool, frame, pc, st, ev, info, info2);
-        if (st == L_STOP) {
+        warp_vm<SMEM>(code, s_code, p.cpool, frame, pc, rpc, ev, info, info2);
+        if (st == L_RUN) {        // this lane stopped on an event
           if (ev == TLAG_EV_HALT) st = L_DONE;
-          else if (ev == TLAG_EV_INVF) { report_min(&p.ctr->viol_inv, (idx << 20) | (unsigned)(info & 0xFFFFF)); st = L_RUN; }
-          else if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); st = L_RUN; }
+          else if (ev == TLAG_EV_INVF) { report_min(&p.ctr->viol_inv, (idx << 20) | (unsigned)(info & 0xFFFFF)); pc = rpc; }
+          else if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); pc = rpc; }
           else {
-            report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) |
-                                              (unsigned)(info2 & 0xFFFF));
+            report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(info & 15) << 16) | (unsigned)(info2 & 0xFFFF));
             st = L_DONE; trapped = true;
           }
         }
-        if (!__any_sync(0xffffffffu, st == L_RUN)) break;
+        if (!__any_sync(0xffffffffu, pc != TLAG_PC_PARKED)) break;
       }
     }
     // ---- successors -------------------------------------------------------------
-    pc = p.entry_next;
     st = (active && !trapped) ? L_RUN : L_DONE;
+    pc = (st == L_RUN) ? p.entry_next : TLAG_PC_PARKED;
     unsigned nsucc = 0;
     for (;;) {
-      warp_vm(code, p.cpool, frame, pc, st, ev, info, info2);
+      warp_vm<SMEM>(code, s_code, p.cpool, frame, pc, rpc, ev, info, info2);
       int32_t act = 0;
-      if (st == L_STOP) {
+      if (st == L_RUN) {
         if (ev == TLAG_EV_EMIT) { st = L_EMIT; ++nsucc; ++gen_local; }
-        else if (ev == TLAG_EV_GEN) { ++nsucc; ++gen_local; st = L_RUN; }
+        else if (ev == TLAG_EV_GEN) { ++nsucc; ++gen_local; pc = rpc; }
         else if (ev == TLAG_EV_HALT) st = L_DONE;
-        else if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); st = L_RUN; }
-        else if (ev == TLAG_EV_INVF) st = L_RUN;
+        else if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); pc = rpc; }
+        else if (ev == TLAG_EV_INVF) pc = rpc;
         else {
-          report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) |
-                                            (unsigned)(info2 & 0xFFFF));
+          report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(info & 15) << 16) | (unsigned)(info2 & 0xFFFF));
           st = L_DONE; trapped = true;
         }
       }
-      if (__any_sync(0xffffffffu, st == L_RUN)) continue;      // resume the lanes that only reported
+      if (__any_sync(0xffffffffu, pc != TLAG_PC_PARKED)) continue;   // resume the lanes that only reported
       bool has = (st == L_EMIT);
       if (!__any_sync(0xffffffffu, has)) break;                 // every lane is done
       act = info;
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(TLAG_BLOCK, MINB) k_wave(DevParams p, unsigned
           }
         }
       }
-      if (st == L_EMIT) st = L_RUN;
+      if (st == L_EMIT) { st = L_RUN; pc = rpc; }
     }
     if (active && nsucc == 0 && !trapped && (p.flags & TLAG_F_DEADLOCK_CHECK)) {
       report_min(&p.ctr->viol_deadlock, idx << 20);
@@ -460,15 +463,15 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   if (blocks == 0) blocks = 1;
   size_t smem = e->p.code_in_smem ? (size_t)e->p.code_len * 8 : 0;
   void (*fn)(DevParams, unsigned long long, unsigned long long) = nullptr;
-  static const bool dense = getenv("TLAG_WAVE_MINB3") == nullptr;   // 4 CTAs/SM (32 regs; measured +4.5 %) unless TLAG_WAVE_MINB3 is set
+  const bool sm = e->p.code_in_smem != 0;
   switch (e->frame_class) {
-    case 0: fn = dense ? k_wave<64, MODE, 4> : k_wave<64, MODE, 3>; break;
-    case 1: fn = dense ? k_wave<128, MODE, 4> : k_wave<128, MODE, 3>; break;
-    case 2: fn = dense ? k_wave<256, MODE, 4> : k_wave<256, MODE, 3>; break;
-    case 3: fn = k_wave<512, MODE, 2>; break;
-    case 4: fn = k_wave<1024, MODE, 1>; break;
-    case 5: fn = k_wave<2048, MODE, 1>; break;
-    default: fn = k_wave<4096, MODE, 1>; break;
+    case 0: fn = sm ? k_wave<64, MODE, true> : k_wave<64, MODE, false>; break;
+    case 1: fn = sm ? k_wave<128, MODE, true> : k_wave<128, MODE, false>; break;
+    case 2: fn = sm ? k_wave<256, MODE, true> : k_wave<256, MODE, false>; break;
+    case 3: fn = sm ? k_wave<512, MODE, true> : k_wave<512, MODE, false>; break;
+    case 4: fn = sm ? k_wave<1024, MODE, true> : k_wave<1024, MODE, false>; break;
+    case 5: fn = sm ? k_wave<2048, MODE, true> : k_wave<2048, MODE, false>; break;
+    default: fn = sm ? k_wave<4096, MODE, true> : k_wave<4096, MODE, false>; break;
   }
   if (smem > 48 * 1024) {
     cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
