@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>   // CUDA-toolkit header library; used only to reorder a level (not on the hot path)
 
 #include "../../include/tlag.h"
 #include "tlag_vm.h"
@@ -91,6 +92,7 @@ struct tlag_engine {
   int frame_class = 0;
   bool restarting = false;
   double growth_hint = 4.0;
+  void* d_sort = nullptr; uint64_t sort_bytes = 0;
   std::string err;
   uint32_t* d_scratch = nullptr; uint64_t scratch_words = 0; uint8_t* d_flags = nullptr; uint64_t flags_cap = 0;
 };
@@ -443,6 +445,35 @@ __global__ void k_digest(DevParams p, unsigned long long n, unsigned long long* 
   if ((threadIdx.x & 31) == 0) { atomicXor(&out2[0], x); atomicAdd(&out2[1], sm); }
 }
 
+// ---- frontier clustering -----------------------------------------------------------------------
+// The warp-scheduled interpreter executes the union of its 32 lanes' paths, so its efficiency is
+// (mean path length) / (union length).  States that agree on the tail of the packed vector (the last
+// variables, for the Paxos models the high bits of the msgs bitset) follow similar paths: measured on
+// a 4096-state window of MCPaxos3_b3 level 14, lane utilisation is 0.35 in discovery order, 0.31 in random
+// order and 0.54 when sorted by the last packed word.  Each newly discovered level slice is therefore
+// reordered (stable data: nothing references those indices yet) by a 64-bit key of its last two words.
+__global__ void k_sort_keys(const uint32_t* __restrict__ states, unsigned long long n, int W,
+                            unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* s = states + i * (unsigned long long)W;
+  const unsigned long long hi = s[W - 1], lo = W >= 2 ? s[W - 2] : 0;
+  keys[i] = (hi << 32) | lo;
+  idx[i] = (uint32_t)i;
+}
+
+__global__ void k_gather_slice(const uint32_t* __restrict__ states, const uint32_t* __restrict__ parent,
+                               const uint32_t* __restrict__ meta, const uint32_t* __restrict__ idx,
+                               unsigned long long n, int W, uint32_t* __restrict__ o_states,
+                               uint32_t* __restrict__ o_parent, uint32_t* __restrict__ o_meta) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long j = idx[i];
+  for (int k = 0; k < W; ++k) o_states[i * (unsigned long long)W + k] = states[j * (unsigned long long)W + k];
+  o_parent[i] = parent[j];
+  o_meta[i] = meta[j];
+}
+
 // rebuild the table from the state store after growing it
 __global__ void k_rehash(DevParams p, unsigned long long n) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -549,6 +580,48 @@ static int grow_store_if_needed(tlag_engine* e, uint64_t need) {
   return TLAG_OK;
 }
 
+static int cluster_slice(tlag_engine* e, uint64_t first, uint64_t count) {
+  static const bool off = getenv("TLAG_NO_SORT") != nullptr;
+  if (off || count < 8192 || count > 0xFFFFFFFFull) return TLAG_OK;
+  const uint64_t W = e->m.words_per_state;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (uint32_t*)nullptr, (uint32_t*)nullptr, (int)0);
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (uint32_t*)nullptr, (uint32_t*)nullptr, (unsigned long long)count);
+  // one scratch allocation: keys in/out, idx in/out, cub temp, gathered slice
+  const uint64_t bytes = count * 8 * 2 + count * 4 * 2 + cub_bytes + 256 + count * (W + 2) * 4;
+  if (bytes > e->sort_bytes) {
+    cudaFree(e->d_sort); e->d_sort = nullptr; e->sort_bytes = 0;
+    if (cudaMalloc(&e->d_sort, bytes) != cudaSuccess) { cudaGetLastError(); return TLAG_OK; }   // no memory: skip (optimisation only)
+    e->sort_bytes = bytes;
+  }
+  uint8_t* b = (uint8_t*)e->d_sort;
+  unsigned long long* k_in = (unsigned long long*)b; b += count * 8;
+  unsigned long long* k_out = (unsigned long long*)b; b += count * 8;
+  uint32_t* i_in = (uint32_t*)b; b += count * 4;
+  uint32_t* i_out = (uint32_t*)b; b += count * 4;
+  uint32_t* g_states = (uint32_t*)b; b += count * W * 4;
+  uint32_t* g_parent = (uint32_t*)b; b += count * 4;
+  uint32_t* g_meta = (uint32_t*)b; b += count * 4;
+  b = (uint8_t*)(((uintptr_t)b + 255) & ~(uintptr_t)255);
+  void* cub_tmp = b;
+  uint32_t* st = e->d_states + first * W;
+  const unsigned blocks = (unsigned)((count + 255) / 256);
+  k_sort_keys<<<blocks, 256, 0, e->stream>>>(st, count, (int)W, k_in, i_in);
+  CK(cudaGetLastError());
+  if (cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k_in, k_out, i_in, i_out, (unsigned long long)count, 0, 64,
+                                      e->stream) != cudaSuccess) { e->err = "cub sort failed"; return TLAG_ECUDA; }
+  k_gather_slice<<<blocks, 256, 0, e->stream>>>(st, e->d_parent + first, e->d_meta + first, i_out, count, (int)W,
+                                                g_states, g_parent, g_meta);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(st, g_states, count * W * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->d_parent + first, g_parent, count * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->d_meta + first, g_meta, count * 4, cudaMemcpyDeviceToDevice, e->stream));
+  e->launches += 3;
+  return TLAG_OK;
+}
+
 extern "C" const char* tlag_version(void) { return "tlag 0.1 (sm_100a)"; }
 
 extern "C" const char* tlag_last_error(const tlag_engine* e) { return e ? e->err.c_str() : "null engine"; }
@@ -618,7 +691,7 @@ extern "C" void tlag_destroy(tlag_engine* e) {
   if (!e) return;
   cudaFree(e->d_code); cudaFree(e->d_cpool); cudaFree(e->d_layout); cudaFree(e->d_states);
   cudaFree(e->d_parent); cudaFree(e->d_meta); cudaFree(e->d_table); cudaFree(e->d_ctr);
-  cudaFree(e->d_scratch); cudaFree(e->d_flags);
+  cudaFree(e->d_scratch); cudaFree(e->d_flags); cudaFree(e->d_sort);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -814,6 +887,10 @@ extern "C" int tlag_step(tlag_engine* e, tlag_wave_stats* out) {
     out->kernel_ms = ms;
   }
   if (n_states > hi) e->depth = e->level + 1;
+  if (n_states > hi && e->verdict == TLAG_V_RUNNING) {
+    int rs = cluster_slice(e, hi, n_states - hi);
+    if (rs) return rs;
+  }
   {  // head-room for the next level: twice the observed discovered/expanded ratio, at least 4x
     const double ratio = (double)(n_states - hi) / (double)(hi - lo);
     e->growth_hint = ratio * 2.0 > 4.0 ? ratio * 2.0 : 4.0;
@@ -989,7 +1066,11 @@ extern "C" int tlag_advance_level(tlag_engine* e, tlag_wave_stats* out) {
   CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
   const uint64_t n_states = hc.n_states;
   if (out) { memset(out, 0, sizeof(*out)); out->level = e->level; out->discovered = n_states - e->hi; out->distinct_total = n_states; out->generated_total = e->generated; out->verdict = e->verdict; }
-  if (n_states > e->hi) e->depth = e->level + 1;
+  if (n_states > e->hi) {
+    e->depth = e->level + 1;
+    int rs = cluster_slice(e, e->hi, n_states - e->hi);
+    if (rs) return rs;
+  }
   e->lo = e->hi; e->hi = n_states; e->level += 1;
   return TLAG_OK;
 }
