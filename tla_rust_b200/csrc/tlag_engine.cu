@@ -191,37 +191,28 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
     int st, ev = 0;
     int32_t info = 0, info2 = 0;
     uint32_t pc, rpc = 0;
-    // ---- invariants on the state being expanded --------------------------------
-    if (p.n_inv > 0) {
-      pc = active ? p.entry_inv : TLAG_PC_PARKED;
-      st = active ? L_RUN : L_DONE;
-      for (;;) {
-        warp_vm<SMEM>(code, s_code, p.cpool, frame, pc, rpc, ev, info, info2);
-        if (st == L_RUN) {        // this lane stopped on an event
-          if (ev == TLAG_EV_HALT) st = L_DONE;
-          else if (ev == TLAG_EV_INVF) { report_min(&p.ctr->viol_inv, (idx << 20) | (unsigned)(info & 0xFFFFF)); pc = rpc; }
-          else if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); pc = rpc; }
-          else {
-            report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(info & 15) << 16) | (unsigned)(info2 & 0xFFFF));
-            st = L_DONE; trapped = true;
-          }
-        }
-        if (!__any_sync(0xffffffffu, pc != TLAG_PC_PARKED)) break;
-      }
-    }
-    // ---- successors -------------------------------------------------------------
-    st = (active && !trapped) ? L_RUN : L_DONE;
-    pc = (st == L_RUN) ? p.entry_next : TLAG_PC_PARKED;
+    // One interpreter loop for both programs (a single copy of the dispatch switch: the first version
+    // inlined it twice and stalled on instruction fetch -- ncu stall_no_instruction 14 per issue).
+    // Each lane first runs the invariant program on the state it expands; at its HALT it continues
+    // with the next-state program (the invariant code sits at lower pcs, so those lanes go first).
+    int phase = p.n_inv > 0 ? 0 : 1;
+    st = active ? L_RUN : L_DONE;
+    pc = active ? (phase == 0 ? p.entry_inv : p.entry_next) : TLAG_PC_PARKED;
     unsigned nsucc = 0;
     for (;;) {
       warp_vm<SMEM>(code, s_code, p.cpool, frame, pc, rpc, ev, info, info2);
       int32_t act = 0;
-      if (st == L_RUN) {
+      if (st == L_RUN) {        // this lane stopped on an event
         if (ev == TLAG_EV_EMIT) { st = L_EMIT; ++nsucc; ++gen_local; }
+        else if (ev == TLAG_EV_HALT) {
+          if (phase == 0) { phase = 1; pc = p.entry_next; } else st = L_DONE;
+        }
         else if (ev == TLAG_EV_GEN) { ++nsucc; ++gen_local; pc = rpc; }
-        else if (ev == TLAG_EV_HALT) st = L_DONE;
+        else if (ev == TLAG_EV_INVF) {
+          if (phase == 0) report_min(&p.ctr->viol_inv, (idx << 20) | (unsigned)(info & 0xFFFFF));
+          pc = rpc;
+        }
         else if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); pc = rpc; }
-        else if (ev == TLAG_EV_INVF) pc = rpc;
         else {
           report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(info & 15) << 16) | (unsigned)(info2 & 0xFFFF));
           st = L_DONE; trapped = true;
