@@ -11,17 +11,14 @@ from __future__ import annotations
 import numpy as np
 
 OPS = [
-    "HALT", "LI", "LIW", "MOV", "MOVN", "ZERO", "LDC",
-    "ADD", "SUB", "MUL", "DIV", "MOD", "NEG",
-    "LT", "LE", "EQ", "NE", "EQN", "NOT", "AND", "OR",
-    "LDX", "STX", "TBL",
-    "BSET", "BCLR", "BTEST", "BOR", "BAND", "BANDN", "BISZ", "BSUB", "BCNT", "BNEXT", "BFILL",
-    "JMP", "JZ", "JNZ", "JNEG",
-    "TRAP", "EMIT", "GEN", "ASSERTF", "INVF",
-    "ADDI", "MULI", "EQI", "NEI", "LTI", "LEI", "GTI", "GEI", "UCLAMP",
-    "BSETI", "BTESTI", "SHRI", "ANDI", "TBLT",
-    # fused compare-and-branch (target = imm28 in (c,d))
-    "JEQ", "JNE", "JLT", "JGE", "JEQI", "JNEI", "JLTI", "JGEI", "JBT", "JBF", "JBTI", "JBFI", "JGEZ",
+    "HALT", "ADD", "SUB", "MUL", "LT", "LE", "EQ", "NE", "AND",
+    "OR", "ADDI", "MULI", "EQI", "NEI", "LTI", "LEI", "GTI", "GEI",
+    "SHRI", "ANDI", "JEQ", "JNE", "JLT", "JGE", "JEQI", "JNEI", "JLTI",
+    "JGEI", "JZ", "JNZ", "JNEG", "JGEZ", "JBT", "JBF", "JBTI", "JBFI",
+    "JMP", "LI", "LIW", "MOV", "MOVN", "ZERO", "LDC", "DIV", "MOD",
+    "NEG", "EQN", "NOT", "LDX", "STX", "TBL", "TBLT", "BSET", "BCLR",
+    "BTEST", "BOR", "BAND", "BANDN", "BISZ", "BSUB", "BCNT", "BNEXT", "BFILL",
+    "BSETI", "BTESTI", "UCLAMP", "TRAP", "EMIT", "GEN", "ASSERTF", "INVF",
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 

@@ -14,21 +14,22 @@
 
 #if defined(__CUDACC__)
 #define TLAG_HD __host__ __device__ __forceinline__
+#define TLAG_NOUNROLL _Pragma("unroll 1")   /* keep the device interpreter small: it must fit the I-cache */
 #else
 #define TLAG_HD static inline
+#define TLAG_NOUNROLL
 #endif
 
 enum {
-  OP_HALT = 0, OP_LI, OP_LIW, OP_MOV, OP_MOVN, OP_ZERO, OP_LDC,
-  OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_MOD, OP_NEG,
-  OP_LT, OP_LE, OP_EQ, OP_NE, OP_EQN, OP_NOT, OP_AND, OP_OR,
-  OP_LDX, OP_STX, OP_TBL,
-  OP_BSET, OP_BCLR, OP_BTEST, OP_BOR, OP_BAND, OP_BANDN, OP_BISZ, OP_BSUB, OP_BCNT, OP_BNEXT, OP_BFILL,
-  OP_JMP, OP_JZ, OP_JNZ, OP_JNEG,
-  OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
-  OP_ADDI, OP_MULI, OP_EQI, OP_NEI, OP_LTI, OP_LEI, OP_GTI, OP_GEI, OP_UCLAMP,
-  OP_BSETI, OP_BTESTI, OP_SHRI, OP_ANDI, OP_TBLT,
-  OP_JEQ, OP_JNE, OP_JLT, OP_JGE, OP_JEQI, OP_JNEI, OP_JLTI, OP_JGEI, OP_JBT, OP_JBF, OP_JBTI, OP_JBFI, OP_JGEZ,
+  OP_HALT = 0, OP_ADD, OP_SUB, OP_MUL, OP_LT, OP_LE, OP_EQ, OP_NE,
+  OP_AND, OP_OR, OP_ADDI, OP_MULI, OP_EQI, OP_NEI, OP_LTI, OP_LEI,
+  OP_GTI, OP_GEI, OP_SHRI, OP_ANDI, OP_JEQ, OP_JNE, OP_JLT, OP_JGE,
+  OP_JEQI, OP_JNEI, OP_JLTI, OP_JGEI, OP_JZ, OP_JNZ, OP_JNEG, OP_JGEZ,
+  OP_JBT, OP_JBF, OP_JBTI, OP_JBFI, OP_JMP, OP_LI, OP_LIW, OP_MOV,
+  OP_MOVN, OP_ZERO, OP_LDC, OP_DIV, OP_MOD, OP_NEG, OP_EQN, OP_NOT,
+  OP_LDX, OP_STX, OP_TBL, OP_TBLT, OP_BSET, OP_BCLR, OP_BTEST, OP_BOR,
+  OP_BAND, OP_BANDN, OP_BISZ, OP_BSUB, OP_BCNT, OP_BNEXT, OP_BFILL, OP_BSETI,
+  OP_BTESTI, OP_UCLAMP, OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
   OP__COUNT
 };
 
@@ -77,28 +78,78 @@ TLAG_HD int tlag_ffs(uint32_t x) {  /* 1-based index of lowest set bit, 0 if non
 TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uint32_t* pc_io,
                          int32_t* info, int32_t* info2) {
   uint32_t pc = *pc_io + 1;
-  {
-    const uint32_t op = (uint32_t)(w & 0xFF);
-    const uint32_t a = (uint32_t)(w >> 8) & 0x3FFF;
-    const uint32_t b = (uint32_t)(w >> 22) & 0x3FFF;
-    const uint32_t c = (uint32_t)(w >> 36) & 0x3FFF;
-    const uint32_t d = (uint32_t)(w >> 50) & 0x3FFF;
-    const int32_t immI = tlag_imm28((uint32_t)(w >> 22) & 0xFFFFFFF);
-    const int32_t immJ = tlag_imm28((uint32_t)(w >> 36) & 0xFFFFFFF);
+  const uint32_t op = (uint32_t)(w & 0xFF);
+  const uint32_t a = (uint32_t)(w >> 8) & 0x3FFF;
+  const uint32_t b = (uint32_t)(w >> 22) & 0x3FFF;
+  const uint32_t c = (uint32_t)(w >> 36) & 0x3FFF;
+  const uint32_t d = (uint32_t)(w >> 50) & 0x3FFF;
+  const int32_t immI = tlag_imm28((uint32_t)(w >> 22) & 0xFFFFFFF);
+  const int32_t immJ = tlag_imm28((uint32_t)(w >> 36) & 0xFFFFFFF);
+  // Operand-class groups first (one operand fetch / write-back sequence per class keeps the device
+  // code small: the interpreter loop has to live in the instruction cache).
+  if (op >= OP_ADD && op <= OP_OR) {                       // f[a] = f[b] (op) f[c]
+    const int32_t x = f[b], y = f[c];
+    int32_t r;
+    switch (op) {
+      case OP_ADD: r = (int32_t)((uint32_t)x + (uint32_t)y); break;
+      case OP_SUB: r = (int32_t)((uint32_t)x - (uint32_t)y); break;
+      case OP_MUL: r = (int32_t)((uint32_t)x * (uint32_t)y); break;
+      case OP_LT: r = x < y; break;
+      case OP_LE: r = x <= y; break;
+      case OP_EQ: r = x == y; break;
+      case OP_NE: r = x != y; break;
+      case OP_AND: r = (x != 0) & (y != 0); break;
+      default: r = (x != 0) | (y != 0); break;             // OP_OR
+    }
+    f[a] = r;
+  } else if (op >= OP_ADDI && op <= OP_ANDI) {             // f[a] = f[b] (op) immJ
+    const int32_t x = f[b];
+    int32_t r;
+    switch (op) {
+      case OP_ADDI: r = (int32_t)((uint32_t)x + (uint32_t)immJ); break;
+      case OP_MULI: r = (int32_t)((uint32_t)x * (uint32_t)immJ); break;
+      case OP_EQI: r = x == immJ; break;
+      case OP_NEI: r = x != immJ; break;
+      case OP_LTI: r = x < immJ; break;
+      case OP_LEI: r = x <= immJ; break;
+      case OP_GTI: r = x > immJ; break;
+      case OP_GEI: r = x >= immJ; break;
+      case OP_SHRI: r = (int32_t)((uint32_t)x >> (immJ & 31)); break;
+      default: r = x & immJ; break;                        // OP_ANDI
+    }
+    f[a] = r;
+  } else if (op >= OP_JEQ && op <= OP_JGEZ) {              // compare-and-branch
+    const int32_t x = f[a];
+    int32_t y = 0;
+    uint32_t tgt = (uint32_t)immJ;
+    if (op <= OP_JGE) y = f[b];
+    else if (op <= OP_JGEI) y = (int32_t)(b << 18) >> 18;
+    else tgt = (uint32_t)immI;                             // JZ / JNZ / JNEG / JGEZ: target in (b,c)
+    int t;
+    switch (op) {
+      case OP_JEQ: case OP_JEQI: case OP_JZ: t = x == y; break;
+      case OP_JNE: case OP_JNEI: case OP_JNZ: t = x != y; break;
+      case OP_JLT: case OP_JLTI: case OP_JNEG: t = x < y; break;
+      default: t = x >= y; break;                          // JGE / JGEI / JGEZ
+    }
+    if (t) pc = tgt;
+  } else if (op >= OP_JBT && op <= OP_JBFI) {              // bit-test-and-branch
+    const uint32_t i = (op <= OP_JBF) ? (uint32_t)f[b] : b;
+    const int bit = (((uint32_t)f[a + (i >> 5)] >> (i & 31)) & 1u) != 0;
+    if (bit == ((op == OP_JBT) | (op == OP_JBTI))) pc = (uint32_t)immJ;
+  } else {
     switch (op) {
       case OP_HALT: *pc_io = pc - 1; return TLAG_EV_HALT;
+      case OP_JMP: pc = (uint32_t)immI; break;
       case OP_LI: f[a] = immI; break;
       case OP_LIW: f[a] = tlag_cp(cpool, immI); break;
       case OP_MOV: f[a] = f[b]; break;
       case OP_MOVN:
-        if (a <= b) { for (uint32_t i = 0; i < c; ++i) f[a + i] = f[b + i]; }
-        else { for (uint32_t i = c; i-- > 0;) f[a + i] = f[b + i]; }
+        if (a <= b) { TLAG_NOUNROLL for (uint32_t i = 0; i < c; ++i) f[a + i] = f[b + i]; }
+        else { TLAG_NOUNROLL for (uint32_t i = c; i-- > 0;) f[a + i] = f[b + i]; }
         break;
-      case OP_ZERO: for (uint32_t i = 0; i < b; ++i) f[a + i] = 0; break;
-      case OP_LDC: for (uint32_t i = 0; i < d; ++i) f[a + i] = tlag_cp(cpool, immI + (int32_t)i); break;
-      case OP_ADD: f[a] = (int32_t)((uint32_t)f[b] + (uint32_t)f[c]); break;
-      case OP_SUB: f[a] = (int32_t)((uint32_t)f[b] - (uint32_t)f[c]); break;
-      case OP_MUL: f[a] = (int32_t)((uint32_t)f[b] * (uint32_t)f[c]); break;
+      case OP_ZERO: TLAG_NOUNROLL for (uint32_t i = 0; i < b; ++i) f[a + i] = 0; break;
+      case OP_LDC: TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = tlag_cp(cpool, immI + (int32_t)i); break;
       case OP_DIV: {  // TLA+ \div: floor division (Integers.tla)
         int32_t x = f[b], y = f[c];
         if (y == 0) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
@@ -108,76 +159,42 @@ TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uin
         if (y <= 0) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
         int32_t r = x % y; if (r < 0) r += y; f[a] = r; break; }
       case OP_NEG: f[a] = -f[b]; break;
-      case OP_LT: f[a] = f[b] < f[c]; break;
-      case OP_LE: f[a] = f[b] <= f[c]; break;
-      case OP_EQ: f[a] = f[b] == f[c]; break;
-      case OP_NE: f[a] = f[b] != f[c]; break;
-      case OP_EQN: { int32_t e = 1; for (uint32_t i = 0; i < d; ++i) e &= (f[b + i] == f[c + i]); f[a] = e; break; }
+      case OP_EQN: { int32_t e = 1; TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) e &= (f[b + i] == f[c + i]); f[a] = e; break; }
       case OP_NOT: f[a] = !f[b]; break;
-      case OP_AND: f[a] = (f[b] != 0) & (f[c] != 0); break;
-      case OP_OR: f[a] = (f[b] != 0) | (f[c] != 0); break;
-      case OP_LDX: { uint32_t base = b + (uint32_t)f[c] * d; for (uint32_t i = 0; i < d; ++i) f[a + i] = f[base + i]; break; }
-      case OP_STX: { uint32_t base = a + (uint32_t)f[b] * d; for (uint32_t i = 0; i < d; ++i) f[base + i] = f[c + i]; break; }
+      case OP_LDX: { uint32_t base = b + (uint32_t)f[c] * d; TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = f[base + i]; break; }
+      case OP_STX: { uint32_t base = a + (uint32_t)f[b] * d; TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[base + i] = f[c + i]; break; }
       case OP_TBL: f[a] = tlag_cp(cpool, immI + f[d]); break;
+      case OP_TBLT: {  // table lookup that traps on the "field absent" sentinel
+        int32_t v = tlag_cp(cpool, immI + f[d]);
+        if (v == (int32_t)0x80000000) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
+        f[a] = v; break; }
       case OP_BSET: { uint32_t i = (uint32_t)f[b]; f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break; }
       case OP_BCLR: { uint32_t i = (uint32_t)f[b]; f[a + (i >> 5)] &= ~(int32_t)(1u << (i & 31)); break; }
       case OP_BTEST: { uint32_t i = (uint32_t)f[c]; f[a] = (int32_t)(((uint32_t)f[b + (i >> 5)] >> (i & 31)) & 1u); break; }
-      case OP_BOR: for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] | f[c + i]; break;
-      case OP_BAND: for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] & f[c + i]; break;
-      case OP_BANDN: for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] & ~f[c + i]; break;
-      case OP_BISZ: { int32_t z = 1; for (uint32_t i = 0; i < c; ++i) z &= (f[b + i] == 0); f[a] = z; break; }
-      case OP_BSUB: { int32_t z = 1; for (uint32_t i = 0; i < d; ++i) z &= ((f[b + i] & ~f[c + i]) == 0); f[a] = z; break; }
-      case OP_BCNT: { int32_t n = 0; for (uint32_t i = 0; i < c; ++i) n += tlag_popc((uint32_t)f[b + i]); f[a] = n; break; }
+      case OP_BOR: TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] | f[c + i]; break;
+      case OP_BAND: TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] & f[c + i]; break;
+      case OP_BANDN: TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] & ~f[c + i]; break;
+      case OP_BISZ: { int32_t z = 1; TLAG_NOUNROLL for (uint32_t i = 0; i < c; ++i) z &= (f[b + i] == 0); f[a] = z; break; }
+      case OP_BSUB: { int32_t z = 1; TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) z &= ((f[b + i] & ~f[c + i]) == 0); f[a] = z; break; }
+      case OP_BCNT: { int32_t n = 0; TLAG_NOUNROLL for (uint32_t i = 0; i < c; ++i) n += tlag_popc((uint32_t)f[b + i]); f[a] = n; break; }
       case OP_BNEXT: {  // a = smallest set bit index > f[c] (f[c] = -1 to start) within d bits, else -1
         int32_t cur = f[c] + 1; int32_t res = -1;
         uint32_t nb = d;
-        while ((uint32_t)cur < nb) {
+        TLAG_NOUNROLL while ((uint32_t)cur < nb) {
           uint32_t word = (uint32_t)f[b + ((uint32_t)cur >> 5)] >> ((uint32_t)cur & 31);
           if (word) { int32_t cand = cur + tlag_ffs(word) - 1; if ((uint32_t)cand < nb) res = cand; break; }
           cur = (int32_t)(((uint32_t)cur | 31u) + 1u);
         }
         f[a] = res; break; }
-      case OP_BFILL: for (uint32_t i = 0; i < b; ++i) f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break;
-      case OP_JMP: pc = (uint32_t)immI; break;
-      case OP_JZ: if (f[a] == 0) pc = (uint32_t)immI; break;
-      case OP_JNZ: if (f[a] != 0) pc = (uint32_t)immI; break;
-      case OP_JNEG: if (f[a] < 0) pc = (uint32_t)immI; break;
+      case OP_BFILL: TLAG_NOUNROLL for (uint32_t i = 0; i < b; ++i) f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break;
+      case OP_BSETI: { uint32_t i = (uint32_t)immI; f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break; }
+      case OP_BTESTI: { uint32_t i = (uint32_t)immJ; f[a] = (int32_t)(((uint32_t)f[b + (i >> 5)] >> (i & 31)) & 1u); break; }
+      case OP_UCLAMP: if ((uint32_t)f[a] >= (uint32_t)immI) f[a] = -1; break;
       case OP_TRAP: *info = (int32_t)a; *info2 = immI; *pc_io = pc; return TLAG_EV_TRAP;
       case OP_EMIT: *info = immI; *pc_io = pc; return TLAG_EV_EMIT;
       case OP_GEN: *pc_io = pc; return TLAG_EV_GEN;
       case OP_ASSERTF: *info = immI; *pc_io = pc; return TLAG_EV_ASSERT;
       case OP_INVF: *info = immI; *pc_io = pc; return TLAG_EV_INVF;
-      case OP_ADDI: f[a] = (int32_t)((uint32_t)f[b] + (uint32_t)immJ); break;
-      case OP_MULI: f[a] = (int32_t)((uint32_t)f[b] * (uint32_t)immJ); break;
-      case OP_EQI: f[a] = f[b] == immJ; break;
-      case OP_NEI: f[a] = f[b] != immJ; break;
-      case OP_LTI: f[a] = f[b] < immJ; break;
-      case OP_LEI: f[a] = f[b] <= immJ; break;
-      case OP_GTI: f[a] = f[b] > immJ; break;
-      case OP_GEI: f[a] = f[b] >= immJ; break;
-      case OP_UCLAMP: if ((uint32_t)f[a] >= (uint32_t)immI) f[a] = -1; break;
-      case OP_BSETI: { uint32_t i = (uint32_t)immI; f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break; }
-      case OP_BTESTI: { uint32_t i = (uint32_t)immJ; f[a] = (int32_t)(((uint32_t)f[b + (i >> 5)] >> (i & 31)) & 1u); break; }
-      case OP_SHRI: f[a] = (int32_t)((uint32_t)f[b] >> (immJ & 31)); break;
-      case OP_ANDI: f[a] = f[b] & immJ; break;
-      case OP_TBLT: {  // table lookup that traps on the "field absent" sentinel
-        int32_t v = tlag_cp(cpool, immI + f[d]);
-        if (v == (int32_t)0x80000000) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
-        f[a] = v; break; }
-      // fused compare-and-branch: target = immJ; b is a register or a signed 14-bit immediate
-      case OP_JEQ: if (f[a] == f[b]) pc = (uint32_t)immJ; break;
-      case OP_JNE: if (f[a] != f[b]) pc = (uint32_t)immJ; break;
-      case OP_JLT: if (f[a] < f[b]) pc = (uint32_t)immJ; break;
-      case OP_JGE: if (f[a] >= f[b]) pc = (uint32_t)immJ; break;
-      case OP_JEQI: if (f[a] == ((int32_t)(b << 18) >> 18)) pc = (uint32_t)immJ; break;
-      case OP_JNEI: if (f[a] != ((int32_t)(b << 18) >> 18)) pc = (uint32_t)immJ; break;
-      case OP_JLTI: if (f[a] < ((int32_t)(b << 18) >> 18)) pc = (uint32_t)immJ; break;
-      case OP_JGEI: if (f[a] >= ((int32_t)(b << 18) >> 18)) pc = (uint32_t)immJ; break;
-      case OP_JBT: { uint32_t i = (uint32_t)f[b]; if (((uint32_t)f[a + (i >> 5)] >> (i & 31)) & 1u) pc = (uint32_t)immJ; break; }
-      case OP_JBF: { uint32_t i = (uint32_t)f[b]; if (!(((uint32_t)f[a + (i >> 5)] >> (i & 31)) & 1u)) pc = (uint32_t)immJ; break; }
-      case OP_JBTI: if (((uint32_t)f[a + (b >> 5)] >> (b & 31)) & 1u) pc = (uint32_t)immJ; break;
-      case OP_JBFI: if (!(((uint32_t)f[a + (b >> 5)] >> (b & 31)) & 1u)) pc = (uint32_t)immJ; break;
-      case OP_JGEZ: if (f[a] >= 0) pc = (uint32_t)immI; break;
       default: *info = 99; *info2 = (int32_t)op; *pc_io = pc; return TLAG_EV_TRAP;
     }
   }
@@ -188,7 +205,7 @@ TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uin
 // Runs from *pc until the next event.  `code` may live in shared memory on the device.
 TLAG_HD int tlag_vm_run(const uint64_t* code, const int32_t* cpool, int32_t* f, uint32_t* pc_io,
                         int32_t* info, int32_t* info2, uint32_t max_steps) {
-  for (uint32_t steps = 0; steps < max_steps; ++steps) {
+  TLAG_NOUNROLL for (uint32_t steps = 0; steps < max_steps; ++steps) {
     const int ev = tlag_vm_exec(code[*pc_io], cpool, f, pc_io, info, info2);
     if (ev >= 0) return ev;
   }
@@ -199,9 +216,9 @@ TLAG_HD int tlag_vm_run(const uint64_t* code, const int32_t* cpool, int32_t* f, 
 // Slots are laid out LSB-first in a little-endian bit stream of W 32-bit words.
 // Returns 0, or 1+slot index when a value does not fit its slot (overflow trap).
 TLAG_HD int tlag_pack(const tlag_slot* lay, int nslots, const int32_t* st, uint32_t* out, int W) {
-  for (int i = 0; i < W; ++i) out[i] = 0;
+  TLAG_NOUNROLL for (int i = 0; i < W; ++i) out[i] = 0;
   uint32_t bitpos = 0;
-  for (int s = 0; s < nslots; ++s) {
+  TLAG_NOUNROLL for (int s = 0; s < nslots; ++s) {
     const int32_t width = lay[s].width;
     uint32_t v = (uint32_t)(st[lay[s].off] - lay[s].bias);
     if (width < 32 && (v >> width) != 0) return 1 + s;
@@ -215,7 +232,7 @@ TLAG_HD int tlag_pack(const tlag_slot* lay, int nslots, const int32_t* st, uint3
 
 TLAG_HD void tlag_unpack(const tlag_slot* lay, int nslots, const uint32_t* in, int32_t* st) {
   uint32_t bitpos = 0;
-  for (int s = 0; s < nslots; ++s) {
+  TLAG_NOUNROLL for (int s = 0; s < nslots; ++s) {
     const int32_t width = lay[s].width;
     const uint32_t wi = bitpos >> 5, sh = bitpos & 31;
     uint32_t v = in[wi] >> sh;
@@ -258,7 +275,7 @@ TLAG_HD uint64_t tlag_fp_final(uint64_t h, int W) {
 TLAG_HD uint64_t tlag_fingerprint(const uint32_t* w, int W) {
   uint64_t h = tlag_fp_init(W);
   int i = 0;
-  for (; i + 1 < W; i += 2) h = tlag_fp_pair(h, w[i], w[i + 1]);
+  TLAG_NOUNROLL for (; i + 1 < W; i += 2) h = tlag_fp_pair(h, w[i], w[i + 1]);
   if (i < W) h = tlag_fp_tail(h, w[i]);
   return tlag_fp_final(h, W);
 }
