@@ -14,7 +14,7 @@
 
 #if defined(__CUDACC__)
 #define TLAG_HD __host__ __device__ __forceinline__
-#define TLAG_NOUNROLL _Pragma("unroll 1")   /* keep the device interpreter small: it must fit the I-cache */
+#define TLAG_NOUNROLL   /* (tried _Pragma("unroll 1") to shrink the kernel: 34 KB instead of 58 KB of SASS but 5% slower) */
 #else
 #define TLAG_HD static inline
 #define TLAG_NOUNROLL
