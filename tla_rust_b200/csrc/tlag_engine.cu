@@ -66,6 +66,7 @@ struct DevParams {
   int n_inv;
   // route mode
   uint32_t* send; unsigned long long region_cap; int n_ranks; int rank;
+  unsigned long long* sent_cache; unsigned long long sent_mask;   // direct-mapped filter of fingerprints already routed
 };
 
 struct tlag_engine {
@@ -93,6 +94,7 @@ struct tlag_engine {
   bool restarting = false;
   double growth_hint = 4.0;
   void* d_sort = nullptr; uint64_t sort_bytes = 0;
+  unsigned long long* d_sent = nullptr;
   std::string err;
   uint32_t* d_scratch = nullptr; uint64_t scratch_words = 0; uint8_t* d_flags = nullptr; uint64_t flags_cap = 0;
 };
@@ -255,7 +257,13 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
           }
         }
       } else {
-        // route: owner = high bits of the fingerprint scaled to n_ranks (hash-range partition)
+        // route: owner = high bits of the fingerprint scaled to n_ranks (hash-range partition).
+        // A successor whose fingerprint this rank has already routed is known to its owner: drop it
+        // here (direct-mapped, exact-compare cache: misses only cost a redundant record).
+        if (has && p.sent_cache) {
+          unsigned long long* cslot = p.sent_cache + (fp & p.sent_mask);
+          if (__ldcv(cslot) == fp) has = false; else *cslot = fp;
+        }
         int owner = has ? (int)__umul64hi(fp, (unsigned long long)p.n_ranks) : -1;
         const unsigned peers = __match_any_sync(0xffffffffu, owner);
         if (has) {
@@ -682,7 +690,7 @@ extern "C" void tlag_destroy(tlag_engine* e) {
   if (!e) return;
   cudaFree(e->d_code); cudaFree(e->d_cpool); cudaFree(e->d_layout); cudaFree(e->d_states);
   cudaFree(e->d_parent); cudaFree(e->d_meta); cudaFree(e->d_table); cudaFree(e->d_ctr);
-  cudaFree(e->d_scratch); cudaFree(e->d_flags); cudaFree(e->d_sort);
+  cudaFree(e->d_scratch); cudaFree(e->d_flags); cudaFree(e->d_sort); cudaFree(e->d_sent);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -802,6 +810,7 @@ extern "C" int tlag_restart(tlag_engine* e) {
   hc.viol_inv = hc.viol_assert = hc.viol_trap = hc.viol_deadlock = ~0ULL;
   CK(cudaMemcpyAsync(e->d_ctr, &hc, sizeof(hc), cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemsetAsync(e->d_table, 0, (1ULL << e->table_log2) * 8, e->stream));
+  if (e->d_sent) CK(cudaMemsetAsync(e->d_sent, 0, (e->p.sent_mask + 1) * 8, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->lo = e->hi = 0; e->level = 0; e->init_states = 0; e->generated = 0; e->depth = 0;
   e->verdict = TLAG_V_RUNNING; e->detail = e->detail2 = 0; e->viol_idx = 0; e->dev_seconds = 0;
@@ -992,6 +1001,13 @@ extern "C" int tlag_expand_route(tlag_engine* e, uint32_t n_ranks, uint64_t firs
   if (lo > e->hi) lo = e->hi;
   if (hi > e->hi) hi = e->hi;
   e->p.n_ranks = (int)n_ranks;
+  if (!e->d_sent && n_ranks > 1 && getenv("TLAG_NO_SENT_CACHE") == nullptr) {
+    const unsigned lg = 26;                                    // 2^26 x 8 B = 512 MB
+    if (cudaMalloc(&e->d_sent, (1ULL << lg) * 8) == cudaSuccess) {
+      CK(cudaMemsetAsync(e->d_sent, 0, (1ULL << lg) * 8, e->stream));
+      e->p.sent_cache = e->d_sent; e->p.sent_mask = (1ULL << lg) - 1;
+    } else { cudaGetLastError(); e->d_sent = nullptr; }
+  }
   e->p.send = (uint32_t*)(uintptr_t)d_send;
   e->p.region_cap = cap_records / n_ranks;
   CK(cudaMemsetAsync(&e->d_ctr->work, 0, 8, e->stream));
