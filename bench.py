@@ -172,9 +172,14 @@ def main():
     dev = f"cuda:{local_rank}"
     torch.cuda.set_device(local_rank)
     peak, peak_src = load_peaks()
-    multi = world > 1
+    multi = world > 1 or bool(os.environ.get("TLAG_FORCE_ROUTE"))   # knob: exercise the routed path on one GPU
     if multi:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(dev))
+        else:
+            dist.init_process_group("nccl", device_id=torch.device(dev))
 
     def barrier():
         if multi:
