@@ -117,8 +117,15 @@ def k1_microbench(dev, peak):
     e.close()
     del states, flags
     torch.cuda.empty_cache()
-    return {"kernel": "k_probe<4>", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(ach / peak, 4), "traffic": None, "n": n, "W": W, "p_new": n_new / n,
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_probe_staged"]
+        if tj["n"] == n and tj["W"] == W:
+            traffic = tj["bytes_per_launch"]
+    except Exception:
+        pass
+    return {"kernel": "k_probe_staged", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(ach / peak, 4), "traffic": traffic, "n": n, "W": W, "p_new": n_new / n,
             "ms_per_launch": round(med, 4), "candidates_per_s": round(n / (med * 1e-3), 1),
             "bytes_per_candidate": bytes_per}, launches
 
@@ -301,7 +308,8 @@ def main():
     roof = {"kernel": "k_wave (fused expand+fingerprint+probe+compact)", "bound": "hbm", "achieved": round(ach, 3),
             "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6), "traffic": None, "peak_source": peak_src,
             "bytes_per_step": int(bytes_step), "kernel_s_per_step": round(stats["kern_s"] / args.steps, 6),
-            "note": "interpreter-bound: the wave kernel executes the Next/invariant bytecode per state; HBM is idle"}
+            "note": "instruction-issue bound (ncu: issue-active 84%): the wave kernel interprets the Next/invariant "
+                    "bytecode per state; per-launch DRAM traffic is in profiles/r1_traffic.json (frame spills dominate)"}
     k1 = None
     k1_launches = 0
     if not args.no_k1 and not multi:

@@ -87,8 +87,8 @@ def _worker(rank, world, port, name, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["pcal_intro", "MCPaxos3"])
-def test_two_rank_partitioned_bfs_matches_single(name):
+@pytest.mark.parametrize("name,world", [("pcal_intro", 2), ("MCPaxos3", 2), ("MCPaxos3", 4), ("pcal_intro", 3)])
+def test_partitioned_bfs_matches_single(name, world):
     from tla_rust_b200.compiled import load_compiled
     _, _, exp, _ = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
     s = socket.socket()
@@ -97,7 +97,7 @@ def test_two_rank_partitioned_bfs_matches_single(name):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
