@@ -47,6 +47,15 @@ def pcal_copy(name, edits=(), cfg=None):
     return p
 
 
+def demo_copy(name):
+    d = tempfile.mkdtemp(prefix="tlag_gold_")
+    for ext in (".tla", ".cfg"):
+        shutil.copy(os.path.join(ROOT, "models", "demo", name + ext), d)
+    p = os.path.join(d, name + ".tla")
+    translate_file(p)
+    return p
+
+
 MODELS = {
     # name: (builder -> (tla path, Model kwargs), deadlock check, run O1?)
     "atomic_add": (lambda: (pcal_copy("atomic_add"), {}), True, True),
@@ -59,6 +68,11 @@ MODELS = {
                               "cfg_text": open(ROOT + "/models/MCPaxos3.cfg").read().replace("MaxBallot = 1", "MaxBallot = 2")}),
                     True, False),
     "MCVoting": (lambda: (REF + "/examples/Paxos/MCVoting.tla", {}), False, True),
+    # verdict kinds other than "ok": deadlock (Voting terminates: MCVoting with deadlock checking ON) and an
+    # invariant violation with a counterexample (builder-authored lost-update demo, models/demo/race.tla)
+    "MCVoting_deadlock": (lambda: (REF + "/examples/Paxos/MCVoting.tla", {}), True, True),
+    "demo_race": (lambda: (demo_copy("race"), {}), True, True),
+    "demo_lock": (lambda: (demo_copy("lock"), {}), True, True),
     "HourClock": (lambda: (REF + "/examples/SpecifyingSystems/HourClock/HourClock.tla", {}), True, True),
     "AsynchInterface": (lambda: (REF + "/examples/SpecifyingSystems/AsynchronousInterface/AsynchInterface.tla", {}), True, True),
 }

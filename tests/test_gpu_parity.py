@@ -18,6 +18,7 @@ def _engine(cm, **kw):
 
 
 @pytest.mark.parametrize("name", ["atomic_add", "pcal_intro", "pcal_intro_readme_buggy", "MCPaxos", "MCVoting",
+                                  "MCVoting_deadlock", "demo_race", "demo_lock",
                                   "HourClock", "AsynchInterface", "MCPaxos3", "MCPaxos3_b2", "MCPaxos3_b3", "MCPaxos3_b4"])
 def test_bfs_matches_oracle(name):
     from oracle import cpu_engine
@@ -66,6 +67,31 @@ def test_assert_trace_is_a_shortest_counterexample():
     last = res.trace[-1][0]
     assert last["alice_account"] < 0 and "C" in last["pc"]
     assert res.trace[0][0]["alice_account"] == 10 and res.trace[0][0]["pc"] == ("Transfer", "Transfer")
+    e.close()
+
+
+def test_invariant_and_deadlock_traces_are_valid_counterexamples():
+    """Verdict kinds other than ok: the reported state really is an error state and the parent chain is a
+    behaviour of minimal length starting in an initial state (level-synchronous BFS => shortest)."""
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, "demo_race.tlagz"))
+    e = _engine(cm)
+    e.seed(init)
+    r = e.run()
+    assert r["verdict"] == 1 and cm.invariants[r["detail"]] == "Correct"
+    res = result_from_engine(cm, r, e.trace(r["state_idx"]))
+    last = res.trace[-1][0]
+    assert last["pc"] == ("Done", "Done") and last["counter"] == 1      # lost update
+    assert len(res.trace) == 5 and res.trace[0][1] is None and res.trace[0][0]["counter"] == 0
+    for (s0, _), (s1, a1) in zip(res.trace, res.trace[1:]):
+        assert a1 is not None and s0 != s1
+    e.close()
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, "MCVoting_deadlock.tlagz"))
+    e = _engine(cm, deadlock=True)
+    e.seed(init)
+    r = e.run()
+    assert r["verdict"] == 3 and r["depth"] == exp["o2"]["depth"]
+    states, acts = e.trace(r["state_idx"])
+    assert len(states) >= 2 and acts[0] == -1 and (states[0] == init[0]).all()
     e.close()
 
 
