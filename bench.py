@@ -236,8 +236,7 @@ def main():
         stats = dict(kern_s=kern_s)
     else:
         from tla_rust_b200.dist import DistributedBFS
-        from tla_rust_b200.fingerprint import fingerprint_words
-        fps = [fingerprint_words(w) for w in init]
+        fps = None   # ownership is computed from the packed words (tla_rust_b200.fingerprint.owner_of_words)
 
         e = Engine(cm, deadlock=info["deadlock"], device=local_rank)
         d = DistributedBFS(e, cm, rank, world, dev, cap_records=1 << 26, chunk_states=1 << 22)

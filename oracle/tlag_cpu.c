@@ -371,8 +371,7 @@ int tlagcpu_shard_expand_route(cpu_shard *s, uint32_t n_ranks, uint64_t first, u
       if (ev == TLAG_EV_EMIT) {
         ++nsucc; ++gen;
         if (tlag_pack(m->layout, (int)m->n_slots, frame + m->unpacked_words, succ, W)) { if (!kind) kind = 4; continue; }
-        uint64_t fp = tlag_fingerprint(succ, W);
-        uint32_t owner = (uint32_t)(((unsigned __int128)fp * n_ranks) >> 64);
+        uint32_t owner = tlag_owner(succ, W, n_ranks);
         if (counts[owner] >= region) { free(frame); return -5; }
         uint32_t *dst = send + (owner * region + counts[owner]) * (uint64_t)(W + 2);
         memcpy(dst, succ, (size_t)W * 4);
@@ -400,3 +399,6 @@ void tlagcpu_shard_advance(cpu_shard *s) {
 void tlagcpu_shard_result(cpu_shard *s, uint64_t *out4) {
   out4[0] = s->e.generated; out4[1] = s->e.n_states; out4[2] = s->depth; out4[3] = (uint64_t)s->verdict;
 }
+
+uint32_t tlagcpu_owner(const uint32_t *w, int W, uint32_t n_ranks) { return tlag_owner(w, W, n_ranks); }
+

@@ -75,11 +75,10 @@ def _worker(rank, world, port, name, q):
     sys.path.insert(0, ROOT)
     from tla_rust_b200.compiled import load_compiled
     from tla_rust_b200.dist import DistributedBFS
-    from tla_rust_b200.fingerprint import fingerprint_words
     cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
     e = CpuShardEngine(cm, deadlock=info["deadlock"])
     d = DistributedBFS(e, cm, rank, world, "cpu", cap_records=1 << 16, chunk_states=500)
-    d.seed(init, [fingerprint_words(w) for w in init])
+    d.seed(init)
     out = d.run()
     if rank == 0:
         q.put((out["verdict"], out["generated"], out["distinct"], out["depth"], out["local"]["distinct"]))

@@ -264,7 +264,7 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
           unsigned long long* cslot = p.sent_cache + (fp & p.sent_mask);
           if (__ldcv(cslot) == fp) has = false; else *cslot = fp;
         }
-        int owner = has ? (int)__umul64hi(fp, (unsigned long long)p.n_ranks) : -1;
+        int owner = has ? (int)tlag_owner(succ, W, (uint32_t)p.n_ranks) : -1;
         const unsigned peers = __match_any_sync(0xffffffffu, owner);
         if (has) {
           const int leader = __ffs((int)peers) - 1;

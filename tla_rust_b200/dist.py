@@ -42,10 +42,11 @@ class DistributedBFS:
         self.comm_ms = 0.0
         self.exchanges = 0
 
-    def seed(self, init_words: np.ndarray, fingerprints):
-        """Every rank sees all initial states and keeps those it owns (owner = umulhi(fp, world))."""
-        from .fingerprint import owner_rank
-        own = np.array([owner_rank(int(fp), self.world) for fp in fingerprints], dtype=np.int64)
+    def seed(self, init_words: np.ndarray, fingerprints=None):
+        """Every rank sees all initial states and keeps those it owns (tlag_owner: hash of the state's
+        clustering key, so that whole clusters stay on one rank)."""
+        from .fingerprint import owner_of_words
+        own = np.array([owner_of_words(w, self.world) for w in init_words], dtype=np.int64)
         mine = init_words[own == self.rank]
         self.e.seed(mine)
         self.n_init_total = len(init_words)
