@@ -487,6 +487,50 @@ class Lowering:
             self.asm.emit("MOVN", dst, src, n)
 
     # --------------------------------------------------------------- ordinals
+    def ord_can_fail(self, E: T, v) -> bool:
+        """Static check: can the ordinal of v in E come out as -1 (value outside the universe)?"""
+        if type(v) is Const:
+            return self.codec.ord_of(E, v.v) < 0
+        if type(v) is OVal and v.t == E:
+            return False
+        s = v.t
+        if isinstance(E, TInt):
+            return not (isinstance(s, TInt) and s.lo is not None and E.lo is not None and E.lo <= s.lo and s.hi <= E.hi)
+        if isinstance(E, TBool):
+            return not isinstance(s, TBool)
+        if isinstance(E, TAtom):
+            return not (isinstance(s, TAtom) and set(s.atoms) <= set(E.atoms))
+        if isinstance(E, TRec):
+            if not isinstance(s, TRec):
+                return True
+            for alt in s.alts:
+                ai = E.alt_index(alt)
+                if ai < 0:
+                    return True
+                for f in alt:
+                    if self.ord_can_fail(E.alt_types[ai][f], Val(s.fields[f], 0)):
+                        return True
+            return False
+        if isinstance(E, TTuple):
+            if not (isinstance(s, TTuple) and len(s.elems) == len(E.elems)):
+                return True
+            return any(self.ord_can_fail(ee, Val(se, 0)) for ee, se in zip(E.elems, s.elems))
+        if isinstance(E, TSet):
+            return not isinstance(s, TSet)
+        if isinstance(E, TFun):
+            if not (isinstance(s, TFun) and s.keys == E.keys):
+                return True
+            return self.ord_can_fail(E.elem, Val(s.elem, 0))
+        return True
+
+    def horner(self, r, card, o):
+        """r = r * card + o  (one fused instruction when the radix fits the 14-bit immediate)."""
+        if 0 < card < (1 << 13):
+            self.asm.emit("MADI", r, card, o)
+        else:
+            self.asm.emit("MULI", r, r, card)
+            self.asm.emit("ADD", r, r, o)
+
     def ord_in(self, E: T, v) -> int:
         """Emit code computing the ordinal of v within E (or -1 when outside); returns the reg."""
         if type(v) is Const:
@@ -507,18 +551,21 @@ class Lowering:
                 return r
             if E.lo is None:
                 raise CompileError("ordinal of an unbounded integer type")
+            fail = self.ord_can_fail(E, v)
+            if E.lo == 0 and not fail:
+                return v.loc              # the value is its own ordinal
             if E.lo != 0:
                 self.asm.emit("ADDI", r, v.loc, -E.lo)
             else:
                 self.asm.emit("MOV", r, v.loc)
-            self.asm.emit("UCLAMP", r, E.card())
+            if fail:
+                self.asm.emit("UCLAMP", r, E.card())
             return r
         if isinstance(E, TBool):
             if not isinstance(s, TBool):
                 self.li(r, -1)
-            else:
-                self.asm.emit("MOV", r, v.loc)
-            return r
+                return r
+            return v.loc
         if isinstance(E, TAtom):
             if not isinstance(s, TAtom):
                 self.li(r, -1)
@@ -558,10 +605,11 @@ class Lowering:
             end = Label("oend")
             self.li(r, 0)
             for ee, se, so in zip(E.elems, s.elems, s.offs):
-                o = self.ord_in(ee, Val(se, v.loc + so))
-                self.asm.emit("JNEG", o, bad)
-                self.asm.emit("MULI", r, r, ee.card())
-                self.asm.emit("ADD", r, r, o)
+                sub = Val(se, v.loc + so)
+                o = self.ord_in(ee, sub)
+                if self.ord_can_fail(ee, sub):
+                    self.asm.emit("JNEG", o, bad)
+                self.horner(r, ee.card(), o)
             self.asm.emit("JMP", end)
             self.asm.label(bad)
             self.li(r, -1)
@@ -584,10 +632,11 @@ class Lowering:
             end = Label("oend")
             self.li(r, 0)
             for j in range(len(E.keys)):
-                o = self.ord_in(E.elem, Val(s.elem, v.loc + j * s.elem.size))
-                self.asm.emit("JNEG", o, bad)
-                self.asm.emit("MULI", r, r, E.elem.card())
-                self.asm.emit("ADD", r, r, o)
+                sub = Val(s.elem, v.loc + j * s.elem.size)
+                o = self.ord_in(E.elem, sub)
+                if self.ord_can_fail(E.elem, sub):
+                    self.asm.emit("JNEG", o, bad)
+                self.horner(r, E.elem.card(), o)
             self.asm.emit("JMP", end)
             self.asm.label(bad)
             self.li(r, -1)
@@ -603,10 +652,11 @@ class Lowering:
         self.li(r, 0)
         for f in E.alts[ai]:
             ft = E.alt_types[ai][f]
-            o = self.ord_in(ft, Val(s.fields[f], v.loc + s.off[f]))
-            self.asm.emit("JNEG", o, bad)
-            self.asm.emit("MULI", r, r, ft.card())
-            self.asm.emit("ADD", r, r, o)
+            sub = Val(s.fields[f], v.loc + s.off[f])
+            o = self.ord_in(ft, sub)
+            if self.ord_can_fail(ft, sub):
+                self.asm.emit("JNEG", o, bad)
+            self.horner(r, ft.card(), o)
         base = E.alt_base(ai)
         if base:
             self.asm.emit("ADDI", r, r, base)
@@ -1210,7 +1260,10 @@ class Lowering:
         return t
 
     def _set_add(self, dst, t: TSet, x, n=None):
-        o = self.ord_in(t.elem, x if type(x) is Const else x)
+        o = self.ord_in(t.elem, x)
+        if not self.ord_can_fail(t.elem, x):
+            self.asm.emit("BSET", dst, o)
+            return
         bad, ok = Label("sb"), Label("so")
         self.asm.emit("JNEG", o, bad)
         self.asm.emit("BSET", dst, o)
@@ -1747,10 +1800,15 @@ class Lowering:
                 alive, masked = keep, True
         if not masked:
             return sv, items
-        mloc = self.alloc(sv.t.size)
-        self.load_words(mloc, self.mask_words(E, alive))
         dst = self.alloc(sv.t.size)
-        self.asm.emit("BAND", dst, sv.loc, mloc, sv.t.size)
+        words = self.mask_words(E, alive)
+        base = self.asm.const_table(words)
+        if base < (1 << 19) and sv.t.size < 256:
+            self.asm.emit("BANDC", dst, sv.loc, (base << 8) | sv.t.size)
+        else:
+            mloc = self.alloc(sv.t.size)
+            self.load_words(mloc, words)
+            self.asm.emit("BAND", dst, sv.loc, mloc, sv.t.size)
         return MVal(sv.t, dst, alive), rest
 
     def forall_val(self, sv: Val, pat, P, env, ctx, base, lf):
@@ -2156,7 +2214,7 @@ class Lowering:
             self.asm.emit("BTESTI", t1, sv.loc, oc)
         else:
             o = self.ord_in(sv.t.elem, e)
-            if not (type(e) is OVal and e.t == sv.t.elem):
+            if self.ord_can_fail(sv.t.elem, e):
                 self.asm.emit("JNEG", o, lf)
             self.asm.emit("BTEST", t1, sv.loc, o)
         self.asm.emit("JNZ", t1, lt)

@@ -30,6 +30,7 @@ enum {
   OP_LDX, OP_STX, OP_TBL, OP_TBLT, OP_BSET, OP_BCLR, OP_BTEST, OP_BOR,
   OP_BAND, OP_BANDN, OP_BISZ, OP_BSUB, OP_BCNT, OP_BNEXT, OP_BFILL, OP_BSETI,
   OP_BTESTI, OP_UCLAMP, OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
+  OP_MADI, OP_BANDC,
   OP__COUNT
 };
 
@@ -195,6 +196,11 @@ TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uin
       case OP_GEN: *pc_io = pc; return TLAG_EV_GEN;
       case OP_ASSERTF: *info = immI; *pc_io = pc; return TLAG_EV_ASSERT;
       case OP_INVF: *info = immI; *pc_io = pc; return TLAG_EV_INVF;
+      case OP_BANDC: {  // f[a..a+n) = f[b..b+n) & cpool[base..): set AND compile-time universe mask (immJ = base<<8 | n)
+        const uint32_t n = (uint32_t)immJ & 0xFF; const int32_t base = (int32_t)((uint32_t)immJ >> 8);
+        for (uint32_t i = 0; i < n; ++i) f[a + i] = f[b + i] & tlag_cp(cpool, base + (int32_t)i);
+        break; }
+      case OP_MADI: f[a] = (int32_t)((uint32_t)f[a] * (uint32_t)((int32_t)(b << 18) >> 18) + (uint32_t)f[c]); break;   // Horner step
       default: *info = 99; *info2 = (int32_t)op; *pc_io = pc; return TLAG_EV_TRAP;
     }
   }
