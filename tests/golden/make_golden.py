@@ -73,6 +73,10 @@ MODELS = {
     "MCVoting_deadlock": (lambda: (REF + "/examples/Paxos/MCVoting.tla", {}), True, True),
     "demo_race": (lambda: (demo_copy("race"), {}), True, True),
     "demo_lock": (lambda: (demo_copy("lock"), {}), True, True),
+    # bounded sequences (Seq(S) with a capacity = constraint bound + 1: states one element past the CONSTRAINT
+    # are generated and counted, then not explored -- FIFO/MCInnerFIFO.cfg:23-31)
+    "MCInnerFIFO": (lambda: (REF + "/examples/SpecifyingSystems/FIFO/MCInnerFIFO.tla", {}), True, True, 4),
+    "MCAlternatingBit": (lambda: (REF + "/examples/SpecifyingSystems/TLC/MCAlternatingBit.tla", {}), True, True, 4),
     "HourClock": (lambda: (REF + "/examples/SpecifyingSystems/HourClock/HourClock.tla", {}), True, True),
     "AsynchInterface": (lambda: (REF + "/examples/SpecifyingSystems/AsynchronousInterface/AsynchInterface.tla", {}), True, True),
 }
@@ -80,7 +84,9 @@ MODELS = {
 
 def main():
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
-    for name, (mk, deadlock, run_o1) in MODELS.items():
+    for name, spec in MODELS.items():
+        mk, deadlock, run_o1 = spec[:3]
+        seq_cap = spec[3] if len(spec) > 3 else None
         if only and name != only:
             continue
         t0 = time.time()
@@ -89,7 +95,7 @@ def main():
         m.check_deadlock = deadlock
         m.check_assumes()
         init = m.initial_states()
-        cm = compile_model(m, init)
+        cm = compile_model(m, init, seq_cap=seq_cap)
         iw = encode_states(cm, init)
         o2 = cpu_engine.run(cm, iw, n_threads=os.cpu_count() or 1, deadlock=deadlock, max_states=1 << 26)
         exp = {"o2": {k: o2[k] for k in ("verdict", "detail", "generated", "distinct", "depth", "init_states",

@@ -218,28 +218,56 @@ class Lowering:
         m = self.m
         types = {}
         hint = self.type_hint
-        cand = [hint] if hint else [n for n in self.ctx.defs
-                                    if re.fullmatch(r"(I?Type(OK|Inv|Invariant|Correct)?)", n)]
-        cand.sort(key=lambda n: (n.startswith("I"), n))
+        # candidate type invariants: an explicit hint, the cfg's INVARIANTs, then every definition whose
+        # name looks like one (TypeOK, TypeInv, ABTypeInv, TypeInvariant, ITypeOK ...)
+        cand = [hint] if hint else []
+        if not hint:
+            cand += [nm for nm, _, _ in m.invariants]
+            named = [n for n in self.ctx.defs if re.search(r"Type(OK|Inv|Invariant|Correct)", n)]
+            named.sort(key=lambda n: (n.startswith("I"), len(n), n))
+            cand += [n for n in named if n not in cand]
+
+        def harvest(node, ctx, got, depth=0):
+            """collect  v \\in S / v \\subseteq S  conjuncts, following nested conjunctions and definitions"""
+            if depth > 6:
+                return
+            if node.k == "and":
+                for x in node.a[0]:
+                    harvest(x, ctx, got, depth)
+                return
+            if node.k == "bin" and node.a[0] in ("\\in", "\\subseteq") and node.a[1].k == "id" \
+                    and node.a[1].a[0] in ctx.varset and node.a[1].a[0] not in ctx.substs:
+                v = node.a[1].a[0]
+                try:
+                    sv = self.ev.eval(node.a[2], {}, Fr(ctx))
+                    et = type_of_set(sv, self.seq_cap)
+                    got.setdefault(v, TSet(et) if node.a[0] == "\\subseteq" else et)
+                except (EvalError, TypeErr) as ex:
+                    self.warnings.append(f"type hint: cannot use conjunct for {v}: {ex}")
+                return
+            if node.k == "id":
+                d2 = ctx.defs.get(node.a[0])
+                if d2 is not None and not d2[0].params and node.a[0] not in ctx.varset:
+                    harvest(d2[0].body, d2[1], got, depth + 1)
+                return
+            if node.k == "sel":
+                try:
+                    r = self.ev.resolve_sel(node.a[0], {}, Fr(ctx))
+                except EvalError:
+                    return
+                if r[0] == "def" and not r[1].params:
+                    # variables of an instance are substituted: only root-module variables are typed here
+                    harvest(r[1].body, r[2], got, depth + 1)
+
         for name in cand:
             d = self.ctx.defs.get(name)
             if d is None or d[0].params:
                 continue
-            body = d[0].body
-            items = body.a[0] if body.k == "and" else (body,)
             got = {}
-            for it in items:
-                if it.k == "bin" and it.a[0] in ("\\in", "\\subseteq") and it.a[1].k == "id" \
-                        and it.a[1].a[0] in self.ctx.varset:
-                    v = it.a[1].a[0]
-                    try:
-                        sv = self.ev.eval(it.a[2], {}, Fr(d[1]))
-                        et = type_of_set(sv, self.seq_cap)
-                        got[v] = TSet(et) if it.a[0] == "\\subseteq" else et
-                    except (EvalError, TypeErr) as ex:
-                        self.warnings.append(f"type hint {name}: cannot use conjunct for {v}: {ex}")
+            harvest(d[0].body, d[1], got)
             for v, t in got.items():
-                types.setdefault(v, t)
+                if v in m.vars:
+                    types.setdefault(v, t)
             if all(v in types for v in m.vars):
                 break
         all_atoms = [self.atoms.val(i) for i in range(1, len(self.atoms.vals))]
@@ -316,13 +344,13 @@ class Lowering:
             pass
         try:
             v = self.ev.eval(node, self.eval_env(env), Fr(ctx, None, None))
+            if isinstance(v, LazyFcn):
+                v = v.force()
         except (EvalError, AssertFailure, RecursionError, TypeErr, TypeError, KeyError, AttributeError,
                 ValueError, IndexError):
             return None
         if isinstance(v, (OpVal, Closure, BuiltinOp)):
             return None
-        if isinstance(v, LazyFcn):
-            v = v.force()
         return Const(v)
 
     # ------------------------------------------------------- materialisation
@@ -1354,6 +1382,40 @@ class Lowering:
             raise CompileError("multi-argument function constructors are not supported")
         pat, sn = bounds[0]
         kind = self.set_elements(sn, env, ctx, base)
+        if kind[0] == "range" and type(kind[1]) is Const and kind[1].v == 1 and isinstance(pat, str):
+            # [j \in 1..n |-> e] with a run-time n: a sequence of run-time length (AlternatingBit.tla Lose)
+            hi = self.as_val(kind[2], TInt())
+            cap = want.cap if isinstance(want, TSeq) else (hi.t.hi if hi.t.lo is not None else self.seq_cap)
+            if cap is None:
+                raise CompileError("sequence comprehension needs a capacity (seq_cap)")
+            et = want.elem if isinstance(want, TSeq) else None
+            if et is None:
+                with self.asm.capture():
+                    save_top = self.top
+                    x0 = self.cx(body, self.bind(env, pat, Const(1)), ctx, base)
+                    et = x0.t if isinstance(x0, Val) else self.natural_type(x0.v)
+                    self.top = save_top
+            t = want if isinstance(want, TSeq) else TSeq(et, cap)
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            done, ovf, okl = Label("scd"), Label("sco"), Label("sck")
+            t1 = self.alloc(1)
+            self.asm.emit("LEI", t1, hi.loc, 0)
+            self.asm.emit("JNZ", t1, done)
+            self.asm.emit("GTI", t1, hi.loc, t.cap)
+            self.asm.emit("JNZ", t1, ovf)
+            self.asm.emit("MOV", dst, hi.loc)
+            for j in range(1, t.cap + 1):
+                t2 = self.alloc(1)
+                self.asm.emit("LTI", t2, hi.loc, j)
+                self.asm.emit("JNZ", t2, done)
+                xv = self.coerce(self.cx(body, self.bind(env, pat, Const(j)), ctx, base, t.elem), t.elem)
+                self.movn(dst + 1 + (j - 1) * t.elem.size, xv.loc, t.elem.size)
+            self.asm.emit("JMP", done)
+            self.asm.label(ovf)
+            self.asm.emit("TRAP", TRAP_OVERFLOW, n.line)
+            self.asm.label(done)
+            return Val(t, dst)
         if kind[0] != "const":
             raise CompileError("function constructor over a runtime domain is not supported")
         keys = sorted(kind[1], key=vkey)
@@ -1414,16 +1476,6 @@ class Lowering:
                 raise CompileError("heterogeneous tuple indexed by a runtime value")
             o = self.ord_in(TInt(1, len(ft.elems)), kx)
             return ("dyn", o)
-        if isinstance(ft, TSeq):
-            kv = self.as_val(kx, TInt())
-            o = self.alloc(1)
-            self.asm.emit("ADDI", o, kv.loc, -1)
-            # (unsigned)(i-1) < len  else -1
-            t1 = self.alloc(1)
-            ok, bad, end = Label("sk"), Label("sb"), Label("se")
-            self.asm.emit("JNEG", o, bad)
-            self.asm.emit("LT", t1, o, None)  # patched below
-            raise CompileError("internal")  # replaced by seq_index
         raise CompileError(f"value of type {ft} is not a function")
 
     def x_fapp(self, n, env, ctx, base, want):
@@ -1465,7 +1517,6 @@ class Lowering:
         if type(f) is OVal:
             f = Val(ft, f.loc)
         ok = Label("ak")
-        self.asm.emit("JNEG", o, Label("dummy")) if False else None
         bad = Label("ab")
         self.asm.emit("JNEG", o, bad)
         dst = self.alloc(et.size)
@@ -1592,7 +1643,6 @@ class Lowering:
             t = TSet(TInt(1, f.t.cap))
             dst = self.alloc(t.size)
             self.asm.emit("ZERO", dst, t.size)
-            self.asm.emit("BFILL", dst, 0)  # placeholder, filled below via loop
             # bits 0..len-1
             i = self.alloc(1)
             tmp = self.alloc(1)
@@ -2221,7 +2271,7 @@ class Lowering:
         self.asm.emit("JMP", lf)
 
     def _in_const_set(self, e: Val, s, lt, lf, n):
-        from ..front.values import SetFuncs, SetSubset, SetRecs, SetTimes, SetUnionLazy
+        from ..front.values import SetFuncs, SetSubset, SetRecs, SetTimes, SetUnionLazy, SetSeq
         t = e.t
         # structural membership in lazy set values (never enumerate [S -> T], SUBSET S, ...)
         if isinstance(s, SetUnionLazy):
@@ -2268,6 +2318,24 @@ class Lowering:
             for f, fs in s.fields:
                 nxt = Label("mr")
                 self._in_const_set(Val(t.fields[f], e.loc + t.off[f]), fs, nxt, lf, n)
+                self.asm.label(nxt)
+            self.asm.emit("JMP", lt)
+            return
+        if isinstance(s, SetSeq) and isinstance(t, (TSeq, TTuple)):
+            if isinstance(t, TTuple):
+                for j in range(len(t.elems)):
+                    nxt = Label("mq")
+                    self._in_const_set(Val(t.elems[j], e.loc + t.offs[j]), s.s, nxt, lf, n)
+                    self.asm.label(nxt)
+                self.asm.emit("JMP", lt)
+                return
+            es = t.elem.size
+            for j in range(t.cap):            # element j is checked only if j < Len
+                nxt = Label("mq")
+                t2 = self.alloc(1)
+                self.asm.emit("LEI", t2, e.loc, j)
+                self.asm.emit("JNZ", t2, lt)
+                self._in_const_set(Val(t.elem, e.loc + 1 + j * es), s.s, nxt, lf, n)
                 self.asm.label(nxt)
             self.asm.emit("JMP", lt)
             return
@@ -2517,6 +2585,9 @@ class Lowering:
             return self._assign_target(lz.node, lz.env, lz.ctx, bound)
         if ln.k == "prime" and ln.a[0].k == "id":
             v = ln.a[0].a[0]
+            if v in env and type(env[v]) is Lazy and env[v].node.k == "id":
+                lz = env[v]
+                return self._assign_target(Node("prime", (lz.node,)), lz.env, lz.ctx, bound)
             if v in ctx.varset and v not in env and v not in ctx.substs and v not in bound \
                     and v in self.var_types:
                 return v

@@ -236,6 +236,11 @@ class Evaluator:
             if name == "Assert" or name == "Print" or name == "PrintT":
                 return op.fn(*[self.eval_arg(a, env, fr) for a in args], node=n)
             return op.fn(*[self.eval_arg(a, env, fr) for a in args])
+        if type(op) is OpVal and fr.t is not None and len(op.d.params) == len(args):
+            # inside an action, parameters are passed by name (a callee may prime them: AlternatingBit.tla Lose(q))
+            argv = [Thunk(a, env, fr.ctx) if (pa[1] == 0 and a.k in ("id", "prime", "fapp", "dot")) else
+                    self.eval_arg(a, env, fr) for a, pa in zip(args, op.d.params)]
+            return self.apply_op(op, argv, fr, n)
         return self.apply_op(op, [self.eval_arg(a, env, fr) for a in args], fr, n)
 
     def apply_op(self, op, args, fr, n=None):
@@ -964,6 +969,12 @@ class Evaluator:
             th = env.get(ln.a[0])
             if type(th) is Thunk and not th.done and th.body.k in ("prime", "id"):
                 return self._assign_target(th.body, th.ctx, asg, target, th.env)
+        if ln.k == "prime" and ln.a[0].k == "id":
+            # q' where q is an operator parameter passed a variable by name: Lose(q) == ... q' = ...
+            # (TLC/AlternatingBit.tla) -- the primed parameter denotes the primed argument
+            th = env.get(ln.a[0].a[0])
+            if type(th) is Thunk and th.body.k == "id":
+                return self._assign_target(Node("prime", (th.body,)), th.ctx, asg, target, th.env)
         if target == "next":
             if ln.k == "prime" and ln.a[0].k == "id":
                 v = ln.a[0].a[0]
