@@ -10,6 +10,7 @@ MCAcceptor == {a1, a2, a3}
 MCValue    == {v1, v2}
 MCQuorum   == {{a1, a2}, {a1, a3}, {a2, a3}}
 MCBallot   == 0..MaxBallot
+MCSymmetry == Permutations(MCAcceptor) \cup Permutations(MCValue)   \* as in the reference's MCPaxos.tla:12
 
 Inv1 == Inv!1
 Inv2 == Inv!2

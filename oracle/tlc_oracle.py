@@ -37,9 +37,24 @@ class Oracle:
         self.m = model
         self.ev = model.ev
         self.vars = model.vars
+        self.group = model.symmetry_group()
 
     def key(self, st):
         return tuple(st[v] for v in self.vars)
+
+    def canon(self, st):
+        """Representative of st's orbit under the SYMMETRY group: the permuted state that is least in the
+        canonical value order (any fixed choice yields the same orbit count)."""
+        if not self.group:
+            return st
+        from tla_rust_b200.front.values import permute_value, vkey
+        best, bk = st, tuple(vkey(st[v]) for v in self.vars)
+        for p in self.group:
+            c = {v: permute_value(st[v], p) for v in self.vars}
+            ck = tuple(vkey(c[v]) for v in self.vars)
+            if ck < bk:
+                best, bk = c, ck
+        return best
 
     def successors(self, st):
         """Yield (next-state dict, action label) in TLC's enumeration order."""
@@ -119,6 +134,7 @@ class Oracle:
             return finish(ASSERT)
         for st in inits:
             res.generated += 1
+            st = self.canon(st)
             k = self.key(st)
             if k in seen:
                 continue
@@ -159,6 +175,7 @@ class Oracle:
                             res.trace = trace_to(cur, (t, act))
                             return finish(PROPERTY)
                     in_model = self.in_model(t) and self.in_actions(st, t)
+                    t = self.canon(t)
                     k = self.key(t)
                     is_seen = False
                     idx = -1

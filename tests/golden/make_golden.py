@@ -63,6 +63,9 @@ MODELS = {
     "pcal_intro_readme_buggy": (lambda: (pcal_copy("pcal_intro", README_BUGGY, cfg="SPECIFICATION Spec\n"), {}), True, True),
     "MCPaxos": (lambda: (REF + "/examples/Paxos/MCPaxos.tla", {}), True, True),
     "MCPaxos3": (lambda: (ROOT + "/models/MCPaxos3.tla", {"extra_dirs": [REF + "/examples/Paxos"]}), True, True),
+    "MCPaxos3_sym": (lambda: (ROOT + "/models/MCPaxos3.tla",
+                              {"extra_dirs": [REF + "/examples/Paxos"], "cfg_path": ROOT + "/models/MCPaxos3_sym.cfg"}),
+                     True, True),
     "MCPaxos3_b2": (lambda: (ROOT + "/models/MCPaxos3.tla",
                              {"extra_dirs": [REF + "/examples/Paxos"],
                               "cfg_text": open(ROOT + "/models/MCPaxos3.cfg").read().replace("MaxBallot = 1", "MaxBallot = 2")}),

@@ -58,14 +58,27 @@ def unpack_words(cm: CompiledModel, words) -> list:
     return st
 
 
+def _frame_of(cm: CompiledModel, st) -> list:
+    frame = [0] * cm.state_words_unpacked
+    for v in cm.vars:
+        r = cm.codec.rep(cm.var_types[v], st[v])
+        o = cm.var_off[v]
+        frame[o:o + len(r)] = r
+    return frame
+
+
 def encode_states(cm: CompiledModel, states) -> np.ndarray:
+    """Pack host states.  Under SYMMETRY every state is first replaced by the representative the device
+    uses: the image under the group whose unpacked frame is word-wise (signed) lexicographically least."""
+    from .front.values import permute_value
+    group = getattr(cm, "group", None) or []
     out = np.zeros((len(states), cm.W), dtype=np.uint32)
     for i, st in enumerate(states):
-        frame = [0] * cm.state_words_unpacked
-        for v in cm.vars:
-            r = cm.codec.rep(cm.var_types[v], st[v])
-            o = cm.var_off[v]
-            frame[o:o + len(r)] = r
+        frame = _frame_of(cm, st)
+        for perm in group:
+            cand = _frame_of(cm, {v: permute_value(st[v], perm) for v in cm.vars})
+            if cand < frame:
+                frame = cand
         out[i] = pack_words(cm, frame)
     return out
 

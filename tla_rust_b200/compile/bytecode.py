@@ -18,7 +18,7 @@ OPS = [
     "JMP", "LI", "LIW", "MOV", "MOVN", "ZERO", "LDC", "DIV", "MOD",
     "NEG", "EQN", "NOT", "LDX", "STX", "TBL", "TBLT", "BSET", "BCLR",
     "BTEST", "BOR", "BAND", "BANDN", "BISZ", "BSUB", "BCNT", "BNEXT", "BFILL",
-    "BSETI", "BTESTI", "UCLAMP", "TRAP", "EMIT", "GEN", "ASSERTF", "INVF", "MADI", "BANDC",
+    "BSETI", "BTESTI", "UCLAMP", "TRAP", "EMIT", "GEN", "ASSERTF", "INVF", "MADI", "BANDC", "LEXLT",
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 
@@ -36,7 +36,7 @@ FMT = {
     "GEI": "rrJ", "UCLAMP": "rI", "BSETI": "rI", "BTESTI": "rrJ", "SHRI": "rrJ", "ANDI": "rrJ", "TBLT": "rIr",
     "JEQ": "rrJ", "JNE": "rrJ", "JLT": "rrJ", "JGE": "rrJ",
     "JEQI": "rkJ", "JNEI": "rkJ", "JLTI": "rkJ", "JGEI": "rkJ",
-    "JBT": "rrJ", "JBF": "rrJ", "JBTI": "rnJ", "JBFI": "rnJ", "JGEZ": "rI", "MADI": "rkr", "BANDC": "rrJ",
+    "JBT": "rrJ", "JBF": "rrJ", "JBTI": "rnJ", "JBFI": "rnJ", "JGEZ": "rI", "MADI": "rkr", "BANDC": "rrJ", "LEXLT": "rrrn",
 }
 
 INVERSE = {"JZ": "JNZ", "JEQ": "JNE", "JLT": "JGE", "JEQI": "JNEI", "JLTI": "JGEI", "JBT": "JBF", "JBTI": "JBFI",

@@ -118,6 +118,7 @@ class CompiledModel:
         self.asserts = []        # id -> message
         self.atoms = None
         self.codec = None
+        self.group = []          # SYMMETRY group (non-identity permutations of model values)
         self.warnings = []
 
 
@@ -145,6 +146,7 @@ class Lowering:
         self.program = "inv"
         self.hoist_keys = []
         self.dry = False
+        self.group = model.symmetry_group() if hasattr(model, "symmetry_group") else []
         self._intern_all_atoms()
 
     @staticmethod
@@ -2609,6 +2611,98 @@ class Lowering:
             return all(self._unchanged_vars(x, env, ctx, out) for x in e.a[0])
         return False
 
+    # ---------------------------------------------------------------- symmetry
+    def _perm_touches(self, t: T, perm) -> bool:
+        """Does applying `perm` (dict ModelValue -> ModelValue) change any value of type t?"""
+        if isinstance(t, TAtom):
+            return any(a in perm and perm[a] != a for a in t.atoms)
+        if isinstance(t, (TInt, TBool, TBottom)):
+            return False
+        if isinstance(t, TRec):
+            return any(self._perm_touches(x, perm) for x in t.fields.values())
+        if isinstance(t, TTuple):
+            return any(self._perm_touches(x, perm) for x in t.elems)
+        if isinstance(t, TFun):
+            return any(k in perm and perm[k] != k for k in t.keys) or self._perm_touches(t.elem, perm)
+        if isinstance(t, (TSet, TSeq)):
+            return self._perm_touches(t.elem, perm)
+        return True
+
+    def gen_perm(self, t: T, src, dst, perm):
+        """Emit code writing the image of the value at frame[src..] under `perm` to frame[dst..]."""
+        from ..front.values import permute_value
+        if not self._perm_touches(t, perm):
+            self.movn(dst, src, t.size)
+            return
+        if isinstance(t, TAtom):
+            tbl = list(range(len(self.atoms.vals)))
+            for a in t.atoms:
+                if a in perm:
+                    tbl[self.atoms.id(a)] = self.atoms.id(perm[a])
+            self.asm.emit("TBL", dst, self.asm.const_table(tbl), src)
+            return
+        if isinstance(t, TRec):
+            if t.tagged:
+                self.asm.emit("MOV", dst, src)
+            for f in t.fnames:
+                self.gen_perm(t.fields[f], src + t.off[f], dst + t.off[f], perm)
+            return
+        if isinstance(t, TTuple):
+            for e, o in zip(t.elems, t.offs):
+                self.gen_perm(e, src + o, dst + o, perm)
+            return
+        if isinstance(t, TFun):
+            es = t.elem.size
+            for i, k in enumerate(t.keys):
+                j = t.kindex[perm.get(k, k)] if (is_atom(k) and not isinstance(k, str)) else i
+                self.gen_perm(t.elem, src + i * es, dst + j * es, perm)
+            return
+        if isinstance(t, TSet):
+            vals = self._enum_cached(t.elem)
+            ptab = [self.codec.ord_of(t.elem, permute_value(v, perm)) for v in vals]
+            if any(o < 0 for o in ptab):
+                raise CompileError("SYMMETRY: a set universe is not closed under the permutation")
+            base = self.asm.const_table(ptab)
+            self.asm.emit("ZERO", dst, t.size)
+            idx, pidx = self.alloc(1), self.alloc(1)
+            top, done = Label("pl"), Label("pd")
+            self.li(idx, -1)
+            self.asm.label(top)
+            self.asm.emit("BNEXT", idx, src, idx, t.nbits)
+            self.asm.emit("JNEG", idx, done)
+            self.asm.emit("TBL", pidx, base, idx)
+            self.asm.emit("BSET", dst, pidx)
+            self.asm.emit("JMP", top)
+            self.asm.label(done)
+            return
+        if isinstance(t, TSeq):
+            self.asm.emit("MOV", dst, src)
+            for j in range(t.cap):
+                self.gen_perm(t.elem, src + 1 + j * t.elem.size, dst + 1 + j * t.elem.size, perm)
+            return
+        raise CompileError(f"SYMMETRY: cannot permute values of type {t}")
+
+    def gen_canonicalize(self, group):
+        """Replace the primed state by the least (word-wise lexicographic on the unpacked frame) of its images
+        under the symmetry group, so that one representative per orbit reaches the seen-set (K6 of SURVEY §2c)."""
+        usz = self.usz
+        best, cand = self.alloc(usz), self.alloc(usz)
+        p0 = self.p_off[self.m.vars[0]]
+        self.movn(best, p0, usz)
+        for perm in group:
+            mk = self.mark()
+            for v in self.m.vars:
+                off = self.n_off[v]
+                self.gen_perm(self.var_types[v], p0 + off, cand + off, perm)
+            t1 = self.alloc(1)
+            skip = Label("cs")
+            self.asm.emit("LEXLT", t1, cand, best, usz)
+            self.asm.emit("JZ", t1, skip)
+            self.movn(best, cand, usz)
+            self.asm.label(skip)
+            self.release(mk)
+        self.movn(p0, best, usz)
+
     # ------------------------------------------------------------------ driver
     def compile(self, init_states) -> CompiledModel:
         """Two passes: a dry pass counts how often each zero-arity state-level definition
@@ -2662,6 +2756,7 @@ class Lowering:
             self.n_off[v] = off
             off += self.var_types[v].size
         usz = off
+        self.usz = usz
         for v in m.vars:
             self.p_off[v] = usz + self.n_off[v]
         self.top = self.high = 2 * usz
@@ -2711,6 +2806,10 @@ class Lowering:
                 self.asserts.append(("\x00property:" + nm, nxt2.loc()))
                 self.asm.emit("ASSERTF", len(self.asserts) - 1)
                 self.asm.label(ok)
+            if self.group:
+                mk = self.mark()
+                self.gen_canonicalize(self.group)
+                self.release(mk)
             if m.constraints or m.action_constraints:
                 ok, bad, end = Label("cok"), Label("cbad"), Label("cend")
                 mk = self.mark()
@@ -2745,6 +2844,7 @@ class Lowering:
         cm.asserts = list(self.asserts)
         cm.invariants = [nm for nm, _, _ in m.invariants]
         cm.atoms, cm.codec = self.atoms, self.codec
+        cm.group = list(self.group)
         cm.warnings = self.warnings
         # packed layout
         lay = []

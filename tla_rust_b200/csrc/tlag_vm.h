@@ -30,7 +30,7 @@ enum {
   OP_LDX, OP_STX, OP_TBL, OP_TBLT, OP_BSET, OP_BCLR, OP_BTEST, OP_BOR,
   OP_BAND, OP_BANDN, OP_BISZ, OP_BSUB, OP_BCNT, OP_BNEXT, OP_BFILL, OP_BSETI,
   OP_BTESTI, OP_UCLAMP, OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
-  OP_MADI, OP_BANDC,
+  OP_MADI, OP_BANDC, OP_LEXLT,
   OP__COUNT
 };
 
@@ -200,6 +200,10 @@ TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uin
         const uint32_t n = (uint32_t)immJ & 0xFF; const int32_t base = (int32_t)((uint32_t)immJ >> 8);
         for (uint32_t i = 0; i < n; ++i) f[a + i] = f[b + i] & tlag_cp(cpool, base + (int32_t)i);
         break; }
+      case OP_LEXLT: {  // f[a] = (f[b..b+d) <lex f[c..c+d)), word-wise signed: SYMMETRY canonicalisation
+        int32_t r = 0;
+        for (uint32_t i = 0; i < d; ++i) { const int32_t x = f[b + i], y = f[c + i]; if (x != y) { r = x < y; break; } }
+        f[a] = r; break; }
       case OP_MADI: f[a] = (int32_t)((uint32_t)f[a] * (uint32_t)((int32_t)(b << 18) >> 18) + (uint32_t)f[c]); break;   // Horner step
       default: *info = 99; *info2 = (int32_t)op; *pc_io = pc; return TLAG_EV_TRAP;
     }

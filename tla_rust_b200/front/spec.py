@@ -388,6 +388,26 @@ class Model:
             return
         self.init_nodes.append((n, ctx))
 
+    def symmetry_group(self):
+        """Non-identity elements of the group generated by the SYMMETRY set (Paxos/MCPaxos.cfg:13:
+        Permutations(MCAcceptor) \\cup Permutations(MCValue)).  TLC applies the listed permutations as given; a
+        set that is not closed under composition does not define an equivalence, so the generated group is used
+        (identical to TLC's result whenever the listed set is itself a group)."""
+        if not self.symmetry:
+            return []
+        from .values import permutation_group, to_finite, Fcn, ModelValue
+        d, c = self._def(self.symmetry)
+        val = to_finite(self.ev.eval(d.body, {}, Fr(c)))
+        perms = []
+        for f in val:
+            if isinstance(f, tuple):
+                raise SpecError("SYMMETRY permutations must be over model values")
+            if not isinstance(f, Fcn) or not all(isinstance(k, ModelValue) and isinstance(x, ModelValue)
+                                                 for k, x in f.d.items()):
+                raise SpecError("SYMMETRY must be a set of permutations of model values")
+            perms.append(dict(f.d))
+        return permutation_group(perms)
+
     def _split_prop(self, n, ctx, acc):
         if n.k == "and":
             for x in n.a[0]:

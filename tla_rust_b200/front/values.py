@@ -435,3 +435,52 @@ def fmt(v):
     if isinstance(v, LazySet):
         return repr(v)
     return repr(v)
+
+
+# --------------------------------------------------------------------------
+# SYMMETRY support: permutations of model values applied to arbitrary values
+def permute_value(v, perm: dict):
+    """Apply a permutation of model values (dict ModelValue -> ModelValue) to a value."""
+    t = type(v)
+    if t is ModelValue:
+        return perm.get(v, v)
+    if t is tuple:
+        return tuple(permute_value(x, perm) for x in v)
+    if t is frozenset:
+        return frozenset(permute_value(x, perm) for x in v)
+    if t is Fcn:
+        return mk_fcn({permute_value(k, perm): permute_value(x, perm) for k, x in v.d.items()})
+    if isinstance(v, LazyFcn):
+        return permute_value(v.force(), perm)
+    if isinstance(v, LazySet):
+        return permute_value(to_finite(v), perm)
+    return v
+
+
+def permutation_group(perms):
+    """Close a set of permutations (dicts) under composition; returns the non-identity elements."""
+    dom = sorted({k for p in perms for k in p}, key=lambda m: m.name)
+    if not dom:
+        return []
+
+    def norm(p):
+        return tuple(p.get(k, k) for k in dom)
+
+    ident = tuple(dom)
+    gens = {norm(p) for p in perms if norm(p) != ident}
+    group = {ident}
+    frontier = [ident]
+    while frontier:
+        nxt = []
+        for g in frontier:
+            gd = dict(zip(dom, g))
+            for h in gens:
+                hd = dict(zip(dom, h))
+                comp = tuple(hd[gd[k]] for k in dom)     # h o g
+                if comp not in group:
+                    group.add(comp)
+                    nxt.append(comp)
+        frontier = nxt
+        if len(group) > 50000:
+            raise EvalError("symmetry group too large")
+    return [dict(zip(dom, g)) for g in sorted(group, key=lambda g: tuple(x.name for x in g)) if g != ident]
