@@ -54,11 +54,18 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
         print("Model checking completed. No error has been found.", file=out)
         print("  (the module has no behaviour specification; only its assumptions were checked)", file=out)
         return 0
-    if m.symmetry:
-        print(f"Warning: SYMMETRY {m.symmetry} is ignored (states are not reduced; the verdict is unaffected)", file=out)
-    if m.properties:
-        print(f"Warning: PROPERTY {' '.join(m.properties)} is not checked (safety search only)", file=out)
     init = m.initial_states()
+    for st in init:      # Init => Init2 of each refinement PROPERTY (the step obligation is checked on the device)
+        pbad = m.check_refinement_init(st)
+        if pbad is not None:
+            from .report import CheckResult, PROPERTY
+            res = CheckResult()
+            res.verdict, res.invariant, res.trace = PROPERTY, pbad, [(st, None)]
+            res.generated = res.distinct = res.init_states = len(init)
+            res.depth = 1
+            res.error_text = f"Property {pbad} is violated by the initial state"
+            print(format_result(res, m.vars, m.module_name), file=out)
+            return 12
     cm = compile_model(m, init, seq_cap=seq_cap)
     for w in cm.warnings:
         print(f"Warning: {w}", file=out)
