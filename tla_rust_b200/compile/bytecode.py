@@ -19,6 +19,7 @@ OPS = [
     "NEG", "EQN", "NOT", "LDX", "STX", "TBL", "TBLT", "BSET", "BCLR",
     "BTEST", "BOR", "BAND", "BANDN", "BISZ", "BSUB", "BCNT", "BNEXT", "BFILL",
     "BSETI", "BTESTI", "UCLAMP", "TRAP", "EMIT", "GEN", "ASSERTF", "INVF", "MADI", "BANDC", "LEXLT",
+    "SFIND", "SINS",
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 
@@ -37,6 +38,7 @@ FMT = {
     "JEQ": "rrJ", "JNE": "rrJ", "JLT": "rrJ", "JGE": "rrJ",
     "JEQI": "rkJ", "JNEI": "rkJ", "JLTI": "rkJ", "JGEI": "rkJ",
     "JBT": "rrJ", "JBF": "rrJ", "JBTI": "rnJ", "JBFI": "rnJ", "JGEZ": "rI", "MADI": "rkr", "BANDC": "rrJ", "LEXLT": "rrrn",
+    "SFIND": "rrrn", "SINS": "rrrn",
 }
 
 INVERSE = {"JZ": "JNZ", "JEQ": "JNE", "JLT": "JGE", "JEQI": "JNEI", "JLTI": "JGEI", "JBT": "JBF", "JBTI": "JBFI",

@@ -18,8 +18,9 @@ from ..front.parser import Node, OpDef
 from ..front.eval import Evaluator, Fr, Thunk, Closure, OpVal, AssertFailure, BuiltinOp
 from ..front.values import (EvalError, ModelValue, Fcn, LazySet, LazyFcn, SetNat, SetInt, mk_fcn, sorted_vals,
                             set_contains, set_iter, to_finite, is_set, is_enumerable, fmt, vkey, fcn_items)
-from .types import (T, TInt, TBool, TAtom, TRec, TTuple, TFun, TSet, TSeq, TBottom, TypeErr, Atoms, Codec, join,
-                    type_of_value, type_of_set, widen_init, is_atom)
+from .types import (T, TInt, TBool, TAtom, TRec, TTuple, TFun, TSet, TSeq, TPFun, TSparse, TBottom, TypeErr, Atoms,
+                    Codec, join, type_of_value, type_of_set, widen_init, is_atom, subset_type)
+from . import types as _types
 from .bytecode import (Asm, Label, TRAP_EVAL, TRAP_OVERFLOW, TRAP_CASE, TRAP_CHOOSE, IMM28_MAX, IMM28_MIN, MAXREG)
 
 UNROLL_MAX = 24
@@ -237,15 +238,47 @@ class Lowering:
                 for x in node.a[0]:
                     harvest(x, ctx, got, depth)
                 return
-            if node.k == "bin" and node.a[0] in ("\\in", "\\subseteq") and node.a[1].k == "id" \
-                    and node.a[1].a[0] in ctx.varset and node.a[1].a[0] not in ctx.substs:
+            isvar = lambda x: x.k == "id" and x.a[0] in ctx.varset and x.a[0] not in ctx.substs
+            if node.k == "bin" and node.a[0] in ("\\in", "\\subseteq") and isvar(node.a[1]):
                 v = node.a[1].a[0]
                 try:
                     sv = self.ev.eval(node.a[2], {}, Fr(ctx))
                     et = type_of_set(sv, self.seq_cap)
-                    got.setdefault(v, TSet(et) if node.a[0] == "\\subseteq" else et)
+                    got.setdefault(v, subset_type(et) if node.a[0] == "\\subseteq" else et)
                 except (EvalError, TypeErr) as ex:
                     self.warnings.append(f"type hint: cannot use conjunct for {v}: {ex}")
+                return
+            # function with a dynamic domain (raft.tla:35 `messages`):  DOMAIN v \subseteq K  /\
+            # \A x \in DOMAIN v : v[x] \in R   [/\ Cardinality(DOMAIN v) <= n]
+            if node.k == "bin" and node.a[0] == "\\subseteq" and node.a[1].k == "domain" and isvar(node.a[1].a[0]):
+                v = node.a[1].a[0].a[0]
+                try:
+                    dyn.setdefault(v, {})["k"] = type_of_set(self.ev.eval(node.a[2], {}, Fr(ctx)), self.seq_cap)
+                except (EvalError, TypeErr) as ex:
+                    self.warnings.append(f"type hint: cannot use conjunct for DOMAIN {v}: {ex}")
+                return
+            if node.k == "forall" and len(node.a[0]) == 1 and isinstance(node.a[0][0][0], str) \
+                    and node.a[0][0][1] is not None and node.a[0][0][1].k == "domain" and isvar(node.a[0][0][1].a[0]):
+                v = node.a[0][0][1].a[0].a[0]
+                b = node.a[1]
+                if b.k == "bin" and b.a[0] == "\\in" and b.a[1].k == "fapp" and b.a[1].a[0].k == "id" \
+                        and b.a[1].a[0].a[0] == v:
+                    try:
+                        dyn.setdefault(v, {})["v"] = type_of_set(self.ev.eval(b.a[2], {}, Fr(ctx)), self.seq_cap)
+                    except (EvalError, TypeErr) as ex:
+                        self.warnings.append(f"type hint: cannot use conjunct for {v}[..]: {ex}")
+                return
+            if node.k == "bin" and node.a[0] in ("<=", "=<", "\\leq", "<") and node.a[1].k == "app" \
+                    and node.a[1].a[0] == "Cardinality":
+                arg = node.a[1].a[1][0]
+                if arg.k == "domain":
+                    arg = arg.a[0]
+                if isvar(arg):
+                    try:
+                        n_ = self.ev.eval(node.a[2], {}, Fr(ctx))
+                        caps.setdefault(arg.a[0], n_ - 1 if node.a[0] == "<" else n_)
+                    except EvalError:
+                        pass
                 return
             if node.k == "id":
                 d2 = ctx.defs.get(node.a[0])
@@ -261,13 +294,19 @@ class Lowering:
                     # variables of an instance are substituted: only root-module variables are typed here
                     harvest(r[1].body, r[2], got, depth + 1)
 
+        dyn, caps = {}, {}
         for name in cand:
             d = self.ctx.defs.get(name)
             if d is None or d[0].params:
                 continue
             got = {}
             harvest(d[0].body, d[1], got)
+            for v, di in dyn.items():
+                if "k" in di and "v" in di:
+                    got.setdefault(v, TSparse(di["k"], di["v"], _types.SPARSE_CAP))
             for v, t in got.items():
+                if isinstance(t, TSparse) and v in caps:
+                    t = TSparse(t.kt, t.vt, int(caps[v]))
                 if v in m.vars:
                     types.setdefault(v, t)
             if all(v in types for v in m.vars):
@@ -495,6 +534,52 @@ class Lowering:
             self.asm.emit("ZERO", dst, t.size)
             self.movn(dst, x.loc, s.size)
             return Val(t, dst)
+        if isinstance(t, TSeq) and isinstance(s, TSeq):
+            # different capacity / element type: element-wise, trapping when the length does not fit
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            self.asm.emit("MOV", dst, x.loc)
+            done = Label("sqd")
+            if s.cap > t.cap:
+                ok = Label("sqk")
+                t1 = self.alloc(1)
+                self.asm.emit("LEI", t1, x.loc, t.cap)
+                self.asm.emit("JNZ", t1, ok)
+                self.asm.emit("TRAP", TRAP_OVERFLOW, 0)
+                self.asm.label(ok)
+            for j in range(min(s.cap, t.cap)):
+                t2 = self.alloc(1)
+                self.asm.emit("LEI", t2, x.loc, j)
+                self.asm.emit("JNZ", t2, done)
+                sub = self.coerce(Val(s.elem, x.loc + 1 + j * s.elem.size), t.elem)
+                self.movn(dst + 1 + j * t.elem.size, sub.loc, t.elem.size)
+            self.asm.label(done)
+            return Val(t, dst)
+        if isinstance(t, TPFun) and isinstance(s, TPFun) and t.keys == s.keys:
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            for j in range(len(t.keys)):
+                skip = Label("pfc")
+                self.asm.emit("JZ", x.loc + j * s.stride, skip)
+                self.li(dst + j * t.stride, 1)
+                sub = self.coerce(Val(s.elem, x.loc + j * s.stride + 1), t.elem)
+                self.movn(dst + j * t.stride + 1, sub.loc, t.elem.size)
+                self.asm.label(skip)
+            return Val(t, dst)
+        if isinstance(t, TSparse) and isinstance(s, TSparse) and (t.vt is None) == (s.vt is None):
+            if t.kt == s.kt and t.vt == s.vt and s.cap <= t.cap:
+                dst = self.alloc(t.size)
+                self.asm.emit("ZERO", dst, t.size)
+                self.movn(dst, x.loc, s.size)
+                return Val(t, dst)
+            out = self.sp_new(t)
+            self.sp_loop(x, lambda k, v: self.sp_insert(out, self.sp_entry(t, k, v)))
+            return out
+        if isinstance(t, TSparse) and t.vt is None and isinstance(s, TSet):
+            out = self.sp_new(t)
+            if not isinstance(s.elem, TBottom):
+                self.loop_set(x, lambda ev: self.sp_insert(out, self.sp_entry(t, ev)))
+            return out
         raise CompileError(f"cannot coerce {s} to {t}")
 
     @staticmethod
@@ -784,8 +869,20 @@ class Lowering:
             lo = self.cx(node.a[1], env, ctx, base)
             hi = self.cx(node.a[2], env, ctx, base)
             return ("range", lo, hi)
+        node, filters = self._peel_filters(node, env, ctx, base)
+        if filters:
+            inner = self.set_elements(node[0], node[1], node[2], node[3])
+            if inner[0] == "sparse":
+                return ("sparse", inner[1], inner[2] + filters)
+            node, env, ctx, base = node[4]
+        else:
+            node, env, ctx, base = node
         if node.k == "domain":
             f = self.cx(node.a[0], env, ctx, base)
+            if isinstance(f, Val) and isinstance(f.t, TSparse):
+                return ("sparse", f, [])
+            if isinstance(f, Val) and isinstance(f.t, TPFun):
+                return ("val", self.pf_domain(f))
             if isinstance(f, Val) and isinstance(f.t, TSeq):
                 return ("range", Const(1), Val(TInt(0, f.t.cap), f.loc))
             if isinstance(f, Val) and isinstance(f.t, TFun):
@@ -795,9 +892,42 @@ class Lowering:
         v = self.cx(node, env, ctx, base)
         if type(v) is Const:
             return ("const", list(set_iter(v.v)))
+        if isinstance(v.t, TSparse) and v.t.vt is None:
+            return ("sparse", v, [])
         if not isinstance(v.t, TSet):
             raise CompileError(f"quantifier domain has non-set type {v.t}")
         return ("val", v)
+
+    def _peel_filters(self, node, env, ctx, base):
+        """Follow operator applications / set filters down to the underlying domain:
+        ValidMessage(messages) == {m \\in DOMAIN messages : msgs[m] > 0}  (raft.tla:127-131) is iterated as
+        DOMAIN messages with the predicate applied inside the loop instead of building the filtered set.
+        -> ((node, env, ctx, base, original), [(pat, pred, env, ctx, base), ...])"""
+        orig = (node, env, ctx, base)
+        filters = []
+        cur = orig
+        for _ in range(8):
+            nd, e_, c_, b_ = cur
+            if self.try_const(nd, e_, c_, b_) is not None:
+                break
+            if nd.k in ("id", "app", "sel"):
+                try:
+                    tgt = self._expand(nd, e_, c_, b_)
+                except (CompileError, EvalError):
+                    tgt = None
+                if tgt is None or tgt[0].k not in ("setfilter", "domain", "id", "app", "sel"):
+                    break
+                cur = tgt
+                continue
+            if nd.k == "setfilter" and isinstance(nd.a[0][0], str):
+                (pat, s2), pred = nd.a
+                filters.append((pat, pred, e_, c_, b_))
+                cur = (s2, e_, c_, b_)
+                continue
+            break
+        if not filters:
+            return orig, []
+        return cur + (orig,), filters
 
     def bind(self, env, pat, x):
         env2 = dict(env)
@@ -877,6 +1007,19 @@ class Lowering:
             self.for_each(bounds, self.bind(env, pat, Val(xt, x)), ctx, base, body, i + 1)
             self.asm.emit("JMP", top)
             self.asm.label(done)
+            return
+        if kind[0] == "sparse":
+            cont, filters = kind[1], kind[2]
+
+            def each_entry(k, v):
+                skip = Label("sfk")
+                for fpat, fpred, fenv, fctx, fbase in filters:
+                    nxt = Label("sfp")
+                    self.cc(fpred, self.bind(fenv, fpat, k), fctx, fbase, nxt, skip)
+                    self.asm.label(nxt)
+                self.for_each(bounds, self.bind(env, pat, k), ctx, base, body, i + 1)
+                self.asm.label(skip)
+            self.sp_loop(cont, each_entry)
             return
         sv = kind[1]
         self.loop_set(sv, lambda xv: self.for_each(bounds, self.bind(env, pat, xv), ctx, base, body, i + 1))
@@ -1059,9 +1202,23 @@ class Lowering:
                 self.asm.emit({"+": "ADD", "-": "SUB", "*": "MUL", "\\div": "DIV", "%": "MOD"}[op],
                               dst, av.loc, bv.loc)
             return Val(rt, dst)
+        if op == "@@":
+            return self.fcn_merge(ln, rn, env, ctx, base, want, n)
+        if op == ":>" and isinstance(want, TSparse) and want.vt is not None:
+            dst = self.sp_new(want)
+            k = self.cx(ln, env, ctx, base, want.kt)
+            v = self.cx(rn, env, ctx, base, want.vt)
+            self.sp_insert(dst, self.sp_entry(want, k, v), n.line)
+            return dst
         if op in ("\\cup", "\\cap", "\\"):
             a = self.cx(ln, env, ctx, base, want)
-            b = self.cx(rn, env, ctx, base, want if want is not None else (a.t if isinstance(a, Val) else None))
+            tw = want if want is not None else (a.t if isinstance(a, Val) else None)
+            if isinstance(tw, TSparse):
+                b = self.cx(rn, env, ctx, base, tw)
+                return self.sp_setop(op, a, b, tw, n.line)
+            b = self.cx(rn, env, ctx, base, tw)
+            if isinstance(b, Val) and isinstance(b.t, TSparse):
+                return self.sp_setop(op, a, b, b.t, n.line)
             if type(a) is Const and isinstance(b, Val) and want is None:
                 a2 = a
                 t = b.t
@@ -1270,14 +1427,20 @@ class Lowering:
         return Val(t.fields[f], r.loc + t.off[f])
 
     def x_setenum(self, n, env, ctx, base, want):
-        items = [self.cx(x, env, ctx, base, want.elem if isinstance(want, TSet) else None) for x in n.a[0]]
-        if isinstance(want, TSet):
+        wel = want.elem if isinstance(want, TSet) else (want.kt if isinstance(want, TSparse) else None)
+        items = [self.cx(x, env, ctx, base, wel) for x in n.a[0]]
+        if isinstance(want, (TSet, TSparse)):
             t = want
         else:
             et = TBottom()
             for x in items:
                 et = join(et, x.t if isinstance(x, Val) else self.natural_type(x.v))
-            t = TSet(self._enumerable(et))
+            t = subset_type(self._enumerable(et))
+        if isinstance(t, TSparse):
+            dst = self.sp_new(t)
+            for x in items:
+                self.sp_insert(dst, self.sp_entry(t, x), n.line)
+            return dst
         dst = self.alloc(t.size)
         self.asm.emit("ZERO", dst, t.size)
         for x in items:
@@ -1305,6 +1468,23 @@ class Lowering:
     def x_setfilter(self, n, env, ctx, base, want):
         (pat, sn), pred = n.a
         kind = self.set_elements(sn, env, ctx, base)
+        if kind[0] == "sparse":
+            cont = kind[1]
+            t = TSparse(cont.t.kt, None, cont.t.cap)
+            if isinstance(want, TSparse) and want.vt is None:
+                t = want
+            dst = self.sp_new(t)
+
+            def each_s(env2):
+                yes, no = Label("sfy"), Label("sfn")
+                self.cc(pred, env2, ctx, base, yes, no)
+                self.asm.label(yes)
+                self.sp_insert(dst, self.sp_entry(t, env2[pat]), n.line)
+                self.asm.label(no)
+            if not isinstance(pat, str):
+                raise CompileError("tuple pattern over a sparse set")
+            self.for_each([(pat, sn)], env, ctx, base, each_s)
+            return dst
         if kind[0] == "val":
             sv = kind[1]
             t = sv.t
@@ -1349,11 +1529,28 @@ class Lowering:
                 self.asm.emit("BSETI", dst, o)
                 self.asm.label(no)
             return Val(t, dst)
+        if kind[0] == "range" and isinstance(pat, str):
+            lo, hi = kind[1], kind[2]
+            tl, th = self._int_t(lo), self._int_t(hi)
+            if tl.lo is None or th.hi is None:
+                raise CompileError("set filter over an unbounded integer range")
+            t = want if isinstance(want, TSet) else TSet(TInt(tl.lo, max(th.hi, tl.lo)))
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+
+            def each_r(env2):
+                yes, no = Label("ry"), Label("rn")
+                self.cc(pred, env2, ctx, base, yes, no)
+                self.asm.label(yes)
+                self._set_add(dst, t, env2[pat], n)
+                self.asm.label(no)
+            self.for_each([(pat, sn)], env, ctx, base, each_r)
+            return Val(t, dst)
         raise CompileError("set filter over a runtime integer range is not supported")
 
     def x_setmap(self, n, env, ctx, base, want):
         e, bounds = n.a
-        t = want if isinstance(want, TSet) else None
+        t = want if isinstance(want, (TSet, TSparse)) else None
         if t is None:
             # infer element type by a dry run
             with self.asm.capture():
@@ -1368,7 +1565,17 @@ class Lowering:
             et = TBottom()
             for x in holder:
                 et = join(et, x)
-            t = TSet(self._enumerable(et))
+            t = subset_type(self._enumerable(et))
+        if isinstance(t, TSparse):
+            sdst = self.sp_new(t)
+
+            def sbody(env2):
+                m0 = self.mark()
+                x = self.cx(e, env2, ctx, base, t.kt)
+                self.sp_insert(sdst, self.sp_entry(t, x), n.line)
+                self.release(m0)
+            self.for_each(bounds, env, ctx, base, sbody)
+            return sdst
         dst = self.alloc(t.size)
         self.asm.emit("ZERO", dst, t.size)
 
@@ -1495,6 +1702,17 @@ class Lowering:
         ft = f.t
         if isinstance(ft, TSeq):
             return self.seq_index(f, kx, n)
+        if isinstance(ft, TPFun):
+            return self.pf_apply(f, kx, n)
+        if isinstance(ft, TSparse) and ft.vt is not None:
+            r = self.sp_find(f, kx)
+            ok = Label("sak")
+            self.asm.emit("JGEZ", r, ok)
+            self.asm.emit("TRAP", TRAP_EVAL, n.line)
+            self.asm.label(ok)
+            ent = self.alloc(ft.stride)
+            self.asm.emit("LDX", ent, f.loc + 1, r, ft.stride)
+            return Val(ft.vt, ent + ft.keyw)
         if isinstance(ft, TSet) or not isinstance(ft, (TFun, TTuple)):
             raise CompileError(f"applying a non-function of type {ft} at line {n.line}")
         ki = self.key_index(ft, kx, n)
@@ -1562,6 +1780,35 @@ class Lowering:
             kx = self.cx(p[0], env, ctx, base)
         else:
             kx = self.cx(Node("tuple", (tuple(p),)), env, ctx, base)
+        if isinstance(t, TSparse) and t.vt is not None:
+            r = self.sp_find(cur, kx)
+            skip = Label("xs")
+            self.asm.emit("JNEG", r, skip)
+            ent = self.alloc(t.stride)
+            self.asm.emit("LDX", ent, cur.loc + 1, r, t.stride)
+            self._except_path(Val(t.vt, ent + t.keyw), path, i + 1, valnode, env, ctx, base, n)
+            self.asm.emit("STX", cur.loc + 1, r, ent, t.stride)
+            self.asm.label(skip)
+            return
+        if isinstance(t, TPFun):
+            ki = self.pf_slot(cur, kx, n)
+            if ki[0] == "none":
+                return
+            skip = Label("xs")
+            if ki[0] == "static":
+                b_ = cur.loc + ki[1] * t.stride
+                self.asm.emit("JZ", b_, skip)
+                self._except_path(Val(t.elem, b_ + 1), path, i + 1, valnode, env, ctx, base, n)
+            else:
+                o = ki[1]
+                self.asm.emit("JNEG", o, skip)
+                slot = self.alloc(t.stride)
+                self.asm.emit("LDX", slot, cur.loc, o, t.stride)
+                self.asm.emit("JZ", slot, skip)
+                self._except_path(Val(t.elem, slot + 1), path, i + 1, valnode, env, ctx, base, n)
+                self.asm.emit("STX", cur.loc, o, slot, t.stride)
+            self.asm.label(skip)
+            return
         if isinstance(t, TSeq):
             et = t.elem
             o = self.seq_index_reg(cur, kx, n, trap=False)
@@ -1637,6 +1884,10 @@ class Lowering:
 
     def x_domain(self, n, env, ctx, base, want):
         f = self.cx(n.a[0], env, ctx, base)
+        if isinstance(f, Val) and isinstance(f.t, TSparse):
+            return self.sp_keys(f)
+        if isinstance(f, Val) and isinstance(f.t, TPFun):
+            return self.pf_domain(f)
         if isinstance(f, Val) and isinstance(f.t, TFun):
             return Const(frozenset(f.t.keys))
         if isinstance(f, Val) and isinstance(f.t, TTuple):
@@ -1663,7 +1914,13 @@ class Lowering:
     # ---------------------------------------------------------------- builtins
     def builtin(self, name, args, n, env, ctx, base, want):
         if name == "Cardinality":
+            if args[0].k == "domain":
+                f = self.cx(args[0].a[0], env, ctx, base)
+                if isinstance(f, Val) and isinstance(f.t, TSparse):
+                    return Val(TInt(0, f.t.cap), f.loc)
             s = self.cx(args[0], env, ctx, base)
+            if isinstance(s, Val) and isinstance(s.t, TSparse):
+                return Val(TInt(0, s.t.cap), s.loc)
             sv = self.as_val(s)
             dst = self.alloc(1)
             self.asm.emit("BCNT", dst, sv.loc, sv.t.size)
@@ -1682,6 +1939,227 @@ class Lowering:
         if name == "IsFiniteSet":
             return Const(True)
         raise CompileError(f"builtin {name} is not supported on the device")
+
+    # ------------------------------------------------ sparse containers / partial functions
+    # TSparse values are built only through SINS (sorted insert), so they are canonical by construction.
+    @staticmethod
+    def sp_desc(t: TSparse):
+        return (t.stride << 7) | t.keyw
+
+    def sp_new(self, t: TSparse) -> Val:
+        dst = self.alloc(t.size)
+        self.asm.emit("ZERO", dst, t.size)
+        return Val(t, dst)
+
+    def sp_entry(self, t: TSparse, key, val=None):
+        """Assemble one entry (key [, value]) of container type t in fresh temporaries."""
+        e = self.alloc(t.stride)
+        kv = self.coerce(key, t.kt)
+        self.movn(e, kv.loc, t.keyw)
+        if t.vt is not None:
+            vv = self.coerce(val, t.vt)
+            self.movn(e + t.keyw, vv.loc, t.vt.size)
+        return e
+
+    def sp_insert(self, cont: Val, eloc, line=0):
+        t = cont.t
+        st = self.alloc(1)
+        self.li(st, t.cap)
+        self.asm.emit("SINS", cont.loc, eloc, st, self.sp_desc(t))
+        ok = Label("sio")
+        self.asm.emit("JNZ", st, ok)
+        self.asm.emit("TRAP", TRAP_OVERFLOW, line)
+        self.asm.label(ok)
+
+    def sp_find(self, cont: Val, key):
+        """-> register holding the entry index of key in cont, or -1."""
+        t = cont.t
+        try:
+            kv = self.coerce(key, t.kt)
+        except CompileError:
+            r = self.alloc(1)
+            self.li(r, -1)
+            return r
+        r = self.alloc(1)
+        self.asm.emit("SFIND", r, cont.loc, kv.loc, self.sp_desc(t))
+        return r
+
+    def sp_loop(self, cont: Val, body):
+        """for each entry of cont: body(key Val, value Val | None) on a private copy of the entry."""
+        t = cont.t
+        i = self.alloc(1)
+        n = self.alloc(1)
+        e = self.alloc(t.stride)
+        self.li(i, -1)
+        self.asm.emit("MOV", n, cont.loc)
+        top, done = Label("spl"), Label("spd")
+        self.asm.label(top)
+        self.asm.emit("ADDI", i, i, 1)
+        tmp = self.alloc(1)
+        self.asm.emit("LT", tmp, i, n)
+        self.asm.emit("JZ", tmp, done)
+        self.asm.emit("LDX", e, cont.loc + 1, i, t.stride)
+        body(Val(t.kt, e), Val(t.vt, e + t.keyw) if t.vt is not None else None)
+        self.asm.emit("JMP", top)
+        self.asm.label(done)
+
+    def sp_copy(self, x, t: TSparse) -> Val:
+        xv = self.coerce(x, t)
+        dst = self.alloc(t.size)
+        self.movn(dst, xv.loc, t.size)
+        return Val(t, dst)
+
+    def sp_keys(self, f: Val) -> Val:
+        """DOMAIN of a sparse function as a sparse set (same order, so a strided copy)."""
+        t = f.t
+        if t.vt is None:
+            return f
+        kt = TSparse(t.kt, None, t.cap)
+        dst = self.alloc(kt.size)
+        self.asm.emit("MOV", dst, f.loc)
+        for j in range(t.cap):
+            self.movn(dst + 1 + j * t.keyw, f.loc + 1 + j * t.stride, t.keyw)
+        return Val(kt, dst)
+
+    def sp_setop(self, op, a, b, t: TSparse, line=0) -> Val:
+        if op == "\\cup":
+            dst = self.sp_copy(a, t)
+            bv = self.coerce(b, t)
+            self.sp_loop(bv, lambda k, v: self.sp_insert(dst, k.loc, line))
+            return dst
+        av = self.coerce(a, t)
+        bv = self.coerce(b, t)
+        dst = self.sp_new(t)
+
+        def each(k, v):
+            r = self.sp_find(bv, k)
+            skip = Label("sps")
+            self.asm.emit("JGEZ" if op == "\\" else "JNEG", r, skip)
+            self.sp_insert(dst, k.loc, line)
+            self.asm.label(skip)
+        self.sp_loop(av, each)
+        return dst
+
+    def pf_slot(self, f: Val, kx, n):
+        """Index register / static index of key kx in partial function f (TPFun)."""
+        t = f.t
+        return self.key_index(TFun(t.keys, TBool()), kx, n)
+
+    def pf_apply(self, f: Val, kx, n) -> Val:
+        t = f.t
+        ki = self.pf_slot(f, kx, n)
+        if ki[0] == "none":
+            self.asm.emit("TRAP", TRAP_EVAL, n.line)
+            return Val(t.elem, f.loc + 1)
+        ok = Label("pfo")
+        if ki[0] == "static":
+            base_ = f.loc + ki[1] * t.stride
+            self.asm.emit("JNZ", base_, ok)
+            self.asm.emit("TRAP", TRAP_EVAL, n.line)
+            self.asm.label(ok)
+            return Val(t.elem, base_ + 1)
+        o = ki[1]
+        bad = Label("pfb")
+        self.asm.emit("JNEG", o, bad)
+        slot = self.alloc(t.stride)
+        self.asm.emit("LDX", slot, f.loc, o, t.stride)
+        self.asm.emit("JNZ", slot, ok)
+        self.asm.label(bad)
+        self.asm.emit("TRAP", TRAP_EVAL, n.line)
+        self.asm.label(ok)
+        return Val(t.elem, slot + 1)
+
+    def pf_domain(self, f: Val) -> Val:
+        t = f.t
+        st = TSet(self._key_type(t.keys))
+        dst = self.alloc(st.size)
+        self.asm.emit("ZERO", dst, st.size)
+        for j, k in enumerate(t.keys):
+            o = self.codec.ord_of(st.elem, k)
+            skip = Label("pds")
+            self.asm.emit("JZ", f.loc + j * t.stride, skip)
+            self.asm.emit("BSETI", dst, o)
+            self.asm.label(skip)
+        return Val(st, dst)
+
+    @staticmethod
+    def _key_type(keys):
+        if all(type(k) is int for k in keys):
+            return TInt(min(keys), max(keys))
+        if all(is_atom(k) for k in keys):
+            return TAtom(sorted(keys, key=vkey))
+        raise CompileError("partial function with non-scalar keys")
+
+    def fcn_merge(self, ln, rn, env, ctx, base, want, n):
+        """a @@ b  (a's entries win) for sparse / partial functions; b is usually `k :> v`."""
+        a = self.cx(ln, env, ctx, base, want)
+        t = want if isinstance(want, (TSparse, TPFun)) else (a.t if isinstance(a, Val) else None)
+        if not isinstance(t, (TSparse, TPFun)):
+            raise CompileError(f"@@ is supported for functions with a dynamic domain only (line {n.line})")
+        pairs = None
+        if rn.k == "bin" and rn.a[0] == ":>":
+            pairs = [(rn.a[1], rn.a[2])]
+        if isinstance(t, TSparse):
+            dst = self.sp_copy(a, t)
+            if pairs is not None:
+                for kn, vn in pairs:
+                    k = self.cx(kn, env, ctx, base, t.kt)
+                    r = self.sp_find(dst, k)
+                    skip = Label("mgs")
+                    self.asm.emit("JGEZ", r, skip)
+                    v = self.cx(vn, env, ctx, base, t.vt)
+                    self.sp_insert(dst, self.sp_entry(t, k, v), n.line)
+                    self.asm.label(skip)
+                return dst
+            bv = self.coerce(self.cx(rn, env, ctx, base, t), t)
+
+            def each(k, v):
+                r = self.sp_find(dst, k)
+                skip = Label("mgs")
+                self.asm.emit("JGEZ", r, skip)
+                self.sp_insert(dst, k.loc, n.line)
+                self.asm.label(skip)
+            self.sp_loop(bv, each)
+            return dst
+        av = self.coerce(a, t)
+        dst = Val(t, self._copy(av))
+        if pairs is None:
+            bv = self.coerce(self.cx(rn, env, ctx, base, t), t)
+            for j in range(len(t.keys)):
+                skip = Label("mgp")
+                self.asm.emit("JNZ", dst.loc + j * t.stride, skip)
+                self.movn(dst.loc + j * t.stride, bv.loc + j * t.stride, t.stride)
+                self.asm.label(skip)
+            return dst
+        for kn, vn in pairs:
+            k = self.cx(kn, env, ctx, base)
+            ki = self.pf_slot(dst, k, n)
+            if ki[0] == "none":
+                self.asm.emit("TRAP", TRAP_OVERFLOW, n.line)
+                continue
+            v = self.cx(vn, env, ctx, base, t.elem)
+            slot = self.alloc(t.stride)
+            self.li(slot, 1)
+            vv = self.coerce(v, t.elem)
+            self.movn(slot + 1, vv.loc, t.elem.size)
+            skip = Label("mgp")
+            if ki[0] == "static":
+                b_ = dst.loc + ki[1] * t.stride
+                self.asm.emit("JNZ", b_, skip)
+                self.movn(b_, slot, t.stride)
+            else:
+                o = ki[1]
+                bad, go = Label("mgb"), Label("mgg")
+                self.asm.emit("JGEZ", o, go)
+                self.asm.label(bad)
+                self.asm.emit("TRAP", TRAP_OVERFLOW, n.line)
+                self.asm.label(go)
+                cur = self.alloc(t.stride)
+                self.asm.emit("LDX", cur, dst.loc, o, t.stride)
+                self.asm.emit("JNZ", cur, skip)
+                self.asm.emit("STX", dst.loc, o, slot, t.stride)
+            self.asm.label(skip)
+        return dst
 
     # --------------------------------------------------------------- sequences
     def _as_seq(self, x, want=None) -> Val:
@@ -1761,6 +2239,42 @@ class Lowering:
                 self.movn(dst + 1, s.loc + 1 + es, (t.cap - 1) * es)
             r = Val(t, dst)
             return r
+        if name == "SubSeq":
+            s = self._as_seq(self.cx(args[0], env, ctx, base))
+            t = want if isinstance(want, TSeq) and want.elem == s.t.elem else s.t
+            es = t.elem.size
+            lo = self.as_val(self.cx(args[1], env, ctx, base), TInt())
+            hi = self.as_val(self.cx(args[2], env, ctx, base), TInt())
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            i = self.alloc(1)
+            hi_s = self.alloc(1)
+            t1 = self.alloc(1)
+            tmp = self.alloc(es)
+            top, done, bad, ok = Label("ssl"), Label("ssd"), Label("ssb"), Label("ssk")
+            self.asm.emit("MOV", i, lo.loc)
+            self.asm.emit("MOV", hi_s, hi.loc)
+            self.asm.label(top)
+            self.asm.emit("LE", t1, i, hi_s)
+            self.asm.emit("JZ", t1, done)
+            self.asm.emit("LTI", t1, i, 1)
+            self.asm.emit("JNZ", t1, bad)
+            self.asm.emit("LE", t1, i, s.loc)
+            self.asm.emit("JZ", t1, bad)
+            self.asm.emit("LTI", t1, dst, t.cap)
+            self.asm.emit("JNZ", t1, ok)
+            self.asm.emit("TRAP", TRAP_OVERFLOW, n.line)
+            self.asm.label(bad)
+            self.asm.emit("TRAP", TRAP_EVAL, n.line)
+            self.asm.label(ok)
+            self.asm.emit("ADDI", t1, i, -1)
+            self.asm.emit("LDX", tmp, s.loc + 1, t1, es)
+            self.asm.emit("STX", dst + 1, dst, tmp, es)
+            self.asm.emit("ADDI", dst, dst, 1)
+            self.asm.emit("ADDI", i, i, 1)
+            self.asm.emit("JMP", top)
+            self.asm.label(done)
+            return Val(t, dst)
         raise CompileError(f"sequence operator {name} is not supported on the device yet")
 
     def seq_concat(self, ln, rn, env, ctx, base, want):
@@ -2248,9 +2762,21 @@ class Lowering:
                 return
             self._in_const_set(e, s, lt, lf, n)
             return
+        if sn.k == "domain":
+            f = self.cx(sn.a[0], env, ctx, base)
+            if isinstance(f, Val) and isinstance(f.t, TSparse):
+                r = self.sp_find(f, e)
+                self.asm.emit("JGEZ", r, lt)
+                self.asm.emit("JMP", lf)
+                return
         sv = self.cx(sn, env, ctx, base)
         if type(sv) is Const:
             self._in_const_set(self.as_val(e), sv.v, lt, lf, n)
+            return
+        if isinstance(sv.t, TSparse) and sv.t.vt is None:
+            r = self.sp_find(sv, e)
+            self.asm.emit("JGEZ", r, lt)
+            self.asm.emit("JMP", lf)
             return
         if not isinstance(sv.t, TSet):
             raise CompileError(f"\\in applied to non-set type {sv.t}")

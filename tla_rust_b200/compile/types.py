@@ -14,6 +14,11 @@ Representations (frame words):
   TFun(keys,T)  |keys| consecutive elements, keys in canonical order
   TSet(E)       bitset over the enumeration of E: ceil(card(E)/32) words
   TSeq(E,cap)   length word + cap elements (unused slots zero => canonical)
+  TPFun(keys,T) partial function over a constant key list: per key a presence word + element (absent => zero)
+  TSparse(K,V,cap)  bounded sparse container: length word + cap entries (K [, V]) kept sorted by the signed
+                word-wise order of the key words, no duplicate keys, unused entries zero => canonical.
+                V = None: a set of K whose universe is too large for a bitset; otherwise a function with a
+                dynamic domain (raft's message bag, raft.tla:35).
 Enumerable types (everything except unbounded ints) have card(T), an ordinal
 bijection ord/unord (Horner / mixed radix), used for set universes and function keys.
 """
@@ -22,9 +27,11 @@ from __future__ import annotations
 import itertools
 
 from ..front.values import (ModelValue, Fcn, LazySet, SetNat, SetInt, SetString, SetSeq, SetSubset, SetFuncs,
-                            SetRecs, SetTimes, SetUnionLazy, mk_fcn, sorted_vals, fmt, vkey, LazyFcn)
+                            SetRecs, SetTimes, SetUnionLazy, SetPFuncs, SetBSeq, mk_fcn, sorted_vals, fmt, vkey,
+                            LazyFcn, fcn_items, is_fcn_like)
 
 MAX_SET_BITS = 8192
+SPARSE_CAP = 8          # default capacity of sparse containers (overridden per variable by a Cardinality bound)
 INT32_MIN = -(1 << 31)
 INT32_MAX = (1 << 31) - 1
 
@@ -209,9 +216,24 @@ class TFun(T):
         return self.elem.card() ** len(self.keys)
 
 
+def has_dynamic(t) -> bool:
+    """True if t contains a sequence / partial function / sparse container (no ordinal encoding)."""
+    if isinstance(t, (TSeq, TPFun, TSparse)):
+        return True
+    if isinstance(t, TRec):
+        return any(has_dynamic(x) for x in t.fields.values())
+    if isinstance(t, TTuple):
+        return any(has_dynamic(x) for x in t.elems)
+    if isinstance(t, TFun):
+        return has_dynamic(t.elem)
+    return False
+
+
 class TSet(T):
     def __init__(self, elem):
         self.elem = elem
+        if has_dynamic(elem):
+            raise TypeErr(f"no bitset universe for element type {elem}")
         n = elem.card()
         if n > MAX_SET_BITS:
             raise TypeErr(f"set universe of {n} elements exceeds the {MAX_SET_BITS}-bit limit ({elem})")
@@ -239,6 +261,37 @@ class TSeq(T):
     def card(self):
         c = self.elem.card()
         return sum(c ** k for k in range(self.cap + 1))
+
+
+class TPFun(T):
+    def __init__(self, keys, elem):
+        self.keys = tuple(keys)
+        self.elem = elem
+        self.stride = 1 + elem.size
+        self.size = len(self.keys) * self.stride
+        self.kindex = {k: i for i, k in enumerate(self.keys)}
+
+    def key(self):
+        return (tuple(vkey(k) for k in self.keys), self.elem)
+
+    def card(self):
+        return (self.elem.card() + 1) ** len(self.keys)
+
+
+class TSparse(T):
+    def __init__(self, kt, vt, cap):
+        self.kt, self.vt, self.cap = kt, vt, cap
+        self.keyw = kt.size
+        self.stride = kt.size + (vt.size if vt is not None else 0)
+        if self.stride > 127:
+            raise TypeErr(f"sparse container entry of {self.stride} words exceeds the 127-word limit")
+        self.size = 1 + cap * self.stride
+
+    def key(self):
+        return (self.kt, self.vt, self.cap)
+
+    def card(self):
+        raise TypeErr("sparse containers are not enumerable")
 
 
 class TBottom(T):
@@ -283,6 +336,15 @@ def join(a: T, b: T) -> T:
         return TFun(a.keys, join(a.elem, b.elem))
     if ta is TSeq and tb is TSeq:
         return TSeq(join(a.elem, b.elem), max(a.cap, b.cap))
+    if ta is TTuple and tb is TTuple:
+        e = TBottom()
+        for x in a.elems + b.elems:
+            e = join(e, x)
+        return TSeq(e, max(len(a.elems), len(b.elems)))
+    if ta is TPFun and tb is TPFun and a.keys == b.keys:
+        return TPFun(a.keys, join(a.elem, b.elem))
+    if ta is TSparse and tb is TSparse and (a.vt is None) == (b.vt is None):
+        return TSparse(join(a.kt, b.kt), None if a.vt is None else join(a.vt, b.vt), max(a.cap, b.cap))
     if ta is TSeq and tb is TTuple:
         return join(b, a)
     if ta is TTuple and tb is TSeq:
@@ -338,7 +400,15 @@ def type_of_set(s, seq_cap=None) -> T:
             return TTuple([rng] * n)
         return TFun(dom, rng)
     if isinstance(s, SetSubset):
-        return TSet(type_of_set(s.s, seq_cap))
+        et = type_of_set(s.s, seq_cap)
+        try:
+            return TSet(et)
+        except TypeErr:
+            return TSparse(et, None, SPARSE_CAP)     # universe too large (or not enumerable) for a bitset
+    if isinstance(s, SetPFuncs):
+        return TPFun(sorted_vals(to_finite_keys(s.dom)), type_of_set(s.rng, seq_cap))
+    if isinstance(s, SetBSeq):
+        return TSeq(type_of_set(s.s, seq_cap), s.n)
     if isinstance(s, SetRecs):
         names = [f for f, _ in s.fields]
         return TRec([names], {f: type_of_set(x, seq_cap) for f, x in s.fields})
@@ -355,6 +425,30 @@ def type_of_set(s, seq_cap=None) -> T:
     if isinstance(s, SetString):
         raise TypeErr("STRING is not a finite type")
     raise TypeErr(f"cannot derive a type from set {s!r}")
+
+
+def to_finite_keys(d):
+    return frozenset(d.enumerate()) if isinstance(d, LazySet) else d
+
+
+def subset_type(et: T) -> T:
+    """Type of a subset of a set with element type et: a bitset when the universe is small, else sparse."""
+    try:
+        return TSet(et)
+    except TypeErr:
+        return TSparse(et, None, SPARSE_CAP)
+
+
+def _zero_safe(slots):
+    """Re-bias packed slots so that the frame value 0 is representable (slots that can be inactive)."""
+    out = []
+    for off, w, b in slots:
+        if w > 0 and b > 0:
+            hi = b + (1 << w) - 1
+            out.append((off, max(1, hi.bit_length()), 0))
+        else:
+            out.append((off, w, b))
+    return out
 
 
 def widen_init(t: T, all_atoms) -> T:
@@ -555,6 +649,38 @@ class Codec:
                 out += self.rep(t.elem, x)
             out += [0] * (t.size - len(out))
             return out
+        if isinstance(t, TPFun):
+            if not is_fcn_like(v):
+                raise TypeErr(f"expected function, got {fmt(v)}")
+            d = dict(fcn_items(v))
+            if not set(d) <= set(t.keys):
+                raise TypeErr(f"function domain {fmt(frozenset(d))} outside the key set of its type")
+            out = []
+            for k in t.keys:
+                if k in d:
+                    out += [1] + self.rep(t.elem, d[k])
+                else:
+                    out += [0] * t.stride
+            return out
+        if isinstance(t, TSparse):
+            if t.vt is None:
+                if isinstance(v, LazySet):
+                    v = frozenset(v.enumerate())
+                if not isinstance(v, frozenset):
+                    raise TypeErr(f"expected set, got {fmt(v)}")
+                ents = [self.rep(t.kt, x) for x in v]
+            else:
+                if not is_fcn_like(v):
+                    raise TypeErr(f"expected function, got {fmt(v)}")
+                ents = [self.rep(t.kt, k) + self.rep(t.vt, x) for k, x in fcn_items(v)]
+            if len(ents) > t.cap:
+                raise TypeErr(f"{len(ents)} entries exceed the sparse capacity {t.cap}")
+            ents.sort()
+            out = [len(ents)]
+            for e in ents:
+                out += e
+            out += [0] * (t.size - len(out))
+            return out
         raise TypeErr(f"rep: unsupported type {t}")
 
     def unrep(self, t: T, w, i=0):
@@ -582,6 +708,18 @@ class Codec:
         if isinstance(t, TSeq):
             n = int(w[i])
             return tuple(self.unrep(t.elem, w, i + 1 + j * t.elem.size) for j in range(n))
+        if isinstance(t, TPFun):
+            d = {}
+            for j, k in enumerate(t.keys):
+                if int(w[i + j * t.stride]):
+                    d[k] = self.unrep(t.elem, w, i + j * t.stride + 1)
+            return mk_fcn(d)
+        if isinstance(t, TSparse):
+            n = int(w[i])
+            if t.vt is None:
+                return frozenset(self.unrep(t.kt, w, i + 1 + j * t.stride) for j in range(n))
+            return mk_fcn({self.unrep(t.kt, w, i + 1 + j * t.stride): self.unrep(t.vt, w, i + 1 + j * t.stride + t.keyw)
+                           for j in range(n)})
         raise TypeErr(f"unrep: unsupported type {t}")
 
     # -- packed layout -------------------------------------------------------
@@ -600,7 +738,8 @@ class Codec:
             if t.tagged:
                 out.append((off, max(1, (len(t.alts) - 1).bit_length()), 0))
             for f in t.fnames:
-                out += self.layout(t.fields[f], off + t.off[f])
+                sub = self.layout(t.fields[f], off + t.off[f])
+                out += _zero_safe(sub) if t.tagged else sub
             return out
         if isinstance(t, TTuple):
             out = []
@@ -622,6 +761,20 @@ class Codec:
         if isinstance(t, TSeq):
             out = [(off, max(1, t.cap.bit_length()), 0)]
             for j in range(t.cap):
-                out += self.layout(t.elem, off + 1 + j * t.elem.size)
+                out += _zero_safe(self.layout(t.elem, off + 1 + j * t.elem.size))
+            return out
+        if isinstance(t, TPFun):
+            out = []
+            for j in range(len(t.keys)):
+                out.append((off + j * t.stride, 1, 0))
+                out += _zero_safe(self.layout(t.elem, off + j * t.stride + 1))
+            return out
+        if isinstance(t, TSparse):
+            out = [(off, max(1, t.cap.bit_length()), 0)]
+            for j in range(t.cap):
+                o = off + 1 + j * t.stride
+                out += _zero_safe(self.layout(t.kt, o))
+                if t.vt is not None:
+                    out += _zero_safe(self.layout(t.vt, o + t.keyw))
             return out
         raise TypeErr(f"layout: unsupported type {t}")

@@ -30,7 +30,7 @@ enum {
   OP_LDX, OP_STX, OP_TBL, OP_TBLT, OP_BSET, OP_BCLR, OP_BTEST, OP_BOR,
   OP_BAND, OP_BANDN, OP_BISZ, OP_BSUB, OP_BCNT, OP_BNEXT, OP_BFILL, OP_BSETI,
   OP_BTESTI, OP_UCLAMP, OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
-  OP_MADI, OP_BANDC, OP_LEXLT,
+  OP_MADI, OP_BANDC, OP_LEXLT, OP_SFIND, OP_SINS,
   OP__COUNT
 };
 
@@ -204,6 +204,36 @@ TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uin
         int32_t r = 0;
         for (uint32_t i = 0; i < d; ++i) { const int32_t x = f[b + i], y = f[c + i]; if (x != y) { r = x < y; break; } }
         f[a] = r; break; }
+      // Sparse containers (raft's message bag / history sets): f[base] = length, then entries of `stride`
+      // words whose first `keyw` words are the key, sorted ascending by the signed word-wise key order.
+      case OP_SFIND: {  // f[a] = index of the entry of container b whose key equals f[c..c+keyw), else -1
+        const uint32_t stride = d >> 7, keyw = d & 127u; const int32_t n = f[b]; int32_t r = -1;
+        for (int32_t i = 0; i < n; ++i) {
+          const uint32_t e = b + 1u + (uint32_t)i * stride; uint32_t k = 0;
+          while (k < keyw && f[e + k] == f[c + k]) ++k;
+          if (k == keyw) { r = i; break; }
+          if (f[e + k] > f[c + k]) break;
+        }
+        f[a] = r; break; }
+      case OP_SINS: {  // insert / overwrite entry f[b..b+stride) in container a; f[c]: in = capacity, out = 1 ok / 0 full
+        const uint32_t stride = d >> 7, keyw = d & 127u; const int32_t n = f[a]; const int32_t cap = f[c];
+        int32_t pos = 0; int32_t hit = 0;
+        for (; pos < n; ++pos) {
+          const uint32_t e = a + 1u + (uint32_t)pos * stride; uint32_t k = 0;
+          while (k < keyw && f[e + k] == f[b + k]) ++k;
+          if (k == keyw) { hit = 1; break; }
+          if (f[e + k] > f[b + k]) break;
+        }
+        if (!hit) {
+          if (n >= cap) { f[c] = 0; break; }
+          for (int32_t i = n; i > pos; --i) {
+            const uint32_t dst = a + 1u + (uint32_t)i * stride;
+            for (uint32_t k = 0; k < stride; ++k) f[dst + k] = f[dst - stride + k];
+          }
+          f[a] = n + 1;
+        }
+        { const uint32_t e = a + 1u + (uint32_t)pos * stride; for (uint32_t k = 0; k < stride; ++k) f[e + k] = f[b + k]; }
+        f[c] = 1; break; }
       case OP_MADI: f[a] = (int32_t)((uint32_t)f[a] * (uint32_t)((int32_t)(b << 18) >> 18) + (uint32_t)f[c]); break;   // Horner step
       default: *info = 99; *info2 = (int32_t)op; *pc_io = pc; return TLAG_EV_TRAP;
     }

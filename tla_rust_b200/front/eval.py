@@ -15,7 +15,7 @@ import sys
 
 from .parser import Node, OpDef
 from .values import (EvalError, ModelValue, Fcn, LazyFcn, LazySet, SetNat, SetInt, SetString, SetSeq,
-                     SetSubset, SetFuncs, SetRecs, SetTimes, SetUnionLazy, mk_fcn, fcn_apply, fcn_domain,
+                     SetSubset, SetFuncs, SetRecs, SetTimes, SetUnionLazy, SetPFuncs, SetBSeq, mk_fcn, fcn_apply, fcn_domain,
                      fcn_items, is_set, is_enumerable, set_contains, set_iter, to_finite, sorted_vals,
                      values_equal, fmt, vkey)
 
@@ -468,11 +468,43 @@ class Evaluator:
         return SetSubset(self.eval(n.a[0], env, fr))
 
     def e_bigunion(self, n, env, fr):
+        lz = self._structured_union(n.a[0], env, fr)
+        if lz is not None:
+            return lz
         s = self.eval(n.a[0], env, fr)
         out = set()
         for x in set_iter(s):
             out |= to_finite(x)
         return frozenset(out)
+
+    def _structured_union(self, m, env, fr):
+        """Two unions that stay lazy (their element count is astronomical for typing definitions such as
+        raft's voterLog / mlog):  UNION {[d -> R] : d \\in SUBSET D}  and  UNION {[1..k -> S] : k \\in 0..n}."""
+        if m.k != "setmap" or len(m.a[1]) != 1:
+            return None
+        body, ((pat, sn),) = m.a
+        if not isinstance(pat, str) or body.k != "funcset" or sn is None:
+            return None
+        dn, rn = body.a
+
+        def mentions(x):
+            if isinstance(x, Node):
+                return (x.k == "id" and x.a[0] == pat) or any(mentions(y) for y in x.a)
+            if isinstance(x, (tuple, list)):
+                return any(mentions(y) for y in x)
+            return False
+        if mentions(rn):
+            return None
+        if sn.k == "subset" and dn.k == "id" and dn.a[0] == pat:
+            return SetPFuncs(self.eval(sn.a[0], env, fr), self.eval(rn, env, fr))
+        if sn.k == "bin" and sn.a[0] == ".." and dn.k == "bin" and dn.a[0] == ".." \
+                and dn.a[2].k == "id" and dn.a[2].a[0] == pat and not mentions(dn.a[1]):
+            lo = self.eval(sn.a[1], env, fr)
+            one = self.eval(dn.a[1], env, fr)
+            hi = self.eval(sn.a[2], env, fr)
+            if lo == 0 and one == 1 and type(hi) is int:
+                return SetBSeq(self.eval(rn, env, fr), hi)
+        return None
 
     def e_domain(self, n, env, fr):
         return fcn_domain(self.eval(n.a[0], env, fr))

@@ -238,6 +238,52 @@ class SetFuncs(LazySet):
         return f"[{fmt(self.dom)} -> {fmt(self.rng)}]"
 
 
+class SetPFuncs(LazySet):
+    """UNION {[d -> R] : d \\in SUBSET D}: the functions from a subset of D into R (partial functions)."""
+    finite = True
+
+    def __init__(self, dom, rng):
+        self.dom = dom
+        self.rng = rng
+
+    def contains(self, v):
+        if isinstance(v, LazyFcn):
+            v = v.force()
+        if not is_fcn_like(v):
+            return False
+        return all(set_contains(self.dom, k) and set_contains(self.rng, x) for k, x in fcn_items(v))
+
+    def enumerate(self):
+        for d in SetSubset(self.dom).enumerate():
+            yield from SetFuncs(d, self.rng).enumerate()
+
+    def __repr__(self):
+        return f"UNION {{[d -> {fmt(self.rng)}] : d \\in SUBSET {fmt(self.dom)}}}"
+
+
+class SetBSeq(LazySet):
+    """UNION {[1..k -> S] : k \\in 0..n}: the sequences over S of length at most n."""
+    finite = True
+
+    def __init__(self, s, n):
+        self.s = s
+        self.n = n
+
+    def contains(self, v):
+        if isinstance(v, Fcn) and not v.d:
+            v = ()
+        return isinstance(v, tuple) and len(v) <= self.n and all(set_contains(self.s, x) for x in v)
+
+    def enumerate(self):
+        base = sorted_vals(to_finite(self.s))
+        for k in range(self.n + 1):
+            for c in itertools.product(base, repeat=k):
+                yield tuple(c)
+
+    def __repr__(self):
+        return f"UNION {{[1..k -> {fmt(self.s)}] : k \\in 0..{self.n}}}"
+
+
 class SetRecs(LazySet):
     finite = True
 
