@@ -22,7 +22,7 @@
 
 #include "../tla_rust_b200/csrc/tlag_vm.h"
 
-#define MAXW 64
+#define MAXW 128
 #define MAX_STEPS (1u << 26)
 
 typedef struct {

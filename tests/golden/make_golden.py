@@ -80,6 +80,12 @@ MODELS = {
     # are generated and counted, then not explored -- FIFO/MCInnerFIFO.cfg:23-31)
     "MCInnerFIFO": (lambda: (REF + "/examples/SpecifyingSystems/FIFO/MCInnerFIFO.tla", {}), True, True, 4),
     "MCAlternatingBit": (lambda: (REF + "/examples/SpecifyingSystems/TLC/MCAlternatingBit.tla", {}), True, True, 4),
+    # BASELINE config #4 (examples/raft.tla): sparse containers for the message bag and the history variables
+    "MCraft": (lambda: (ROOT + "/models/MCraft.tla", {"extra_dirs": [REF + "/examples"]}), True, True),
+    "MCraft_s3": (lambda: (ROOT + "/models/MCraft.tla",
+                           {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3.cfg"}), True, True),
+    "MCraft_s3_m": (lambda: (ROOT + "/models/MCraft.tla",
+                             {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3_m.cfg"}), True, False),
     "HourClock": (lambda: (REF + "/examples/SpecifyingSystems/HourClock/HourClock.tla", {}), True, True),
     "AsynchInterface": (lambda: (REF + "/examples/SpecifyingSystems/AsynchronousInterface/AsynchInterface.tla", {}), True, True),
 }

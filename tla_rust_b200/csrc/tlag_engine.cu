@@ -24,7 +24,7 @@
 #include "../../include/tlag.h"
 #include "tlag_vm.h"
 
-#define TLAG_MAXW 64
+#define TLAG_MAXW 128
 #define TLAG_BLOCK 512
 #define TLAG_MAX_STEPS (1u << 26)
 
@@ -633,7 +633,7 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   tlag_engine* e = new tlag_engine();
   *out = e;   // returned even on failure so that tlag_last_error works; caller destroys it
   e->m = *m;
-  if (m->words_per_state == 0 || m->words_per_state > TLAG_MAXW) { e->err = "words_per_state out of range (1..64)"; return TLAG_EINVAL; }
+  if (m->words_per_state == 0 || m->words_per_state > TLAG_MAXW) { e->err = "words_per_state out of range (1..128)"; return TLAG_EINVAL; }
   if (m->frame_words > 4096) { e->err = "frame_words > 4096 not supported"; return TLAG_EINVAL; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { e->err = "no CUDA device available"; return TLAG_ECUDA; }

@@ -703,8 +703,6 @@ class Evaluator:
         if op == "\\cup":
             if isinstance(a, frozenset) and isinstance(b, frozenset):
                 return a | b
-            if is_enumerable(a) and is_enumerable(b):
-                return to_finite(a) | to_finite(b)
             if not (is_set(a) and is_set(b)):
                 raise EvalError(f"\\cup applied to non-sets {fmt(a)}, {fmt(b)}")
             return SetUnionLazy(a, b)
