@@ -86,6 +86,7 @@ MODELS = {
                            {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3.cfg"}), True, True),
     "MCraft_s3_m": (lambda: (ROOT + "/models/MCraft.tla",
                              {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3_m.cfg"}), True, False),
+    "Containers": (lambda: (ROOT + "/tests/specs/Containers.tla", {}), False, True),
     "HourClock": (lambda: (REF + "/examples/SpecifyingSystems/HourClock/HourClock.tla", {}), True, True),
     "AsynchInterface": (lambda: (REF + "/examples/SpecifyingSystems/AsynchronousInterface/AsynchInterface.tla", {}), True, True),
 }

@@ -1,0 +1,87 @@
+"""Dynamically-shaped values on the device (raft's message bag and history sets,
+SSI's sequences / recursion): the bytecode lowering (sparse containers, partial functions, SubSeq, SelectSeq,
+run-time \\X, UNION, tuple CHOOSE, unrolled RECURSIVE operators) against the AST oracle O1."""
+import os
+
+import pytest
+
+from conftest import REF, ROOT, needs_reference
+from tla_rust_b200.front.spec import Model
+from tla_rust_b200.checker import compile_model, encode_states, decode_state
+from tla_rust_b200.compile.types import TSparse, TPFun, TSeq
+from oracle import cpu_engine
+from oracle.tlc_oracle import Oracle
+
+SPECS = os.path.join(ROOT, "tests", "specs")
+
+
+def _o2(m, **kw):
+    init = m.initial_states()
+    cm = compile_model(m, init)
+    return cm, cpu_engine.run(cm, encode_states(cm, init), deadlock=m.check_deadlock, **kw)
+
+
+def test_containers_spec_matches_oracle():
+    m = Model(os.path.join(SPECS, "Containers.tla"))
+    o1 = Oracle(m).run()
+    cm, o2 = _o2(m, want_states=True, max_states=1 << 16)
+    assert isinstance(cm.var_types["bag"], TSparse) and cm.var_types["bag"].vt is not None
+    assert isinstance(cm.var_types["seen"], TSparse) and cm.var_types["seen"].vt is None
+    assert isinstance(cm.var_types["pf"], TPFun) and isinstance(cm.var_types["q"], TSeq)
+    assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == ("ok", 138101, 33884, 18)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 138101, 33884, 18)
+    # the stored vectors decode to exactly the oracle's reachable set (canonical sparse encoding: one vector per value)
+    seen = {tuple(sorted((k, repr(v)) for k, v in decode_state(cm, w).items())) for w in o2["states"][:o2["distinct"]]}
+    assert len(seen) == o2["distinct"]
+
+
+def test_containers_invariant_violation_depth_matches_oracle():
+    import tempfile
+    d = tempfile.mkdtemp(prefix="tlag_cont_")
+    src = open(os.path.join(SPECS, "Containers.tla")).read()
+    src = src.replace("BagOK    ==", "SeenShort == \\A s \\in seen : Len(s) <= 1\nBagOK    ==")
+    open(os.path.join(d, "Containers.tla"), "w").write(src)
+    open(os.path.join(d, "Containers.cfg"), "w").write(
+        open(os.path.join(SPECS, "Containers.cfg")).read().replace("SeenOK", "SeenShort"))
+    m = Model(os.path.join(d, "Containers.tla"))
+    o1 = Oracle(m).run()
+    cm, o2 = _o2(m)
+    assert o1.verdict == "invariant" and o2["verdict"] == 1
+    assert cm.invariants[o2["detail"]] == "SeenShort" == o1.invariant
+    # invariants are evaluated when a state is expanded: the violating level may already have been expanded
+    assert len(o1.trace) <= o2["depth"] <= len(o1.trace) + 1
+
+
+@needs_reference
+def test_raft_small_bounds_on_bytecode_engine():
+    """BASELINE config #4 at builder-chosen small bounds (the reference ships no cfg for raft.tla): O1 pins
+    6185 / 694 / 12 (tests/test_oracle_golden.py); the compiled model must agree and TypeOK must hold."""
+    m = Model(ROOT + "/models/MCraft.tla", extra_dirs=[REF + "/examples"])
+    cm, o2 = _o2(m)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 6185, 694, 12)
+    assert isinstance(cm.var_types["messages"], TSparse) and cm.var_types["messages"].cap == 3
+    cfg = open(ROOT + "/models/MCraft.cfg").read().replace("INVARIANT AtMostOneLeaderPerTerm",
+                                                         "INVARIANT AtMostOneLeaderPerTerm TypeOK")
+    m2 = Model(ROOT + "/models/MCraft.tla", cfg_text=cfg, extra_dirs=[REF + "/examples"])
+    r = Oracle(m2).run()
+    assert (r.verdict, r.distinct) == ("ok", 694)
+
+
+@needs_reference
+def test_raft_three_servers_matches_oracle():
+    m = Model(ROOT + "/models/MCraft.tla", cfg_path=ROOT + "/models/MCraft_s3.cfg", extra_dirs=[REF + "/examples"])
+    cm, o2 = _o2(m)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 93022, 7156, 14)
+
+
+@needs_reference
+def test_raft_capacity_overflow_traps_instead_of_truncating():
+    """A sparse container that is too small must stop the run with an evaluation error (verdict 4 / trap 2)."""
+    src = open(ROOT + "/models/MCraft.tla").read().replace("<= MaxMessages + 1", "<= MaxMessages")
+    import tempfile
+    d = tempfile.mkdtemp(prefix="tlag_raft_")
+    open(os.path.join(d, "MCraft.tla"), "w").write(src)
+    open(os.path.join(d, "MCraft.cfg"), "w").write(open(ROOT + "/models/MCraft.cfg").read())
+    m = Model(os.path.join(d, "MCraft.tla"), extra_dirs=[REF + "/examples"])
+    cm, o2 = _o2(m)
+    assert o2["verdict"] == 4

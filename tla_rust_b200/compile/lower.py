@@ -148,6 +148,8 @@ class Lowering:
         self.hoist_keys = []
         self.dry = False
         self.group = model.symmetry_group() if hasattr(model, "symmetry_group") else []
+        self._rec_depth = {}
+        self.rec_depth = 6
         self._intern_all_atoms()
 
     @staticmethod
@@ -444,6 +446,10 @@ class Lowering:
         s = x.t
         if s == t:
             return x
+        if isinstance(s, TBottom):          # value of an activation past the recursion bound (already trapped)
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            return Val(t, dst)
         if isinstance(t, TInt) and isinstance(s, TInt):
             return Val(t, x.loc)
         if isinstance(t, TAtom) and isinstance(s, TAtom):
@@ -1139,15 +1145,118 @@ class Lowering:
             op = r[1]
             env2 = dict(op.env)
             env2.update(self.bind_args(op.params, args, env, ctx, base))
-            return self.cx(op.body, env2, op.ctx, base, want)
+            return self._inline(op.body, env2, op.ctx, base, want, n)
         if r[0] == "def":
             d = r[1]
             if len(d.params) != len(args):
                 raise CompileError(f"arity mismatch calling {name}")
-            return self.cx(d.body, self.bind_args(d.params, args, env, ctx, base), r[2], base, want)
+            return self._inline(d.body, self.bind_args(d.params, args, env, ctx, base), r[2], base, want, n)
         if r[0] == "builtin":
             return self.builtin(name, args, n, env, ctx, base, want)
         raise CompileError(f"cannot apply {name} at line {n.line}")
+
+    def _inline(self, body, env2, ctx2, base, want, n):
+        """Inline an operator body.  RECURSIVE operators (serializableSnapshotIsolation.tla:465,823,1042,1094)
+        are unrolled: every nested activation of the same body is a fresh copy, up to `rec_depth` levels; an
+        activation beyond that traps at run time (evaluation error), it is never silently cut off."""
+        key = id(body)
+        d = self._rec_depth.get(key, 0)
+        if d >= self.rec_depth:
+            self.asm.emit("TRAP", TRAP_EVAL, n.line)
+            return Val(want if want is not None else TBottom(), 0)
+        self._rec_depth[key] = d + 1
+        try:
+            return self.cx(body, env2, ctx2, base, want)
+        finally:
+            self._rec_depth[key] = d
+
+    def x_times(self, n, env, ctx, base, want):
+        """A \\X B \\X ... with run-time operands: bitset over the tuple universe."""
+        ops = [self.cx(x, env, ctx, base) for x in n.a[0]]
+        ets = []
+        for o in ops:
+            ot = o.t if isinstance(o, Val) else self.natural_type(o.v)
+            if not isinstance(ot, TSet):
+                raise CompileError(f"\\X operand is not a bitset-typed set (line {n.line})")
+            ets.append(ot.elem)
+        t = want if isinstance(want, TSet) and isinstance(want.elem, TTuple) else TSet(TTuple(ets))
+        dst = self.alloc(t.size)
+        self.asm.emit("ZERO", dst, t.size)
+        env2 = dict(env)
+        bounds = []
+        for i, o in enumerate(ops):
+            env2[f"__xo{i}"] = o
+            bounds.append((f"__xt{i}", Node("id", (f"__xo{i}",), n.line, n.col)))
+
+        def body(env3):
+            m0 = self.mark()
+            tt = t.elem
+            loc = self.alloc(tt.size)
+            for i in range(len(ops)):
+                xv = self.coerce(env3[f"__xt{i}"], tt.elems[i])
+                self.movn(loc + tt.offs[i], xv.loc, tt.elems[i].size)
+            self._set_add(dst, t, Val(tt, loc), n)
+            self.release(m0)
+        self.for_each(bounds, env2, ctx, base, body)
+        return Val(t, dst)
+
+    def x_bigunion(self, n, env, ctx, base, want):
+        arg = n.a[0]
+        for _ in range(6):          # UNION Range(f): look through operator applications
+            if arg.k not in ("id", "app", "sel"):
+                break
+            tgt = self._expand(arg, env, ctx, base)
+            if tgt is None:
+                break
+            arg, env, ctx, base = tgt
+        if arg.k == "setenum":
+            parts = [lambda w, x=x: self.cx(x, env, ctx, base, w) for x in arg.a[0]]
+            loop = None
+        elif arg.k == "setmap":
+            parts, loop = None, arg
+        else:
+            raise CompileError(f"UNION of a computed set of sets is not supported (line {n.line})")
+        t = want if isinstance(want, (TSet, TSparse)) else None
+        if t is None:
+            # element type from a dry run of the member expression(s)
+            holder = []
+            with self.asm.capture():
+                save_top = self.top
+                if loop is not None:
+                    def probe(env2):
+                        x = self.cx(loop.a[0], env2, ctx, base)
+                        holder.append(x.t if isinstance(x, Val) else self.natural_type(x.v))
+                    self.for_each(loop.a[1], env, ctx, base, probe)
+                else:
+                    for p_ in parts:
+                        x = p_(None)
+                        holder.append(x.t if isinstance(x, Val) else self.natural_type(x.v))
+                self.top = save_top
+            t = TBottom()
+            for h in holder:
+                t = join(t, h)
+            if isinstance(t, TBottom):
+                t = TSet(TBottom())
+        if isinstance(t, TSparse):
+            dst = self.sp_new(t)
+            add = lambda x: self.sp_loop(self.coerce(x, t), lambda k, v: self.sp_insert(dst, k.loc, n.line))
+        else:
+            dst = Val(t, self.alloc(t.size))
+            self.asm.emit("ZERO", dst.loc, t.size)
+
+            def add(x):
+                xv = self.coerce(x, t)
+                self.asm.emit("BOR", dst.loc, dst.loc, xv.loc, t.size)
+        if loop is not None:
+            def body(env2):
+                m0 = self.mark()
+                add(self.cx(loop.a[0], env2, ctx, base, t))
+                self.release(m0)
+            self.for_each(loop.a[1], env, ctx, base, body)
+        else:
+            for p_ in parts:
+                add(p_(t))
+        return dst
 
     def x_sel(self, n, env, ctx, base, want):
         r = self.ev.resolve_sel(n.a[0], self.eval_env(env), Fr(ctx))
@@ -1866,13 +1975,17 @@ class Lowering:
         dst = self.alloc(t.size)
         end = Label("che")
 
+        pat0 = pat
+        if not isinstance(pat, str):
+            pat = "__choose_elem"
+
         def each(env2):
-            x = env2[pat] if isinstance(pat, str) else None
+            x = env2[pat]
+            if pat0 is not pat:
+                env2 = self.bind(env2, pat0, x)
             yes, no = Label("chy"), Label("chn")
             self.cc(body, env2, ctx, base, yes, no)
             self.asm.label(yes)
-            if x is None:
-                raise CompileError("CHOOSE with tuple pattern is not supported")
             xv = self.coerce(x, t) if isinstance(x, Val) else self.materialize(x, t)
             self.movn(dst, xv.loc, t.size)
             self.asm.emit("JMP", end)
@@ -2165,7 +2278,14 @@ class Lowering:
     def _as_seq(self, x, want=None) -> Val:
         if type(x) is Const:
             if want is None:
-                raise CompileError("constant sequence without an expected type")
+                if not isinstance(x.v, tuple):
+                    raise CompileError("constant sequence without an expected type")
+                et = TBottom()
+                for e in x.v:
+                    et = join(et, self.natural_type(e))
+                if isinstance(et, TBottom):
+                    raise CompileError("empty constant sequence without an expected type")
+                want = TSeq(self._widen_elem(et), max(len(x.v), self.seq_cap or len(x.v) + 8))
             return self.materialize(x, want)
         if isinstance(x.t, TSeq):
             return x
@@ -2178,6 +2298,16 @@ class Lowering:
             cap = max(len(x.t.elems), self.seq_cap or len(x.t.elems))
             return self.coerce(x, TSeq(et, cap))
         raise CompileError(f"sequence expected, got {x.t}")
+
+    def _widen_elem(self, t):
+        """Element type for a sequence that starts from constants and grows at run time."""
+        if isinstance(t, TAtom):
+            mv = any(isinstance(a, ModelValue) for a in t.atoms)
+            pool = self.all_mvs if mv else self.all_strings
+            return TAtom(sorted(set(pool) | set(t.atoms), key=vkey))
+        if isinstance(t, TInt):
+            return TInt()
+        return t
 
     def seq_index_reg(self, s: Val, kx, n, trap=True):
         kv = self.as_val(kx, TInt())
@@ -2239,6 +2369,35 @@ class Lowering:
                 self.movn(dst + 1, s.loc + 1 + es, (t.cap - 1) * es)
             r = Val(t, dst)
             return r
+        if name == "SelectSeq":
+            s = self._as_seq(self.cx(args[0], env, ctx, base, want), want if isinstance(want, TSeq) else None)
+            t = s.t
+            es = t.elem.size
+            test = self.op_value(args[1], env, ctx)
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            i = self.alloc(1)
+            t1 = self.alloc(1)
+            ev = self.alloc(es)
+            top, done = Label("sel"), Label("sed")
+            self.li(i, 0)
+            self.asm.label(top)
+            self.asm.emit("LT", t1, i, s.loc)
+            self.asm.emit("JZ", t1, done)
+            self.asm.emit("LDX", ev, s.loc + 1, i, es)
+            self.asm.emit("ADDI", i, i, 1)
+            env2 = dict(test.env)
+            env2[test.params[0][0]] = Val(t.elem, ev)
+            m0 = self.mark()
+            yes = Label("sey")
+            self.cc(test.body, env2, test.ctx, base, yes, top)
+            self.asm.label(yes)
+            self.asm.emit("STX", dst + 1, dst, ev, es)
+            self.asm.emit("ADDI", dst, dst, 1)
+            self.release(m0)
+            self.asm.emit("JMP", top)
+            self.asm.label(done)
+            return Val(t, dst)
         if name == "SubSeq":
             s = self._as_seq(self.cx(args[0], env, ctx, base))
             t = want if isinstance(want, TSeq) and want.elem == s.t.elem else s.t
