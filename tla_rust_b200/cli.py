@@ -41,11 +41,12 @@ def pcal2tla_main(argv=None):
     return rc
 
 
-def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq_cap=None, verbose=True):
+def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq_cap=None, verbose=True, lib_dirs=()):
     from .checker import compile_model, encode_states, result_from_engine
     from .engine import Engine
     t0 = time.time()
-    m = Model(path, cfg_path=cfg_path)
+    lib_dirs = list(lib_dirs) + [d for d in os.environ.get("TLA_LIBRARY", "").split(os.pathsep) if d]
+    m = Model(path, cfg_path=cfg_path, extra_dirs=lib_dirs)
     m.ev.out = out
     for w in m.warnings:
         print(f"Warning: {w}", file=out)
@@ -96,7 +97,7 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
 
 def tlc_main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
-    files, deadlock, cfg, dev = [], True, None, 0
+    files, deadlock, cfg, dev, libs, seq_cap = [], True, None, 0, [], None
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -105,6 +106,12 @@ def tlc_main(argv=None):
         elif a == "-config":
             i += 1
             cfg = argv[i]
+        elif a == "-I":                     # module search path (TLC: -DTLA-Library=...); also $TLA_LIBRARY
+            i += 1
+            libs.append(argv[i])
+        elif a == "-seqcap":                # capacity of Seq(S)-typed variables (bounded by the model's CONSTRAINT)
+            i += 1
+            seq_cap = int(argv[i])
         elif a in ("-workers", "-gpus", "-device", "-fpmem", "-depth", "-coverage", "-checkpoint"):
             i += 1
             if a == "-device":
@@ -115,7 +122,7 @@ def tlc_main(argv=None):
             files.append(a)
         i += 1
     if not files:
-        print("usage: tlc [-deadlock] [-config FILE.cfg] FILE.tla ...", file=sys.stderr)
+        print("usage: tlc [-deadlock] [-config FILE.cfg] [-I DIR] [-seqcap N] FILE.tla ...", file=sys.stderr)
         return 2
     rc = 0
     for f in files:
@@ -123,7 +130,7 @@ def tlc_main(argv=None):
             f += ".tla"
         print(f"Parsing file {os.path.abspath(f)}")
         try:
-            r = check_file(f, deadlock=deadlock, cfg_path=cfg, device=dev)
+            r = check_file(f, deadlock=deadlock, cfg_path=cfg, device=dev, lib_dirs=libs, seq_cap=seq_cap)
         except (SpecError, ParseError, LexError, EvalError, CompileError, TypeErr) as ex:
             print(f"Error: {type(ex).__name__}: {ex}")
             r = 150

@@ -19,7 +19,7 @@ from ..front.eval import Evaluator, Fr, Thunk, Closure, OpVal, AssertFailure, Bu
 from ..front.values import (EvalError, ModelValue, Fcn, LazySet, LazyFcn, SetNat, SetInt, mk_fcn, sorted_vals,
                             set_contains, set_iter, to_finite, is_set, is_enumerable, fmt, vkey, fcn_items)
 from .types import (T, TInt, TBool, TAtom, TRec, TTuple, TFun, TSet, TSeq, TPFun, TSparse, TBottom, TypeErr, Atoms,
-                    Codec, join, type_of_value, type_of_set, widen_init, is_atom, subset_type)
+                    Codec, join, type_of_value, type_of_set, widen_init, is_atom, subset_type, has_dynamic)
 from . import types as _types
 from .bytecode import (Asm, Label, TRAP_EVAL, TRAP_OVERFLOW, TRAP_CASE, TRAP_CHOOSE, IMM28_MAX, IMM28_MIN, MAXREG)
 
@@ -78,6 +78,17 @@ class OVal(Val):
 
     def __repr__(self):
         return f"OVal({self.t}#{self.oreg})"
+
+
+class PVal(Val):
+    """A call-by-name binding (operator argument / LET definition) that was evaluated ONCE at its binding
+    site because it is referenced several times and yields a large value (raft.tla:117-147: the message bag
+    flows through WithMessage / WithoutMessage by name).  Lazy semantics are kept: a trap raised while
+    computing it only sets `poison`, and is re-raised where the value is used."""
+    __slots__ = ("poison", "lazy")
+
+    def __init__(self, t, loc, poison, lazy):
+        self.t, self.loc, self.poison, self.lazy = t, loc, poison, lazy
 
 
 class Lazy:
@@ -1058,15 +1069,84 @@ class Lowering:
             return Val(self.var_types[name], self.p_off[name])
         return Val(self.var_types[name], self.n_off[name])
 
-    def bind_args(self, params, args, env, ctx, base):
+    def bind_args(self, params, args, env, ctx, base, body=None):
         env2 = {}
         for (pn, ar), a in zip(params, args):
             if ar > 0:
                 env2[pn] = self.op_value(a, env, ctx)
             else:
                 c = self.try_const(a, env, ctx, base) if a.k in ("num", "str", "bool", "id") else None
-                env2[pn] = c if c is not None else Lazy(a, env, ctx, base)
+                if c is not None:
+                    env2[pn] = c
+                else:
+                    env2[pn] = self._bind_by_name(Lazy(a, env, ctx, base), pn, (body,))
         return env2
+
+    @staticmethod
+    def _count_uses(name, x):
+        if isinstance(x, Node):
+            if x.k == "id" and x.a[0] == name:
+                return 1
+            return sum(Lowering._count_uses(name, y) for y in x.a)
+        if isinstance(x, (tuple, list)):
+            return sum(Lowering._count_uses(name, y) for y in x)
+        if isinstance(x, OpDef):
+            return Lowering._count_uses(name, x.body)
+        return 0
+
+    @staticmethod
+    def _has_prime(x):
+        if isinstance(x, Node):
+            return x.k in ("prime", "unchanged") or any(Lowering._has_prime(y) for y in x.a)
+        if isinstance(x, (tuple, list)):
+            return any(Lowering._has_prime(y) for y in x)
+        if isinstance(x, OpDef):
+            return Lowering._has_prime(x.body)
+        return False
+
+    EAGER_MIN_WORDS = 8
+
+    def _bind_by_name(self, lz: Lazy, name, scope):
+        """Decide between call-by-name re-lowering at every use (Lazy) and one evaluation at the binding site
+        (PVal): the latter when the name is used at least twice and the value is large or dynamically shaped."""
+        if lz.base != "N" or self.dry or scope is None or any(x is None for x in scope):
+            return lz
+        node = lz.node
+        if node.k in ("id", "num", "str", "bool", "lambda") or self._has_prime(node):
+            return lz
+        if sum(self._count_uses(name, x) for x in scope) < 2:
+            return lz
+        save_top, save_bound = self.top, self.bound
+        try:
+            with self.asm.capture() as cap:
+                poison = self.alloc(1)
+                x = self.cx(node, lz.env, lz.ctx, "N")
+        except (CompileError, TypeErr):
+            self.top, self.bound = save_top, save_bound
+            return lz
+        self.bound = save_bound
+        if type(x) is Const:
+            self.top = save_top
+            return x
+        if type(x) is not Val or not (x.t.size >= self.EAGER_MIN_WORDS or has_dynamic(x.t)) \
+                or any(i[0] in ("ASSERTF", "EMIT", "GEN", "INVF") for i in cap.buf):
+            self.top = save_top
+            return lz
+        end = Label("pve")
+        ntrap = 0
+        out = []
+        for ins in cap.buf:
+            if ins[0] == "TRAP":
+                ntrap += 1
+                out.append(("LI", poison, int(ins[1]) | (int(ins[2]) << 4)))
+                out.append(("JMP", end))
+            else:
+                out.append(ins)
+        if ntrap:
+            self.li(poison, 0)
+        self.asm.splice(out)
+        self.asm.label(end)
+        return PVal(x.t, x.loc, poison if ntrap else None, lz)
 
     def op_value(self, a, env, ctx) -> OpC:
         if a.k == "lambda":
@@ -1079,13 +1159,14 @@ class Lowering:
                 return OpC(r[1].params, r[1].body, {}, r[2], r[1].name)
         raise CompileError(f"operator argument expected at line {a.line}")
 
-    def let_env(self, defs, env, ctx, base):
+    def let_env(self, defs, env, ctx, base, body=None):
         env2 = dict(env)
-        for d in defs:
+        for i, d in enumerate(defs):
             if d.params:
                 env2[d.name] = OpC(d.params, d.body, env2, ctx, d.name)
             else:
-                env2[d.name] = Lazy(d.body, env2, ctx, base)
+                env2[d.name] = self._bind_by_name(Lazy(d.body, env2, ctx, base), d.name,
+                                                  None if body is None else (body,) + tuple(defs[i + 1:]))
         return env2
 
     # ------------------------------------------------------------ expressions
@@ -1111,6 +1192,15 @@ class Lowering:
                 return self.cx(x.node, x.env, x.ctx, x.base if x.base == "P" else base, want)
             if type(x) is OpC:
                 raise CompileError(f"operator {n.a[0]} used as a value")
+            if type(x) is PVal:
+                if base == "P":
+                    return self.cx(x.lazy.node, x.lazy.env, x.lazy.ctx, "P", want)
+                if x.poison is not None:
+                    ok = Label("pvk")
+                    self.asm.emit("JZ", x.poison, ok)
+                    self.asm.emit("TRAP", TRAP_EVAL, n.line)
+                    self.asm.label(ok)
+                return Val(x.t, x.loc)
             return x
         if r[0] == "var":
             return self.var_val(r[1], base)
@@ -1144,13 +1234,13 @@ class Lowering:
         if r[0] == "env" and type(r[1]) is OpC:
             op = r[1]
             env2 = dict(op.env)
-            env2.update(self.bind_args(op.params, args, env, ctx, base))
+            env2.update(self.bind_args(op.params, args, env, ctx, base, op.body))
             return self._inline(op.body, env2, op.ctx, base, want, n)
         if r[0] == "def":
             d = r[1]
             if len(d.params) != len(args):
                 raise CompileError(f"arity mismatch calling {name}")
-            return self._inline(d.body, self.bind_args(d.params, args, env, ctx, base), r[2], base, want, n)
+            return self._inline(d.body, self.bind_args(d.params, args, env, ctx, base, d.body), r[2], base, want, n)
         if r[0] == "builtin":
             return self.builtin(name, args, n, env, ctx, base, want)
         raise CompileError(f"cannot apply {name} at line {n.line}")
@@ -1270,7 +1360,7 @@ class Lowering:
         return self.cx(node, self.bind_args(od.params, args, env, ctx, base), dctx, base, want)
 
     def x_let(self, n, env, ctx, base, want):
-        return self.cx(n.a[1], self.let_env(n.a[0], env, ctx, base), ctx, base, want)
+        return self.cx(n.a[1], self.let_env(n.a[0], env, ctx, base, n.a[1]), ctx, base, want)
 
     # booleans in value context
     def _bool_value(self, n, env, ctx, base, want):
@@ -2635,7 +2725,7 @@ class Lowering:
             self.cc(node, env, ctx, base, lt, lf)
             return
         if k == "let":
-            self.cc(n.a[1], self.let_env(n.a[0], env, ctx, base), ctx, base, lt, lf)
+            self.cc(n.a[1], self.let_env(n.a[0], env, ctx, base, n.a[1]), ctx, base, lt, lf)
             return
         if k == "prime":
             self.cc(n.a[0], env, ctx, "P", lt, lf)
@@ -2777,7 +2867,7 @@ class Lowering:
             r = self.ev.resolve_sel(n.a[0], self.eval_env(env), Fr(ctx))
             if r[0] == "def":
                 _, od, dctx, args = r
-                return (od.body, self.bind_args(od.params, args, env, ctx, base), dctx, base)
+                return (od.body, self.bind_args(od.params, args, env, ctx, base, od.body), dctx, base)
             if r[0] == "expr":
                 _, node, dctx, (od, args) = r
                 return (node, self.bind_args(od.params, args, env, ctx, base), dctx, base)
@@ -2794,14 +2884,14 @@ class Lowering:
                 return (x.node, x.env, x.ctx, x.base if x.base == "P" else base)
             if type(x) is OpC:
                 env2 = dict(x.env)
-                env2.update(self.bind_args(x.params, args, env, ctx, base))
+                env2.update(self.bind_args(x.params, args, env, ctx, base, x.body))
                 return (x.body, env2, x.ctx, base)
             return None
         if r[0] == "def":
             d = r[1]
             if len(d.params) != len(args):
                 raise CompileError(f"arity mismatch calling {name}")
-            return (d.body, self.bind_args(d.params, args, env, ctx, base), r[2], base)
+            return (d.body, self.bind_args(d.params, args, env, ctx, base, d.body), r[2], base)
         if r[0] == "subst" and not args:
             return (r[1], {}, r[2], base)
         return None
@@ -3194,7 +3284,7 @@ class Lowering:
             self.ca(node, env, ctx, bound, k, act)
             return
         if kind == "let":
-            self.ca(n.a[1], self.let_env(n.a[0], env, ctx, "N"), ctx, bound, k, act)
+            self.ca(n.a[1], self.let_env(n.a[0], env, ctx, "N", n.a[1]), ctx, bound, k, act)
             return
         if kind in ("id", "app", "sel"):
             is_assert = kind == "app" and n.a[0] == "Assert"

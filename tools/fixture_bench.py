@@ -1,0 +1,50 @@
+"""Time the CUDA engine on committed fixtures (tests/golden/*.tlagz): whole-BFS device time and distinct
+states/s, with the counts checked against the recorded oracle result.  Used for the raft numbers in
+DESIGN.md (the contract bench, bench.py, stays on MCPaxos3_b4).
+
+    python tools/fixture_bench.py MCraft_s3_m [MCraft_s3_l ...] [--reps 3]
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tla_rust_b200.compiled import load_compiled  # noqa: E402
+from tla_rust_b200.engine import Engine  # noqa: E402
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 3
+    for name in args:
+        cm, init, exp, info = load_compiled(os.path.join(ROOT, "tests", "golden", name + ".tlagz"))
+        o2 = exp["o2"]
+        e = Engine(cm, deadlock=info["deadlock"])
+        best = None
+        for r in range(reps):
+            if r:
+                e.restart()
+            t0 = time.time()
+            e.seed(init)
+            res = e.run()
+            wall = time.time() - t0
+            ok = (res["generated"], res["distinct"], res["depth"]) == (o2["generated"], o2["distinct"], o2["depth"])
+            dev = res["device_seconds"]
+            if best is None or dev < best[0]:
+                best = (dev, wall)
+            if not ok:
+                print(json.dumps({"fixture": name, "error": "count mismatch", "got": res, "want": o2}))
+                break
+        print(json.dumps({"fixture": name, "W": cm.W, "code_len": int(len(cm.code)), "frame_words": cm.frame_words,
+                          "distinct": res["distinct"], "generated": res["generated"], "depth": res["depth"],
+                          "device_s": round(best[0], 4), "wall_s": round(best[1], 4),
+                          "distinct_per_s": round(res["distinct"] / best[0]), "generated_per_s": round(res["generated"] / best[0]),
+                          "counts_match_oracle": ok, "launches": e.launches()}), flush=True)
+        e.close()
+
+
+if __name__ == "__main__":
+    main()
