@@ -86,6 +86,8 @@ MODELS = {
                            {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3.cfg"}), True, True),
     "MCraft_s3_m": (lambda: (ROOT + "/models/MCraft.tla",
                              {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3_m.cfg"}), True, False),
+    "MCraft_s3_l": (lambda: (ROOT + "/models/MCraft.tla",
+                             {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3_l.cfg"}), True, False),
     "Containers": (lambda: (ROOT + "/tests/specs/Containers.tla", {}), False, True),
     "HourClock": (lambda: (REF + "/examples/SpecifyingSystems/HourClock/HourClock.tla", {}), True, True),
     "AsynchInterface": (lambda: (REF + "/examples/SpecifyingSystems/AsynchronousInterface/AsynchInterface.tla", {}), True, True),
@@ -107,7 +109,7 @@ def main():
         init = m.initial_states()
         cm = compile_model(m, init, seq_cap=seq_cap)
         iw = encode_states(cm, init)
-        o2 = cpu_engine.run(cm, iw, n_threads=os.cpu_count() or 1, deadlock=deadlock, max_states=1 << 26)
+        o2 = cpu_engine.run(cm, iw, n_threads=os.cpu_count() or 1, deadlock=deadlock, max_states=1 << 27)
         exp = {"o2": {k: o2[k] for k in ("verdict", "detail", "generated", "distinct", "depth", "init_states",
                                          "fp_xor", "fp_sum", "levels", "state_idx")}}
         if run_o1:

@@ -18,7 +18,7 @@ def _engine(cm, **kw):
 
 
 @pytest.mark.parametrize("name", ["atomic_add", "pcal_intro", "pcal_intro_readme_buggy", "MCPaxos", "MCVoting",
-                                  "MCVoting_deadlock", "demo_race", "demo_lock", "MCInnerFIFO", "MCAlternatingBit", "MCPaxos3_sym", "MCraft", "MCraft_s3", "MCraft_s3_m", "Containers",
+                                  "MCVoting_deadlock", "demo_race", "demo_lock", "MCInnerFIFO", "MCAlternatingBit", "MCPaxos3_sym", "MCraft", "MCraft_s3", "MCraft_s3_m", "MCraft_s3_l", "Containers",
                                   "HourClock", "AsynchInterface", "MCPaxos3", "MCPaxos3_b2", "MCPaxos3_b3", "MCPaxos3_b4"])
 def test_bfs_matches_oracle(name):
     from oracle import cpu_engine

@@ -1105,6 +1105,7 @@ class Lowering:
         return False
 
     EAGER_MIN_WORDS = 8
+    EAGER_MIN_CODE = 40
 
     def _bind_by_name(self, lz: Lazy, name, scope):
         """Decide between call-by-name re-lowering at every use (Lazy) and one evaluation at the binding site
@@ -1128,7 +1129,9 @@ class Lowering:
         if type(x) is Const:
             self.top = save_top
             return x
-        if type(x) is not Val or not (x.t.size >= self.EAGER_MIN_WORDS or has_dynamic(x.t)) \
+        ninstr = sum(1 for i in cap.buf if i[0] != "label")
+        if type(x) is not Val or not (x.t.size >= self.EAGER_MIN_WORDS or has_dynamic(x.t)
+                                      or ninstr >= self.EAGER_MIN_CODE) \
                 or any(i[0] in ("ASSERTF", "EMIT", "GEN", "INVF") for i in cap.buf):
             self.top = save_top
             return lz
