@@ -86,7 +86,8 @@ def _worker(rank, world, port, name, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("pcal_intro", 2), ("MCPaxos3", 2), ("MCPaxos3", 4), ("pcal_intro", 3)])
+@pytest.mark.parametrize("name,world", [("pcal_intro", 2), ("MCPaxos3", 2), ("MCPaxos3", 4), ("pcal_intro", 3),
+                                        ("MCraft", 2), ("MCraft_s3", 3)])
 def test_partitioned_bfs_matches_single(name, world):
     from tla_rust_b200.compiled import load_compiled
     _, _, exp, _ = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))

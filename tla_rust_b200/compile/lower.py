@@ -3630,12 +3630,48 @@ class Lowering:
         for v in m.vars:
             for (fo, w, bias) in self.codec.layout(self.var_types[v], self.n_off[v]):
                 lay.append((fo, aw if w < 0 else w, bias))
+        if any(has_dynamic(self.var_types[v]) for v in m.vars):
+            lay = self._cluster_slots_last(lay)
         import numpy as np
         cm.layout = np.array(lay, dtype=np.int32).reshape(-1, 3)
         bits = int(cm.layout[:, 1].sum())
         cm.W = max(1, (bits + 31) // 32)
         cm.state_bits = bits
         return cm
+
+    def _cluster_slots_last(self, lay):
+        """Pack order for models with containers.  The engine clusters each BFS level, and partitions the state
+        space over GPUs, by the LAST TWO packed words (tlag_owner, k_sort_keys).  With containers laid out in
+        variable order those words would hold the zero tail of the last container (no entropy: every state on one
+        rank).  So the "control" slots -- scalar variables, elements of small per-process functions, container
+        lengths, presence flags -- are packed last, up to 64 bits of them."""
+        ctrl = []
+
+        def walk(t, off):
+            if t.scalar:
+                ctrl.append(off)
+            elif isinstance(t, TFun):
+                for j in range(len(t.keys)):
+                    walk(t.elem, off + j * t.elem.size)
+            elif isinstance(t, TSet):
+                if t.nbits <= 16:
+                    ctrl.append(off)
+            elif isinstance(t, (TSeq, TSparse)):
+                ctrl.append(off)
+            elif isinstance(t, TPFun):
+                for j in range(len(t.keys)):
+                    ctrl.append(off + j * t.stride)
+        for v in self.m.vars:
+            walk(self.var_types[v], self.n_off[v])
+        ctrl = set(ctrl)
+        head, tail, used = [], [], 0
+        for slot in lay:
+            if slot[0] in ctrl and used + slot[1] <= 64:
+                tail.append(slot)
+                used += slot[1]
+            else:
+                head.append(slot)
+        return head + tail
 
     def _action_id(self, act):
         if act is None:

@@ -672,7 +672,13 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   CK(cudaMalloc(&e->d_meta, cap * 4));
   memset(&e->p, 0, sizeof(e->p));
   e->p.code = e->d_code; e->p.code_len = m->code_len;
-  e->p.code_in_smem = ((size_t)m->code_len * 8 <= 200 * 1024) ? 1 : 0;
+  {
+    // bytecode image in shared memory when it fits; TLAG_CODE_SMEM_MAX (bytes) lowers the threshold (tuning knob:
+    // a large image takes L1 capacity away from the per-thread frames of big models)
+    size_t lim = 200 * 1024;
+    if (const char* s_ = getenv("TLAG_CODE_SMEM_MAX")) { const long v = atol(s_); if (v >= 0 && (size_t)v < lim) lim = (size_t)v; }
+    e->p.code_in_smem = ((size_t)m->code_len * 8 <= lim) ? 1 : 0;
+  }
   e->p.cpool = e->d_cpool; e->p.layout = e->d_layout; e->p.n_slots = (int)m->n_slots;
   e->p.entry_inv = m->entry_inv; e->p.entry_next = m->entry_next;
   e->p.n_off = 0; e->p.p_off = m->unpacked_words; e->p.W = (int)m->words_per_state;

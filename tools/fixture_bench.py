@@ -25,11 +25,22 @@ def main():
         e = Engine(cm, deadlock=info["deadlock"])
         best = None
         for r in range(reps):
-            if r:
-                e.restart()
             t0 = time.time()
-            e.seed(init)
-            res = e.run()
+            if r:
+                e.restart()          # clears the table and re-seeds the retained initial states
+            else:
+                e.seed(init)
+            if "--waves" in sys.argv:
+                while True:
+                    ws = e.step()
+                    if ws["expanded"]:
+                        print(json.dumps({"fixture": name, "rep": r, "level": ws["level"], "expanded": ws["expanded"],
+                                          "generated": ws["generated"], "kernel_ms": round(ws["kernel_ms"], 3)}), flush=True)
+                    if ws["verdict"] != 5:
+                        break
+                res = e.result()
+            else:
+                res = e.run()
             wall = time.time() - t0
             ok = (res["generated"], res["distinct"], res["depth"]) == (o2["generated"], o2["distinct"], o2["depth"])
             dev = res["device_seconds"]
