@@ -160,6 +160,7 @@ class Lowering:
         self.dry = False
         self.group = model.symmetry_group() if hasattr(model, "symmetry_group") else []
         self._rec_depth = {}
+        self.copy_once = False
         self.rec_depth = 6
         self._intern_all_atoms()
 
@@ -3314,6 +3315,8 @@ class Lowering:
                     b2 = bound | {tv}
                     self.bound = b2
                     k(b2, act)
+                    if self.copy_once:
+                        self.movn(self.p_off[tv], self.n_off[tv], t.size)
                     return
                 # x' \in S : one alternative per element
                 def each(env2):
@@ -3326,6 +3329,8 @@ class Lowering:
                     self.bound = b2
                     k(b2, act)
                 self.for_each([("__asg", n.a[2])], env, ctx, "N", each)
+                if self.copy_once:
+                    self.movn(self.p_off[tv], self.n_off[tv], t.size)
                 return
         if kind == "unchanged":
             names = []
@@ -3342,7 +3347,8 @@ class Lowering:
                             self.asm.emit("EQN", t1, self.p_off[v], self.n_off[v], t.size)
                         self.asm.emit("JZ", t1, end)
                     else:
-                        self.movn(self.p_off[v], self.n_off[v], t.size)
+                        if not self.copy_once:
+                            self.movn(self.p_off[v], self.n_off[v], t.size)
                         b2.add(v)
                 b2 = frozenset(b2)
                 self.bound = b2
@@ -3561,6 +3567,13 @@ class Lowering:
         entries["next"] = lnext
         self.program = "next"
         inv_top = self.top
+        # Wide states (container models): the primed copy is initialised ONCE per state (primed := current) and kept
+        # "clean" -- UNCHANGED is then free, an assignment x' = e restores x' := x when its continuation returns.
+        # Per successor this replaces a copy of every unchanged variable (raft: ~500 words of containers) by a copy
+        # of the changed ones.  (Not with SYMMETRY: canonicalisation rewrites the whole primed state in place.)
+        self.copy_once = (not self.group) and self.usz >= 64
+        if self.copy_once:
+            self.movn(self.usz, 0, self.usz)
         self._hoist_prologue("next")
         allv = frozenset(m.vars)
 

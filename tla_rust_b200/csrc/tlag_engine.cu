@@ -162,7 +162,7 @@ __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, cons
 
 // MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
 template <int FRAME, int MODE, bool SMEM>
-__global__ void __launch_bounds__(TLAG_BLOCK, (FRAME <= 256 ? 4 : (FRAME <= 512 ? 2 : 1)))
+__global__ void __launch_bounds__(TLAG_BLOCK, (FRAME <= 256 ? 4 : (FRAME <= 512 ? 2 : (SMEM ? 1 : 2))))
 k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
   extern __shared__ uint64_t s_code[];
   if (SMEM) {
@@ -677,6 +677,9 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
     // a large image takes L1 capacity away from the per-thread frames of big models)
     size_t lim = 200 * 1024;
     if (const char* s_ = getenv("TLAG_CODE_SMEM_MAX")) { const long v = atol(s_); if (v >= 0 && (size_t)v < lim) lim = (size_t)v; }
+    // Big frames (container models such as raft) are bound by local-memory latency (ncu: long-scoreboard 37 per issue,
+    // 16 warps/SM): they run with the image in global memory (read through L1) so that two CTAs fit per SM.
+    if (m->frame_words > 512 && !getenv("TLAG_CODE_SMEM_FORCE")) lim = 0;
     e->p.code_in_smem = ((size_t)m->code_len * 8 <= lim) ? 1 : 0;
   }
   e->p.cpool = e->d_cpool; e->p.layout = e->d_layout; e->p.n_slots = (int)m->n_slots;
