@@ -25,6 +25,9 @@
 #include "tlag_vm.h"
 
 #define TLAG_MAXW 128
+#ifndef TLAG_BIG_OCC
+#define TLAG_BIG_OCC 4   /* resident CTAs per SM for the big-frame (> 512 words) wave kernels: latency-bound on local memory */
+#endif
 #define TLAG_BLOCK 512
 #define TLAG_MAX_STEPS (1u << 26)
 
@@ -162,7 +165,7 @@ __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, cons
 
 // MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
 template <int FRAME, int MODE, bool SMEM>
-__global__ void __launch_bounds__(TLAG_BLOCK, (FRAME <= 256 ? 4 : (FRAME <= 512 ? 2 : (SMEM ? 1 : 2))))
+__global__ void __launch_bounds__(TLAG_BLOCK, (FRAME <= 256 ? 4 : (FRAME <= 512 ? 2 : (SMEM ? 1 : TLAG_BIG_OCC))))
 k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
   extern __shared__ uint64_t s_code[];
   if (SMEM) {

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtlag.so")
+LIB_PATH = os.environ.get("TLAG_LIB") or os.path.join(_HERE, "csrc", "libtlag.so")   # TLAG_LIB: tuning builds
 _LIB = None
 
 F_DEADLOCK_CHECK = 1
