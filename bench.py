@@ -318,6 +318,29 @@ def main():
         except Exception as ex:  # noqa: BLE001
             k1 = {"error": str(ex)}
     cpu_r, cpu_dt, _ = cpu_reference(cm, init, info, threads, exp["o2"]["distinct"])
+    other = None
+    if not multi and not args.no_k1:
+        # second workload, reported next to the headline (not part of `value`): BASELINE config #4 (raft, 3 servers)
+        # at the committed fixture's bounds -- container-typed state (W = 44 words), counts checked against the oracle
+        try:
+            from tla_rust_b200.compiled import load_compiled as _lc
+            fx = os.path.join(ROOT, "tests", "golden", "MCraft_s3_l.tlagz")
+            if os.path.exists(fx):
+                cm_r, init_r, exp_r, info_r = _lc(fx)
+                e3 = Engine(cm_r, deadlock=info_r["deadlock"], device=local_rank)
+                e3.seed(init_r)
+                r3 = e3.run()
+                e3.restart()
+                r3 = e3.run()
+                ok3 = (r3["generated"], r3["distinct"], r3["depth"]) == (exp_r["o2"]["generated"], exp_r["o2"]["distinct"],
+                                                                       exp_r["o2"]["depth"])
+                other = {"workload": "MCraft_s3_l: examples/raft.tla via models/MCraft.tla, 3 servers, MaxTerm 3, MaxLogLen 2, "
+                                     "MaxMessages 4 (compiled fixture)", "W": cm_r.W, "distinct": r3["distinct"],
+                         "generated": r3["generated"], "depth": r3["depth"], "kernel_s": round(r3["device_seconds"], 4),
+                         "distinct_per_s": round(r3["distinct"] / r3["device_seconds"], 1), "counts_match_oracle": ok3}
+                e3.close()
+        except Exception as ex:  # noqa: BLE001
+            other = {"error": str(ex)}
     line = {"metric": "distinct states/sec", "value": round(value, 1), "unit": "states/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -327,7 +350,8 @@ def main():
                              "kind": "port", "sample": cpu_r["sample"]},
             "e2e": {"value": round(distinct * args.steps / dt_e2e, 1), "unit": "states/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 96},
-            "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None}
+            "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
+            "other_workloads": [other] if other else []}
     if multi:
         line["comm_ms_per_step"] = round(stats["comm_ms"] / args.steps, 3)
         dist.destroy_process_group()
