@@ -116,7 +116,11 @@ static void *worker(void *arg) {
         if (ev == TLAG_EV_INVF) continue;
         if (ev == TLAG_EV_EMIT) {
           ++nsucc; ++gen;
-          int ov = tlag_pack(m->layout, (int)m->n_slots, frame + m->unpacked_words, succ, W);
+          int ov;
+          if (info2 > 0) {      /* EMITD: re-pack only the dirty slot ranges over the parent's packed words */
+            memcpy(succ, e->states + idx * W, (size_t)W * 4);
+            ov = tlag_pack_ranges(m->layout, m->cpool, info2, frame + m->unpacked_words, succ);
+          } else ov = tlag_pack(m->layout, (int)m->n_slots, frame + m->unpacked_words, succ, W);
           if (ov) { atomic_min64(&e->viol_trap, (idx << 20) | (2ULL << 16) | (uint32_t)((ov - 1) & 0xFFFF)); continue; }
           uint64_t fp = tlag_fingerprint(succ, W);
           int ins = seen_insert(e->table, e->mask, fp);
@@ -370,7 +374,12 @@ int tlagcpu_shard_expand_route(cpu_shard *s, uint32_t n_ranks, uint64_t first, u
       if (ev == TLAG_EV_ASSERT) { if (!kind) { kind = 2; s->detail = info; } continue; }
       if (ev == TLAG_EV_EMIT) {
         ++nsucc; ++gen;
-        if (tlag_pack(m->layout, (int)m->n_slots, frame + m->unpacked_words, succ, W)) { if (!kind) kind = 4; continue; }
+        int ov;
+        if (info2 > 0) {
+          memcpy(succ, s->e.states + idx * W, (size_t)W * 4);
+          ov = tlag_pack_ranges(m->layout, m->cpool, info2, frame + m->unpacked_words, succ);
+        } else ov = tlag_pack(m->layout, (int)m->n_slots, frame + m->unpacked_words, succ, W);
+        if (ov) { if (!kind) kind = 4; continue; }
         uint32_t owner = tlag_owner(succ, W, n_ranks);
         if (counts[owner] >= region) { free(frame); return -5; }
         uint32_t *dst = send + (owner * region + counts[owner]) * (uint64_t)(W + 2);

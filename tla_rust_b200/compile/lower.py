@@ -3312,7 +3312,7 @@ class Lowering:
                     xv = self.coerce(x, t)
                     self.movn(self.p_off[tv], xv.loc, t.size)
                     self.release(m)
-                    b2 = bound | {tv}
+                    b2 = bound | {tv, "*" + tv}
                     self.bound = b2
                     k(b2, act)
                     if self.copy_once:
@@ -3325,7 +3325,7 @@ class Lowering:
                     xv = self.coerce(x, t)
                     self.movn(self.p_off[tv], xv.loc, t.size)
                     self.release(m)
-                    b2 = bound | {tv}
+                    b2 = bound | {tv, "*" + tv}
                     self.bound = b2
                     k(b2, act)
                 self.for_each([("__asg", n.a[2])], env, ctx, "N", each)
@@ -3577,6 +3577,36 @@ class Lowering:
         self._hoist_prologue("next")
         allv = frozenset(m.vars)
 
+        slot_ranges = self._var_slot_ranges() if self.copy_once else None
+
+        def emit_succ(b, aid):
+            """EMIT, or EMITD with the packed-slot ranges of the variables assigned on this path (wide states:
+            the engine re-packs those over the parent's packed words instead of packing every slot)."""
+            if slot_ranges is None or aid > MAXREG:
+                self.asm.emit("EMIT", aid)
+                return
+            rs = []
+            for v in m.vars:
+                if "*" + v in b:
+                    rs += slot_ranges[v]
+            rs.sort()
+            merged = []
+            for first, cnt, pos in rs:
+                if merged and merged[-1][0] + merged[-1][1] == first:
+                    merged[-1][1] += cnt
+                else:
+                    merged.append([first, cnt, pos])
+            if sum(c for _, c, _ in merged) * 2 > self._n_slots:      # most of the state changed: plain pack
+                self.asm.emit("EMIT", aid)
+                return
+            tbl = [len(merged)]
+            for first, cnt, pos in merged:
+                tbl += [first, cnt, pos]
+            if not self.asm.cpool:             # table index 0 means "no table" to the engines: occupy it
+                self.asm.const_table([0])
+            base = self.asm.const_table(tbl)
+            self.asm.emit("EMITD", aid, base)
+
         def emit_k(b, act):
             missing = [v for v in m.vars if v not in b]
             if missing:
@@ -3613,10 +3643,10 @@ class Lowering:
                 self.asm.emit("GEN")
                 self.asm.emit("JMP", end)
                 self.asm.label(ok)
-                self.asm.emit("EMIT", aid)
+                emit_succ(b, aid)
                 self.asm.label(end)
             else:
-                self.asm.emit("EMIT", aid)
+                emit_succ(b, aid)
         if m.next_node is None:
             raise CompileError("no next-state action")
         self.ca(m.next_node, {}, m.next_ctx, frozenset(), emit_k, None)
@@ -3637,20 +3667,45 @@ class Lowering:
         cm.atoms, cm.codec = self.atoms, self.codec
         cm.group = list(self.group)
         cm.warnings = self.warnings
-        # packed layout
-        lay = []
-        aw = self.atoms.width()
-        for v in m.vars:
-            for (fo, w, bias) in self.codec.layout(self.var_types[v], self.n_off[v]):
-                lay.append((fo, aw if w < 0 else w, bias))
-        if any(has_dynamic(self.var_types[v]) for v in m.vars):
-            lay = self._cluster_slots_last(lay)
+        lay = self._packed_layout()
         import numpy as np
         cm.layout = np.array(lay, dtype=np.int32).reshape(-1, 3)
         bits = int(cm.layout[:, 1].sum())
         cm.W = max(1, (bits + 31) // 32)
         cm.state_bits = bits
         return cm
+
+    def _packed_layout(self):
+        """Pack order: (frame offset, bit width, bias) per scalar slot."""
+        lay = []
+        aw = self.atoms.width()
+        for v in self.m.vars:
+            for (fo, w, bias) in self.codec.layout(self.var_types[v], self.n_off[v]):
+                lay.append((fo, aw if w < 0 else w, bias))
+        if any(has_dynamic(self.var_types[v]) for v in self.m.vars):
+            lay = self._cluster_slots_last(lay)
+        return lay
+
+    def _var_slot_ranges(self):
+        """variable -> [(first slot, slot count, bit position of the first slot)] in pack order."""
+        lay = self._packed_layout()
+        self._n_slots = len(lay)
+        pos, bitpos = {}, 0
+        for i, (fo, w, _b) in enumerate(lay):
+            pos[fo] = (i, bitpos)
+            bitpos += w
+        out = {}
+        for v in self.m.vars:
+            t = self.var_types[v]
+            idx = sorted(pos[fo] for fo in range(self.n_off[v], self.n_off[v] + t.size) if fo in pos)
+            rs = []
+            for i, bp in idx:
+                if rs and rs[-1][0] + rs[-1][1] == i:
+                    rs[-1][1] += 1
+                else:
+                    rs.append([i, 1, bp])
+            out[v] = [tuple(r) for r in rs]
+        return out
 
     def _cluster_slots_last(self, lay):
         """Pack order for models with containers.  The engine clusters each BFS level, and partitions the state

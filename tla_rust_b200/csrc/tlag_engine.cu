@@ -229,7 +229,14 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
       act = info;
       unsigned long long fp = 0;
       if (has) {
-        int ov = tlag_pack(p.layout, p.n_slots, frame + p.p_off, succ, W);
+        int ov;
+        if (info2 > 0) {        // EMITD: copy of the parent's packed words, dirty slot ranges re-packed
+          const uint32_t* src = p.states + idx * (unsigned long long)W;
+          for (int i = 0; i < W; ++i) succ[i] = src[i];
+          ov = tlag_pack_ranges(p.layout, p.cpool, info2, frame + p.p_off, succ);
+        } else {
+          ov = tlag_pack(p.layout, p.n_slots, frame + p.p_off, succ, W);
+        }
         if (ov) {
           report_min(&p.ctr->viol_trap, (idx << 20) | (2ULL << 16) | (unsigned)((ov - 1) & 0xFFFF));
           has = false;

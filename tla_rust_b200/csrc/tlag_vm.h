@@ -30,7 +30,7 @@ enum {
   OP_LDX, OP_STX, OP_TBL, OP_TBLT, OP_BSET, OP_BCLR, OP_BTEST, OP_BOR,
   OP_BAND, OP_BANDN, OP_BISZ, OP_BSUB, OP_BCNT, OP_BNEXT, OP_BFILL, OP_BSETI,
   OP_BTESTI, OP_UCLAMP, OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
-  OP_MADI, OP_BANDC, OP_LEXLT, OP_SFIND, OP_SINS,
+  OP_MADI, OP_BANDC, OP_LEXLT, OP_SFIND, OP_SINS, OP_EMITD,
   OP__COUNT
 };
 
@@ -192,7 +192,10 @@ TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uin
       case OP_BTESTI: { uint32_t i = (uint32_t)immJ; f[a] = (int32_t)(((uint32_t)f[b + (i >> 5)] >> (i & 31)) & 1u); break; }
       case OP_UCLAMP: if ((uint32_t)f[a] >= (uint32_t)immI) f[a] = -1; break;
       case OP_TRAP: *info = (int32_t)a; *info2 = immI; *pc_io = pc; return TLAG_EV_TRAP;
-      case OP_EMIT: *info = immI; *pc_io = pc; return TLAG_EV_EMIT;
+      case OP_EMIT: *info = immI; *info2 = 0; *pc_io = pc; return TLAG_EV_EMIT;
+      // EMIT with a dirty-slot table (cpool index in info2): the successor differs from the state being expanded only in
+      // the listed packed-slot ranges, so the engine re-packs those into a copy of the parent's packed words.
+      case OP_EMITD: *info = (int32_t)a; *info2 = immI; *pc_io = pc; return TLAG_EV_EMIT;
       case OP_GEN: *pc_io = pc; return TLAG_EV_GEN;
       case OP_ASSERTF: *info = immI; *pc_io = pc; return TLAG_EV_ASSERT;
       case OP_INVF: *info = immI; *pc_io = pc; return TLAG_EV_INVF;
@@ -266,6 +269,27 @@ TLAG_HD int tlag_pack(const tlag_slot* lay, int nslots, const int32_t* st, uint3
     out[wi] |= v << sh;
     if (sh + (uint32_t)width > 32) out[wi + 1] |= v >> (32 - sh);
     bitpos += (uint32_t)width;
+  }
+  return 0;
+}
+
+// Re-pack the slot ranges listed at cpool[tbl]: [n, (first_slot, n_slots, bit position of first_slot) x n] into `out`,
+// which holds the packed words of the state being expanded.  Same overflow convention as tlag_pack.
+TLAG_HD int tlag_pack_ranges(const tlag_slot* lay, const int32_t* cpool, int32_t tbl, const int32_t* st, uint32_t* out) {
+  const int32_t n = tlag_cp(cpool, tbl);
+  for (int32_t r = 0; r < n; ++r) {
+    const int32_t first = tlag_cp(cpool, tbl + 1 + 3 * r), cnt = tlag_cp(cpool, tbl + 2 + 3 * r);
+    uint32_t bitpos = (uint32_t)tlag_cp(cpool, tbl + 3 + 3 * r);
+    for (int32_t s = first; s < first + cnt; ++s) {
+      const int32_t width = lay[s].width;
+      const uint32_t v = (uint32_t)(st[lay[s].off] - lay[s].bias);
+      if (width < 32 && (v >> width) != 0) return 1 + s;
+      const uint32_t mask = width < 32 ? ((1u << width) - 1u) : 0xFFFFFFFFu;
+      const uint32_t wi = bitpos >> 5, sh = bitpos & 31;
+      out[wi] = (out[wi] & ~(mask << sh)) | (v << sh);
+      if (sh + (uint32_t)width > 32) out[wi + 1] = (out[wi + 1] & ~(mask >> (32 - sh))) | (v >> (32 - sh));
+      bitpos += (uint32_t)width;
+    }
   }
   return 0;
 }
