@@ -1113,11 +1113,21 @@ class Lowering:
         (PVal): the latter when the name is used at least twice and the value is large or dynamically shaped."""
         if lz.base != "N" or self.dry or scope is None or any(x is None for x in scope):
             return lz
-        node = lz.node
-        if node.k in ("id", "num", "str", "bool", "lambda") or self._has_prime(node):
-            return lz
         if sum(self._count_uses(name, x) for x in scope) < 2:
             return lz
+        # an alias of an outer by-name binding (a history prefix handed down through several operators,
+        # serializableSnapshotIsolation.tla:269-399): decide on the underlying expression, here, where it is
+        # used repeatedly -- each level of the chain on its own sees a single use
+        orig = lz
+        for _ in range(16):
+            nd = lz.node
+            if nd.k == "id" and type(lz.env.get(nd.a[0])) is Lazy and lz.env[nd.a[0]].base == "N":
+                lz = lz.env[nd.a[0]]
+            else:
+                break
+        node = lz.node
+        if node.k in ("id", "num", "str", "bool", "lambda") or self._has_prime(node):
+            return orig
         save_top, save_bound = self.top, self.bound
         try:
             with self.asm.capture() as cap:
@@ -1125,7 +1135,7 @@ class Lowering:
                 x = self.cx(node, lz.env, lz.ctx, "N")
         except (CompileError, TypeErr):
             self.top, self.bound = save_top, save_bound
-            return lz
+            return orig
         self.bound = save_bound
         if type(x) is Const:
             self.top = save_top
@@ -1133,9 +1143,9 @@ class Lowering:
         ninstr = sum(1 for i in cap.buf if i[0] != "label")
         if type(x) is not Val or not (x.t.size >= self.EAGER_MIN_WORDS or has_dynamic(x.t)
                                       or ninstr >= self.EAGER_MIN_CODE) \
-                or any(i[0] in ("ASSERTF", "EMIT", "GEN", "INVF") for i in cap.buf):
+                or any(i[0] in ("ASSERTF", "EMIT", "GEN", "INVF", "EMITD") for i in cap.buf):
             self.top = save_top
-            return lz
+            return orig
         end = Label("pve")
         ntrap = 0
         out = []
