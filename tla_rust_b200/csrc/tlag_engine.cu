@@ -23,6 +23,12 @@
 
 #include "../../include/tlag.h"
 #include "tlag_vm.h"
+// second copy of the instruction executor without the extension ops (see tlag_vm_exec.inc)
+#define TLAG_VM_EXEC_FN tlag_vm_exec_lean
+#define TLAG_VM_EXT 0
+#include "tlag_vm_exec.inc"
+#undef TLAG_VM_EXEC_FN
+#undef TLAG_VM_EXT
 
 #define TLAG_MAXW 128
 #ifndef TLAG_BIG_OCC
@@ -94,6 +100,7 @@ struct tlag_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 148;
   int frame_class = 0;
+  bool uses_ext = false;            // the image contains LEXLT / SFIND / SINS / EMITD (full interpreter needed)
   bool restarting = false;
   double growth_hint = 4.0;
   void* d_sort = nullptr; uint64_t sort_bytes = 0;
@@ -148,7 +155,7 @@ enum { L_RUN = 0, L_EMIT = 1, L_DONE = 2, L_STOP = 3 };
 // decode/dispatch; only lanes whose pc equals the minimum execute.  (v1 of this loop spent 41 of ~73
 // SASS instructions per step on bookkeeping and fetched the instruction with a generic per-lane load:
 // profiles/r1_k_wave_warpsched_b2_ncu.txt.)
-template <bool SMEM>
+template <bool SMEM, bool LEAN>
 __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, const uint64_t* scode,
                                         const int32_t* __restrict__ cpool, int32_t* frame, uint32_t& pc,
                                         uint32_t& rpc, int& ev_out, int32_t& info, int32_t& info2) {
@@ -157,14 +164,16 @@ __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, cons
     if (pcm == TLAG_PC_PARKED) break;
     const uint64_t w = SMEM ? scode[pcm] : __ldg(gcode + pcm);
     if (pc == pcm) {
-      const int ev = tlag_vm_exec(w, cpool, frame, &pc, &info, &info2);
+      const int ev = LEAN ? tlag_vm_exec_lean(w, cpool, frame, &pc, &info, &info2)
+                          : tlag_vm_exec(w, cpool, frame, &pc, &info, &info2);
       if (ev >= 0) { ev_out = ev; rpc = pc; pc = TLAG_PC_PARKED; }
     }
   }
 }
 
 // MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
-template <int FRAME, int MODE, bool SMEM>
+// LEAN: interpreter without the extension ops, for models that do not use them (small frames only).
+template <int FRAME, int MODE, bool SMEM, bool LEAN = false>
 __global__ void __launch_bounds__(TLAG_BLOCK, (FRAME <= 256 ? 4 : (FRAME <= 512 ? 2 : (SMEM ? 1 : TLAG_BIG_OCC))))
 k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
   extern __shared__ uint64_t s_code[];
@@ -205,7 +214,7 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
     pc = active ? (phase == 0 ? p.entry_inv : p.entry_next) : TLAG_PC_PARKED;
     unsigned nsucc = 0;
     for (;;) {
-      warp_vm<SMEM>(code, s_code, p.cpool, frame, pc, rpc, ev, info, info2);
+      warp_vm<SMEM, LEAN>(code, s_code, p.cpool, frame, pc, rpc, ev, info, info2);
       int32_t act = 0;
       if (st == L_RUN) {        // this lane stopped on an event
         if (ev == TLAG_EV_EMIT) { st = L_EMIT; ++nsucc; ++gen_local; }
@@ -230,7 +239,7 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
       unsigned long long fp = 0;
       if (has) {
         int ov;
-        if (info2 > 0) {        // EMITD: copy of the parent's packed words, dirty slot ranges re-packed
+        if (!LEAN && info2 > 0) {   // EMITD: copy of the parent's packed words, dirty slot ranges re-packed
           const uint32_t* src = p.states + idx * (unsigned long long)W;
           for (int i = 0; i < W; ++i) succ[i] = src[i];
           ov = tlag_pack_ranges(p.layout, p.cpool, info2, frame + p.p_off, succ);
@@ -504,11 +513,16 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   size_t smem = e->p.code_in_smem ? (size_t)e->p.code_len * 8 : 0;
   void (*fn)(DevParams, unsigned long long, unsigned long long) = nullptr;
   const bool sm = e->p.code_in_smem != 0;
+  const bool lean = !e->uses_ext;
   switch (e->frame_class) {
-    case 0: fn = sm ? k_wave<64, MODE, true> : k_wave<64, MODE, false>; break;
-    case 1: fn = sm ? k_wave<128, MODE, true> : k_wave<128, MODE, false>; break;
-    case 2: fn = sm ? k_wave<256, MODE, true> : k_wave<256, MODE, false>; break;
-    case 3: fn = sm ? k_wave<512, MODE, true> : k_wave<512, MODE, false>; break;
+    case 0: fn = lean ? (sm ? k_wave<64, MODE, true, true> : k_wave<64, MODE, false, true>)
+                      : (sm ? k_wave<64, MODE, true> : k_wave<64, MODE, false>); break;
+    case 1: fn = lean ? (sm ? k_wave<128, MODE, true, true> : k_wave<128, MODE, false, true>)
+                      : (sm ? k_wave<128, MODE, true> : k_wave<128, MODE, false>); break;
+    case 2: fn = lean ? (sm ? k_wave<256, MODE, true, true> : k_wave<256, MODE, false, true>)
+                      : (sm ? k_wave<256, MODE, true> : k_wave<256, MODE, false>); break;
+    case 3: fn = lean ? (sm ? k_wave<512, MODE, true, true> : k_wave<512, MODE, false, true>)
+                      : (sm ? k_wave<512, MODE, true> : k_wave<512, MODE, false>); break;
     case 4: fn = sm ? k_wave<1024, MODE, true> : k_wave<1024, MODE, false>; break;
     case 5: fn = sm ? k_wave<2048, MODE, true> : k_wave<2048, MODE, false>; break;
     default: fn = sm ? k_wave<4096, MODE, true> : k_wave<4096, MODE, false>; break;
@@ -659,6 +673,11 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   CK(cudaEventCreate(&e->ev1));
   e->frame_class = 6;
   for (int i = 0; i < 7; ++i) if ((int)m->frame_words <= kFrameClasses[i]) { e->frame_class = i; break; }
+  e->uses_ext = getenv("TLAG_VM_FULL") != nullptr;
+  for (uint32_t i = 0; i < m->code_len && !e->uses_ext; ++i) {
+    const uint32_t op = (uint32_t)(m->code[i] & 0xFF);
+    if (op == OP_LEXLT || op == OP_SFIND || op == OP_SINS || op == OP_EMITD) e->uses_ext = true;
+  }
   // program image
   CK(cudaMalloc(&e->d_code, (size_t)(m->code_len ? m->code_len : 1) * 8));
   CK(cudaMemcpy(e->d_code, m->code, (size_t)m->code_len * 8, cudaMemcpyHostToDevice));

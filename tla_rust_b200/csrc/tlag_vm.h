@@ -76,174 +76,11 @@ TLAG_HD int tlag_ffs(uint32_t x) {  /* 1-based index of lowest set bit, 0 if non
 // (action id / trap code / assert id / invariant index), info2 the secondary payload (source line).
 // The scalar interpreter (tlag_vm_run) and the warp-scheduled interpreter of the CUDA engine both
 // call this, so the ISA semantics have a single definition.
-TLAG_HD int tlag_vm_exec(const uint64_t w, const int32_t* cpool, int32_t* f, uint32_t* pc_io,
-                         int32_t* info, int32_t* info2) {
-  uint32_t pc = *pc_io + 1;
-  const uint32_t op = (uint32_t)(w & 0xFF);
-  const uint32_t a = (uint32_t)(w >> 8) & 0x3FFF;
-  const uint32_t b = (uint32_t)(w >> 22) & 0x3FFF;
-  const uint32_t c = (uint32_t)(w >> 36) & 0x3FFF;
-  const uint32_t d = (uint32_t)(w >> 50) & 0x3FFF;
-  const int32_t immI = tlag_imm28((uint32_t)(w >> 22) & 0xFFFFFFF);
-  const int32_t immJ = tlag_imm28((uint32_t)(w >> 36) & 0xFFFFFFF);
-  // Operand-class groups first (one operand fetch / write-back sequence per class keeps the device
-  // code small: the interpreter loop has to live in the instruction cache).
-  if (op >= OP_ADD && op <= OP_OR) {                       // f[a] = f[b] (op) f[c]
-    const int32_t x = f[b], y = f[c];
-    int32_t r;
-    switch (op) {
-      case OP_ADD: r = (int32_t)((uint32_t)x + (uint32_t)y); break;
-      case OP_SUB: r = (int32_t)((uint32_t)x - (uint32_t)y); break;
-      case OP_MUL: r = (int32_t)((uint32_t)x * (uint32_t)y); break;
-      case OP_LT: r = x < y; break;
-      case OP_LE: r = x <= y; break;
-      case OP_EQ: r = x == y; break;
-      case OP_NE: r = x != y; break;
-      case OP_AND: r = (x != 0) & (y != 0); break;
-      default: r = (x != 0) | (y != 0); break;             // OP_OR
-    }
-    f[a] = r;
-  } else if (op >= OP_ADDI && op <= OP_ANDI) {             // f[a] = f[b] (op) immJ
-    const int32_t x = f[b];
-    int32_t r;
-    switch (op) {
-      case OP_ADDI: r = (int32_t)((uint32_t)x + (uint32_t)immJ); break;
-      case OP_MULI: r = (int32_t)((uint32_t)x * (uint32_t)immJ); break;
-      case OP_EQI: r = x == immJ; break;
-      case OP_NEI: r = x != immJ; break;
-      case OP_LTI: r = x < immJ; break;
-      case OP_LEI: r = x <= immJ; break;
-      case OP_GTI: r = x > immJ; break;
-      case OP_GEI: r = x >= immJ; break;
-      case OP_SHRI: r = (int32_t)((uint32_t)x >> (immJ & 31)); break;
-      default: r = x & immJ; break;                        // OP_ANDI
-    }
-    f[a] = r;
-  } else if (op >= OP_JEQ && op <= OP_JGEZ) {              // compare-and-branch
-    const int32_t x = f[a];
-    int32_t y = 0;
-    uint32_t tgt = (uint32_t)immJ;
-    if (op <= OP_JGE) y = f[b];
-    else if (op <= OP_JGEI) y = (int32_t)(b << 18) >> 18;
-    else tgt = (uint32_t)immI;                             // JZ / JNZ / JNEG / JGEZ: target in (b,c)
-    int t;
-    switch (op) {
-      case OP_JEQ: case OP_JEQI: case OP_JZ: t = x == y; break;
-      case OP_JNE: case OP_JNEI: case OP_JNZ: t = x != y; break;
-      case OP_JLT: case OP_JLTI: case OP_JNEG: t = x < y; break;
-      default: t = x >= y; break;                          // JGE / JGEI / JGEZ
-    }
-    if (t) pc = tgt;
-  } else if (op >= OP_JBT && op <= OP_JBFI) {              // bit-test-and-branch
-    const uint32_t i = (op <= OP_JBF) ? (uint32_t)f[b] : b;
-    const int bit = (((uint32_t)f[a + (i >> 5)] >> (i & 31)) & 1u) != 0;
-    if (bit == ((op == OP_JBT) | (op == OP_JBTI))) pc = (uint32_t)immJ;
-  } else {
-    switch (op) {
-      case OP_HALT: *pc_io = pc - 1; return TLAG_EV_HALT;
-      case OP_JMP: pc = (uint32_t)immI; break;
-      case OP_LI: f[a] = immI; break;
-      case OP_LIW: f[a] = tlag_cp(cpool, immI); break;
-      case OP_MOV: f[a] = f[b]; break;
-      case OP_MOVN:
-        if (a <= b) { TLAG_NOUNROLL for (uint32_t i = 0; i < c; ++i) f[a + i] = f[b + i]; }
-        else { TLAG_NOUNROLL for (uint32_t i = c; i-- > 0;) f[a + i] = f[b + i]; }
-        break;
-      case OP_ZERO: TLAG_NOUNROLL for (uint32_t i = 0; i < b; ++i) f[a + i] = 0; break;
-      case OP_LDC: TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = tlag_cp(cpool, immI + (int32_t)i); break;
-      case OP_DIV: {  // TLA+ \div: floor division (Integers.tla)
-        int32_t x = f[b], y = f[c];
-        if (y == 0) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
-        int32_t q = x / y; if ((x % y != 0) && ((x < 0) != (y < 0))) --q; f[a] = q; break; }
-      case OP_MOD: {  // TLA+ %: result in 0..y-1
-        int32_t x = f[b], y = f[c];
-        if (y <= 0) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
-        int32_t r = x % y; if (r < 0) r += y; f[a] = r; break; }
-      case OP_NEG: f[a] = -f[b]; break;
-      case OP_EQN: { int32_t e = 1; TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) e &= (f[b + i] == f[c + i]); f[a] = e; break; }
-      case OP_NOT: f[a] = !f[b]; break;
-      case OP_LDX: { uint32_t base = b + (uint32_t)f[c] * d; TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = f[base + i]; break; }
-      case OP_STX: { uint32_t base = a + (uint32_t)f[b] * d; TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[base + i] = f[c + i]; break; }
-      case OP_TBL: f[a] = tlag_cp(cpool, immI + f[d]); break;
-      case OP_TBLT: {  // table lookup that traps on the "field absent" sentinel
-        int32_t v = tlag_cp(cpool, immI + f[d]);
-        if (v == (int32_t)0x80000000) { *info = 1; *info2 = 0; *pc_io = pc; return TLAG_EV_TRAP; }
-        f[a] = v; break; }
-      case OP_BSET: { uint32_t i = (uint32_t)f[b]; f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break; }
-      case OP_BCLR: { uint32_t i = (uint32_t)f[b]; f[a + (i >> 5)] &= ~(int32_t)(1u << (i & 31)); break; }
-      case OP_BTEST: { uint32_t i = (uint32_t)f[c]; f[a] = (int32_t)(((uint32_t)f[b + (i >> 5)] >> (i & 31)) & 1u); break; }
-      case OP_BOR: TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] | f[c + i]; break;
-      case OP_BAND: TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] & f[c + i]; break;
-      case OP_BANDN: TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) f[a + i] = f[b + i] & ~f[c + i]; break;
-      case OP_BISZ: { int32_t z = 1; TLAG_NOUNROLL for (uint32_t i = 0; i < c; ++i) z &= (f[b + i] == 0); f[a] = z; break; }
-      case OP_BSUB: { int32_t z = 1; TLAG_NOUNROLL for (uint32_t i = 0; i < d; ++i) z &= ((f[b + i] & ~f[c + i]) == 0); f[a] = z; break; }
-      case OP_BCNT: { int32_t n = 0; TLAG_NOUNROLL for (uint32_t i = 0; i < c; ++i) n += tlag_popc((uint32_t)f[b + i]); f[a] = n; break; }
-      case OP_BNEXT: {  // a = smallest set bit index > f[c] (f[c] = -1 to start) within d bits, else -1
-        int32_t cur = f[c] + 1; int32_t res = -1;
-        uint32_t nb = d;
-        TLAG_NOUNROLL while ((uint32_t)cur < nb) {
-          uint32_t word = (uint32_t)f[b + ((uint32_t)cur >> 5)] >> ((uint32_t)cur & 31);
-          if (word) { int32_t cand = cur + tlag_ffs(word) - 1; if ((uint32_t)cand < nb) res = cand; break; }
-          cur = (int32_t)(((uint32_t)cur | 31u) + 1u);
-        }
-        f[a] = res; break; }
-      case OP_BFILL: TLAG_NOUNROLL for (uint32_t i = 0; i < b; ++i) f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break;
-      case OP_BSETI: { uint32_t i = (uint32_t)immI; f[a + (i >> 5)] |= (int32_t)(1u << (i & 31)); break; }
-      case OP_BTESTI: { uint32_t i = (uint32_t)immJ; f[a] = (int32_t)(((uint32_t)f[b + (i >> 5)] >> (i & 31)) & 1u); break; }
-      case OP_UCLAMP: if ((uint32_t)f[a] >= (uint32_t)immI) f[a] = -1; break;
-      case OP_TRAP: *info = (int32_t)a; *info2 = immI; *pc_io = pc; return TLAG_EV_TRAP;
-      case OP_EMIT: *info = immI; *info2 = 0; *pc_io = pc; return TLAG_EV_EMIT;
-      // EMIT with a dirty-slot table (cpool index in info2): the successor differs from the state being expanded only in
-      // the listed packed-slot ranges, so the engine re-packs those into a copy of the parent's packed words.
-      case OP_EMITD: *info = (int32_t)a; *info2 = immI; *pc_io = pc; return TLAG_EV_EMIT;
-      case OP_GEN: *pc_io = pc; return TLAG_EV_GEN;
-      case OP_ASSERTF: *info = immI; *pc_io = pc; return TLAG_EV_ASSERT;
-      case OP_INVF: *info = immI; *pc_io = pc; return TLAG_EV_INVF;
-      case OP_BANDC: {  // f[a..a+n) = f[b..b+n) & cpool[base..): set AND compile-time universe mask (immJ = base<<8 | n)
-        const uint32_t n = (uint32_t)immJ & 0xFF; const int32_t base = (int32_t)((uint32_t)immJ >> 8);
-        for (uint32_t i = 0; i < n; ++i) f[a + i] = f[b + i] & tlag_cp(cpool, base + (int32_t)i);
-        break; }
-      case OP_LEXLT: {  // f[a] = (f[b..b+d) <lex f[c..c+d)), word-wise signed: SYMMETRY canonicalisation
-        int32_t r = 0;
-        for (uint32_t i = 0; i < d; ++i) { const int32_t x = f[b + i], y = f[c + i]; if (x != y) { r = x < y; break; } }
-        f[a] = r; break; }
-      // Sparse containers (raft's message bag / history sets): f[base] = length, then entries of `stride`
-      // words whose first `keyw` words are the key, sorted ascending by the signed word-wise key order.
-      case OP_SFIND: {  // f[a] = index of the entry of container b whose key equals f[c..c+keyw), else -1
-        const uint32_t stride = d >> 7, keyw = d & 127u; const int32_t n = f[b]; int32_t r = -1;
-        for (int32_t i = 0; i < n; ++i) {
-          const uint32_t e = b + 1u + (uint32_t)i * stride; uint32_t k = 0;
-          while (k < keyw && f[e + k] == f[c + k]) ++k;
-          if (k == keyw) { r = i; break; }
-          if (f[e + k] > f[c + k]) break;
-        }
-        f[a] = r; break; }
-      case OP_SINS: {  // insert / overwrite entry f[b..b+stride) in container a; f[c]: in = capacity, out = 1 ok / 0 full
-        const uint32_t stride = d >> 7, keyw = d & 127u; const int32_t n = f[a]; const int32_t cap = f[c];
-        int32_t pos = 0; int32_t hit = 0;
-        for (; pos < n; ++pos) {
-          const uint32_t e = a + 1u + (uint32_t)pos * stride; uint32_t k = 0;
-          while (k < keyw && f[e + k] == f[b + k]) ++k;
-          if (k == keyw) { hit = 1; break; }
-          if (f[e + k] > f[b + k]) break;
-        }
-        if (!hit) {
-          if (n >= cap) { f[c] = 0; break; }
-          for (int32_t i = n; i > pos; --i) {
-            const uint32_t dst = a + 1u + (uint32_t)i * stride;
-            for (uint32_t k = 0; k < stride; ++k) f[dst + k] = f[dst - stride + k];
-          }
-          f[a] = n + 1;
-        }
-        { const uint32_t e = a + 1u + (uint32_t)pos * stride; for (uint32_t k = 0; k < stride; ++k) f[e + k] = f[b + k]; }
-        f[c] = 1; break; }
-      case OP_MADI: f[a] = (int32_t)((uint32_t)f[a] * (uint32_t)((int32_t)(b << 18) >> 18) + (uint32_t)f[c]); break;   // Horner step
-      default: *info = 99; *info2 = (int32_t)op; *pc_io = pc; return TLAG_EV_TRAP;
-    }
-  }
-  *pc_io = pc;
-  return -1;
-}
+#define TLAG_VM_EXEC_FN tlag_vm_exec
+#define TLAG_VM_EXT 1
+#include "tlag_vm_exec.inc"
+#undef TLAG_VM_EXEC_FN
+#undef TLAG_VM_EXT
 
 // Runs from *pc until the next event.  `code` may live in shared memory on the device.
 TLAG_HD int tlag_vm_run(const uint64_t* code, const int32_t* cpool, int32_t* f, uint32_t* pc_io,
