@@ -21,6 +21,7 @@ from ..front.values import (EvalError, ModelValue, Fcn, LazySet, LazyFcn, SetNat
 from .types import (T, TInt, TBool, TAtom, TRec, TTuple, TFun, TSet, TSeq, TPFun, TSparse, TBottom, TypeErr, Atoms,
                     Codec, join, type_of_value, type_of_set, widen_init, is_atom, subset_type, has_dynamic)
 from . import types as _types
+from .types import ATOM_ALT
 from .bytecode import (Asm, Label, TRAP_EVAL, TRAP_OVERFLOW, TRAP_CASE, TRAP_CHOOSE, IMM28_MAX, IMM28_MIN, MAXREG)
 
 UNROLL_MAX = 24
@@ -328,12 +329,16 @@ class Lowering:
         all_atoms = [self.atoms.val(i) for i in range(1, len(self.atoms.vals))]
         str_atoms = [a for a in all_atoms if isinstance(a, str)]
         mv_atoms = [a for a in all_atoms if isinstance(a, ModelValue)]
-        for v in m.vars:
-            if v in types:
-                continue
+        untyped = [v for v in m.vars if v not in types]
+        sample = self._sample_reachable(init_states) if untyped else init_states
+        for v in untyped:
             t = None
-            for st in init_states:
-                t = join(t, type_of_value(st[v], self.seq_cap))
+            for st in sample:
+                try:
+                    t = join(t, type_of_value(st[v], self.seq_cap))
+                except TypeErr as ex:
+                    raise CompileError(f"cannot infer a fixed-width type for variable {v}: {ex}; add a TypeOK-style "
+                                       f"definition")
             if t is None:
                 raise CompileError(f"cannot infer a type for variable {v}: no initial states")
             types[v] = self._widen(t, str_atoms, mv_atoms, all_atoms)
@@ -345,6 +350,41 @@ class Lowering:
                 except TypeErr as ex:
                     raise CompileError(f"initial value of {v} does not fit its type {types[v]}: {ex}")
         return types
+
+    SAMPLE_STATES = 400
+
+    def _sample_reachable(self, init_states):
+        """Shapes for variables that no type invariant mentions (MemoryInterface.tla:2 `memInt`): the host front end
+        enumerates a bounded prefix of the reachable states (initial states and a few hundred successors) and the
+        types are the widened join of what it sees.  This is compile-time typing only -- the search itself runs on
+        the device, and a value outside the inferred type traps there (capacity overflow), it is never wrong."""
+        m = self.m
+        seen, out, queue = set(), [], []
+        key = lambda st: tuple(repr(st[v]) for v in m.vars)
+        for st in init_states:
+            k = key(st)
+            if k not in seen:
+                seen.add(k)
+                out.append(st)
+                queue.append(st)
+        qi = 0
+        while qi < len(queue) and len(out) < self.SAMPLE_STATES:
+            st = queue[qi]
+            qi += 1
+            try:
+                for asg, _act in self.ev.solve(m.next_node, {}, m.next_ctx, st, {}, "next"):
+                    if len(asg) != len(m.vars):
+                        continue
+                    k = key(asg)
+                    if k not in seen:
+                        seen.add(k)
+                        out.append(asg)
+                        queue.append(asg)
+                        if len(out) >= self.SAMPLE_STATES:
+                            break
+            except (EvalError, AssertFailure):
+                continue
+        return out
 
     def _widen(self, t, strs, mvs, alla):
         if isinstance(t, TAtom):
@@ -468,19 +508,30 @@ class Lowering:
             return Val(t, x.loc)
         if isinstance(t, TBool) and isinstance(s, TBool):
             return x
+        if isinstance(t, TRec) and isinstance(s, TAtom) and ATOM_ALT in t.fields:
+            dst = self.alloc(t.size)
+            self.asm.emit("ZERO", dst, t.size)
+            if t.tagged:
+                self.li(dst, t.alt_index((ATOM_ALT,)))
+            self.asm.emit("MOV", dst + t.off[ATOM_ALT], x.loc)
+            return Val(t, dst)
         if isinstance(t, TRec) and isinstance(s, TRec):
             dst = self.alloc(t.size)
             self.asm.emit("ZERO", dst, t.size)
             if s.tagged:
-                if not t.tagged:
-                    raise CompileError(f"cannot coerce union {s} to record {t}")
-                # map tags through a table
+                # map tags through a table; an alternative the target type does not have is a run-time narrowing
+                # failure (trap), e.g. buf[p] : MReq | Val | NoVal appended to a queue of requests
+                # (WriteThroughCache.tla:112) after the guard r.op = "Wr" has established that it is a request
                 tbl = []
                 for alt in s.alts:
-                    tbl.append(t.alt_index(alt))
-                if any(i < 0 for i in tbl):
-                    raise CompileError(f"record alternatives of {s} missing from {t}")
-                self.asm.emit("TBL", dst, self.asm.const_table(tbl), x.loc)
+                    ai = t.alt_index(alt)
+                    tbl.append(ai if ai >= 0 else -(1 << 31))
+                if all(i < 0 for i in tbl):
+                    raise CompileError(f"no record alternative of {s} fits {t}")
+                tagr = self.alloc(1)
+                self.asm.emit("TBLT" if any(i < 0 for i in tbl) else "TBL", tagr, self.asm.const_table(tbl), x.loc)
+                if t.tagged:
+                    self.asm.emit("MOV", dst, tagr)
             else:
                 ai = t.alt_index(s.alts[0])
                 if ai < 0:
@@ -489,6 +540,8 @@ class Lowering:
                     self.li(dst, ai)
             for f in s.fnames:
                 if f not in t.fields:
+                    if s.tagged:
+                        continue            # only in alternatives the target lacks (those trapped above)
                     raise CompileError(f"field {f} missing in target record type")
                 sub = self.coerce(Val(s.fields[f], x.loc + s.off[f]), t.fields[f])
                 self.movn(dst + t.off[f], sub.loc, t.fields[f].size)
@@ -1609,6 +1662,8 @@ class Lowering:
         f = n.a[1]
         if type(r) is Const:
             return Const(r.v.d[f])
+        if isinstance(r.t, TBottom):
+            return r
         if not isinstance(r.t, TRec) or f not in r.t.fields:
             raise CompileError(f"no field {f} in type {r.t} (line {n.line})")
         t = r.t
@@ -1900,8 +1955,38 @@ class Lowering:
             return ("dyn", o)
         raise CompileError(f"value of type {ft} is not a function")
 
+    def _fcndef_target(self, fn, env, ctx, base):
+        """fn names a function defined by  f[x \\in S] == e  (LET or module level): -> (fcndef node, env, ctx)."""
+        if fn.k != "id":
+            return None
+        try:
+            r = self.resolve(fn.a[0], env, ctx)
+        except CompileError:
+            return None
+        if r[0] == "env" and type(r[1]) is Lazy and r[1].node.k == "fcndef":
+            return r[1].node, r[1].env, r[1].ctx
+        if r[0] == "env" and type(r[1]) is PVal and r[1].lazy.node.k == "fcndef":
+            return r[1].lazy.node, r[1].lazy.env, r[1].lazy.ctx
+        if r[0] == "def" and not r[1].params and r[1].body.k == "fcndef":
+            return r[1].body, {}, r[2]
+        return None
+
     def x_fapp(self, n, env, ctx, base, want):
         fn, args = n.a
+        tgt = self._fcndef_target(fn, env, ctx, base)
+        if tgt is not None and self.try_const(fn, env, ctx, base) is None:
+            # application of a (possibly recursive) function definition whose body depends on the state
+            # (WriteThroughCache.tla:116-123 `vmem`: a fold over the memory queue): the body is inlined with the
+            # bound variable := the argument, recursive applications unroll like RECURSIVE operators
+            node, fenv, fctx = tgt
+            _nm, bounds, body = node.a
+            if len(bounds) == 1 and isinstance(bounds[0][0], str) and len(args) == 1:
+                a = args[0]
+                c = self.try_const(a, env, ctx, base)
+                arg = c if c is not None else self._bind_by_name(Lazy(a, env, ctx, base), bounds[0][0], (body,))
+                env2 = dict(fenv)
+                env2[bounds[0][0]] = arg
+                return self._inline(body, env2, fctx, base, want, n)
         f = self.cx(fn, env, ctx, base)
         if len(args) == 1:
             kx = self.cx(args[0], env, ctx, base)
@@ -1913,6 +1998,8 @@ class Lowering:
                 return Const(fcn_apply(f.v, kx.v))
             f = self.as_val(f)
         ft = f.t
+        if isinstance(ft, TBottom):
+            return f
         if isinstance(ft, TSeq):
             return self.seq_index(f, kx, n)
         if isinstance(ft, TPFun):
@@ -1963,6 +2050,8 @@ class Lowering:
     def x_except(self, n, env, ctx, base, want):
         fn, ups = n.a
         f = self.cx(fn, env, ctx, base, want)
+        if isinstance(f, Val) and isinstance(f.t, TBottom):
+            return f                    # value of an activation past the recursion bound (already trapped)
         f = self.as_val(f, want)
         if want is not None and f.t != want:
             f = self.coerce(f, want)

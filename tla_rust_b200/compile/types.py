@@ -31,6 +31,7 @@ from ..front.values import (ModelValue, Fcn, LazySet, SetNat, SetInt, SetString,
                             LazyFcn, fcn_items, is_fcn_like)
 
 MAX_SET_BITS = 8192
+ATOM_ALT = "\x00atom"     # pseudo-field of the record alternative that holds a bare atom (atom | record unions)
 SPARSE_CAP = 8          # default capacity of sparse containers (overridden per variable by a Cardinality bound)
 INT32_MIN = -(1 << 31)
 INT32_MAX = (1 << 31) - 1
@@ -330,6 +331,12 @@ def join(a: T, b: T) -> T:
         return TSet(join(a.elem, b.elem))
     if ta is TRec and tb is TRec:
         return TRec(a.alt_dicts() + b.alt_dicts())
+    # a slot that holds either a record or a bare atom (InternalMemory.tla:12: buf \in [Proc -> MReq \cup Val \cup
+    # {NoVal}]): the atom becomes one more alternative of the tagged union
+    if ta is TRec and tb is TAtom:
+        return TRec(a.alt_dicts() + [{ATOM_ALT: b}])
+    if ta is TAtom and tb is TRec:
+        return join(b, a)
     if ta is TTuple and tb is TTuple and len(a.elems) == len(b.elems):
         return TTuple([join(x, y) for x, y in zip(a.elems, b.elems)])
     if ta is TFun and tb is TFun and a.keys == b.keys:
@@ -497,6 +504,8 @@ class Codec:
             except ValueError:
                 return -1
         if isinstance(t, TRec):
+            if is_atom(v) and ATOM_ALT in t.fields:
+                v = Fcn({ATOM_ALT: v})
             if not isinstance(v, Fcn):
                 return -1
             ai = t.alt_index(v.d.keys())
@@ -562,7 +571,7 @@ class Codec:
             out = []
             for alt, ts in zip(t.alts, t.alt_types):
                 for combo in itertools.product(*[self.enum(ts[f]) for f in alt]):
-                    out.append(Fcn(dict(zip(alt, combo))))
+                    out.append(combo[0] if alt == (ATOM_ALT,) else Fcn(dict(zip(alt, combo))))
             return out
         if isinstance(t, TTuple):
             return [tuple(c) for c in itertools.product(*[self.enum(e) for e in t.elems])]
@@ -595,6 +604,8 @@ class Codec:
                 raise TypeErr(f"expected string/model value, got {fmt(v)}")
             return [self.atoms.id(v)]
         if isinstance(t, TRec):
+            if is_atom(v) and ATOM_ALT in t.fields:
+                v = Fcn({ATOM_ALT: v})
             if not isinstance(v, Fcn):
                 raise TypeErr(f"expected record, got {fmt(v)}")
             ai = t.alt_index(v.d.keys())
@@ -693,6 +704,8 @@ class Codec:
             return self.atoms.val(int(w[i]))
         if isinstance(t, TRec):
             ai = int(w[i]) if t.tagged else 0
+            if t.alts[ai] == (ATOM_ALT,):
+                return self.unrep(t.fields[ATOM_ALT], w, i + t.off[ATOM_ALT])
             return Fcn({f: self.unrep(t.fields[f], w, i + t.off[f]) for f in t.alts[ai]})
         if isinstance(t, TTuple):
             return tuple(self.unrep(e, w, i + o) for e, o in zip(t.elems, t.offs))
