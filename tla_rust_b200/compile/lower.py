@@ -232,8 +232,36 @@ class Lowering:
         self.top = m
 
     # ------------------------------------------------------------- var types
+    def _auto_seq_cap(self, init_states):
+        """No -seqcap given: capacity of Seq(S)-typed variables = longest sequence in a bounded sample of reachable
+        states + 2, at least 4.  Longer sequences trap at run time (capacity overflow), they are never truncated."""
+        def longest(v):
+            if isinstance(v, tuple):
+                return max([len(v)] + [longest(x) for x in v])
+            if isinstance(v, frozenset):
+                return max([0] + [longest(x) for x in v])
+            if isinstance(v, Fcn):
+                return max([0] + [longest(x) for x in v.d.values()])
+            return 0
+        n = 0
+        for st in self._sample_reachable(init_states):
+            for v in self.m.vars:
+                n = max(n, longest(st[v]))
+        self.seq_cap = max(4, n + 2)
+        self.warnings.append(f"sequence capacity set to {self.seq_cap} (from a sample of reachable states; "
+                             f"override with -seqcap)")
+
     def infer_var_types(self, init_states):
         m = self.m
+        if self.seq_cap is None:
+            def mentions_seq(x):
+                if isinstance(x, Node):
+                    return (x.k == "app" and x.a[0] == "Seq") or any(mentions_seq(y) for y in x.a)
+                if isinstance(x, (tuple, list)):
+                    return any(mentions_seq(y) for y in x)
+                return isinstance(x, OpDef) and mentions_seq(x.body)
+            if any(mentions_seq(d[0].body) for d in self.ctx.defs.values()):
+                self._auto_seq_cap(init_states)
         types = {}
         hint = self.type_hint
         # candidate type invariants: an explicit hint, the cfg's INVARIANTs, then every definition whose
@@ -352,6 +380,7 @@ class Lowering:
         return types
 
     SAMPLE_STATES = 400
+    SAMPLE_SECONDS = 8.0
 
     def _sample_reachable(self, init_states):
         """Shapes for variables that no type invariant mentions (MemoryInterface.tla:2 `memInt`): the host front end
@@ -367,23 +396,45 @@ class Lowering:
                 seen.add(k)
                 out.append(st)
                 queue.append(st)
+        # bounded in time as well: one successor of some specs costs the host evaluator minutes
+        # (AdvancedExamples/InnerSerial.tla enumerates sets of orderings)
+        import signal
+        import threading
+
+        class _Budget(Exception):
+            pass
+
+        def _expired(*_a):
+            raise _Budget()
+        use_alarm = threading.current_thread() is threading.main_thread() and hasattr(signal, "setitimer")
+        old = None
+        if use_alarm:
+            old = signal.signal(signal.SIGALRM, _expired)
+            signal.setitimer(signal.ITIMER_REAL, self.SAMPLE_SECONDS)
         qi = 0
-        while qi < len(queue) and len(out) < self.SAMPLE_STATES:
-            st = queue[qi]
-            qi += 1
-            try:
-                for asg, _act in self.ev.solve(m.next_node, {}, m.next_ctx, st, {}, "next"):
-                    if len(asg) != len(m.vars):
-                        continue
-                    k = key(asg)
-                    if k not in seen:
-                        seen.add(k)
-                        out.append(asg)
-                        queue.append(asg)
-                        if len(out) >= self.SAMPLE_STATES:
-                            break
-            except (EvalError, AssertFailure):
-                continue
+        try:
+            while qi < len(queue) and len(out) < self.SAMPLE_STATES:
+                st = queue[qi]
+                qi += 1
+                try:
+                    for asg, _act in self.ev.solve(m.next_node, {}, m.next_ctx, st, {}, "next"):
+                        if len(asg) != len(m.vars):
+                            continue
+                        k = key(asg)
+                        if k not in seen:
+                            seen.add(k)
+                            out.append(asg)
+                            queue.append(asg)
+                            if len(out) >= self.SAMPLE_STATES:
+                                break
+                except (EvalError, AssertFailure, RecursionError):
+                    continue
+        except _Budget:
+            self.warnings.append(f"type sampling stopped after {self.SAMPLE_SECONDS}s ({len(out)} states)")
+        finally:
+            if use_alarm:
+                signal.setitimer(signal.ITIMER_REAL, 0)
+                signal.signal(signal.SIGALRM, old)
         return out
 
     def _widen(self, t, strs, mvs, alla):
@@ -1983,7 +2034,28 @@ class Lowering:
             if len(bounds) == 1 and isinstance(bounds[0][0], str) and len(args) == 1:
                 a = args[0]
                 c = self.try_const(a, env, ctx, base)
-                arg = c if c is not None else self._bind_by_name(Lazy(a, env, ctx, base), bounds[0][0], (body,))
+                if c is not None:
+                    arg = c
+                else:
+                    # evaluate the argument once and clamp its integer type to the function's domain lo..hi (an
+                    # application outside the domain is an error in TLC): this is what ends the unrolling of
+                    # f[i-1] after Len(q)+1 levels
+                    arg = self.cx(a, env, ctx, base)
+                    dn = bounds[0][1]
+                    if isinstance(arg, Val) and isinstance(arg.t, TInt) and arg.t.lo is not None \
+                            and dn is not None and dn.k == "bin" and dn.a[0] == "..":
+                        try:
+                            dlo = self.cx(dn.a[1], fenv, fctx, base)
+                            dhi = self.cx(dn.a[2], fenv, fctx, base)
+                            tl, th = self._int_t(dlo), self._int_t(dhi)
+                            lo2 = max(arg.t.lo, tl.lo) if tl.lo is not None else arg.t.lo
+                            hi2 = min(arg.t.hi, th.hi) if th.hi is not None else arg.t.hi
+                            if lo2 > hi2:
+                                self.asm.emit("TRAP", TRAP_EVAL, n.line)
+                                return Val(want if want is not None else TBottom(), 0)
+                            arg = Val(TInt(lo2, hi2), arg.loc)
+                        except CompileError:
+                            pass
                 env2 = dict(fenv)
                 env2[bounds[0][0]] = arg
                 return self._inline(body, env2, fctx, base, want, n)
@@ -3011,6 +3083,13 @@ class Lowering:
         t1 = self.alloc(1)
         if type(b) is Const:
             if a.t.scalar:
+                if isinstance(a.t, TInt) and type(b.v) is int and a.t.lo is not None:
+                    if not (a.t.lo <= b.v <= a.t.hi):
+                        self.asm.emit("JMP", lf)        # outside the static range of a
+                        return
+                    if a.t.lo == a.t.hi:
+                        self.asm.emit("JMP", lt)
+                        return
                 if isinstance(a.t, TInt) and type(b.v) is int and IMM28_MIN < b.v < IMM28_MAX:
                     self.asm.emit("EQI", t1, a.loc, b.v)
                 elif isinstance(a.t, TAtom) and is_atom(b.v):
@@ -3331,6 +3410,9 @@ class Lowering:
                 self.ca(items[i], env, ctx, b, lambda b2, _a: chain(i + 1, b2), act)
             chain(0, bound)
             return
+        if kind == "abox":        # [A]_v as an action: A \/ UNCHANGED v
+            n = Node("or", ((n.a[0], Node("unchanged", (n.a[1],), n.line, n.col)),), n.line, n.col)
+            kind = "or"
         if kind == "or":
             for x in n.a[0]:
                 self.bound = bound

@@ -969,6 +969,11 @@ class Evaluator:
         if k == "unchanged" and target == "next":
             yield from self._solve_unchanged(n.a[0], env, ctx, s, asg, act)
             return
+        if k == "abox" and target == "next":
+            # [A]_v used as an action (MCRealTimeHourClock.tla:23-24): A \/ UNCHANGED v
+            yield from self.solve(n.a[0], env, ctx, s, asg, target, act)
+            yield from self._solve_unchanged(n.a[1], env, ctx, s, asg, act)
+            return
         # plain boolean filter
         fr = self._fr(ctx, s, asg, target)
         if self.truth(n, env, fr):
