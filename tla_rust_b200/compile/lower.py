@@ -1630,14 +1630,18 @@ class Lowering:
         lt, lf, end = Label("it"), Label("if"), Label("ie")
         if want is not None:
             dst = self.alloc(want.size)
+            m0 = self.mark()
             self.cc(c, env, ctx, base, lt, lf)
-            self.asm.label(lt)
+            self.release(m0)                # temporaries of the condition and of each branch are dead once the
+            self.asm.label(lt)              # selected value sits in dst: the branches share one scratch area
             va = self.coerce(self.cx(a, env, ctx, base, want), want)
             self.movn(dst, va.loc, want.size)
+            self.release(m0)
             self.asm.emit("JMP", end)
             self.asm.label(lf)
             vb = self.coerce(self.cx(b, env, ctx, base, want), want)
             self.movn(dst, vb.loc, want.size)
+            self.release(m0)
             self.asm.label(end)
             return Val(want, dst)
         with self.asm.capture() as ca:
