@@ -56,3 +56,57 @@ def test_make_flow_on_gpu_reports_like_tlc():
     assert "State 1: <Initial predicate>" in out and "/\\ counter = 0" in out
     assert "State 5: <Action line" in out and "of module race>" in out
     assert '/\\ pc = <<"Done", "Done">>' in out and "/\\ counter = 1" in out
+
+
+class _CpuShimEngine:
+    """Stand-in for tla_rust_b200.engine.Engine backed by the CPU bytecode oracle: lets the CPU suite drive the
+    whole `tlc` control flow (compile, report formatting, capacity retry).  Test infrastructure only."""
+
+    def __init__(self, cm, deadlock=True, device=0):
+        self.cm, self.deadlock, self.r = cm, deadlock, None
+
+    def seed(self, iw):
+        self.iw = iw
+
+    def result(self):
+        import numpy as np
+        if self.r is None:
+            return {"distinct": int(len(np.unique(self.iw, axis=0)))}
+        return self.r
+
+    def step(self):
+        from oracle import cpu_engine
+        r = cpu_engine.run(self.cm, self.iw, deadlock=self.deadlock, want_states=True, max_states=1 << 17)
+        self.states = r.pop("states")
+        r.update(queue_left=0, device_seconds=r["seconds"])
+        self.r = r
+        return {"verdict": r["verdict"], "expanded": 0}
+
+    def trace(self, idx):
+        import numpy as np
+        return self.states[idx:idx + 1], np.array([-1])
+
+    def launches(self):
+        return 0
+
+    def close(self):
+        pass
+
+
+def test_tlc_flow_and_capacity_retry_on_cpu_shim(monkeypatch):
+    import io
+    import tla_rust_b200.engine as eng
+    from tla_rust_b200.cli import check_file
+    from tla_rust_b200.compile import types as T
+    monkeypatch.setattr(eng, "Engine", _CpuShimEngine)
+    spec = os.path.join(ROOT, "tests", "specs", "Containers.tla")
+    # default sparse capacity too small for `seen` (two elements are reachable): one doubling 1 -> 2, then success
+    monkeypatch.setattr(T, "SPARSE_CAP", 1)
+    out = io.StringIO()
+    rc = check_file(spec, out=out, verbose=False)
+    text = out.getvalue()
+    assert rc == 0, text
+    assert text.count("Note: a default container capacity was exceeded") == 1
+    assert "Model checking completed. No error has been found." in text
+    assert "138101 states generated, 33884 distinct states found, 0 states left on queue." in text
+    assert T.SPARSE_CAP == 1                      # restored

@@ -67,23 +67,39 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
             res.error_text = f"Property {pbad} is violated by the initial state"
             print(format_result(res, m.vars, m.module_name), file=out)
             return 12
-    cm = compile_model(m, init, seq_cap=seq_cap)
-    for w in cm.warnings:
-        print(f"Warning: {w}", file=out)
-    iw = encode_states(cm, init)
-    e = Engine(cm, deadlock=deadlock and m.check_deadlock, device=device)
-    e.seed(iw)
-    r0 = e.result()
-    print(f"Finished computing initial states: {r0['distinct']} distinct state"
-          f"{'s' if r0['distinct'] != 1 else ''} generated.", file=out)
-    while True:
-        ws = e.step()
-        if ws["verdict"] != 5:
+    from .compile import types as _types
+    base_sparse = _types.SPARSE_CAP
+    try:
+        for attempt in range(4):
+            cm = compile_model(m, init, seq_cap=seq_cap)
+            for w in cm.warnings:
+                print(f"Warning: {w}", file=out)
+            iw = encode_states(cm, init)
+            e = Engine(cm, deadlock=deadlock and m.check_deadlock, device=device)
+            e.seed(iw)
+            r0 = e.result()
+            print(f"Finished computing initial states: {r0['distinct']} distinct state"
+                  f"{'s' if r0['distinct'] != 1 else ''} generated.", file=out)
+            while True:
+                ws = e.step()
+                if ws["verdict"] != 5:
+                    break
+                if verbose and ws["expanded"]:
+                    print(f"Progress({ws['level']}): {ws['generated_total']} states generated, {ws['distinct_total']} "
+                          f"distinct states found, {ws['discovered']} states left on queue.", file=out)
+            r = e.result()
+            # a container / sequence capacity chosen by default (not by the model's TypeOK) was too small: the run
+            # stopped with a capacity trap (never a wrong answer) -- double the defaults and search again
+            if r["verdict"] == 4 and r["detail"] == 2 and attempt < 3:
+                _types.SPARSE_CAP *= 2
+                seq_cap = 2 * (seq_cap or getattr(cm, "seq_cap", None) or 4)
+                print(f"Note: a default container capacity was exceeded; retrying with sparse capacity "
+                      f"{_types.SPARSE_CAP} and sequence capacity {seq_cap}.", file=out)
+                e.close()
+                continue
             break
-        if verbose and ws["expanded"]:
-            print(f"Progress({ws['level']}): {ws['generated_total']} states generated, {ws['distinct_total']} distinct "
-                  f"states found, {ws['discovered']} states left on queue.", file=out)
-    r = e.result()
+    finally:
+        _types.SPARSE_CAP = base_sparse
     trace = None
     if r["verdict"] != 0:
         trace = e.trace(r["state_idx"])

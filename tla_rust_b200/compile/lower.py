@@ -273,8 +273,11 @@ class Lowering:
             named.sort(key=lambda n: (n.startswith("I"), len(n), n))
             cand += [n for n in named if n not in cand]
 
+        quiet = False
+
         def harvest(node, ctx, got, depth=0):
             """collect  v \\in S / v \\subseteq S  conjuncts, following nested conjunctions and definitions"""
+            nonlocal quiet
             if depth > 6:
                 return
             if node.k == "and":
@@ -289,7 +292,8 @@ class Lowering:
                     et = type_of_set(sv, self.seq_cap)
                     got.setdefault(v, subset_type(et) if node.a[0] == "\\subseteq" else et)
                 except (EvalError, TypeErr) as ex:
-                    self.warnings.append(f"type hint: cannot use conjunct for {v}: {ex}")
+                    if quiet is False:
+                        self.warnings.append(f"type hint: cannot use conjunct for {v}: {ex}")
                 return
             # function with a dynamic domain (raft.tla:35 `messages`):  DOMAIN v \subseteq K  /\
             # \A x \in DOMAIN v : v[x] \in R   [/\ Cardinality(DOMAIN v) <= n]
@@ -342,6 +346,9 @@ class Lowering:
             d = self.ctx.defs.get(name)
             if d is None or d[0].params:
                 continue
+            # ordinary invariants are scanned too, but only a definition that looks like a type invariant is
+            # worth a warning when one of its conjuncts cannot be used
+            quiet = not (name == hint or re.search(r"Type(OK|Inv|Invariant|Correct)", name))
             got = {}
             harvest(d[0].body, d[1], got)
             for v, di in dyn.items():
@@ -3852,6 +3859,7 @@ class Lowering:
         cm.atoms, cm.codec = self.atoms, self.codec
         cm.group = list(self.group)
         cm.warnings = self.warnings
+        cm.seq_cap = self.seq_cap
         lay = self._packed_layout()
         import numpy as np
         cm.layout = np.array(lay, dtype=np.int32).reshape(-1, 3)
