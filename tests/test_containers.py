@@ -85,3 +85,48 @@ def test_raft_capacity_overflow_traps_instead_of_truncating():
     m = Model(os.path.join(d, "MCraft.tla"), extra_dirs=[REF + "/examples"])
     cm, o2 = _o2(m)
     assert o2["verdict"] == 4
+
+
+# ---- serializableSnapshotIsolation.tla (BASELINE config #5) on the bytecode engine -------------------------------
+# Its invariants nest by-name definitions so deeply that inline expansion explodes; the compiler falls back to
+# CALL/RET subroutines (one compiled copy per operator instance, static frames by call-graph level).
+@needs_reference
+def test_ssi_compiles_with_subroutines_and_matches_oracle():
+    import numpy as np
+    from tla_rust_b200.compile.bytecode import OP
+    m = Model(ROOT + "/models/MCssi.tla", extra_dirs=[REF + "/examples"])
+    init = m.initial_states()
+    cm = compile_model(m, init, seq_cap=12, subroutines=True)
+    ops = (cm.code & np.uint64(0xFF)).astype(int)
+    assert int((ops == OP["CALL"]).sum()) > 50 and int((ops == OP["RET"]).sum()) > 10
+    o2 = cpu_engine.run(cm, encode_states(cm, init), deadlock=m.check_deadlock)
+    # O1 pins 945 / 569 / 9 for 2 transactions x 1 key with all eight invariants (tests/test_oracle_golden.py)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 945, 569, 9)
+
+
+@needs_reference
+def test_ssi_two_keys_matches_the_numbers_o1_produced():
+    """2 transactions x 2 keys: O1 needs 136 s (run once, numbers pinned here); O2 takes 2 s."""
+    cfg = open(ROOT + "/models/MCssi.cfg").read().replace("Key = {K1}", "Key = {K1, K2}")
+    m = Model(ROOT + "/models/MCssi.tla", cfg_text=cfg, extra_dirs=[REF + "/examples"])
+    init = m.initial_states()
+    cm = compile_model(m, init, seq_cap=16, subroutines=True)
+    o2 = cpu_engine.run(cm, encode_states(cm, init), deadlock=m.check_deadlock, n_threads=4)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 50121, 29629, 13)
+
+
+@needs_reference
+def test_inline_budget_falls_back_to_subroutines(monkeypatch):
+    from tla_rust_b200.compile.lower import Lowering
+    monkeypatch.setattr(Lowering, "CX_BUDGET", 20000)
+    m = Model(ROOT + "/models/MCssi.tla", extra_dirs=[REF + "/examples"])
+    cm = compile_model(m, m.initial_states(), seq_cap=12)
+    assert any("subroutines" in w for w in cm.warnings)
+
+
+def test_subroutine_mode_is_equivalent_on_models_that_also_inline():
+    m = Model(os.path.join(SPECS, "Containers.tla"))
+    init = m.initial_states()
+    cm = compile_model(m, init, subroutines=True)
+    o2 = cpu_engine.run(cm, encode_states(cm, init), deadlock=False)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 138101, 33884, 18)

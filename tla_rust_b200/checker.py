@@ -9,15 +9,25 @@ import numpy as np
 
 from .front.spec import Model
 from .front.report import CheckResult, OK, INVARIANT, ASSERT, DEADLOCK, EVAL_ERROR, PROPERTY
-from .compile.lower import Lowering, CompiledModel, CompileError
+from .compile.lower import Lowering, CompiledModel, CompileError, CompileBudget
 from .compile.bytecode import TRAP_NAMES
 
 
-def compile_model(model: Model, init_states=None, seq_cap=None, type_hint=None) -> CompiledModel:
+def compile_model(model: Model, init_states=None, seq_cap=None, type_hint=None, subroutines=False) -> CompiledModel:
     if init_states is None:
         init_states = model.initial_states()
     lw = Lowering(model, seq_cap=seq_cap, type_hint=type_hint)
-    cm = lw.compile(init_states)
+    if subroutines:
+        lw.use_subs = True
+    try:
+        cm = lw.compile(init_states)
+    except CompileBudget:
+        # inline expansion explodes (deeply nested by-name definitions, e.g. serializableSnapshotIsolation.tla):
+        # compile the module-level operators as CALL/RET subroutines instead
+        lw = Lowering(model, seq_cap=seq_cap, type_hint=type_hint)
+        lw.use_subs = True
+        cm = lw.compile(init_states)
+        cm.warnings.append("operators compiled as subroutines (inline expansion exceeded its budget)")
     cm.module_name = model.module_name
     return cm
 

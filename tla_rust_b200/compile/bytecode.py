@@ -19,7 +19,7 @@ OPS = [
     "NEG", "EQN", "NOT", "LDX", "STX", "TBL", "TBLT", "BSET", "BCLR",
     "BTEST", "BOR", "BAND", "BANDN", "BISZ", "BSUB", "BCNT", "BNEXT", "BFILL",
     "BSETI", "BTESTI", "UCLAMP", "TRAP", "EMIT", "GEN", "ASSERTF", "INVF", "MADI", "BANDC", "LEXLT",
-    "SFIND", "SINS", "EMITD",
+    "SFIND", "SINS", "EMITD", "CALL", "RET",
 ]
 OP = {n: i for i, n in enumerate(OPS)}
 
@@ -38,7 +38,7 @@ FMT = {
     "JEQ": "rrJ", "JNE": "rrJ", "JLT": "rrJ", "JGE": "rrJ",
     "JEQI": "rkJ", "JNEI": "rkJ", "JLTI": "rkJ", "JGEI": "rkJ",
     "JBT": "rrJ", "JBF": "rrJ", "JBTI": "rnJ", "JBFI": "rnJ", "JGEZ": "rI", "MADI": "rkr", "BANDC": "rrJ", "LEXLT": "rrrn",
-    "SFIND": "rrrn", "SINS": "rrrn", "EMITD": "nI",
+    "SFIND": "rrrn", "SINS": "rrrn", "EMITD": "nI", "CALL": "rI", "RET": "r",
 }
 
 INVERSE = {"JZ": "JNZ", "JEQ": "JNE", "JLT": "JGE", "JEQI": "JNEI", "JLTI": "JGEI", "JBT": "JBF", "JBTI": "JBFI",

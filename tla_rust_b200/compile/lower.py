@@ -32,6 +32,10 @@ class CompileError(Exception):
     pass
 
 
+class CompileBudget(CompileError):
+    """Inline expansion exceeded its budget: the caller retries with operator subroutines."""
+
+
 class Const:
     __slots__ = ("v",)
 
@@ -161,6 +165,16 @@ class Lowering:
         self.dry = False
         self.group = model.symmetry_group() if hasattr(model, "symmetry_group") else []
         self._rec_depth = {}
+        self.use_subs = False          # compile module-level operators as CALL/RET subroutines instead of inlining
+        self.subs = {}
+        self.sub_bufs = []
+        self.sub_base0 = MAXREG // 2   # discovery pass: every subroutine frame starts here (only sizes matter)
+        self.sub_plan = None           # final pass: key -> base of the subroutine's static frame
+        self.sub_calls = {}            # caller key (None = main programs) -> set of callee keys
+        self._sub_stack = []
+        self._sub_active = set()
+        self._cx_count = 0
+        self.cx_budget = self.CX_BUDGET
         self.copy_once = False
         self.rec_depth = 6
         self._intern_all_atoms()
@@ -1216,6 +1230,7 @@ class Lowering:
             return Lowering._has_prime(x.body)
         return False
 
+    CX_BUDGET = 1_000_000      # expression nodes lowered before inline expansion is abandoned for subroutines
     EAGER_MIN_WORDS = 8
     EAGER_MIN_CODE = 40
 
@@ -1300,6 +1315,9 @@ class Lowering:
         c = self.try_const(n, env, ctx, base)
         if c is not None:
             return c
+        self._cx_count += 1
+        if self._cx_count > self.cx_budget and not self.use_subs:
+            raise CompileBudget(f"inline expansion of the specification exceeds {self.cx_budget} expression nodes")
         k = n.k
         if n.line:
             self.asm.cur_line = n.line
@@ -1342,6 +1360,10 @@ class Lowering:
                 return hv
             self.def_uses[key] = self.def_uses.get(key, 0) + 1
             self.def_info[key] = (r[1], r[2])
+            if self.use_subs:
+                v = self._sub_call(r[1], r[2], (), env, ctx, base, want, n)
+                if v is not None:
+                    return v
             return self.cx(r[1].body, {}, r[2], base, want)
         raise CompileError(f"cannot compile identifier {n.a[0]}")
 
@@ -1365,6 +1387,10 @@ class Lowering:
             d = r[1]
             if len(d.params) != len(args):
                 raise CompileError(f"arity mismatch calling {name}")
+            if self.use_subs:
+                v = self._sub_call(d, r[2], args, env, ctx, base, want, n)
+                if v is not None:
+                    return v
             return self._inline(d.body, self.bind_args(d.params, args, env, ctx, base, d.body), r[2], base, want, n)
         if r[0] == "builtin":
             return self.builtin(name, args, n, env, ctx, base, want)
@@ -1384,6 +1410,181 @@ class Lowering:
             return self.cx(body, env2, ctx2, base, want)
         finally:
             self._rec_depth[key] = d
+
+    # ------------------------------------------------------------ subroutines
+    SUB_MIN_NODES = 12
+
+    @staticmethod
+    def _node_count(x, lim=64):
+        """Size of an operator body (AST nodes), capped."""
+        n = 0
+        stack = [x]
+        while stack and n < lim:
+            y = stack.pop()
+            if isinstance(y, Node):
+                n += 1
+                stack.extend(y.a)
+            elif isinstance(y, (tuple, list)):
+                stack.extend(y)
+            elif isinstance(y, OpDef):
+                stack.append(y.body)
+        return n
+
+    def _sub_call(self, d, dctx, args, env, ctx, base, want, n):
+        """Call module-level operator d as a subroutine (one compiled copy per (operator, constant arguments, types
+        of run-time arguments, expected type)); None => the caller inlines it as before.
+        Arguments are evaluated once at the call site; a trap while evaluating one is deferred (poison word) to the
+        first use of the parameter inside the body, which keeps call-by-name semantics."""
+        if base != "N" or self.dry and False:
+            return None
+        if any(ar > 0 for _p, ar in d.params) or self._has_prime(d.body) or d.body.k == "fcndef":
+            return None
+        if self._node_count(d.body) < self.SUB_MIN_NODES:
+            return None
+        if id(d.body) in self._sub_active or id(d.body) in self._rec_depth and self._rec_depth[id(d.body)] > 0:
+            return None                          # (mutually) recursive: unrolled by _inline
+        m0 = self.mark()
+        avals, key = [], [id(d.body), id(dctx), want]
+        try:
+            for (pn, _ar), a in zip(d.params, args):
+                c = self.try_const(a, env, ctx, base)
+                if c is not None:
+                    avals.append(c)
+                    key.append(("c", vkey(c.v)))
+                    continue
+                with self.asm.capture() as cap:
+                    poison = self.alloc(1)
+                    x = self.cx(a, env, ctx, "N")
+                if type(x) is Const:
+                    avals.append(x)
+                    key.append(("c", vkey(x.v)))
+                    continue
+                if any(i[0] in ("ASSERTF", "EMIT", "GEN", "INVF", "EMITD") for i in cap.buf):
+                    self.release(m0)
+                    return None
+                if type(x) is OVal:
+                    x = Val(x.t, x.loc)
+                end = Label("sae")
+                ntrap = 0
+                out = []
+                for ins in cap.buf:
+                    if ins[0] == "TRAP":
+                        ntrap += 1
+                        out.append(("LI", poison, 1))
+                        out.append(("JMP", end))
+                    else:
+                        out.append(ins)
+                self.li(poison, 0)
+                self.asm.splice(out)
+                self.asm.label(end)
+                avals.append((x, poison))
+                key.append(("t", x.t))
+        except (CompileError, TypeErr):
+            self.release(m0)
+            return None
+        key = tuple(key)
+        sub = self.subs.get(key)
+        if sub is None:
+            sub = self._sub_compile(key, d, dctx, avals, want, n)
+            if sub is None:
+                self.release(m0)
+                return None
+        self.sub_calls.setdefault(self._sub_stack[-1] if self._sub_stack else None, set()).add(key)
+        for (pslot, ppoison), av in zip(sub["params"], [a for a in avals if type(a) is not Const]):
+            x, poison = av
+            self.movn(pslot, x.loc, x.t.size)
+            self.asm.emit("MOV", ppoison, poison)
+        self.asm.emit("CALL", sub["ret"], sub["entry"])
+        rt = sub["type"]
+        self.release(m0)
+        dst = self.alloc(rt.size)
+        self.movn(dst, sub["res"], rt.size)
+        return Val(rt, dst)
+
+    def _sub_compile(self, key, d, dctx, avals, want, n):
+        """Lower the body of d once into its own buffer (spliced after the main programs).  The subroutine owns a
+        static frame region [base, base+size): return address, parameters (+ poison words), temporaries, result.
+        Discovery pass: base is a dummy (frames overlap; the code is discarded, sizes and the call graph are kept).
+        Final pass: base comes from the plan -- subroutines of one call-graph level share a region (they never call
+        each other), callers sit on higher levels, the main programs below all of them."""
+        base = self.sub_base0 if self.sub_plan is None else self.sub_plan.get(key)
+        if base is None:
+            return None                     # not in the plan (did not occur in the discovery pass): inline
+        self._sub_active.add(id(d.body))
+        self._sub_stack.append(key)
+        save = (self.top, self.high, self.bound)
+        self.top = self.high = base
+        entry = Label("sub_" + d.name)
+        ok = False
+        try:
+            with self.asm.capture() as cap:
+                self.asm.label(entry)
+                ret = self.alloc(1)
+                params, env2 = [], {}
+                for (pn, _ar), av in zip(d.params, avals):
+                    if type(av) is Const:
+                        env2[pn] = av
+                    else:
+                        x, _p = av
+                        pslot = self.alloc(x.t.size)
+                        ppoison = self.alloc(1)
+                        params.append((pslot, ppoison))
+                        env2[pn] = PVal(x.t, pslot, ppoison, Lazy(Node("runtime", ()), {}, dctx, "N"))
+                r = self.cx(d.body, env2, dctx, "N", want)
+                if type(r) is Const:
+                    rt = want if want is not None else self.natural_type(r.v)
+                    rv = self.materialize(r, rt)
+                else:
+                    rv = self.coerce(r, want) if want is not None and r.t != want else r
+                    if type(rv) is OVal:
+                        rv = Val(rv.t, rv.loc)
+                    rt = rv.t
+                res = self.alloc(rt.size)
+                self.movn(res, rv.loc, rt.size)
+                self.asm.emit("RET", ret)
+            ok = True
+        except CompileBudget:
+            raise
+        except (CompileError, TypeErr):
+            ok = False
+        finally:
+            self._sub_active.discard(id(d.body))
+            self._sub_stack.pop()
+            size = self.high - base
+            self.top, self.high, self.bound = save
+        if not ok:
+            return None
+        self.sub_bufs.append(cap.buf)
+        sub = {"entry": entry, "ret": ret, "params": params, "res": res, "type": rt, "size": size}
+        self.subs[key] = sub
+        return sub
+
+    def _plan_sub_frames(self, main_high):
+        """Static frame bases from the discovery pass: level(K) = 0 for leaves, else 1 + max level of its callees;
+        all subroutines of a level share one region, regions are stacked above the main programs' temporaries."""
+        level = {}
+
+        def lv(k, seen=()):
+            if k in level:
+                return level[k]
+            if k in seen:
+                raise CompileError("internal: cycle in the subroutine call graph")
+            cs = [c for c in self.sub_calls.get(k, ()) if c in self.subs]
+            level[k] = 0 if not cs else 1 + max(lv(c, seen + (k,)) for c in cs)
+            return level[k]
+        for k in self.subs:
+            lv(k)
+        nlev = 1 + max(level.values()) if level else 0
+        sizes = [0] * nlev
+        for k, sub in self.subs.items():
+            sizes[level[k]] = max(sizes[level[k]], sub["size"] + 2)
+        bases, b = [], main_high + 8
+        for L in range(nlev):
+            bases.append(b)
+            b += sizes[L]
+        if b > MAXREG:
+            raise CompileError(f"frame of {b} words exceeds the 16K-word limit (subroutine frames)")
+        return {k: bases[level[k]] for k in self.subs}, b
 
     def x_times(self, n, env, ctx, base, want):
         """A \\X B \\X ... with run-time operands: bitset over the tuple universe."""
@@ -2246,6 +2447,8 @@ class Lowering:
                     t = join(t, type_of_value(v, self.seq_cap))
         elif kind[0] == "val":
             t = kind[1].t.elem
+        elif kind[0] == "sparse":
+            t = kind[1].t.kt
         else:
             t = TInt()
         dst = self.alloc(t.size)
@@ -3031,6 +3234,20 @@ class Lowering:
             self.asm.emit("TRAP", TRAP_CASE, n.line)
             self.asm.emit("JMP", lf)
             return
+        if k == "app" and self.use_subs:
+            try:
+                r = self.resolve(n.a[0], env, ctx)
+            except CompileError:
+                r = None
+            if r is not None and r[0] == "def" and len(r[1].params) == len(n.a[1]):
+                v = self._sub_call(r[1], r[2], n.a[1], env, ctx, base, TBool(), n)
+                if v is not None:
+                    if type(v) is Const:
+                        self.asm.emit("JMP", lt if v.v is True else lf)
+                    else:
+                        self.asm.emit("JNZ", v.loc, lt)
+                        self.asm.emit("JMP", lf)
+                    return
         if k in ("id", "app", "sel"):
             # expand user operators in control context (keeps short-circuiting)
             tgt = self._expand(n, env, ctx, base)
@@ -3685,6 +3902,8 @@ class Lowering:
         (e.g. Paxos.tla:185 `votes`) is expanded; definitions used more than once and free of
         traps are then evaluated once per state in the program prologue (hoisted)."""
         self.var_types = self.infer_var_types(init_states)
+        if self.use_subs:
+            return self._compile_with_subs()
         self.dry = True
         try:
             self._compile_pass()
@@ -3703,6 +3922,33 @@ class Lowering:
         self.__dict__.pop("_field_cache", None)
         self.hoist_keys = [(k, info[k]) for k in keys]
         return self._compile_pass()
+
+    def _reset_pass_state(self):
+        self.asm = Asm()
+        self.actions, self.asserts = [], []
+        self.hoisted, self.def_uses, self.def_info = {}, {}, {}
+        self._evenv_cache = {}
+        self.__dict__.pop("_univ_cache", None)
+        self.__dict__.pop("_field_cache", None)
+        self.subs, self.sub_bufs, self.sub_calls = {}, [], {}
+        self._sub_stack, self._sub_active = [], set()
+
+    def _compile_with_subs(self):
+        """Operator definitions as CALL/RET subroutines (for specifications whose inline expansion explodes).
+        Pass 1 discovers the subroutine instances, their frame sizes and the call graph; pass 2 generates the same
+        code with the planned static frames."""
+        self.hoist_keys = []
+        self.sub_plan = None
+        self._compile_pass()
+        main_high = self._main_high
+        plan, total = self._plan_sub_frames(main_high)
+        self._reset_pass_state()
+        self.sub_plan = plan
+        cm = self._compile_pass()
+        if self._main_high > main_high:
+            raise CompileError("internal: non-deterministic lowering between the subroutine passes")
+        cm.frame_words = max(cm.frame_words, total + 4)
+        return cm
 
     def _hoist_prologue(self, program):
         for key, (od, dctx) in self.hoist_keys:
@@ -3843,6 +4089,9 @@ class Lowering:
             raise CompileError("no next-state action")
         self.ca(m.next_node, {}, m.next_ctx, frozenset(), emit_k, None)
         self.asm.emit("HALT")
+        self._main_high = self.high
+        for buf in self.sub_bufs:            # subroutine bodies (entered by CALL only)
+            self.asm.splice(buf)
         code, cpool, ent = self.asm.assemble(entries)
         cm = CompiledModel()
         cm.code, cm.cpool, cm.entries = code, cpool, ent

@@ -352,6 +352,10 @@ def join(a: T, b: T) -> T:
         return TPFun(a.keys, join(a.elem, b.elem))
     if ta is TSparse and tb is TSparse and (a.vt is None) == (b.vt is None):
         return TSparse(join(a.kt, b.kt), None if a.vt is None else join(a.vt, b.vt), max(a.cap, b.cap))
+    if ta is TSet and tb is TSparse and b.vt is None:
+        return TSparse(join(a.elem, b.kt), None, b.cap)
+    if ta is TSparse and tb is TSet and a.vt is None:
+        return TSparse(join(a.kt, b.elem), None, a.cap)
     if ta is TSeq and tb is TTuple:
         return join(b, a)
     if ta is TTuple and tb is TSeq:

@@ -676,7 +676,7 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   e->uses_ext = getenv("TLAG_VM_FULL") != nullptr;
   for (uint32_t i = 0; i < m->code_len && !e->uses_ext; ++i) {
     const uint32_t op = (uint32_t)(m->code[i] & 0xFF);
-    if (op == OP_LEXLT || op == OP_SFIND || op == OP_SINS || op == OP_EMITD) e->uses_ext = true;
+    if (op == OP_LEXLT || op == OP_SFIND || op == OP_SINS || op == OP_EMITD || op == OP_CALL || op == OP_RET) e->uses_ext = true;
   }
   // program image
   CK(cudaMalloc(&e->d_code, (size_t)(m->code_len ? m->code_len : 1) * 8));

@@ -30,7 +30,7 @@ enum {
   OP_LDX, OP_STX, OP_TBL, OP_TBLT, OP_BSET, OP_BCLR, OP_BTEST, OP_BOR,
   OP_BAND, OP_BANDN, OP_BISZ, OP_BSUB, OP_BCNT, OP_BNEXT, OP_BFILL, OP_BSETI,
   OP_BTESTI, OP_UCLAMP, OP_TRAP, OP_EMIT, OP_GEN, OP_ASSERTF, OP_INVF,
-  OP_MADI, OP_BANDC, OP_LEXLT, OP_SFIND, OP_SINS, OP_EMITD,
+  OP_MADI, OP_BANDC, OP_LEXLT, OP_SFIND, OP_SINS, OP_EMITD, OP_CALL, OP_RET,
   OP__COUNT
 };
 
