@@ -88,6 +88,8 @@ MODELS = {
                              {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3_m.cfg"}), True, False),
     "MCraft_s3_l": (lambda: (ROOT + "/models/MCraft.tla",
                              {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3_l.cfg"}), True, False),
+    # BASELINE config #5 at its smallest bounds (2 transactions x 1 key), all eight invariants: operator subroutines
+    "MCssi": (lambda: (ROOT + "/models/MCssi.tla", {"extra_dirs": [REF + "/examples"]}), True, True, 8, {"subroutines": True}),
     "Containers": (lambda: (ROOT + "/tests/specs/Containers.tla", {}), False, True),
     "HourClock": (lambda: (REF + "/examples/SpecifyingSystems/HourClock/HourClock.tla", {}), True, True),
     "AsynchInterface": (lambda: (REF + "/examples/SpecifyingSystems/AsynchronousInterface/AsynchInterface.tla", {}), True, True),
@@ -99,6 +101,7 @@ def main():
     for name, spec in MODELS.items():
         mk, deadlock, run_o1 = spec[:3]
         seq_cap = spec[3] if len(spec) > 3 else None
+        ckw = spec[4] if len(spec) > 4 else {}
         if only and name != only:
             continue
         t0 = time.time()
@@ -107,7 +110,7 @@ def main():
         m.check_deadlock = deadlock
         m.check_assumes()
         init = m.initial_states()
-        cm = compile_model(m, init, seq_cap=seq_cap)
+        cm = compile_model(m, init, seq_cap=seq_cap, **ckw)
         iw = encode_states(cm, init)
         o2 = cpu_engine.run(cm, iw, n_threads=os.cpu_count() or 1, deadlock=deadlock, max_states=1 << 27)
         exp = {"o2": {k: o2[k] for k in ("verdict", "detail", "generated", "distinct", "depth", "init_states",

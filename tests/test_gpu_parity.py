@@ -52,6 +52,21 @@ def test_bfs_matches_oracle(name):
     e.close()
 
 
+@pytest.mark.xfail(strict=False, reason="operator subroutines (CALL/RET) were added after the last GPU session of round 1: "
+                                        "bit-exact on the CPU bytecode engine, not yet run on a device")
+def test_ssi_subroutine_model_on_device():
+    """serializableSnapshotIsolation.tla, 2 transactions x 1 key, eight invariants (frame 3920 words: 4096 class)."""
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, "MCssi.tlagz"))
+    e = _engine(cm, deadlock=info["deadlock"])
+    e.seed(init)
+    r = e.run()
+    o2 = exp["o2"]
+    assert (r["verdict"], r["generated"], r["distinct"], r["depth"]) == (o2["verdict"], o2["generated"], o2["distinct"],
+                                                                        o2["depth"]) == (0, 945, 569, 9)
+    assert e.digest() == (o2["fp_xor"], o2["fp_sum"])
+    e.close()
+
+
 def test_assert_trace_is_a_shortest_counterexample():
     """README.md:267-316: the failing assertion is reached after 5 steps from an initial state; the GPU
     trace must be a valid 6-state behaviour ending in a state with pc = C for a process whose alice < 0."""
