@@ -178,6 +178,11 @@ class Lowering:
         self.copy_once = False
         self.rec_depth = 6
         self._intern_all_atoms()
+        # unrolling depth of RECURSIVE operators: recursions in the bundled specs walk a set of model values (a path of
+        # transactions, visited nodes), so |largest constant set| + 2 levels suffice; deeper activations trap
+        big = max([len(v) for c in [self.ctx] + self.ctx.all_instances for v in c.consts.values()
+                   if isinstance(v, frozenset)] + [1])
+        self.rec_depth = min(6, max(3, big + 2))
 
     @staticmethod
     def _runtime_node(n, env, fr):
@@ -1396,6 +1401,23 @@ class Lowering:
             return self.builtin(name, args, n, env, ctx, base, want)
         raise CompileError(f"cannot apply {name} at line {n.line}")
 
+    COMPACT_MIN = 24
+
+    def _compact(self, m0, x):
+        """x was computed with temporaries allocated since mark m0, all of which are dead except x itself: slide x down
+        to m0 and give the rest back (keeps the VM frame -- per-thread local memory on the GPU -- small)."""
+        if type(x) is not Val or self.dry:
+            return x
+        size = x.t.size
+        if x.loc + size <= m0:                       # lives in older storage
+            self.release(m0)
+            return x
+        if x.loc < m0 or self.top - (m0 + size) < self.COMPACT_MIN:
+            return x
+        self.movn(m0, x.loc, size)
+        self.top = m0 + size
+        return Val(x.t, m0)
+
     def _inline(self, body, env2, ctx2, base, want, n):
         """Inline an operator body.  RECURSIVE operators (serializableSnapshotIsolation.tla:465,823,1042,1094)
         are unrolled: every nested activation of the same body is a fresh copy, up to `rec_depth` levels; an
@@ -1406,8 +1428,9 @@ class Lowering:
             self.asm.emit("TRAP", TRAP_EVAL, n.line)
             return Val(want if want is not None else TBottom(), 0)
         self._rec_depth[key] = d + 1
+        m0 = self.mark()
         try:
-            return self.cx(body, env2, ctx2, base, want)
+            return self._compact(m0, self.cx(body, env2, ctx2, base, want))
         finally:
             self._rec_depth[key] = d
 
@@ -1686,7 +1709,8 @@ class Lowering:
         return self.cx(node, self.bind_args(od.params, args, env, ctx, base), dctx, base, want)
 
     def x_let(self, n, env, ctx, base, want):
-        return self.cx(n.a[1], self.let_env(n.a[0], env, ctx, base, n.a[1]), ctx, base, want)
+        m0 = self.mark()
+        return self._compact(m0, self.cx(n.a[1], self.let_env(n.a[0], env, ctx, base, n.a[1]), ctx, base, want))
 
     # booleans in value context
     def _bool_value(self, n, env, ctx, base, want):
@@ -1852,10 +1876,19 @@ class Lowering:
             self.release(m0)
             self.asm.label(end)
             return Val(want, dst)
+        m0 = self.mark()
         with self.asm.capture() as ca:
             va = self.cx(a, env, ctx, base)
+            if type(va) is OVal:
+                va = Val(va.t, va.loc)
+        top_a = self.top
+        if not self.dry:
+            self.release(m0)                  # only one branch runs: they share one scratch area
         with self.asm.capture() as cb:
             vb = self.cx(b, env, ctx, base)
+            if type(vb) is OVal:
+                vb = Val(vb.t, vb.loc)
+        self.top = max(self.top, top_a)
         ta = va.t if isinstance(va, Val) else self.natural_type(va.v)
         tb = vb.t if isinstance(vb, Val) else self.natural_type(vb.v)
         t = join(ta, tb)
@@ -1871,7 +1904,7 @@ class Lowering:
         vb2 = self.coerce(vb, t)
         self.movn(dst, vb2.loc, t.size)
         self.asm.label(end)
-        return Val(t, dst)
+        return self._compact(m0, Val(t, dst))
 
     def x_case(self, n, env, ctx, base, want):
         arms, other = n.a
