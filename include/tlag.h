@@ -37,7 +37,7 @@ enum { TLAG_F_DEADLOCK_CHECK = 1u,   /* report states without successors        
        TLAG_F_KEEP_GOING     = 2u }; /* do not stop a run at the first violation    */
 
 typedef struct {
-  uint32_t words_per_state;      /* W: packed state vector width in u32 words                 */
+  uint32_t words_per_state;      /* W: packed state vector width in u32 words (1..128)        */
   const uint64_t *code;          /* bytecode image (compile/bytecode.py), host-owned, copied   */
   uint32_t code_len;             /* in 64-bit instructions                                     */
   uint32_t entry_inv;            /* pc of the invariant program (runs on each expanded state)  */
@@ -46,7 +46,7 @@ typedef struct {
   uint32_t cpool_len;
   const int32_t *layout;         /* n_slots x {frame_off, width_bits, bias}: packed layout     */
   uint32_t n_slots;
-  uint32_t frame_words;          /* per-thread VM frame size                                   */
+  uint32_t frame_words;          /* per-thread VM frame size in words (<= 4096)                */
   uint32_t unpacked_words;       /* words of one unpacked state (primed copy follows it)       */
   uint32_t n_invariants;
   uint32_t n_actions;
