@@ -116,6 +116,18 @@ def test_ssi_two_keys_matches_the_numbers_o1_produced():
 
 
 @needs_reference
+def test_ssi_three_transactions_matches_the_numbers_o1_produced():
+    """3 transactions x 1 key: O1 needs 438 s (run once: ok 152554 / 90430 / 13); O2 takes 3 s."""
+    cfg = open(ROOT + "/models/MCssi.cfg").read().replace("TxnId = {T1, T2}", "TxnId = {T1, T2, T3}")
+    m = Model(ROOT + "/models/MCssi.tla", cfg_text=cfg, extra_dirs=[REF + "/examples"])
+    init = m.initial_states()
+    cm = compile_model(m, init, seq_cap=13, subroutines=True)
+    assert cm.frame_words <= 4096          # the CUDA engine's largest frame class
+    o2 = cpu_engine.run(cm, encode_states(cm, init), deadlock=m.check_deadlock, n_threads=4)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 152554, 90430, 13)
+
+
+@needs_reference
 def test_inline_budget_falls_back_to_subroutines(monkeypatch):
     from tla_rust_b200.compile.lower import Lowering
     monkeypatch.setattr(Lowering, "CX_BUDGET", 20000)
