@@ -110,3 +110,25 @@ def test_tlc_flow_and_capacity_retry_on_cpu_shim(monkeypatch):
     assert "Model checking completed. No error has been found." in text
     assert "138101 states generated, 33884 distinct states found, 0 states left on queue." in text
     assert T.SPARSE_CAP == 1                      # restored
+
+
+def test_demo_specs_through_tlc_flow_on_cpu_shim(monkeypatch):
+    """The specs of the GPU make-flow test (models/demo), compiled by the current compiler and checked through
+    check_file with the CPU shim: lock.tla passes, race.tla violates its invariant."""
+    import io
+    import tla_rust_b200.engine as eng
+    from tla_rust_b200.cli import check_file
+    from tla_rust_b200.front.pcal import translate_file
+    monkeypatch.setattr(eng, "Engine", _CpuShimEngine)
+    d = tempfile.mkdtemp(prefix="tlag_demo_")
+    for f in ("lock.tla", "lock.cfg", "race.tla", "race.cfg"):
+        shutil.copy(os.path.join(ROOT, "models", "demo", f), d)
+    translate_file(os.path.join(d, "lock.tla"))
+    translate_file(os.path.join(d, "race.tla"))
+    out = io.StringIO()
+    assert check_file(os.path.join(d, "lock.tla"), out=out, verbose=False) == 0
+    assert "Model checking completed. No error has been found." in out.getvalue()
+    assert "45 states generated, 26 distinct states found, 0 states left on queue." in out.getvalue()
+    out = io.StringIO()
+    assert check_file(os.path.join(d, "race.tla"), out=out, verbose=False) == 12
+    assert "Invariant Correct is violated" in out.getvalue()
