@@ -2267,6 +2267,62 @@ class Lowering:
             return r[1].body, {}, r[2]
         return None
 
+    def _share_recursive_apps(self, fname, body):
+        """f[x \\in S] == ... f[e] ... f[e] ...: when the body applies f to the SAME argument expression more than once
+        (WriteThroughCache.tla:117-123: THEN f[i-1] ELSE [f[i-1] EXCEPT ...]) wrap it as LET r == f[e] IN body[r/f[e]],
+        so that unrolling the recursion is linear in the depth instead of 2^depth (the LET is evaluated once, with
+        deferred traps, by the by-name binding logic)."""
+        cache = self.__dict__.setdefault("_shared_rec_cache", {})
+        hit = cache.get(id(body))
+        if hit is not None:
+            return hit[1]
+        found = {}
+
+        def key(x):
+            if isinstance(x, Node):
+                return (x.k,) + tuple(key(y) for y in x.a)
+            if isinstance(x, (tuple, list)):
+                return tuple(key(y) for y in x)
+            if isinstance(x, OpDef):
+                return ("opdef", x.name, key(x.body))
+            return x
+
+        def scan(x):
+            if isinstance(x, Node):
+                if x.k == "fapp" and x.a[0].k == "id" and x.a[0].a[0] == fname and len(x.a[1]) == 1:
+                    found.setdefault(key(x.a[1][0]), []).append(x)
+                for y in x.a:
+                    scan(y)
+            elif isinstance(x, (tuple, list)):
+                for y in x:
+                    scan(y)
+        scan(body)
+        shared = {k: v for k, v in found.items() if len(v) >= 2}
+        out = body
+        if shared:
+            names = {}
+            defs = []
+            for i, (k, apps) in enumerate(shared.items()):
+                nm = f"__rec{i}_{fname}"
+                names[k] = nm
+                defs.append(OpDef(nm, [], apps[0]))
+
+            def subst(x):
+                if isinstance(x, Node):
+                    if x.k == "fapp" and x.a[0].k == "id" and x.a[0].a[0] == fname and len(x.a[1]) == 1:
+                        nm = names.get(key(x.a[1][0]))
+                        if nm is not None:
+                            return Node("id", (nm,), x.line, x.col)
+                    return Node(x.k, tuple(subst(y) for y in x.a), x.line, x.col)
+                if isinstance(x, tuple):
+                    return tuple(subst(y) for y in x)
+                if isinstance(x, list):
+                    return [subst(y) for y in x]
+                return x
+            out = Node("let", (tuple(defs), subst(body)), body.line, body.col)
+        cache[id(body)] = (body, out)
+        return out
+
     def x_fapp(self, n, env, ctx, base, want):
         fn, args = n.a
         tgt = self._fcndef_target(fn, env, ctx, base)
@@ -2303,6 +2359,7 @@ class Lowering:
                             pass
                 env2 = dict(fenv)
                 env2[bounds[0][0]] = arg
+                body = self._share_recursive_apps(fn.a[0], body)
                 return self._inline(body, env2, fctx, base, want, n)
         f = self.cx(fn, env, ctx, base)
         if len(args) == 1:
