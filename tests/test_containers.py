@@ -75,6 +75,19 @@ def test_raft_three_servers_matches_oracle():
 
 
 @needs_reference
+def test_raft_three_servers_larger_bounds_match_the_numbers_o1_produced():
+    """3 servers, MaxTerm 3, MaxLogLen 2, MaxMessages 2, MaxClientRequests 2: O1 needs 175 s
+    (run once: ok 1214920 / 91116 / 17); O2 takes 3 s."""
+    import re
+    cfg = open(ROOT + "/models/MCraft_s3.cfg").read()
+    for k, v in (("MaxTerm", 3), ("MaxLogLen", 2), ("MaxClientRequests", 2)):
+        cfg = re.sub(rf"{k} = .*", f"{k} = {v}", cfg)
+    m = Model(ROOT + "/models/MCraft.tla", cfg_text=cfg, extra_dirs=[REF + "/examples"])
+    cm, o2 = _o2(m, n_threads=4)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 1214920, 91116, 17)
+
+
+@needs_reference
 def test_raft_capacity_overflow_traps_instead_of_truncating():
     """A sparse container that is too small must stop the run with an evaluation error (verdict 4 / trap 2)."""
     src = open(ROOT + "/models/MCraft.tla").read().replace("<= MaxMessages + 1", "<= MaxMessages")
