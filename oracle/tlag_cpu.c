@@ -46,15 +46,22 @@ typedef struct {
   uint64_t level_sizes[4096];
 } cpu_result;
 
+/* The counters every worker hammers (work dispenser, tail of the state store) each get a cache line of their own:
+ * in the first version they shared one with table/mask/lo/hi, which every thread reads for every state, and the run
+ * on the GPU box's 128 host cores was slower than on 8 (false sharing). */
 typedef struct {
   cpu_model m;
   uint32_t *states; uint32_t *parent; uint32_t *meta;
   uint64_t cap;
   uint64_t *table; uint64_t mask;
-  uint64_t n_states, generated;
-  uint64_t work, lo, hi;
-  uint64_t viol_inv, viol_assert, viol_trap, viol_deadlock;
+  uint64_t lo, hi;
+  _Alignas(64) uint64_t work;
+  _Alignas(64) uint64_t n_states;
+  _Alignas(64) uint64_t generated;
+  _Alignas(64) uint64_t viol_inv;
+  uint64_t viol_assert, viol_trap, viol_deadlock;
   int overflow, table_full;
+  _Alignas(64) char tail_pad[64];
 } cpu_engine;
 
 static int seen_insert(uint64_t *table, uint64_t mask, uint64_t fp) {
