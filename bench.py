@@ -324,7 +324,6 @@ def main():
         # at the committed fixture's bounds -- container-typed state (W = 44 words), counts checked against the oracle.
         # Runs tools/fixture_bench.py in a child process with a time limit, so that it can never cost the headline.
         try:
-            import subprocess
             fx = os.path.join(ROOT, "tests", "golden", "MCraft_s3_l.tlagz")
             if os.path.exists(fx):
                 p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fixture_bench.py"), "MCraft_s3_l", "--reps", "2"],
