@@ -155,3 +155,13 @@ def test_subroutine_mode_is_equivalent_on_models_that_also_inline():
     cm = compile_model(m, init, subroutines=True)
     o2 = cpu_engine.run(cm, encode_states(cm, init), deadlock=False)
     assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 138101, 33884, 18)
+
+
+def test_runtime_record_sets_and_domain_of_records():
+    """[f : S, ...] with run-time components, membership in it, "f" \\in DOMAIN r on a tagged union
+    (constructs of AdvancedExamples/InnerSerial.tla:5-30) -- tests/specs/RecSets.tla."""
+    m = Model(os.path.join(SPECS, "RecSets.tla"))
+    o1 = Oracle(m).run()
+    cm, o2 = _o2(m)
+    assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == ("ok", 573, 169, 6)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 573, 169, 6)

@@ -1609,6 +1609,38 @@ class Lowering:
             raise CompileError(f"frame of {b} words exceeds the 16K-word limit (subroutine frames)")
         return {k: bases[level[k]] for k in self.subs}, b
 
+    def x_recset(self, n, env, ctx, base, want):
+        """[f1 : S1, ..., fk : Sk] with run-time component sets (InnerSerial.tla:5 `opId`): bitset over the record
+        universe, filled by nested loops over the components."""
+        pairs = list(n.a[0])
+        ops = [self.cx(x, env, ctx, base) for _f, x in pairs]
+        fts = {}
+        for (f, _x), o in zip(pairs, ops):
+            ot = o.t if isinstance(o, Val) else self.natural_type(o.v)
+            if not isinstance(ot, TSet):
+                raise CompileError(f"component {f} of the record set is not a bitset-typed set (line {n.line})")
+            fts[f] = ot.elem
+        rt = TRec([sorted(fts)], fts)
+        t = want if isinstance(want, TSet) and isinstance(want.elem, TRec) else TSet(rt)
+        dst = self.alloc(t.size)
+        self.asm.emit("ZERO", dst, t.size)
+        env2 = dict(env)
+        bounds = []
+        for i, o in enumerate(ops):
+            env2[f"__ro{i}"] = o
+            bounds.append((f"__rt{i}", Node("id", (f"__ro{i}",), n.line, n.col)))
+
+        def body(env3):
+            m0 = self.mark()
+            loc = self.alloc(rt.size)
+            for i, (f, _x) in enumerate(pairs):
+                xv = self.coerce(env3[f"__rt{i}"], rt.fields[f])
+                self.movn(loc + rt.off[f], xv.loc, rt.fields[f].size)
+            self._set_add(dst, t, Val(rt, loc), n)
+            self.release(m0)
+        self.for_each(bounds, env2, ctx, base, body)
+        return Val(t, dst)
+
     def x_times(self, n, env, ctx, base, want):
         """A \\X B \\X ... with run-time operands: bitset over the tuple universe."""
         ops = [self.cx(x, env, ctx, base) for x in n.a[0]]
@@ -3483,6 +3515,51 @@ class Lowering:
                 self.asm.emit("JNZ", t1, lt)
                 self.asm.emit("JMP", lf)
                 return
+            if sn.k == "recset":
+                # r \in [f1 : S1, ...]: r has exactly these fields and every r.fi \in Si (no enumeration)
+                e = self.cx(en, env, ctx, base)
+                names = sorted(f for f, _x in sn.a[0])
+                if type(e) is Const:
+                    if not (isinstance(e.v, Fcn) and sorted(e.v.d) == names):
+                        self.asm.emit("JMP", lf)
+                        return
+                elif not isinstance(e.t, TRec) or e.t.alt_index(names) < 0:
+                    self.asm.emit("JMP", lf)
+                    return
+                elif e.t.tagged:
+                    t1 = self.alloc(1)
+                    self.asm.emit("EQI", t1, e.loc, e.t.alt_index(names))
+                    self.asm.emit("JZ", t1, lf)
+                env2 = dict(env)
+                env2["__rs_lhs"] = e
+                for f, x in sn.a[0]:
+                    nxt = Label("irs")
+                    fld = Node("dot", (Node("id", ("__rs_lhs",), sn.line, sn.col), f), sn.line, sn.col)
+                    self.cc_in(fld, x, env2, ctx, base, nxt, lf, n)
+                    self.asm.label(nxt)
+                self.asm.emit("JMP", lt)
+                return
+            if sn.k == "domain":
+                # "f" \in DOMAIN r  for a record / tagged union r (InnerSerial.tla:30): a test on the alternative
+                c = self.try_const(en, env, ctx, base)
+                if c is not None and isinstance(c.v, str):
+                    r = self.cx(sn.a[0], env, ctx, base)
+                    if isinstance(r, Val) and isinstance(r.t, TRec):
+                        if c.v not in r.t.fields:
+                            self.asm.emit("JMP", lf)
+                        elif not r.t.tagged:
+                            self.asm.emit("JMP", lt)
+                        else:
+                            mask = sum(1 << j for j, alt in enumerate(r.t.alts) if c.v in alt)
+                            mreg, tst = self.alloc(1), self.alloc(1)
+                            self.li(mreg, mask)
+                            self.asm.emit("BTEST", tst, mreg, r.loc)
+                            self.asm.emit("JNZ", tst, lt)
+                            self.asm.emit("JMP", lf)
+                        return
+                    if type(r) is Const and isinstance(r.v, Fcn):
+                        self.asm.emit("JMP", lt if c.v in r.v.d else lf)
+                        return
             if sn.k == "setfilter":
                 (pat, s2), pred = sn.a
                 nxt = Label("isf")
