@@ -23,7 +23,7 @@
 #include "../tla_rust_b200/csrc/tlag_vm.h"
 
 #define MAXW 128
-#define MAX_STEPS (1u << 26)
+#define MAX_STEPS (1ull << 38)   /* runaway-program backstop (InnerSerial needs ~10^9 instructions for one successor) */
 
 typedef struct {
   uint32_t W;

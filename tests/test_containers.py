@@ -165,3 +165,12 @@ def test_runtime_record_sets_and_domain_of_records():
     cm, o2 = _o2(m)
     assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == ("ok", 573, 169, 6)
     assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 573, 169, 6)
+
+
+def test_subsets_of_runtime_sets():
+    """x' \\in SUBSET S, {R \\in SUBSET (S \\X S) : p}, \\E / \\A over it -- tests/specs/Subsets.tla."""
+    m = Model(os.path.join(SPECS, "Subsets.tla"))
+    o1 = Oracle(m).run()
+    cm, o2 = _o2(m)
+    assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == ("ok", 124, 27, 4)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 124, 27, 4)

@@ -960,8 +960,9 @@ class Lowering:
         ft = E.fields[f]
         cols = [[] for _ in range(ft.size)]
         for v in vals:
-            if f in v.d:
-                r = self.codec.rep(ft, v.d[f])
+            d = v.d if isinstance(v, Fcn) else {ATOM_ALT: v}       # bare atom of an atom | record union
+            if f in d:
+                r = self.codec.rep(ft, d[f])
             else:
                 r = [-(1 << 31)] + [0] * (ft.size - 1)
             for w in range(ft.size):
@@ -1020,11 +1021,20 @@ class Lowering:
         node, filters = self._peel_filters(node, env, ctx, base)
         if filters:
             inner = self.set_elements(node[0], node[1], node[2], node[3])
-            if inner[0] == "sparse":
-                return ("sparse", inner[1], inner[2] + filters)
+            if inner[0] in ("sparse", "subsets"):
+                return (inner[0], inner[1], inner[2] + filters)
             node, env, ctx, base = node[4]
         else:
             node, env, ctx, base = node
+        if node.k == "subset":
+            # SUBSET S for a run-time S (InnerSerial.tla:47,67): the sub-masks of S's bitset are enumerated in place
+            sv = self.cx(node.a[0], env, ctx, base)
+            if type(sv) is Const:
+                t0 = self.natural_type(sv.v)
+                sv = self.materialize(sv, t0)
+            if isinstance(sv.t, TSet) and not isinstance(sv.t.elem, TBottom) and sv.t.nbits <= 31:
+                return ("subsets", sv, [])
+            raise CompileError(f"SUBSET of a run-time set over a universe of more than 31 values (line {node.line})")
         if node.k == "domain":
             f = self.cx(node.a[0], env, ctx, base)
             if isinstance(f, Val) and isinstance(f.t, TSparse):
@@ -1153,6 +1163,26 @@ class Lowering:
             self.asm.emit("LE", tmp, x, hi_s)
             self.asm.emit("JZ", tmp, done)
             self.for_each(bounds, self.bind(env, pat, Val(xt, x)), ctx, base, body, i + 1)
+            self.asm.emit("JMP", top)
+            self.asm.label(done)
+            return
+        if kind[0] == "subsets":
+            sv, filters = kind[1], kind[2]
+            full, sub, t1 = self.alloc(1), self.alloc(1), self.alloc(1)
+            self.asm.emit("MOV", full, sv.loc)
+            self.asm.emit("MOV", sub, full)
+            top, skip, done = Label("sbl"), Label("sbs"), Label("sbd")
+            self.asm.label(top)
+            rv = Val(sv.t, sub)
+            for fpat, fpred, fenv, fctx, fbase in filters:
+                nxt = Label("sbp")
+                self.cc(fpred, self.bind(fenv, fpat, rv), fctx, fbase, nxt, skip)
+                self.asm.label(nxt)
+            self.for_each(bounds, self.bind(env, pat, rv), ctx, base, body, i + 1)
+            self.asm.label(skip)
+            self.asm.emit("JZ", sub, done)             # the empty set was the last sub-mask
+            self.asm.emit("ADDI", t1, sub, -1)
+            self.asm.emit("BAND", sub, t1, full, 1)     # next sub-mask: (sub - 1) & full
             self.asm.emit("JMP", top)
             self.asm.label(done)
             return
@@ -3515,6 +3545,37 @@ class Lowering:
                 self.asm.emit("JNZ", t1, lt)
                 self.asm.emit("JMP", lf)
                 return
+            if sn.k == "funcset":
+                # f \in [D -> R] with a constant domain and a state-dependent range: every f[k] \in R
+                dc = self.try_const(sn.a[0], env, ctx, base)
+                e = self.cx(en, env, ctx, base)
+                if dc is not None and isinstance(e, Val) and isinstance(e.t, TFun) \
+                        and set(e.t.keys) == set(set_iter(dc.v)):
+                    env2 = dict(env)
+                    for j in range(len(e.t.keys)):
+                        nxt = Label("ifs")
+                        env2["__fs_elem"] = Val(e.t.elem, e.loc + j * e.t.elem.size)
+                        self.cc_in(Node("id", ("__fs_elem",), sn.line, sn.col), sn.a[1], env2, ctx, base, nxt, lf, n)
+                        self.asm.label(nxt)
+                    self.asm.emit("JMP", lt)
+                    return
+            if sn.k == "app" and sn.a[0] == "Seq" and len(sn.a[1]) == 1 and self.resolve("Seq", env, ctx)[0] == "builtin":
+                # s \in Seq(S) with a state-dependent S: every element \in S
+                e = self.cx(en, env, ctx, base)
+                if isinstance(e, Val) and isinstance(e.t, TSeq):
+                    es = e.t.elem.size
+                    i, t1, ev = self.alloc(1), self.alloc(1), self.alloc(es)
+                    top, ok = Label("iql"), Label("iqk")
+                    self.li(i, 0)
+                    self.asm.label(top)
+                    self.asm.emit("LT", t1, i, e.loc)
+                    self.asm.emit("JZ", t1, lt)
+                    self.asm.emit("LDX", ev, e.loc + 1, i, es)
+                    self.asm.emit("ADDI", i, i, 1)
+                    env2 = dict(env)
+                    env2["__sq_elem"] = Val(e.t.elem, ev)
+                    self.cc_in(Node("id", ("__sq_elem",), sn.line, sn.col), sn.a[1][0], env2, ctx, base, top, lf, n)
+                    return
             if sn.k == "recset":
                 # r \in [f1 : S1, ...]: r has exactly these fields and every r.fi \in Si (no enumeration)
                 e = self.cx(en, env, ctx, base)

@@ -84,8 +84,8 @@ TLAG_HD int tlag_ffs(uint32_t x) {  /* 1-based index of lowest set bit, 0 if non
 
 // Runs from *pc until the next event.  `code` may live in shared memory on the device.
 TLAG_HD int tlag_vm_run(const uint64_t* code, const int32_t* cpool, int32_t* f, uint32_t* pc_io,
-                        int32_t* info, int32_t* info2, uint32_t max_steps) {
-  TLAG_NOUNROLL for (uint32_t steps = 0; steps < max_steps; ++steps) {
+                        int32_t* info, int32_t* info2, uint64_t max_steps) {
+  TLAG_NOUNROLL for (uint64_t steps = 0; steps < max_steps; ++steps) {
     const int ev = tlag_vm_exec(code[*pc_io], cpool, f, pc_io, info, info2);
     if (ev >= 0) return ev;
   }
