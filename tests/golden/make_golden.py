@@ -90,6 +90,11 @@ MODELS = {
                              {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3_l.cfg"}), True, False),
     # BASELINE config #5 at its smallest bounds (2 transactions x 1 key), all eight invariants: operator subroutines
     "MCssi": (lambda: (ROOT + "/models/MCssi.tla", {"extra_dirs": [REF + "/examples"]}), True, True, 8, {"subroutines": True}),
+    # AdvancedExamples/MCInnerSerial: the reference's second TLC transcript (testout2: 6181 generated / 195 distinct /
+    # diameter 5, 22 h of CPU in 2001).  O1 cannot finish it; O2 takes ~7 min on 8 cores and reproduces it exactly.
+    "MCInnerSerial": (lambda: (ROOT + "/models/MCInnerSerialTyped.tla",
+                               {"extra_dirs": [REF + "/examples/SpecifyingSystems/AdvancedExamples"]}),
+                      True, False, None, {"type_hint": "TypeOK"}),
     "Containers": (lambda: (ROOT + "/tests/specs/Containers.tla", {}), False, True),
     "HourClock": (lambda: (REF + "/examples/SpecifyingSystems/HourClock/HourClock.tla", {}), True, True),
     "AsynchInterface": (lambda: (REF + "/examples/SpecifyingSystems/AsynchronousInterface/AsynchInterface.tla", {}), True, True),

@@ -36,7 +36,7 @@ def test_fixtures_reproduce_on_cpu_engine(golden_names):
     assert "MCPaxos3" in golden_names and "pcal_intro" in golden_names
     for name in golden_names:
         cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
-        if exp["o2"]["distinct"] > 50000:
+        if exp["o2"]["distinct"] > 50000 or name == "MCInnerSerial":   # 195 states, but 7 minutes of CPU (TLAG_SLOW test)
             continue
         r = cpu_engine.run(cm, init, n_threads=2, deadlock=info["deadlock"])
         for k in ("verdict", "generated", "distinct", "depth", "fp_xor", "fp_sum", "levels"):

@@ -6,7 +6,7 @@ import tempfile
 
 import pytest
 
-from conftest import REF, needs_reference
+from conftest import REF, ROOT, needs_reference
 from tla_rust_b200.front.spec import Model
 from tla_rust_b200.front.pcal import translate_file
 from tla_rust_b200.front.report import format_result
@@ -93,3 +93,41 @@ def test_oracle_handles_raft_and_ssi_at_small_bounds():
     m.check_deadlock = False
     r = Oracle(m).run()
     assert (r.verdict, r.generated, r.distinct, r.depth) == ("ok", 6185, 694, 12)
+
+
+# ---- the reference's SECOND known-answer transcript: AdvancedExamples/testout2 (TLC 1.57 on MCInnerSerial) ---------
+def _testout2_numbers():
+    import re
+    txt = open(REF + "/examples/SpecifyingSystems/AdvancedExamples/testout2").read()
+    m1 = re.search(r"Finished computing initial states: (\d+) distinct states generated", txt)
+    m2 = re.search(r"^(\d+) states generated, (\d+) distinct states found, (\d+) states left on queue\.\s*$", txt, re.M)
+    m3 = re.search(r"The state graph has diameter (\d+)\.", txt)
+    return int(m1.group(1)), int(m2.group(1)), int(m2.group(2)), int(m2.group(3)), int(m3.group(1))
+
+
+@needs_reference
+def test_testout2_initial_states_match_the_front_end():
+    """`Finished computing initial states: 4 distinct states generated.` (testout2:3)"""
+    from tla_rust_b200.front.spec import Model
+    m = Model(ROOT + "/models/MCInnerSerialTyped.tla",
+              extra_dirs=[REF + "/examples/SpecifyingSystems/AdvancedExamples"])
+    assert len(m.initial_states()) == _testout2_numbers()[0] == 4
+
+
+@needs_reference
+def test_testout2_final_counts_match_the_recorded_bytecode_run():
+    """TLC: `6181 states generated, 195 distinct states found, 0 states left on queue.  The state graph has diameter
+    5.` (22 h of CPU in 2001).  The AST oracle O1 cannot finish this model (a successor costs it minutes); the compiled
+    model on the CPU bytecode engine O2 takes ~7 min on 8 cores, so its result is recorded in the fixture
+    (tests/golden/make_golden.py) and re-run only with TLAG_SLOW=1."""
+    import os
+    from tla_rust_b200.compiled import load_compiled
+    _init, gen, dist, queue, diam = _testout2_numbers()
+    cm, init, exp, info = load_compiled(os.path.join(ROOT, "tests", "golden", "MCInnerSerial.tlagz"))
+    o2 = exp["o2"]
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, gen, dist, diam) == (0, 6181, 195, 5)
+    assert queue == 0 and sum(o2["levels"]) == dist and o2["levels"][0] == 4
+    if os.environ.get("TLAG_SLOW"):
+        from oracle import cpu_engine
+        r = cpu_engine.run(cm, init, n_threads=os.cpu_count() or 1, deadlock=info["deadlock"])
+        assert (r["generated"], r["distinct"], r["depth"], r["fp_xor"]) == (gen, dist, diam, o2["fp_xor"])
