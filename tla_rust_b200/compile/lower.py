@@ -1488,7 +1488,7 @@ class Lowering:
         of run-time arguments, expected type)); None => the caller inlines it as before.
         Arguments are evaluated once at the call site; a trap while evaluating one is deferred (poison word) to the
         first use of the parameter inside the body, which keeps call-by-name semantics."""
-        if base != "N" or self.dry and False:
+        if base != "N":
             return None
         if any(ar > 0 for _p, ar in d.params) or self._has_prime(d.body) or d.body.k == "fcndef":
             return None
