@@ -50,3 +50,31 @@ def test_assumption_only_modules(name):
     m = Model(SS + name + ".tla")
     m.check_assumes()
     assert m.next_node is None and not m.init_nodes
+
+
+VARIATIONS = [
+    # spec, (cfg text replacement ...), seq_cap, O1's counts -- other bounds than the shipped cfg, same specs
+    (SS + "FIFO/MCInnerFIFO.tla", (("qLen = 3", "qLen = 4"),), 6, ("ok", 29100, 11640, 13)),
+    (SS + "TLC/MCAlternatingBit.tla", (("msgQLen = 2", "msgQLen = 3"),), 5, ("ok", 2404, 372, 11)),
+    (SS + "TLC/MCAlternatingBit.tla", (("ackQLen = 2", "ackQLen = 3"),), 5, ("ok", 2212, 344, 11)),
+    (SS + "CachingMemory/MCInternalMemory.tla", (("Adr = {a1, a2, a3}", "Adr = {a1, a2}"),
+                                                 ("Proc = {p1, p2}", "Proc = {p1, p2, p3}")), None,
+     ("ok", 153916, 23544, 13)),
+]
+
+
+@needs_reference
+@pytest.mark.parametrize("path,subs,seq_cap,want", VARIATIONS,
+                         ids=[c[0].split("/")[-1][:-4] + "-" + c[1][0][1].replace(" ", "") for c in VARIATIONS])
+def test_bundled_spec_at_other_bounds(path, subs, seq_cap, want):
+    cfg = open(path[:-4] + ".cfg").read()
+    for a, b in subs:
+        assert a in cfg
+        cfg = cfg.replace(a, b)
+    m = Model(path, cfg_text=cfg)
+    init = m.initial_states()
+    o1 = Oracle(m).run()
+    assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == want
+    cm = compile_model(m, init, seq_cap=seq_cap)
+    o2 = cpu_engine.run(cm, encode_states(cm, init), deadlock=m.check_deadlock, n_threads=2)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (V[want[0]],) + want[1:]
