@@ -48,8 +48,10 @@ def lib():
 
 
 def run(cm, init_words: np.ndarray, n_threads=1, deadlock=True, max_states=1 << 22, stop_after=0,
-        want_states=False):
-    """BFS of a CompiledModel on host cores.  Returns dict(verdict, generated, distinct, depth, ...)."""
+        want_states=False, exact=False):
+    """BFS of a CompiledModel on host cores.  Returns dict(verdict, generated, distinct, depth, ...).
+    exact=True: one worker in FIFO order that stops at the first Assert failure / deadlock, i.e. the counts TLC's
+    single worker prints at the moment of the error (`queue` = states discovered but not yet dequeued)."""
     L = lib()
     code = np.ascontiguousarray(cm.code, dtype=np.uint64)
     cpool = np.ascontiguousarray(cm.cpool, dtype=np.int32)
@@ -58,7 +60,7 @@ def run(cm, init_words: np.ndarray, n_threads=1, deadlock=True, max_states=1 << 
     m = CpuModel(cm.W, code.ctypes.data, len(code), cm.entries["inv"], cm.entries["next"],
                  cpool.ctypes.data, len(cpool), layout.ctypes.data, layout.shape[0],
                  cm.frame_words, cm.state_words_unpacked, len(cm.invariants),
-                 1 if deadlock else 0, 0, max_states)
+                 (1 if deadlock else 0) | (4 if exact else 0), 0, max_states)
     res = CpuResult()
     states = None
     sp, cap = None, 0
@@ -73,6 +75,8 @@ def run(cm, init_words: np.ndarray, n_threads=1, deadlock=True, max_states=1 << 
                generated=res.generated, distinct=res.distinct, depth=res.depth, init_states=res.init_states,
                fp_xor=res.fp_xor, fp_sum=res.fp_sum, seconds=res.seconds,
                levels=[int(res.level_sizes[i]) for i in range(res.n_levels)])
+    if exact and out["verdict"] in (2, 3):
+        out["queue"] = out["distinct"] - out["state_idx"] - 1
     if want_states:
         out["states"] = states[:res.distinct].copy()
     return out

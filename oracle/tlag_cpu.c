@@ -32,7 +32,8 @@ typedef struct {
   const int32_t *cpool; uint32_t cpool_len;
   const tlag_slot *layout; uint32_t n_slots;
   uint32_t frame_words, unpacked_words, n_invariants;
-  uint32_t flags;           /* 1 = deadlock check */
+  uint32_t flags;           /* 1 = deadlock check; 4 = sequential TLC-exact mode: one worker, FIFO order, stop at the
+                             * first Assert failure / deadlock the way TLC's single worker does (error-time counts) */
   uint32_t table_log2;
   uint64_t max_states;
 } cpu_model;
@@ -61,6 +62,7 @@ typedef struct {
   _Alignas(64) uint64_t viol_inv;
   uint64_t viol_assert, viol_trap, viol_deadlock;
   int overflow, table_full;
+  int stop_now;             /* sequential-exact mode: an error was found, stop immediately */
   _Alignas(64) char tail_pad[64];
 } cpu_engine;
 
@@ -119,7 +121,11 @@ static void *worker(void *arg) {
         int ev = tlag_vm_run(m->code, m->cpool, frame, &pc, &info, &info2, MAX_STEPS);
         if (ev == TLAG_EV_HALT) break;
         if (ev == TLAG_EV_GEN) { ++nsucc; ++gen; continue; }
-        if (ev == TLAG_EV_ASSERT) { atomic_min64(&e->viol_assert, (idx << 20) | (uint32_t)(info & 0xFFFFF)); continue; }
+        if (ev == TLAG_EV_ASSERT) {
+          atomic_min64(&e->viol_assert, (idx << 20) | (uint32_t)(info & 0xFFFFF));
+          if (m->flags & 4) { e->stop_now = 1; break; }
+          continue;
+        }
         if (ev == TLAG_EV_INVF) continue;
         if (ev == TLAG_EV_EMIT) {
           ++nsucc; ++gen;
@@ -145,8 +151,13 @@ static void *worker(void *arg) {
         atomic_min64(&e->viol_trap, (idx << 20) | ((uint64_t)(ev == TLAG_EV_STEPS ? 15 : (info & 15)) << 16) | (uint32_t)(info2 & 0xFFFF));
         trapped = 1;
       }
-      if (nsucc == 0 && !trapped && (m->flags & 1)) atomic_min64(&e->viol_deadlock, idx << 20);
+      if (e->stop_now) break;
+      if (nsucc == 0 && !trapped && (m->flags & 1)) {
+        atomic_min64(&e->viol_deadlock, idx << 20);
+        if (m->flags & 4) { e->stop_now = 1; break; }
+      }
     }
+    if (e->stop_now) break;
   }
   __atomic_fetch_add(&e->generated, gen, __ATOMIC_RELAXED);
   free(frame);
@@ -193,7 +204,7 @@ int tlagcpu_run(const cpu_model *m, const uint32_t *init, uint64_t n_init, int n
   out->level_sizes[0] = hi;
   out->n_levels = 1;
   int verdict = 0;
-  if (n_threads < 1) n_threads = 1;
+  if (n_threads < 1 || (m->flags & 4)) n_threads = 1;
   pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
   while (lo < hi) {
     e.lo = lo; e.hi = hi; e.work = 0;
@@ -205,7 +216,7 @@ int tlagcpu_run(const cpu_model *m, const uint32_t *init, uint64_t n_init, int n
     if (e.viol_assert != ~0ULL && (e.viol_assert >> 20) < best) { best = e.viol_assert >> 20; kind = 2; }
     if (e.viol_inv != ~0ULL && (e.viol_inv >> 20) < best) { best = e.viol_inv >> 20; kind = 1; }
     if (e.viol_deadlock != ~0ULL && (e.viol_deadlock >> 20) < best) { best = e.viol_deadlock >> 20; kind = 3; }
-    if (e.n_states > hi) depth = level + 1;
+    if (e.n_states > hi || e.stop_now) depth = level + 1;
     if (out->n_levels < 4096) out->level_sizes[out->n_levels++] = e.n_states - hi;
     lo = hi; hi = e.n_states; level++;
     if (kind) {

@@ -131,3 +131,17 @@ def test_testout2_final_counts_match_the_recorded_bytecode_run():
         from oracle import cpu_engine
         r = cpu_engine.run(cm, init, n_threads=os.cpu_count() or 1, deadlock=info["deadlock"])
         assert (r["generated"], r["distinct"], r["depth"], r["fp_xor"]) == (gen, dist, diam, o2["fp_xor"])
+
+
+def test_readme_transcript_counts_from_the_bytecode_engine():
+    """README.md:319-320 again, this time from the COMPILED model: the CPU bytecode engine in its sequential mode
+    (one worker, FIFO order, stop at the first Assert failure) prints TLC's error-time numbers -- 9097 states
+    generated, 6164 distinct, 999 left on queue, depth 7.  This pins the compiler's successor order and the
+    initial-state order, not only the set of reachable states."""
+    import os
+    from tla_rust_b200.compiled import load_compiled
+    from oracle import cpu_engine
+    cm, init, exp, info = load_compiled(os.path.join(ROOT, "tests", "golden", "pcal_intro_readme_buggy.tlagz"))
+    r = cpu_engine.run(cm, init, exact=True)
+    assert (r["verdict"], r["generated"], r["distinct"], r["queue"], r["depth"]) == (2, 9097, 6164, 999, 7)
+    assert cm.asserts[r["detail"]][0] == "Failure of assertion at line 16, column 4."
