@@ -44,6 +44,7 @@ SYMS = [
     "==", "=>", "=<", "<=", ">=", "/=", "/\\", "\\/", "..", "<<", ">>", "<-", "->", "~>",
     "[]", "<>", "@@", ":>", "<:", "::", "||", "&&", "(+)", "(-)", "(.)", "(/)", "^+", "^*", "^#",
     "|-", "-|", "|=", "=|", "++", "--", "**", "//", "^^", "??", "%%", "##", "$$", "!!",
+    "-.",      # name of the prefix minus operator (Standard/Integers.tla:6  -. a == 0 - a)
 ]
 SINGLE = set("=#<>+-*/%^~()[]{},:;!'.@_|&$?")
 

@@ -393,6 +393,8 @@ class Parser:
             return d
         if t.t == "op":
             # prefix operator definition  -. a == e
+            if t.v == "-" and self.is_op("."):
+                self.p += 1
             a = self.expect_id().v
             self.expect_op("==")
             body = self.parse_expr(0)
@@ -462,6 +464,17 @@ class Parser:
         left = self.parse_prefix()
         while True:
             t = self.peek()
+            if t is not _CUT and t.t == "id":
+                # instance-qualified infix operator:  a R!+ b  (Standard/Naturals.tla:6-14)
+                t1 = self.toks[self.p + 1] if self.p + 1 < len(self.toks) else None
+                t2 = self.toks[self.p + 2] if self.p + 2 < len(self.toks) else None
+                if t1 is not None and t2 is not None and t1.t == "op" and t1.v == "!" and t2.t == "op" \
+                        and t2.v in INFIX and t2.v not in ("/\\", "\\/") and INFIX[t2.v][0] >= minp:
+                    lo, hi, lassoc = INFIX[t2.v]
+                    self.p += 3
+                    rhs = self.parse_expr(lo + 1 if lassoc else hi + 1)
+                    left = self.mk("bin", (t.v + "!" + t2.v, left, rhs), left)
+                    continue
             if t is _CUT or t.t != "op":
                 break
             v = t.v
