@@ -4210,6 +4210,17 @@ class Lowering:
         for v in m.vars:
             self.p_off[v] = usz + self.n_off[v]
         self.top = self.high = 2 * usz
+        # SYMMETRY: the canonicalisation code is one subroutine (CALL at every EMIT site) with a static scratch region
+        # right after the two state copies; its size is measured by a trial lowering
+        self._canon = None
+        if self.group:
+            with self.asm.capture():
+                self.gen_canonicalize(self.group)
+            base0 = 2 * usz
+            ret = base0
+            need = self.high - base0
+            self._canon = {"label": Label("canon"), "ret": ret, "base": base0 + 1}
+            self.top = self.high = base0 + 1 + need
         entries = {}
         # ---- invariants (evaluated on the state being expanded) ----
         linv = Label("inv")
@@ -4294,9 +4305,7 @@ class Lowering:
                 self.asm.emit("ASSERTF", len(self.asserts) - 1)
                 self.asm.label(ok)
             if self.group:
-                mk = self.mark()
-                self.gen_canonicalize(self.group)
-                self.release(mk)
+                self.asm.emit("CALL", self._canon["ret"], self._canon["label"])
             if m.constraints or m.action_constraints:
                 ok, bad, end = Label("cok"), Label("cbad"), Label("cend")
                 mk = self.mark()
@@ -4318,6 +4327,13 @@ class Lowering:
         self.ca(m.next_node, {}, m.next_ctx, frozenset(), emit_k, None)
         self.asm.emit("HALT")
         self._main_high = self.high
+        if self._canon is not None:
+            save_top = self.top
+            self.top = self._canon["base"]
+            self.asm.label(self._canon["label"])
+            self.gen_canonicalize(self.group)
+            self.asm.emit("RET", self._canon["ret"])
+            self.top = save_top
         for buf in self.sub_bufs:            # subroutine bodies (entered by CALL only)
             self.asm.splice(buf)
         code, cpool, ent = self.asm.assemble(entries)
