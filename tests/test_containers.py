@@ -174,3 +174,19 @@ def test_subsets_of_runtime_sets():
     cm, o2 = _o2(m)
     assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == ("ok", 124, 27, 4)
     assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 124, 27, 4)
+
+
+def test_pluscal_control_statements_end_to_end():
+    """while / either / with / if-else / await / assert through pcal2tla, the compiler and O2 (tests/specs/loopy.tla)."""
+    import shutil
+    import tempfile
+    from tla_rust_b200.front.pcal import translate_file
+    d = tempfile.mkdtemp(prefix="tlag_loopy_")
+    for f in ("loopy.tla", "loopy.cfg"):
+        shutil.copy(os.path.join(SPECS, f), d)
+    translate_file(os.path.join(d, "loopy.tla"))
+    m = Model(os.path.join(d, "loopy.tla"))
+    o1 = Oracle(m).run()
+    cm, o2 = _o2(m)
+    assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == ("ok", 1222, 512, 11)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 1222, 512, 11)
