@@ -190,3 +190,20 @@ def test_pluscal_control_statements_end_to_end():
     cm, o2 = _o2(m)
     assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == ("ok", 1222, 512, 11)
     assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 1222, 512, 11)
+
+
+@pytest.mark.parametrize("name,want", [("mac", ("ok", 26, 16, 7)), ("defn", ("deadlock", 17, 13, 5))])
+def test_pluscal_macro_and_define_blocks(name, want):
+    """macro (nested, token substitution) and define blocks of the PlusCal p-syntax (manual p.61), end to end."""
+    import shutil
+    import tempfile
+    from tla_rust_b200.front.pcal import translate_file
+    d = tempfile.mkdtemp(prefix="tlag_pc_")
+    for ext in (".tla", ".cfg"):
+        shutil.copy(os.path.join(SPECS, name + ext), d)
+    translate_file(os.path.join(d, name + ".tla"))
+    m = Model(os.path.join(d, name + ".tla"))
+    o1 = Oracle(m).run()
+    cm, o2 = _o2(m)
+    assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == want
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == ({"ok": 0, "deadlock": 3}[want[0]],) + want[1:]

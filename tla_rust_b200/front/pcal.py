@@ -47,11 +47,65 @@ def _tok_text(t: Tok):
 
 
 class PParser:
-    def __init__(self, toks, line_off, col_off_first):
+    def __init__(self, toks, line_off, col_off_first, macros=None):
         self.toks = toks
         self.p = 0
         self.line_off = line_off
         self.col_off_first = col_off_first
+        self.macros = macros if macros is not None else {}     # name -> (parameter names, body tokens)
+
+    def macro_def(self):
+        """macro Name(p1, ..., pn) begin <statements> end macro [;]   (manual p.61): body kept as tokens."""
+        self.expect_word("macro")
+        name = self.next().v
+        params = []
+        self.expect_op("(")
+        while not self.is_op(")"):
+            params.append(self.next().v)
+            if self.is_op(","):
+                self.p += 1
+        self.expect_op(")")
+        self.expect_word("begin")
+        body = []
+        while not (self.is_word("end") and self.is_word("macro", 1)):
+            t = self.next()
+            if t.t == "eof":
+                raise PcalError(f"PlusCal: macro {name} is not closed by `end macro`")
+            body.append(t)
+        self.p += 2
+        self.skip_semi()
+        self.macros[name] = (params, body)
+
+    def macro_call(self, name):
+        """Name(e1, ..., en): the body with every parameter token replaced by the (parenthesised) argument."""
+        params, body = self.macros[name]
+        self.p += 1
+        self.expect_op("(")
+        args = []
+        while not self.is_op(")"):
+            args.append(self.expr(stop_ops=(")",), stop_comma=True))
+            if self.is_op(","):
+                self.p += 1
+        self.expect_op(")")
+        if len(args) != len(params):
+            raise PcalError(f"PlusCal: macro {name} expects {len(params)} arguments")
+        sub = dict(zip(params, args))
+        toks = []
+        for t in body:
+            if t.t == "id" and t.v in sub:
+                a = sub[t.v]
+                if len(a) == 1:
+                    toks.append(a[0])
+                else:
+                    toks.append(Tok("op", "(", t.line, t.col, t.col))
+                    toks.extend(a)
+                    toks.append(Tok("op", ")", t.line, t.col, t.col))
+            else:
+                toks.append(t)
+        toks.append(Tok("eof", None, body[-1].line if body else 0, 0, 0))
+        inner = PParser(toks, self.line_off, self.col_off_first, self.macros)
+        stmts = inner.stmt_seq(set())
+        return Stmt("macro_expansion", body=stmts)
 
     def peek(self, k=0):
         i = self.p + k
@@ -151,7 +205,13 @@ class PParser:
             t = self.peek()
             if t.t == "eof" or (t.t in ("id", "kw") and t.v in enders):
                 break
-            stmts.append(self.stmt())
+            st = self.stmt()
+            if st.kind == "macro_expansion":          # spliced in place; a label on the call labels its first statement
+                if st.label and st.body:
+                    st.body[0].label = st.label
+                stmts.extend(st.body)
+            else:
+                stmts.append(st)
         return stmts
 
     def stmt(self):
@@ -168,6 +228,8 @@ class PParser:
 
     def stmt_unlabeled(self):
         t = self.peek()
+        if t.t == "id" and t.v in self.macros and self.is_op("(", 1):
+            return self.macro_call(t.v)
         w = t.v if t.t in ("id", "kw") else None
         if w == "if":
             self.p += 1
@@ -363,6 +425,8 @@ def wrap_list(prefix, names, closing=" >>", first_indent=None):
 
 class Translator:
     def __init__(self, text, line_off=0, col_off_first=0):
+        self.text = text
+        self.define_text = None
         self.toks = lex(text, whole_file=False)
         self.pp = PParser(self.toks, line_off, col_off_first)
         self.line_off = line_off
@@ -381,8 +445,29 @@ class Translator:
         if pp.is_word("variables") or pp.is_word("variable"):
             pp.p += 1
             self.gdecls = pp.var_decls()
-        if pp.is_word("define") or pp.is_word("macro") or pp.is_word("procedure"):
-            raise PcalError("PlusCal define/macro/procedure blocks are not supported")
+        if pp.is_word("define"):
+            # define <TLA+ definitions> end define [;]  (manual p.61): copied verbatim into the translation, after the
+            # declaration of the global variables (the definitions may mention them)
+            pp.p += 1
+            first = pp.peek()
+            last = None
+            while not (pp.is_word("end") and pp.is_word("define", 1)):
+                last = pp.next()
+                if last.t == "eof":
+                    raise PcalError("PlusCal: `define` is not closed by `end define`")
+            pp.p += 2
+            pp.skip_semi()
+            lines = self.text.split("\n")
+            if last is not None:
+                seg = lines[first.line - 1:last.line]
+                seg[-1] = seg[-1][:last.ecol]
+                seg[0] = " " * (first.col - 1) + seg[0][first.col - 1:]
+                ind = min(len(x) - len(x.lstrip()) for x in seg if x.strip())
+                self.define_text = "\n".join(x[ind:].rstrip() for x in seg)
+        while pp.is_word("macro"):
+            pp.macro_def()
+        if pp.is_word("procedure"):
+            raise PcalError("PlusCal procedures are not supported")
         self.procs = []
         if pp.is_word("begin"):
             pp.p += 1
@@ -458,6 +543,10 @@ class Translator:
         out = []
         out.append("VARIABLES " + wrap_list("", self.allvars, closing="").replace("\n", "\n          "))
         out.append("")
+        if self.define_text:
+            out.append("(* define statement *)")
+            out.extend(self.define_text.split("\n"))
+            out.append("")
         out.append(wrap_list("vars == << ", self.allvars))
         out.append("")
         if not uni:
