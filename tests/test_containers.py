@@ -207,3 +207,13 @@ def test_pluscal_macro_and_define_blocks(name, want):
     cm, o2 = _o2(m)
     assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == want
     assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == ({"ok": 0, "deadlock": 3}[want[0]],) + want[1:]
+
+
+def test_subsets_of_a_runtime_set_over_a_two_word_universe():
+    """Sub-mask enumeration with borrow across 32-bit words (universe 1..40) -- tests/specs/SubsetsWide.tla."""
+    m = Model(os.path.join(SPECS, "SubsetsWide.tla"))
+    o1 = Oracle(m).run()
+    cm, o2 = _o2(m)
+    assert cm.var_types["s"].size == 2
+    assert (o1.verdict, o1.generated, o1.distinct, o1.depth) == ("ok", 2561, 243, 6)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, 2561, 243, 6)

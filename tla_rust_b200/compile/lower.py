@@ -1032,9 +1032,9 @@ class Lowering:
             if type(sv) is Const:
                 t0 = self.natural_type(sv.v)
                 sv = self.materialize(sv, t0)
-            if isinstance(sv.t, TSet) and not isinstance(sv.t.elem, TBottom) and sv.t.nbits <= 31:
+            if isinstance(sv.t, TSet) and not isinstance(sv.t.elem, TBottom) and sv.t.size <= 8:
                 return ("subsets", sv, [])
-            raise CompileError(f"SUBSET of a run-time set over a universe of more than 31 values (line {node.line})")
+            raise CompileError(f"SUBSET of a run-time set over a universe of more than 256 values (line {node.line})")
         if node.k == "domain":
             f = self.cx(node.a[0], env, ctx, base)
             if isinstance(f, Val) and isinstance(f.t, TSparse):
@@ -1168,9 +1168,10 @@ class Lowering:
             return
         if kind[0] == "subsets":
             sv, filters = kind[1], kind[2]
-            full, sub, t1 = self.alloc(1), self.alloc(1), self.alloc(1)
-            self.asm.emit("MOV", full, sv.loc)
-            self.asm.emit("MOV", sub, full)
+            nw = sv.t.size
+            full, sub, t1 = self.alloc(nw), self.alloc(nw), self.alloc(1)
+            self.movn(full, sv.loc, nw)
+            self.movn(sub, full, nw)
             top, skip, done = Label("sbl"), Label("sbs"), Label("sbd")
             self.asm.label(top)
             rv = Val(sv.t, sub)
@@ -1180,9 +1181,22 @@ class Lowering:
                 self.asm.label(nxt)
             self.for_each(bounds, self.bind(env, pat, rv), ctx, base, body, i + 1)
             self.asm.label(skip)
-            self.asm.emit("JZ", sub, done)             # the empty set was the last sub-mask
-            self.asm.emit("ADDI", t1, sub, -1)
-            self.asm.emit("BAND", sub, t1, full, 1)     # next sub-mask: (sub - 1) & full
+            # next sub-mask: (sub - 1) & full on the multi-word integer; the empty set was the last one
+            self.asm.emit("BISZ", t1, sub, nw)
+            self.asm.emit("JNZ", t1, done)
+            andl = Label("sba")
+            for w in range(nw):
+                dec = Label("sbw")
+                self.asm.emit("JNZ", sub + w, dec)
+                self.li(sub + w, -1)                    # borrow from the next word
+                continue_l = Label("sbc")
+                self.asm.emit("JMP", continue_l)
+                self.asm.label(dec)
+                self.asm.emit("ADDI", sub + w, sub + w, -1)
+                self.asm.emit("JMP", andl)
+                self.asm.label(continue_l)
+            self.asm.label(andl)
+            self.asm.emit("BAND", sub, sub, full, nw)
             self.asm.emit("JMP", top)
             self.asm.label(done)
             return
