@@ -46,7 +46,7 @@ typedef struct {
   uint32_t cpool_len;
   const int32_t *layout;         /* n_slots x {frame_off, width_bits, bias}: packed layout     */
   uint32_t n_slots;
-  uint32_t frame_words;          /* per-thread VM frame size in words (<= 4096)                */
+  uint32_t frame_words;          /* per-thread VM frame size in words (<= 8192)                */
   uint32_t unpacked_words;       /* words of one unpacked state (primed copy follows it)       */
   uint32_t n_invariants;
   uint32_t n_actions;

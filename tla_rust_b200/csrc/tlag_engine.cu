@@ -502,7 +502,7 @@ __global__ void k_rehash(DevParams p, unsigned long long n) {
 }
 
 // ------------------------------------------------------------------ host side
-static const int kFrameClasses[] = {64, 128, 256, 512, 1024, 2048, 4096};
+static const int kFrameClasses[] = {64, 128, 256, 512, 1024, 2048, 4096, 8192};
 
 template <int MODE>
 static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
@@ -525,7 +525,9 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
                       : (sm ? k_wave<512, MODE, true> : k_wave<512, MODE, false>); break;
     case 4: fn = sm ? k_wave<1024, MODE, true> : k_wave<1024, MODE, false>; break;
     case 5: fn = sm ? k_wave<2048, MODE, true> : k_wave<2048, MODE, false>; break;
-    default: fn = sm ? k_wave<4096, MODE, true> : k_wave<4096, MODE, false>; break;
+    case 6: fn = sm ? k_wave<4096, MODE, true> : k_wave<4096, MODE, false>; break;
+    // 8192 words = 32 KB of local memory per thread (SSI at 4 transactions x 3 keys needs 6.9 K words)
+    default: fn = sm ? k_wave<8192, MODE, true> : k_wave<8192, MODE, false>; break;
   }
   if (smem > 48 * 1024) {
     cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -658,7 +660,7 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   *out = e;   // returned even on failure so that tlag_last_error works; caller destroys it
   e->m = *m;
   if (m->words_per_state == 0 || m->words_per_state > TLAG_MAXW) { e->err = "words_per_state out of range (1..128)"; return TLAG_EINVAL; }
-  if (m->frame_words > 4096) { e->err = "frame_words > 4096 not supported"; return TLAG_EINVAL; }
+  if (m->frame_words > 8192) { e->err = "frame_words > 8192 not supported"; return TLAG_EINVAL; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { e->err = "no CUDA device available"; return TLAG_ECUDA; }
   CK(cudaSetDevice(m->device));
@@ -671,8 +673,8 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&e->ev0));
   CK(cudaEventCreate(&e->ev1));
-  e->frame_class = 6;
-  for (int i = 0; i < 7; ++i) if ((int)m->frame_words <= kFrameClasses[i]) { e->frame_class = i; break; }
+  e->frame_class = 7;
+  for (int i = 0; i < 8; ++i) if ((int)m->frame_words <= kFrameClasses[i]) { e->frame_class = i; break; }
   e->uses_ext = getenv("TLAG_VM_FULL") != nullptr;
   for (uint32_t i = 0; i < m->code_len && !e->uses_ext; ++i) {
     const uint32_t op = (uint32_t)(m->code[i] & 0xFF);
