@@ -1,0 +1,26 @@
+#!/bin/bash
+# One gpurun call that settles everything round 1 left unverified on a device:
+#
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
+#
+# Every step runs under its own `timeout`, writes into gpurun_out/, and a failing step does not stop the next.
+# Nothing printed under ncu is a bench value.
+set -u
+OUT=gpurun_out
+mkdir -p "$OUT"
+step() { echo "=== $1" | tee -a "$OUT/session.log"; shift; ( "$@" ) >> "$OUT/session.log" 2>&1; echo "rc=$?" | tee -a "$OUT/session.log"; }
+
+# 1. the parity suite (includes the xfail-guarded SSI subroutine fixture and the recompiled raft fixtures)
+step "pytest -m gpu" timeout 900 python -m pytest tests -m gpu -q -rxX
+# 2. SSI (CALL/RET subroutines, 4096 and 8192 frame classes) and the symmetric subroutine models, with timing
+step "fixture bench: MCssi" timeout 300 python tools/fixture_bench.py MCssi --reps 2
+step "fixture bench: MCssi_3x1 (8192 class if present)" timeout 600 python tools/fixture_bench.py MCssi_3x1 --reps 1
+# 3. contract bench at N=1, then the raft workload on its own
+step "bench N=1" timeout 900 python bench.py --steps 3 --warmup 3
+step "fixture bench: raft" timeout 600 python tools/fixture_bench.py MCraft_s3_m MCraft_s3_l --reps 2
+# 4. launch list of a short bench (share of the step per kernel) and one full capture of the wave kernel
+step "ncu launch list" timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+     --log-file "$OUT/r2_launches_bench_b3.csv" python bench.py --steps 1 --warmup 1 --no-k1 --workload MCPaxos3_b3
+step "ncu k_wave full" timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_wave -s 12 -c 1 \
+     -o "$OUT/r2_k_wave_b3" -f python bench.py --steps 1 --warmup 0 --no-k1 --workload MCPaxos3_b3
+tail -5 "$OUT/session.log"
