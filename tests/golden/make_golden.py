@@ -90,8 +90,9 @@ MODELS = {
                              {"extra_dirs": [REF + "/examples"], "cfg_path": ROOT + "/models/MCraft_s3_l.cfg"}), True, False),
     # BASELINE config #5 at its smallest bounds (2 transactions x 1 key), all eight invariants: operator subroutines
     "MCssi": (lambda: (ROOT + "/models/MCssi.tla", {"extra_dirs": [REF + "/examples"]}), True, True, 8, {"subroutines": True}),
-    # ... 3 transactions x 1 key (frame 3710 words: 4096 class; O1 ran once: 152554 / 90430 / 13, tests/test_containers.py)
-    # and 2 x 2 (sequence capacity 16, frame 4341 words: the 8192 class; O1: 50121 / 29629 / 13)
+    # ... 3 transactions x 1 key (frame 2910 words; O1 ran once: 152554 / 90430 / 13, tests/test_containers.py), 2 x 2
+    # (sequence capacity 16, frame 3400 words; O1: 50121 / 29629 / 13) and the same state space with capacity 24
+    # (wider packed states, frame 5080 words: the engine's 8192-word frame class)
     "MCssi_3x1": (lambda: (ROOT + "/models/MCssi.tla",
                            {"extra_dirs": [REF + "/examples"],
                             "cfg_text": open(ROOT + "/models/MCssi.cfg").read().replace("TxnId = {T1, T2}", "TxnId = {T1, T2, T3}")}),
@@ -100,6 +101,10 @@ MODELS = {
                            {"extra_dirs": [REF + "/examples"],
                             "cfg_text": open(ROOT + "/models/MCssi.cfg").read().replace("Key = {K1}", "Key = {K1, K2}")}),
                   True, False, 16, {"subroutines": True}),
+    "MCssi_2x2_wide": (lambda: (ROOT + "/models/MCssi.tla",
+                                {"extra_dirs": [REF + "/examples"],
+                                 "cfg_text": open(ROOT + "/models/MCssi.cfg").read().replace("Key = {K1}", "Key = {K1, K2}")}),
+                       True, False, 24, {"subroutines": True}),
     # AdvancedExamples/MCInnerSerial: the reference's second TLC transcript (testout2: 6181 generated / 195 distinct /
     # diameter 5, 22 h of CPU in 2001).  O1 cannot finish it; O2 takes ~7 min on 8 cores and reproduces it exactly.
     "MCInnerSerial": (lambda: (ROOT + "/models/MCInnerSerialTyped.tla",

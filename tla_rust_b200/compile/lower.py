@@ -1627,8 +1627,11 @@ class Lowering:
         return sub
 
     def _plan_sub_frames(self, main_high):
-        """Static frame bases from the discovery pass: level(K) = 0 for leaves, else 1 + max level of its callees;
-        all subroutines of a level share one region, regions are stacked above the main programs' temporaries."""
+        """Static frame bases from the discovery pass.  Two instances are live together only along a call chain, so
+        a subroutine sits just above the highest-ending of its callers (the main programs' temporaries for those
+        called from there): the frame is as deep as the deepest call chain, like a stack's high-water mark, not the
+        sum of the largest frame of every call-graph level.  (SSI 2 x 2: 4341 -> 3390 words -- the 1.6 K-word leaf
+        `WellFormedTransactionsInHistory` is only ever called from an invariant.)"""
         level = {}
 
         def lv(k, seen=()):
@@ -1641,17 +1644,20 @@ class Lowering:
             return level[k]
         for k in self.subs:
             lv(k)
-        nlev = 1 + max(level.values()) if level else 0
-        sizes = [0] * nlev
-        for k, sub in self.subs.items():
-            sizes[level[k]] = max(sizes[level[k]], sub["size"] + 2)
-        bases, b = [], main_high + 8
-        for L in range(nlev):
-            bases.append(b)
-            b += sizes[L]
+        callers = {k: [] for k in self.subs}
+        for p, cs in self.sub_calls.items():
+            if p is None or p not in self.subs:
+                continue
+            for c in cs:
+                if c in callers:
+                    callers[c].append(p)
+        base, b = {}, main_high + 8
+        for k in sorted(self.subs, key=lambda k: -level[k]):     # callers (higher levels) before their callees
+            base[k] = max([main_high + 8] + [base[p] + self.subs[p]["size"] + 2 for p in callers[k]])
+            b = max(b, base[k] + self.subs[k]["size"] + 2)
         if b > MAXREG:
             raise CompileError(f"frame of {b} words exceeds the 16K-word limit (subroutine frames)")
-        return {k: bases[level[k]] for k in self.subs}, b
+        return base, b
 
     def x_recset(self, n, env, ctx, base, want):
         """[f1 : S1, ..., fk : Sk] with run-time component sets (InnerSerial.tla:5 `opId`): bitset over the record

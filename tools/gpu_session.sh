@@ -14,7 +14,7 @@ step() { echo "=== $1" | tee -a "$OUT/session.log"; shift; ( "$@" ) >> "$OUT/ses
 step "pytest -m gpu" timeout 900 python -m pytest tests -m gpu -q -rxX
 # 2. SSI (CALL/RET subroutines, 4096 and 8192 frame classes) and the symmetric subroutine models, with timing
 step "fixture bench: MCssi" timeout 300 python tools/fixture_bench.py MCssi --reps 2
-step "fixture bench: MCssi_3x1 (8192 class if present)" timeout 600 python tools/fixture_bench.py MCssi_3x1 --reps 1
+step "fixture bench: MCssi 3x1, 2x2, 2x2_wide (8192 class)" timeout 600 python tools/fixture_bench.py MCssi_3x1 MCssi_2x2 MCssi_2x2_wide --reps 2
 # 3. contract bench at N=1, then the raft workload on its own
 step "bench N=1" timeout 900 python bench.py --steps 3 --warmup 3
 step "fixture bench: raft" timeout 600 python tools/fixture_bench.py MCraft_s3_m MCraft_s3_l --reps 2
