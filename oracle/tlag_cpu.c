@@ -22,6 +22,23 @@
 
 #include "../tla_rust_b200/csrc/tlag_vm.h"
 
+#ifdef TLAG_NATIVE_INC
+/* Test hook (tests/test_native.py): run the model-specialised native code that tla_rust_b200/compile/native.py
+ * generates for the CUDA engine inside this engine, in place of the interpreter, so that its results can be compared
+ * with the interpreter's on a machine without a GPU.  The library built this way serves ONE model. */
+#define TLAG_VM_EXEC_QUAL static inline __attribute__((always_inline))
+#define TLAG_VM_EXEC_FN tlag_vm_exec_inl
+#define TLAG_VM_EXT 1
+#include "../tla_rust_b200/csrc/tlag_vm_exec.inc"
+#undef TLAG_VM_EXEC_FN
+#undef TLAG_VM_EXT
+#undef TLAG_VM_EXEC_QUAL
+#define TLAG_NATIVE_X tlag_vm_exec_inl
+#define TLAG_NATIVE_QUAL static
+#include TLAG_NATIVE_INC
+#define tlag_vm_run(code, cpool, f, pc, info, info2, steps) tlag_native_run(cpool, f, pc, info, info2)
+#endif
+
 #define MAXW 128
 #define MAX_STEPS (1ull << 38)   /* runaway-program backstop (InnerSerial needs ~10^9 instructions for one successor) */
 

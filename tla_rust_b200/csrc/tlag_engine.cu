@@ -30,6 +30,18 @@
 #undef TLAG_VM_EXEC_FN
 #undef TLAG_VM_EXT
 
+// Model-specialised build (tla_rust_b200/compile/native.py, engine.py: build_native_library): the program of ONE
+// model compiled to straight-line code.  -DTLAG_NATIVE_INC="<generated .inc>" -DTLAG_NATIVE_FRAME=<frame class>;
+// tlag_create refuses any other program (length + FNV-1a of the code words).
+#ifdef TLAG_NATIVE_INC
+#ifndef TLAG_NATIVE_FRAME
+#error "TLAG_NATIVE_FRAME (frame class of the model: 64 ... 8192) must be defined with TLAG_NATIVE_INC"
+#endif
+#define TLAG_NATIVE_X tlag_vm_exec
+#define TLAG_NATIVE_QUAL static __device__ __forceinline__
+#include TLAG_NATIVE_INC
+#endif
+
 #define TLAG_MAXW 128
 #ifndef TLAG_BIG_OCC
 #define TLAG_BIG_OCC 4   /* resident CTAs per SM for the big-frame (> 512 words) wave kernels: latency-bound on local memory */
@@ -155,6 +167,22 @@ enum { L_RUN = 0, L_EMIT = 1, L_DONE = 2, L_STOP = 3 };
 // decode/dispatch; only lanes whose pc equals the minimum execute.  (v1 of this loop spent 41 of ~73
 // SASS instructions per step on bookkeeping and fetched the instruction with a generic per-lane load:
 // profiles/r1_k_wave_warpsched_b2_ncu.txt.)
+#ifdef TLAG_NATIVE_INC
+// Native build: every lane runs the compiled program from its pc to its next event; the hardware reconverges the
+// warp (no min-pc election, no instruction fetch / decode).  Same contract as the interpreter below.
+template <bool SMEM, bool LEAN>
+__device__ __forceinline__ void warp_vm(const uint64_t* __restrict__, const uint64_t*,
+                                        const int32_t* __restrict__ cpool, int32_t* frame, uint32_t& pc,
+                                        uint32_t& rpc, int& ev_out, int32_t& info, int32_t& info2) {
+  if (pc != TLAG_PC_PARKED) {
+    uint32_t p = pc;
+    ev_out = tlag_native_run(cpool, frame, &p, &info, &info2);
+    rpc = p;
+    pc = TLAG_PC_PARKED;
+  }
+  __syncwarp();
+}
+#else
 template <bool SMEM, bool LEAN>
 __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, const uint64_t* scode,
                                         const int32_t* __restrict__ cpool, int32_t* frame, uint32_t& pc,
@@ -170,6 +198,8 @@ __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, cons
     }
   }
 }
+
+#endif
 
 // MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
 // LEAN: interpreter without the extension ops, for models that do not use them (small frames only).
@@ -514,6 +544,11 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   void (*fn)(DevParams, unsigned long long, unsigned long long) = nullptr;
   const bool sm = e->p.code_in_smem != 0;
   const bool lean = !e->uses_ext;
+#ifdef TLAG_NATIVE_INC
+  fn = k_wave<TLAG_NATIVE_FRAME, MODE, false, false>;   // LEAN only selects an interpreter variant
+  smem = 0;
+  (void)sm; (void)lean;
+#else
   switch (e->frame_class) {
     case 0: fn = lean ? (sm ? k_wave<64, MODE, true, true> : k_wave<64, MODE, false, true>)
                       : (sm ? k_wave<64, MODE, true> : k_wave<64, MODE, false>); break;
@@ -529,6 +564,7 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
     // 8192 words = 32 KB of local memory per thread (SSI at 4 transactions x 3 keys needs 6.9 K words)
     default: fn = sm ? k_wave<8192, MODE, true> : k_wave<8192, MODE, false>; break;
   }
+#endif
   if (smem > 48 * 1024) {
     cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (r != cudaSuccess) return r;
@@ -647,7 +683,11 @@ static int cluster_slice(tlag_engine* e, uint64_t first, uint64_t count) {
   return TLAG_OK;
 }
 
+#ifdef TLAG_NATIVE_INC
+extern "C" const char* tlag_version(void) { return "tlag 0.1 (sm_100a) native"; }
+#else
 extern "C" const char* tlag_version(void) { return "tlag 0.1 (sm_100a)"; }
+#endif
 
 extern "C" const char* tlag_last_error(const tlag_engine* e) { return e ? e->err.c_str() : "null engine"; }
 
@@ -661,6 +701,16 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   e->m = *m;
   if (m->words_per_state == 0 || m->words_per_state > TLAG_MAXW) { e->err = "words_per_state out of range (1..128)"; return TLAG_EINVAL; }
   if (m->frame_words > 8192) { e->err = "frame_words > 8192 not supported"; return TLAG_EINVAL; }
+#ifdef TLAG_NATIVE_INC
+  {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (uint32_t i = 0; i < m->code_len; ++i) h = (h ^ m->code[i]) * 0x100000001b3ULL;
+    if (m->code_len != TLAG_NATIVE_CODE_LEN || h != TLAG_NATIVE_CODE_FNV || m->frame_words > TLAG_NATIVE_FRAME) {
+      e->err = "this library was compiled for another model's program (native build)";
+      return TLAG_EINVAL;
+    }
+  }
+#endif
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { e->err = "no CUDA device available"; return TLAG_ECUDA; }
   CK(cudaSetDevice(m->device));

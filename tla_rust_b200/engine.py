@@ -68,28 +68,85 @@ def build_library(verbose=False):
     subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")] + ([] if verbose else ["-s"]))
 
 
+def _bind(path):
+    L = C.CDLL(path)
+    L.tlag_last_error.restype = C.c_char_p
+    L.tlag_version.restype = C.c_char_p
+    L.tlag_kernel_launches.restype = C.c_uint64
+    L.tlag_destroy.restype = None
+    for fn in EXPORTS:
+        getattr(L, fn)
+    return L
+
+
 def load_library():
     global _LIB
     if _LIB is None:
         if not os.path.exists(LIB_PATH):
             raise EngineUnavailable(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                     f"(the product has no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
-        L.tlag_last_error.restype = C.c_char_p
-        L.tlag_version.restype = C.c_char_p
-        L.tlag_kernel_launches.restype = C.c_uint64
-        L.tlag_destroy.restype = None
-        for fn in EXPORTS:
-            getattr(L, fn)
-        _LIB = L
+        _LIB = _bind(LIB_PATH)
     return _LIB
+
+
+FRAME_CLASSES = (64, 128, 256, 512, 1024, 2048, 4096, 8192)     # csrc/tlag_engine.cu: kFrameClasses
+NATIVE_DIR = os.path.join(_HERE, "csrc", "native")
+_NATIVE_LIBS = {}
+
+
+def native_library_path(cm):
+    from .compile.native import model_key
+    return os.path.join(NATIVE_DIR, f"libtlag_{model_key(cm)}.so")
+
+
+def build_native_library(cm, force=False, verbose=False):
+    """Model-specialised engine library: the model's bytecode compiled to straight-line CUDA (compile/native.py)
+    inside the same engine source, one frame class, same C ABI.  Built in-tree (csrc/native/) so that it travels with
+    the repo snapshot; nvcc takes about a minute for a 5 K-instruction program.  Returns the library path."""
+    from .compile.native import emit_c, model_key
+    os.makedirs(NATIVE_DIR, exist_ok=True)
+    key = model_key(cm)
+    inc = os.path.join(NATIVE_DIR, f"{key}.inc")
+    so = os.path.join(NATIVE_DIR, f"libtlag_{key}.so")
+    if os.path.exists(so) and not force:
+        return so
+    frame = next((c for c in FRAME_CLASSES if cm.frame_words <= c), None)
+    if frame is None:
+        raise EngineError(f"frame of {cm.frame_words} words exceeds the largest frame class")
+    with open(inc, "w") as f:
+        f.write(emit_c(cm))
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+           f'-DTLAG_NATIVE_INC="{inc}"', f"-DTLAG_NATIVE_FRAME={frame}", "-shared", "-o", so + ".tmp",
+           os.path.join(_HERE, "csrc", "tlag_engine.cu")]
+    p = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if p.returncode != 0:
+        raise EngineError(f"nvcc failed for the native build of model {key}: {(p.stderr or '')[-2000:]}")
+    os.replace(so + ".tmp", so)
+    return so
+
+
+def load_native_library(cm, build=True):
+    so = native_library_path(cm)
+    if so not in _NATIVE_LIBS:
+        if not os.path.exists(so):
+            if not build:
+                raise EngineUnavailable(f"{so} is missing (native build of this model)")
+            build_native_library(cm)
+        _NATIVE_LIBS[so] = _bind(so)
+    return _NATIVE_LIBS[so]
 
 
 class Engine:
     """One BFS engine instance on one GPU (mirrors tlag_engine)."""
 
-    def __init__(self, cm, deadlock=True, device=0, table_log2=0, max_states=0, keep_going=False):
-        self.L = load_library()
+    def __init__(self, cm, deadlock=True, device=0, table_log2=0, max_states=0, keep_going=False, native=None):
+        """native=True: use (build if needed) the model-specialised library instead of the bytecode interpreter;
+        None: follow the environment variable TLAG_NATIVE (1 = on)."""
+        if native is None:
+            native = os.environ.get("TLAG_NATIVE", "0") == "1"
+        self.native = bool(native)
+        self.L = load_native_library(cm) if self.native else load_library()
         self.cm = cm
         self._code = np.ascontiguousarray(cm.code, dtype=np.uint64)
         self._cpool = np.ascontiguousarray(cm.cpool, dtype=np.int32)

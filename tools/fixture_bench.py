@@ -22,7 +22,7 @@ def main():
     for name in args:
         cm, init, exp, info = load_compiled(os.path.join(ROOT, "tests", "golden", name + ".tlagz"))
         o2 = exp["o2"]
-        e = Engine(cm, deadlock=info["deadlock"])
+        e = Engine(cm, deadlock=info["deadlock"], native="--native" in sys.argv)
         best = None
         for r in range(reps):
             t0 = time.time()
@@ -53,7 +53,9 @@ def main():
                           "distinct": res["distinct"], "generated": res["generated"], "depth": res["depth"],
                           "device_s": round(best[0], 4), "wall_s": round(best[1], 4),
                           "distinct_per_s": round(res["distinct"] / best[0]), "generated_per_s": round(res["generated"] / best[0]),
-                          "counts_match_oracle": ok, "launches": e.launches()}), flush=True)
+                          "counts_match_oracle": ok, "launches": e.launches(),
+                          "native": "--native" in sys.argv,
+                          "digest_matches_oracle": tuple(e.digest()) == (o2["fp_xor"], o2["fp_sum"])}), flush=True)
         e.close()
 
 
