@@ -336,6 +336,26 @@ def main():
                          "distinct_per_s": r3["distinct_per_s"], "counts_match_oracle": r3["counts_match_oracle"]}
         except Exception as ex:  # noqa: BLE001
             other = {"error": str(ex)[:300]}
+    native = None
+    if not multi and not args.no_k1 and args.workload == "MCPaxos3_b4":
+        # Third, clearly labelled leg (not part of `value`): the same workload on the model-specialised native build of
+        # the engine (compile/native.py: the program as straight-line CUDA instead of the bytecode interpreter), if
+        # __graft_entry__.build() left its library in csrc/native/.  Child process with a time limit; counts and the
+        # fingerprint digest are checked against the oracle record, and a failure only shows up here.
+        try:
+            from tla_rust_b200.engine import native_library_path
+            if os.path.exists(native_library_path(cm)):
+                p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fixture_bench.py"), "MCPaxos3_b4", "--native",
+                                    "--reps", "2"], capture_output=True, text=True, timeout=300,
+                                   env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank))))
+                rn = json.loads(p.stdout.strip().splitlines()[-1])
+                native = {"workload": "MCPaxos3_b4 on the model-specialised native build (experimental leg)",
+                          "kernel_s": rn.get("device_s"), "distinct_per_s": rn.get("distinct_per_s"),
+                          "counts_match_oracle": rn.get("counts_match_oracle"),
+                          "digest_matches_oracle": rn.get("digest_matches_oracle"), "error": rn.get("error")}
+        except Exception as ex:  # noqa: BLE001
+            native = {"workload": "MCPaxos3_b4 on the model-specialised native build (experimental leg)",
+                      "error": str(ex)[:300]}
     line = {"metric": "distinct states/sec", "value": round(value, 1), "unit": "states/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -346,7 +366,7 @@ def main():
             "e2e": {"value": round(distinct * args.steps / dt_e2e, 1), "unit": "states/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 96},
             "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
-            "other_workloads": [other] if other else []}
+            "other_workloads": ([other] if other else []) + ([native] if native else [])}
     if multi:
         line["comm_ms_per_step"] = round(stats["comm_ms"] / args.steps, 3)
         dist.destroy_process_group()

@@ -90,6 +90,37 @@ def test_ssi_subroutine_model_on_device(name, counts):
     assert got["digest"] == [o2["fp_xor"], o2["fp_sum"]]
 
 
+@pytest.mark.xfail(strict=False, reason="the model-specialised native build (compile/native.py) was written after the last "
+                                        "GPU session of round 1: bit-exact inside the CPU engine, not yet run on a device")
+@pytest.mark.parametrize("name", ["MCPaxos3", "MCPaxos3_b2", "Containers"])
+def test_native_build_matches_oracle_on_device(name):
+    """Same fixtures, same C ABI, but the library is the engine compiled with the model's program as straight-line
+    CUDA (prebuilt by __graft_entry__.build() into csrc/native/).  Child process with a time limit, as above."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(GOLDEN.rstrip('/')).rsplit('/tests', 1)[0]
+    prog = (
+        "import json, os, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from tla_rust_b200.compiled import load_compiled\n"
+        "from tla_rust_b200.engine import Engine\n"
+        "cm, init, exp, info = load_compiled(%r)\n"
+        "e = Engine(cm, deadlock=info['deadlock'], native=True)\n"
+        "assert b'native' in e.L.tlag_version()\n"
+        "e.seed(init)\n"
+        "r = e.run()\n"
+        "print(json.dumps({'r': [r['verdict'], r['generated'], r['distinct'], r['depth']], 'digest': list(e.digest())}))\n"
+        "e.close()\n") % (root, os.path.join(GOLDEN, name + ".tlagz"))
+    p = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=240)
+    assert p.returncode == 0, p.stderr[-2000:]
+    got = json.loads(p.stdout.strip().splitlines()[-1])
+    _, _, exp, _ = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
+    o2 = exp["o2"]
+    assert got["r"] == [o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]]
+    assert got["digest"] == [o2["fp_xor"], o2["fp_sum"]]
+
+
 def test_assert_trace_is_a_shortest_counterexample():
     """README.md:267-316: the failing assertion is reached after 5 steps from an initial state; the GPU
     trace must be a valid 6-state behaviour ending in a state with pc = C for a process whose alice < 0."""

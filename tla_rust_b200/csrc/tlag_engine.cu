@@ -42,6 +42,18 @@
 #include TLAG_NATIVE_INC
 #endif
 
+// Resident CTAs per SM the wave kernel is compiled for (register cap = 65536 / (512 x this)).  The interpreter is happy
+// with 32 registers; compiled model code keeps frame values in registers, so the native build defaults to 2 CTAs
+// (64 registers) and exposes the choice for sweeps (-DTLAG_NATIVE_OCC=1|2|4).
+#ifdef TLAG_NATIVE_INC
+#ifndef TLAG_NATIVE_OCC
+#define TLAG_NATIVE_OCC 2
+#endif
+#define TLAG_WAVE_OCC(FRAME, SMEM) TLAG_NATIVE_OCC
+#else
+#define TLAG_WAVE_OCC(FRAME, SMEM) ((FRAME) <= 256 ? 4 : ((FRAME) <= 512 ? 2 : ((SMEM) ? 1 : TLAG_BIG_OCC)))
+#endif
+
 #define TLAG_MAXW 128
 #ifndef TLAG_BIG_OCC
 #define TLAG_BIG_OCC 4   /* resident CTAs per SM for the big-frame (> 512 words) wave kernels: latency-bound on local memory */
@@ -204,7 +216,7 @@ __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, cons
 // MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
 // LEAN: interpreter without the extension ops, for models that do not use them (small frames only).
 template <int FRAME, int MODE, bool SMEM, bool LEAN = false>
-__global__ void __launch_bounds__(TLAG_BLOCK, (FRAME <= 256 ? 4 : (FRAME <= 512 ? 2 : (SMEM ? 1 : TLAG_BIG_OCC))))
+__global__ void __launch_bounds__(TLAG_BLOCK, TLAG_WAVE_OCC(FRAME, SMEM))
 k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
   extern __shared__ uint64_t s_code[];
   if (SMEM) {

@@ -94,20 +94,39 @@ NATIVE_DIR = os.path.join(_HERE, "csrc", "native")
 _NATIVE_LIBS = {}
 
 
-def native_library_path(cm):
+def _native_tag(cm):
+    """Program key + a hash of the engine sources the library is compiled from (a stale library is never picked up)."""
+    import hashlib
     from .compile.native import model_key
-    return os.path.join(NATIVE_DIR, f"libtlag_{model_key(cm)}.so")
+    h = hashlib.sha256()
+    for rel in ("csrc/tlag_engine.cu", "csrc/tlag_vm.h", "csrc/tlag_vm_exec.inc", "compile/native.py", "../include/tlag.h"):
+        with open(os.path.join(_HERE, rel), "rb") as f:
+            h.update(f.read())
+    return f"{model_key(cm)}_{h.hexdigest()[:8]}"
+
+
+def _native_occ():
+    """Resident CTAs per SM the native wave kernel is compiled for (TLAG_NATIVE_OCC: 1, 2 or 4; default 2)."""
+    occ = int(os.environ.get("TLAG_NATIVE_OCC", "2"))
+    if occ not in (1, 2, 4):
+        raise EngineError("TLAG_NATIVE_OCC must be 1, 2 or 4")
+    return occ
+
+
+def native_library_path(cm):
+    occ = _native_occ()
+    return os.path.join(NATIVE_DIR, f"libtlag_{_native_tag(cm)}{'' if occ == 2 else f'_occ{occ}'}.so")
 
 
 def build_native_library(cm, force=False, verbose=False):
     """Model-specialised engine library: the model's bytecode compiled to straight-line CUDA (compile/native.py)
     inside the same engine source, one frame class, same C ABI.  Built in-tree (csrc/native/) so that it travels with
     the repo snapshot; nvcc takes about a minute for a 5 K-instruction program.  Returns the library path."""
-    from .compile.native import emit_c, model_key
+    from .compile.native import emit_c
     os.makedirs(NATIVE_DIR, exist_ok=True)
-    key = model_key(cm)
+    key = _native_tag(cm)
     inc = os.path.join(NATIVE_DIR, f"{key}.inc")
-    so = os.path.join(NATIVE_DIR, f"libtlag_{key}.so")
+    so = native_library_path(cm)
     if os.path.exists(so) and not force:
         return so
     frame = next((c for c in FRAME_CLASSES if cm.frame_words <= c), None)
@@ -117,7 +136,7 @@ def build_native_library(cm, force=False, verbose=False):
         f.write(emit_c(cm))
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
-           f'-DTLAG_NATIVE_INC="{inc}"', f"-DTLAG_NATIVE_FRAME={frame}", "-shared", "-o", so + ".tmp",
+           f'-DTLAG_NATIVE_INC="{inc}"', f"-DTLAG_NATIVE_FRAME={frame}", f"-DTLAG_NATIVE_OCC={_native_occ()}", "-shared", "-o", so + ".tmp",
            os.path.join(_HERE, "csrc", "tlag_engine.cu")]
     p = subprocess.run(cmd, capture_output=not verbose, text=True)
     if p.returncode != 0:

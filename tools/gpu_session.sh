@@ -15,6 +15,10 @@ step "pytest -m gpu" timeout 900 python -m pytest tests -m gpu -q -rxX
 # 2. SSI (CALL/RET subroutines, 4096 and 8192 frame classes) and the symmetric subroutine models, with timing
 step "fixture bench: MCssi" timeout 300 python tools/fixture_bench.py MCssi --reps 2
 step "fixture bench: MCssi 3x1, 2x2, 2x2_wide (8192 class)" timeout 600 python tools/fixture_bench.py MCssi_3x1 MCssi_2x2 MCssi_2x2_wide --reps 2
+# 2b. model-specialised native builds (prebuilt by __graft_entry__.build() into csrc/native/): parity + timing next to
+#     the interpreter on the same fixtures
+step "fixture bench: native MCPaxos3_b2 / Containers / MCPaxos3_b4" timeout 900 python tools/fixture_bench.py MCPaxos3_b2 Containers MCPaxos3_b4 --native --reps 2
+step "fixture bench: interpreter MCPaxos3_b2 / Containers / MCPaxos3_b4" timeout 900 python tools/fixture_bench.py MCPaxos3_b2 Containers MCPaxos3_b4 --reps 2
 # 3. contract bench at N=1, then the raft workload on its own
 step "bench N=1" timeout 900 python bench.py --steps 3 --warmup 3
 step "fixture bench: raft" timeout 600 python tools/fixture_bench.py MCraft_s3_m MCraft_s3_l --reps 2
