@@ -112,7 +112,7 @@ def test_native_build_matches_oracle_on_device(name):
         "r = e.run()\n"
         "print(json.dumps({'r': [r['verdict'], r['generated'], r['distinct'], r['depth']], 'digest': list(e.digest())}))\n"
         "e.close()\n") % (root, os.path.join(GOLDEN, name + ".tlagz"))
-    p = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=240)
+    p = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=150)
     assert p.returncode == 0, p.stderr[-2000:]
     got = json.loads(p.stdout.strip().splitlines()[-1])
     _, _, exp, _ = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
