@@ -38,7 +38,16 @@
 #error "TLAG_NATIVE_FRAME (frame class of the model: 64 ... 8192) must be defined with TLAG_NATIVE_INC"
 #endif
 #define TLAG_NATIVE_X tlag_vm_exec
+// Small frames: inlined into k_wave, so that the compiler sees the frame as a local array with constant indices and
+// keeps hot words in registers.  Big frames (> 512 words): a separate function that receives the frame as a pointer --
+// scalar replacement of a 2048-word array over a 6 K-block goto graph takes cicc many minutes (raft) and buys nothing.
+#ifndef TLAG_NATIVE_QUAL
+#if TLAG_NATIVE_FRAME > 512
+#define TLAG_NATIVE_QUAL static __device__ __noinline__
+#else
 #define TLAG_NATIVE_QUAL static __device__ __forceinline__
+#endif
+#endif
 #include TLAG_NATIVE_INC
 #endif
 
