@@ -102,7 +102,7 @@ def k1_microbench(dev, peak):
     states = torch.cat([half, half[perm]])
     del half, perm
     flags = torch.zeros(n, dtype=torch.uint8, device=dev)
-    e = Engine(ProbeOnlyModel(W), table_log2=28, device=torch.device(dev).index or 0)
+    e = Engine(ProbeOnlyModel(W), table_log2=28, device=torch.device(dev).index or 0, native=False)
     times = []
     for it in range(2 + 5):
         e.reset_table()
@@ -152,7 +152,9 @@ def main():
                        f"{exp['o2']['distinct']} distinct / {exp['o2']['generated']} generated states, "
                        f"{len(cm.invariants)} invariants", "l2": "state store + seen-set rebuilt every step (restart), "
                                                                  "working set streamed; see DESIGN.md",
-           "parallelism": f"fp-hash-range x{args.gpus}"}
+           "parallelism": f"fp-hash-range x{args.gpus}",
+           # TLAG_NATIVE=1 runs the headline on the model-specialised native build
+           "engine_build": "native" if os.environ.get("TLAG_NATIVE", "0") == "1" else "interpreter"}
     threads = os.cpu_count() or 1
 
     if args.impl == "reference":

@@ -21,6 +21,7 @@ step "fixture bench: native MCPaxos3_b2 / Containers / MCPaxos3_b4" timeout 900 
 step "fixture bench: interpreter MCPaxos3_b2 / Containers / MCPaxos3_b4" timeout 900 python tools/fixture_bench.py MCPaxos3_b2 Containers MCPaxos3_b4 --reps 2
 # 3. contract bench at N=1, then the raft workload on its own
 step "bench N=1" timeout 900 python bench.py --steps 3 --warmup 3
+step "bench N=1 on the native build" env TLAG_NATIVE=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-k1
 step "fixture bench: raft" timeout 600 python tools/fixture_bench.py MCraft_s3_m MCraft_s3_l --reps 2
 # 4. launch list of a short bench (share of the step per kernel) and one full capture of the wave kernel
 step "ncu launch list" timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \

@@ -10,7 +10,7 @@ for logn, tl in ((20, 22), (24, 26), (26, 28), (27, 28)):
     perm = torch.randint(0, n // 2, (n // 2,), device='cuda', generator=g)
     states = torch.cat([half, half[perm]]); del half, perm
     flags = torch.zeros(n, dtype=torch.uint8, device='cuda')
-    e = Engine(ProbeOnlyModel(W), table_log2=tl)
+    e = Engine(ProbeOnlyModel(W), table_log2=tl, native=False)
     for it in range(3):
         e.reset_table()
         t = time.time()
