@@ -36,6 +36,12 @@
 #define TLAG_NATIVE_X tlag_vm_exec_inl
 #define TLAG_NATIVE_QUAL static
 #include TLAG_NATIVE_INC
+#ifdef TLAG_NATIVE_SCHED_WARP
+/* block form: a single lane simply runs block after block */
+static int tlag_native_run(const int32_t *cpool, int32_t *f, uint32_t *pc_io, int32_t *info, int32_t *info2) {
+  for (;;) { const int ev = tlag_native_block(cpool, f, pc_io, info, info2); if (ev >= 0) return ev; }
+}
+#endif
 #define tlag_vm_run(code, cpool, f, pc, info, info2, steps) tlag_native_run(cpool, f, pc, info, info2)
 #endif
 

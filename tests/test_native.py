@@ -14,12 +14,15 @@ from tla_rust_b200.compiled import load_compiled
 from tla_rust_b200.compile.native import emit_c, model_key
 
 
-def _cpu_native_lib(tmp_path, cm, generic=False):
+def _cpu_native_lib(tmp_path, cm, generic=False, sched="warp"):
+    """sched="warp": the block form the CUDA build uses by default (one lane runs block after block here);
+    "lane": the run-to-next-event form."""
     inc = tmp_path / f"{model_key(cm)}{'_g' if generic else ''}.inc"
     inc.write_text(emit_c(cm, generic=generic))
-    so = tmp_path / (inc.stem + ".so")
-    subprocess.check_call(["gcc", "-O1", "-std=gnu11", "-fPIC", "-shared", "-pthread", "-Wno-unused-label",
-                           f'-DTLAG_NATIVE_INC="{inc}"', "-o", str(so), os.path.join(ROOT, "oracle", "tlag_cpu.c")])
+    so = tmp_path / (inc.stem + "_" + sched + ".so")
+    subprocess.check_call(["gcc", "-O1", "-std=gnu11", "-fPIC", "-shared", "-pthread", "-Wno-unused-label"]
+                          + (["-DTLAG_NATIVE_SCHED_WARP"] if sched == "warp" else [])
+                          + [f'-DTLAG_NATIVE_INC="{inc}"', "-o", str(so), os.path.join(ROOT, "oracle", "tlag_cpu.c")])
     L = C.CDLL(str(so))
     L.tlagcpu_run.restype = C.c_int
     L.tlagcpu_probe_batch.restype = C.c_double
@@ -42,9 +45,10 @@ def _run_with(L, cm, init, info):
                                   "MCInnerFIFO", "MCAlternatingBit", "MCPaxos3", "Containers", "HourClock"])
 def test_native_code_reproduces_the_fixture_on_the_cpu_engine(tmp_path, name):
     cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
-    r = _run_with(_cpu_native_lib(tmp_path, cm), cm, init, info)
-    for k in ("verdict", "generated", "distinct", "depth", "fp_xor", "fp_sum", "levels"):
-        assert r[k] == exp["o2"][k], (name, k)
+    for sched in ("warp", "lane"):
+        r = _run_with(_cpu_native_lib(tmp_path, cm, sched=sched), cm, init, info)
+        for k in ("verdict", "generated", "distinct", "depth", "fp_xor", "fp_sum", "levels"):
+            assert r[k] == exp["o2"][k], (name, sched, k)
 
 
 def test_direct_templates_agree_with_the_inlined_executor_form(tmp_path):
@@ -59,11 +63,11 @@ def test_direct_templates_agree_with_the_inlined_executor_form(tmp_path):
 
 def test_subroutines_sparse_containers_and_symmetry_ops_in_native_code(tmp_path):
     """CALL/RET (return through the resume switch), SFIND/SINS, LEXLT: raft and SSI at their smallest bounds."""
-    for name in ("MCraft", "MCssi"):
+    for name, sched in (("MCraft", "warp"), ("MCssi", "warp"), ("MCPaxos3_sym", "warp"), ("MCraft", "lane")):
         cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
-        r = _run_with(_cpu_native_lib(tmp_path, cm), cm, init, info)
+        r = _run_with(_cpu_native_lib(tmp_path, cm, sched=sched), cm, init, info)
         for k in ("verdict", "generated", "distinct", "depth", "fp_xor", "fp_sum"):
-            assert r[k] == exp["o2"][k], (name, k)
+            assert r[k] == exp["o2"][k], (name, sched, k)
 
 
 def test_native_engine_library_cross_compiles_and_keeps_the_c_abi():

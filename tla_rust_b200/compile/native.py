@@ -13,9 +13,15 @@ opcode switch away and what is left is the operation itself on constant frame of
 end to end by running the generated code inside the CPU bytecode engine against the recorded digests of every
 fixture (tests/test_native.py).
 
-The generated function is
-    int tlag_native_run(const int32_t* cpool, int32_t* f, uint32_t* pc_io, int32_t* info, int32_t* info2)
-with the contract of tlag_vm_run (tlag_vm.h): run from *pc_io to the next event, leave the pc to resume at in *pc_io.
+The generated file holds the program once, in two selectable forms (same statements, different control macros):
+  * block form (-DTLAG_NATIVE_SCHED_WARP, the default of the CUDA build): `tlag_native_block` runs the lanes sitting at
+    one block leader up to the next merge point (jump target / resumable pc), taken branch or event; the engine elects
+    the warp's minimum pc every round, so lanes that took different paths re-join exactly as under the interpreter
+    (per-lane native code would only reconverge at the next event: lanes resuming after different EMITs would run
+    one after the other) while fetch / decode / operand dispatch are gone and the election is paid per block
+    (~6 instructions) instead of per instruction;
+  * lane form: `int tlag_native_run(cpool, f, pc_io, info, info2)` with the contract of tlag_vm_run (tlag_vm.h): one
+    lane runs from *pc_io to its next event.
 `csrc/tlag_engine.cu` compiled with -DTLAG_NATIVE_INC=<file> calls it per lane instead of the warp interpreter
 (`tla_rust_b200/engine.py: build_native_library`)."""
 from __future__ import annotations
@@ -170,6 +176,7 @@ def emit_c(cm, generic: bool = False) -> str:
     code = [int(x) for x in np.ascontiguousarray(cm.code, dtype=np.uint64)]
     n = len(code)
     resume = set(int(v) for v in cm.entries.values())
+    targets = set()
     lines = []
     n_generic = 0
     for k, w in enumerate(code):
@@ -181,28 +188,29 @@ def emit_c(cm, generic: bool = False) -> str:
             t = immJ if op in _COND_J else immI
             if not 0 <= t < n:
                 raise ValueError(f"branch target {t} outside the program at pc {k}")
+            targets.add(t)
         if not generic:
             st = None
             if op in ("JEQ", "JNE", "JLT", "JGE"):
-                st = f"if (f[{a}] {_CMP[op]} f[{b}]) goto L_{immJ};"
+                st = f"if (f[{a}] {_CMP[op]} f[{b}]) TLAG_GOTO({immJ});"
             elif op in ("JEQI", "JNEI", "JLTI", "JGEI"):
                 k14 = b - (1 << 14) if b & (1 << 13) else b
-                st = f"if (f[{a}] {_CMP[op]} ({k14})) goto L_{immJ};"
+                st = f"if (f[{a}] {_CMP[op]} ({k14})) TLAG_GOTO({immJ});"
             elif op in _COND_I:
-                st = f"if (f[{a}] {_CMP[op]} 0) goto L_{immI};"
+                st = f"if (f[{a}] {_CMP[op]} 0) TLAG_GOTO({immI});"
             elif op in ("JBT", "JBF"):
                 st = (f"{{ const uint32_t i = (uint32_t)f[{b}]; if (((((uint32_t)f[{a} + (i >> 5)] >> (i & 31)) & 1u) != 0) == "
-                      f"{1 if op == 'JBT' else 0}) goto L_{immJ}; }}")
+                      f"{1 if op == 'JBT' else 0}) TLAG_GOTO({immJ}); }}")
             elif op in ("JBTI", "JBFI"):
                 st = (f"if (((((uint32_t)f[{a + (b >> 5)}] >> {b & 31}) & 1u) != 0) == {1 if op == 'JBTI' else 0}) "
-                      f"goto L_{immJ};")
+                      f"TLAG_GOTO({immJ});")
             elif op == "JMP":
-                st = f"goto L_{immI};"
+                st = f"TLAG_GOTO({immI});"
             elif op == "CALL":
                 resume.add(k + 1)
-                st = f"f[{a}] = {k + 1}; goto L_{immI};"
+                st = f"f[{a}] = {k + 1}; TLAG_GOTO({immI});"
             elif op == "RET":
-                st = f"gpc = (uint32_t)f[{a}]; goto dispatch;"
+                st = f"TLAG_GOTO_DYN((uint32_t)f[{a}]);"
             elif op == "HALT":
                 resume.add(k)
                 st = f"*pc_io = {k}u; return TLAG_EV_HALT;"
@@ -226,19 +234,19 @@ def emit_c(cm, generic: bool = False) -> str:
                 if st is not None and op in ("DIV", "MOD", "TBLT"):
                     resume.add(k + 1)
             if st is not None:
-                lines.append(f"L_{k}: {{ {st} }}")
+                lines.append((k, f"{{ {st} }}"))
                 continue
         n_generic += 1
-        call = f"L_{k}: {{ uint32_t pc = {k}u; const int ev = TLAG_NATIVE_X(0x{w:016x}ULL, cpool, f, &pc, info, info2);"
+        call = f"{{ uint32_t pc = {k}u; const int ev = TLAG_NATIVE_X(0x{w:016x}ULL, cpool, f, &pc, info, info2);"
         if op in _COND_J or op in _COND_I:
             t = immJ if op in _COND_J else immI
-            post = f" (void)ev; if (pc != {k + 1}u) goto L_{t}; }}"
+            post = f" (void)ev; if (pc != {k + 1}u) TLAG_GOTO({t}); }}"
         elif op in ("JMP", "CALL"):
             if op == "CALL":
                 resume.add(k + 1)
-            post = f" (void)ev; (void)pc; goto L_{immI}; }}"
+            post = f" (void)ev; (void)pc; TLAG_GOTO({immI}); }}"
         elif op == "RET":
-            post = " (void)ev; gpc = pc; goto dispatch; }"
+            post = " (void)ev; TLAG_GOTO_DYN(pc); }"
         elif op in _EVENTS or op is None:
             # the executor leaves the pc to resume at in `pc` (K for HALT, K + 1 otherwise)
             resume.add(k)
@@ -246,30 +254,60 @@ def emit_c(cm, generic: bool = False) -> str:
             post = " if (ev >= 0) { *pc_io = pc; return ev; } }"
         else:
             post = " (void)ev; (void)pc; }"
-        lines.append(call + post)
+        lines.append((k, call + post))
     resume = sorted(r for r in resume if 0 <= r < n)
+    leaders = set(resume) | targets
+    body = []
+    for k, text in lines:
+        if k in leaders:
+            body.append(f"  {'TLAG_FALL(%d) ' % k if k else ''}TLAG_LABEL({k}) {text}")
+        else:
+            body.append(f"  {text}")
     fnv = 0xcbf29ce484222325
     for w in code:
         fnv = ((fnv ^ w) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    sig = ("(const int32_t* __restrict__ cpool, int32_t* __restrict__ f, uint32_t* pc_io,\n"
+           "                                     int32_t* info, int32_t* info2) {")
     out = [
         "// generated by tla_rust_b200/compile/native.py -- do not edit",
         f"// model key {model_key(cm)}: {n} instructions ({n_generic} through the inlined executor), "
-        f"{len(resume)} resumable pcs",
+        f"{len(resume)} resumable pcs, {len(leaders)} block leaders",
         "#ifndef TLAG_NATIVE_X",
         "#error \"define TLAG_NATIVE_X (the force-inlined single-instruction executor) before including\"",
         "#endif",
         f"#define TLAG_NATIVE_CODE_LEN {n}u",
         f"#define TLAG_NATIVE_CODE_FNV 0x{fnv:016x}ULL   /* FNV-1a over the 64-bit program words */",
-        "TLAG_NATIVE_QUAL int tlag_native_run(const int32_t* __restrict__ cpool, int32_t* __restrict__ f, uint32_t* pc_io,",
-        "                                     int32_t* info, int32_t* info2) {",
-        "  uint32_t gpc = *pc_io;",
-        "dispatch:",
-        "  switch (gpc) {",
+        "#ifdef TLAG_NATIVE_SCHED_WARP",
+        "// Block form: runs the lanes that sit at *pc_io from that block leader up to the next merge point (a jump target or",
+        "// a resumable pc), a taken branch, or an event; returns -1 with the successor pc in *pc_io, or the event.  The",
+        "// caller elects the minimum pc of the warp each round, so lanes re-join exactly as under the interpreter.",
+        "#define TLAG_LABEL(K) case K:",
+        "#define TLAG_GOTO(T) do { *pc_io = T; return -1; } while (0)",
+        "#define TLAG_GOTO_DYN(X) do { *pc_io = (X); return -1; } while (0)",
+        "#define TLAG_FALL(K) *pc_io = K; return -1;",
+        "TLAG_NATIVE_QUAL int tlag_native_block" + sig,
+        "  switch (*pc_io) {",
     ]
+    out += body
+    out += ["    default: *info = 98; *info2 = (int32_t)*pc_io; return TLAG_EV_TRAP;",
+            "  }",
+            f"  *info = 97; *info2 = {n}; *pc_io = {n}u; return TLAG_EV_TRAP;", "}",
+            "#else",
+            "// Lane form: one lane runs from *pc_io to its next event (contract of tlag_vm_run).",
+            "#define TLAG_LABEL(K) L_##K:",
+            "#define TLAG_GOTO(T) goto L_##T",
+            "#define TLAG_GOTO_DYN(X) do { gpc = (X); goto dispatch; } while (0)",
+            "#define TLAG_FALL(K)",
+            "TLAG_NATIVE_QUAL int tlag_native_run" + sig,
+            "  uint32_t gpc = *pc_io;",
+            "dispatch:",
+            "  switch (gpc) {"]
     out += [f"    case {r}u: goto L_{r};" for r in resume]
     out += ["    default: *info = 98; *info2 = (int32_t)gpc; *pc_io = gpc; return TLAG_EV_TRAP;",
             "  }"]
-    out += ["  " + ln for ln in lines]
+    out += body
     # falling off the end of the program is a compiler bug, not a model error
-    out += [f"  *info = 97; *info2 = {n}; *pc_io = {n}u; return TLAG_EV_TRAP;", "}", ""]
+    out += [f"  *info = 97; *info2 = {n}; *pc_io = {n}u; return TLAG_EV_TRAP;", "}",
+            "#endif",
+            "#undef TLAG_LABEL", "#undef TLAG_GOTO", "#undef TLAG_GOTO_DYN", "#undef TLAG_FALL", ""]
     return "\n".join(out)

@@ -38,6 +38,9 @@
 #error "TLAG_NATIVE_FRAME (frame class of the model: 64 ... 8192) must be defined with TLAG_NATIVE_INC"
 #endif
 #define TLAG_NATIVE_X tlag_vm_exec
+#ifndef TLAG_NATIVE_SCHED_LANE
+#define TLAG_NATIVE_SCHED_WARP 1   /* block form + min-pc election (default); -DTLAG_NATIVE_SCHED_LANE: per-lane runs */
+#endif
 // Small frames: inlined into k_wave, so that the compiler sees the frame as a local array with constant indices and
 // keeps hot words in registers.  Big frames (> 512 words): a separate function that receives the frame as a pointer --
 // scalar replacement of a 2048-word array over a 6 K-block goto graph takes cicc many minutes (raft) and buys nothing.
@@ -189,12 +192,23 @@ enum { L_RUN = 0, L_EMIT = 1, L_DONE = 2, L_STOP = 3 };
 // SASS instructions per step on bookkeeping and fetched the instruction with a generic per-lane load:
 // profiles/r1_k_wave_warpsched_b2_ncu.txt.)
 #ifdef TLAG_NATIVE_INC
-// Native build: every lane runs the compiled program from its pc to its next event; the hardware reconverges the
-// warp (no min-pc election, no instruction fetch / decode).  Same contract as the interpreter below.
+// Native build: the compiled program instead of fetch / decode / dispatch.  Same contract as the interpreter below.
 template <bool SMEM, bool LEAN>
 __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__, const uint64_t*,
                                         const int32_t* __restrict__ cpool, int32_t* frame, uint32_t& pc,
                                         uint32_t& rpc, int& ev_out, int32_t& info, int32_t& info2) {
+#ifdef TLAG_NATIVE_SCHED_WARP
+  // Same election as the interpreter, per basic block instead of per instruction: the lanes at the warp's minimum pc
+  // run their block (a warp-uniform switch target), everyone else waits; lanes re-join whenever their pcs meet.
+  for (;;) {
+    const uint32_t pcm = __reduce_min_sync(0xffffffffu, pc);
+    if (pcm == TLAG_PC_PARKED) break;
+    if (pc == pcm) {
+      const int ev = tlag_native_block(cpool, frame, &pc, &info, &info2);
+      if (ev >= 0) { ev_out = ev; rpc = pc; pc = TLAG_PC_PARKED; }
+    }
+  }
+#else
   if (pc != TLAG_PC_PARKED) {
     uint32_t p = pc;
     ev_out = tlag_native_run(cpool, frame, &p, &info, &info2);
@@ -202,6 +216,7 @@ __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__, const uint
     pc = TLAG_PC_PARKED;
   }
   __syncwarp();
+#endif
 }
 #else
 template <bool SMEM, bool LEAN>

@@ -113,9 +113,18 @@ def _native_occ():
     return occ
 
 
+def _native_sched():
+    """warp (default): block form with min-pc election; lane: every lane runs to its next event (TLAG_NATIVE_SCHED)."""
+    sched = os.environ.get("TLAG_NATIVE_SCHED", "warp")
+    if sched not in ("warp", "lane"):
+        raise EngineError("TLAG_NATIVE_SCHED must be warp or lane")
+    return sched
+
+
 def native_library_path(cm):
-    occ = _native_occ()
-    return os.path.join(NATIVE_DIR, f"libtlag_{_native_tag(cm)}{'' if occ == 2 else f'_occ{occ}'}.so")
+    occ, sched = _native_occ(), _native_sched()
+    return os.path.join(NATIVE_DIR, f"libtlag_{_native_tag(cm)}{'' if occ == 2 else f'_occ{occ}'}"
+                                    f"{'' if sched == 'warp' else '_lane'}.so")
 
 
 def build_native_library(cm, force=False, verbose=False):
@@ -136,7 +145,8 @@ def build_native_library(cm, force=False, verbose=False):
         f.write(emit_c(cm))
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
-           f'-DTLAG_NATIVE_INC="{inc}"', f"-DTLAG_NATIVE_FRAME={frame}", f"-DTLAG_NATIVE_OCC={_native_occ()}", "-shared", "-o", so + ".tmp",
+           f'-DTLAG_NATIVE_INC="{inc}"', f"-DTLAG_NATIVE_FRAME={frame}", f"-DTLAG_NATIVE_OCC={_native_occ()}",
+           *(["-DTLAG_NATIVE_SCHED_LANE"] if _native_sched() == "lane" else []), "-shared", "-o", so + ".tmp",
            os.path.join(_HERE, "csrc", "tlag_engine.cu")]
     p = subprocess.run(cmd, capture_output=not verbose, text=True)
     if p.returncode != 0:
