@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call that settles everything round 1 left unverified on a device:
 #
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_session.sh'
 #
 # Every step runs under its own `timeout`, writes into gpurun_out/, and a failing step does not stop the next.
 # Nothing printed under ncu is a bench value.
@@ -19,6 +19,9 @@ step "fixture bench: MCssi 3x1, 2x2, 2x2_wide (8192 class)" timeout 600 python t
 #     the interpreter on the same fixtures
 step "fixture bench: native MCPaxos3_b2 / Containers / MCPaxos3_b4" timeout 900 python tools/fixture_bench.py MCPaxos3_b2 Containers MCPaxos3_b4 --native --reps 2
 step "fixture bench: interpreter MCPaxos3_b2 / Containers / MCPaxos3_b4" timeout 900 python tools/fixture_bench.py MCPaxos3_b2 Containers MCPaxos3_b4 --reps 2
+step "fixture bench: native raft (prebuilt library; nvcc needs 5 min otherwise)" timeout 900 python tools/fixture_bench.py MCraft_s3_l --native --reps 2
+step "fixture bench: native b4, lane form (built here: ~1 min of nvcc)" env TLAG_NATIVE_SCHED=lane timeout 900 python tools/fixture_bench.py MCPaxos3_b4 --native --reps 2
+step "fixture bench: native b4, 1 and 4 CTAs/SM" bash -c 'for o in 1 4; do TLAG_NATIVE_OCC=$o timeout 600 python tools/fixture_bench.py MCPaxos3_b4 --native --reps 2; done'
 # 3. contract bench at N=1, then the raft workload on its own
 step "bench N=1" timeout 900 python bench.py --steps 3 --warmup 3
 step "bench N=1 on the native build" env TLAG_NATIVE=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-k1
