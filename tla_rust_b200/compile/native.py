@@ -4,14 +4,13 @@ Why: the wave kernel is instruction-issue bound in its interpreter loop (fetch, 
 the warp's min-pc election cost ~70 SASS instructions per bytecode instruction: profiles/r1_k_wave_final_b3_ncu.txt,
 DESIGN.md section 4).  The program of a model is fixed for a whole run, so it can be compiled instead of interpreted.
 
-How: the ISA keeps its single definition (`csrc/tlag_vm_exec.inc`).  For every instruction word `w` at pc `K` the
-generator emits one call of the force-inlined executor with `w` as a literal; the C compiler folds the decode and the
-opcode switch away and what is left is the operation itself on constant frame offsets.  Control flow becomes direct
-`goto`s (branch targets are literals too); only RET (return address in a frame word) and the re-entry after an event
-(EMIT / GEN / ASSERTF / INVF / TRAP hand control to the engine, which resumes at the following pc) go through a
-`switch` over the pcs that can be resumed at.  Semantics are therefore identical by construction, and are checked
-end to end by running the generated code inside the CPU bytecode engine against the recorded digests of every
-fixture (tests/test_native.py).
+How: every instruction at pc `K` becomes one C statement with its operand fields as literals
+(`f[113] = f[97] & f[105];`, `if (f[12] == f[40]) TLAG_GOTO(731);`) -- `_direct` below restates the arithmetic of
+`csrc/tlag_vm_exec.inc` op by op; branch targets are literals too.  `emit_c(generic=True)` writes the same program as
+calls of the force-inlined single ISA definition (`tlag_vm_exec`) with the instruction word as a literal, which the C
+compiler folds down to the same operation: slow to compile, identical by construction, and the cross-check of the
+templates.  Either way the result is checked end to end by running the generated code inside the CPU bytecode engine
+against the recorded digests of the fixtures (tests/test_native.py).
 
 The generated file holds the program once, in two selectable forms (same statements, different control macros):
   * block form (-DTLAG_NATIVE_SCHED_WARP, the default of the CUDA build): `tlag_native_block` runs the lanes sitting at
