@@ -27,7 +27,9 @@ class CpuResult(C.Structure):
     _fields_ = [("verdict", C.c_int32), ("detail", C.c_int32), ("detail2", C.c_int32), ("pad", C.c_int32),
                 ("state_idx", C.c_uint64), ("generated", C.c_uint64), ("distinct", C.c_uint64),
                 ("depth", C.c_uint64), ("init_states", C.c_uint64), ("fp_xor", C.c_uint64), ("fp_sum", C.c_uint64),
-                ("seconds", C.c_double), ("n_levels", C.c_uint64), ("level_sizes", C.c_uint64 * 4096)]
+                ("seconds", C.c_double), ("n_levels", C.c_uint64), ("level_sizes", C.c_uint64 * 4096),
+                ("level_xor", C.c_uint64 * 4096), ("level_sum", C.c_uint64 * 4096),
+                ("level_generated", C.c_uint64 * 4096)]
 
 
 def build():
@@ -42,16 +44,19 @@ def lib():
             build()
         _LIB = C.CDLL(p)
         _LIB.tlagcpu_run.restype = C.c_int
+        _LIB.tlagcpu_run2.restype = C.c_int
         _LIB.tlagcpu_probe_batch.restype = C.c_double
         _LIB.tlagcpu_fingerprint.restype = C.c_uint64
     return _LIB
 
 
 def run(cm, init_words: np.ndarray, n_threads=1, deadlock=True, max_states=1 << 22, stop_after=0,
-        want_states=False, exact=False):
+        want_states=False, exact=False, max_levels=0):
     """BFS of a CompiledModel on host cores.  Returns dict(verdict, generated, distinct, depth, ...).
     exact=True: one worker in FIFO order that stops at the first Assert failure / deadlock, i.e. the counts TLC's
-    single worker prints at the moment of the error (`queue` = states discovered but not yet dequeued)."""
+    single worker prints at the moment of the error (`queue` = states discovered but not yet dequeued).
+    max_levels=L: depth-bounded prefix -- levels 1..L-1 are expanded, the result holds every state of levels 1..L.
+    `level_digests[k]` = (xor, sum, generated) cumulative after level k+1 exists: one run pins every shorter prefix."""
     L = lib()
     code = np.ascontiguousarray(cm.code, dtype=np.uint64)
     cpool = np.ascontiguousarray(cm.cpool, dtype=np.int32)
@@ -67,14 +72,16 @@ def run(cm, init_words: np.ndarray, n_threads=1, deadlock=True, max_states=1 << 
     if want_states:
         states = np.zeros((max_states, cm.W), dtype=np.uint32)
         sp, cap = states.ctypes.data_as(C.c_void_p), max_states
-    rc = L.tlagcpu_run(C.byref(m), init.ctypes.data_as(C.c_void_p), C.c_uint64(init.shape[0]), C.c_int(n_threads),
-                       C.c_uint64(stop_after), C.byref(res), sp, C.c_uint64(cap))
+    rc = L.tlagcpu_run2(C.byref(m), init.ctypes.data_as(C.c_void_p), C.c_uint64(init.shape[0]), C.c_int(n_threads),
+                        C.c_uint64(stop_after), C.c_uint64(max_levels), C.byref(res), sp, C.c_uint64(cap))
     if rc != 0:
         raise RuntimeError(f"tlagcpu_run failed: {rc}")
     out = dict(verdict=res.verdict, detail=res.detail, detail2=res.detail2, state_idx=res.state_idx,
                generated=res.generated, distinct=res.distinct, depth=res.depth, init_states=res.init_states,
                fp_xor=res.fp_xor, fp_sum=res.fp_sum, seconds=res.seconds,
-               levels=[int(res.level_sizes[i]) for i in range(res.n_levels)])
+               levels=[int(res.level_sizes[i]) for i in range(res.n_levels)],
+               level_digests=[(int(res.level_xor[i]), int(res.level_sum[i]), int(res.level_generated[i]))
+                              for i in range(res.n_levels)])
     if exact and out["verdict"] in (2, 3):
         out["queue"] = out["distinct"] - out["state_idx"] - 1
     if want_states:

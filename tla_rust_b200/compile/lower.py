@@ -163,6 +163,9 @@ class Lowering:
         self.program = "inv"
         self.hoist_keys = []
         self.dry = False
+        self._seg_top, self._seg_buf, self._seg_clean, self._seg_last = False, None, -1, -1
+        self.seg_cuts = {"inv": [], "next": []}
+        self.blocks = set()
         self.group = model.symmetry_group() if hasattr(model, "symmetry_group") else []
         self._rec_depth = {}
         self.use_subs = False          # compile module-level operators as CALL/RET subroutines instead of inlining
@@ -238,6 +241,8 @@ class Lowering:
     def alloc(self, n):
         loc = self.top
         self.top += max(n, 0)
+        if n > 1:
+            self.blocks.add((loc, n))       # extents for the scalar form of the sliced build (compile/sliced.py)
         if self.top > self.high:
             self.high = self.top
         if self.high > MAXREG and not self.dry:
@@ -3874,8 +3879,15 @@ class Lowering:
         Control falls through after all alternatives are exhausted."""
         self.bound = bound
         kind = n.k
+        # Segment cuts (compile/native.py, sliced build): `top` is true while nothing but disjunction structure lies
+        # between the root of Next and this node, i.e. the code of each alternative below is a self-contained slice of
+        # the program (entered by falling in, left by falling out) that can become a kernel of its own.
+        top = self._seg_top
+        self._seg_top = False
         if kind == "and":
             items = n.a[0]
+            # the first conjunct may still be sliced: the conjuncts after it are lowered inside its continuations
+            self._seg_top = top
             if len(items) > 1 and act is not None and act[0] == "split":
                 act = ("fixed",) + act[1:]
 
@@ -3893,8 +3905,12 @@ class Lowering:
             for x in n.a[0]:
                 self.bound = bound
                 m = self.mark()
+                if top:
+                    top = self._seg_begin()
                 self.ca(x, env, ctx, bound, k, act)
                 self.release(m)
+                if top:
+                    self._seg_end()
             return
         if kind == "exists":
             bounds, body = n.a
@@ -3914,16 +3930,23 @@ class Lowering:
                     self.loop_set(sv2, each1)
                     return
 
+            topbox = [top]
+
             def each(env2):
                 m = self.mark()
                 self.bound = bound
+                if topbox[0]:
+                    topbox[0] = self._seg_begin()
                 self.ca(body, env2, ctx, bound, k, act)
                 self.release(m)
+                if topbox[0]:
+                    self._seg_end()
             self.for_each(bounds, env, ctx, "N", each)
             return
         if kind == "if":
             c1 = self.try_const(n.a[0], env, ctx, "N")
             if c1 is not None:
+                self._seg_top = top
                 self.ca(n.a[1] if c1.v else n.a[2], env, ctx, bound, k, act)
                 return
             lt, lf, end = Label("at"), Label("af"), Label("ae")
@@ -3945,7 +3968,9 @@ class Lowering:
             self.ca(node, env, ctx, bound, k, act)
             return
         if kind == "let":
-            self.ca(n.a[1], self.let_env(n.a[0], env, ctx, "N", n.a[1]), ctx, bound, k, act)
+            env_l = self.let_env(n.a[0], env, ctx, "N", n.a[1])
+            self._seg_top = top
+            self.ca(n.a[1], env_l, ctx, bound, k, act)
             return
         if kind in ("id", "app", "sel"):
             is_assert = kind == "app" and n.a[0] == "Assert"
@@ -3957,6 +3982,7 @@ class Lowering:
                     r = self.resolve(n.a[0], env, ctx)
                     if r[0] == "def":
                         act2 = ("split", r[1].name, r[1].body.loc(), r[2].name)
+                self._seg_top = top
                 self.ca(node2, env2, ctx2, bound, k, act2)
                 return
         if kind == "bin" and n.a[0] in ("=", "\\in"):
@@ -4021,6 +4047,25 @@ class Lowering:
         self.asm.label(lt)
         k(bound, act)
         self.asm.label(lf)
+
+    def _seg_begin(self) -> bool:
+        """Start a slice of the Next program here if nothing has been emitted since the last slice boundary (code
+        emitted at this level would be shared by the alternatives that follow and has to stay in one slice)."""
+        code = self.asm.code
+        if code is not self._seg_buf or len(code) != self._seg_clean:
+            self._seg_top = False
+            return False
+        if self._seg_last != len(code):
+            L = Label("seg")
+            self.asm.label(L)
+            self.seg_cuts["next"].append(L)
+            self._seg_clean = self._seg_last = len(self.asm.code)
+        self._seg_top = True
+        return True
+
+    def _seg_end(self):
+        if self.asm.code is self._seg_buf:
+            self._seg_clean = len(self.asm.code)
 
     def _assign_target(self, ln, env, ctx, bound):
         if ln.k == "id" and ln.a[0] in env and type(env[ln.a[0]]) is Lazy:
@@ -4229,6 +4274,10 @@ class Lowering:
         self.usz = usz
         for v in m.vars:
             self.p_off[v] = usz + self.n_off[v]
+        self.blocks = set()
+        for v in m.vars:
+            self.blocks.add((self.n_off[v], self.var_types[v].size))
+            self.blocks.add((self.p_off[v], self.var_types[v].size))
         self.top = self.high = 2 * usz
         # SYMMETRY: the canonicalisation code is one subroutine (CALL at every EMIT site) with a static scratch region
         # right after the two state copies; its size is measured by a trial lowering
@@ -4248,7 +4297,12 @@ class Lowering:
         entries["inv"] = linv
         self.program = "inv"
         self._hoist_prologue("inv")
+        self.seg_cuts = {"inv": [], "next": []}
+        self._seg_top, self._seg_buf, self._seg_clean, self._seg_last = False, None, -1, -1
         for i, (nm, node, c) in enumerate(m.invariants):
+            cut = Label("segi")
+            self.asm.label(cut)
+            self.seg_cuts["inv"].append(cut)
             ok, bad = Label("iok"), Label("ibad")
             mk = self.mark()
             self.bound = frozenset()
@@ -4344,7 +4398,15 @@ class Lowering:
                 emit_succ(b, aid)
         if m.next_node is None:
             raise CompileError("no next-state action")
+        # slices of Next: the first one starts right after the prologue (copy of the state, hoisted definitions)
+        cut0 = Label("seg")
+        self.asm.label(cut0)
+        self.seg_cuts["next"].append(cut0)
+        self._seg_buf = self.asm.code
+        self._seg_clean = self._seg_last = len(self.asm.code)
+        self._seg_top = True
         self.ca(m.next_node, {}, m.next_ctx, frozenset(), emit_k, None)
+        self._seg_top, self._seg_buf = False, None
         self.asm.emit("HALT")
         self._main_high = self.high
         if self._canon is not None:
@@ -4359,6 +4421,8 @@ class Lowering:
         code, cpool, ent = self.asm.assemble(entries)
         cm = CompiledModel()
         cm.code, cm.cpool, cm.entries = code, cpool, ent
+        cm.segments = {k: sorted(set(int(L.pos) for L in v)) for k, v in self.seg_cuts.items()}
+        cm.blocks = sorted(self.blocks) if len(self.blocks) <= 8192 else None
         cm.line_table = self.asm.line_table
         cm.frame_words = self.high + 4
         cm.var_types = self.var_types

@@ -20,6 +20,7 @@ def save_compiled(path, cm: CompiledModel, init_words: np.ndarray, expected: dic
                 actions=[[a[0], list(a[1]), a[2]] for a in cm.actions],
                 asserts=[[a[0], list(a[1])] for a in cm.asserts],
                 module_name=getattr(cm, "module_name", ""), state_bits=getattr(cm, "state_bits", 0),
+                segments=getattr(cm, "segments", None), blocks=getattr(cm, "blocks", None),
                 expected=expected or {}, info=info or {})
     typing = pickle.dumps(dict(var_types=cm.var_types, var_off=cm.var_off, atoms=cm.atoms.vals))
     with open(path, "wb") as f:
@@ -45,6 +46,8 @@ def load_compiled(path):
     cm.asserts = [(a[0], tuple(a[1])) for a in meta["asserts"]]
     cm.module_name = meta.get("module_name", "")
     cm.state_bits = meta.get("state_bits", 0)
+    cm.segments = meta.get("segments")
+    cm.blocks = [tuple(b) for b in meta["blocks"]] if meta.get("blocks") else None
     ty = pickle.loads(bytes(z["typing"]))
     cm.var_types, cm.var_off = ty["var_types"], ty["var_off"]
     at = Atoms()

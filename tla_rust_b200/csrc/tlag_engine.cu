@@ -109,7 +109,9 @@ struct DevParams {
   Counters* ctr;
   uint32_t flags;
   int n_inv;
+  uint8_t* succ_flag;               // sliced build: one byte per frontier state, set when a slice produced a successor
   // route mode
+  int route;                        // sliced build: successors go to the send regions instead of the local seen-set
   uint32_t* send; unsigned long long region_cap; int n_ranks; int rank;
   unsigned long long* sent_cache; unsigned long long sent_mask;   // direct-mapped filter of fingerprints already routed
 };
@@ -141,6 +143,7 @@ struct tlag_engine {
   double growth_hint = 4.0;
   void* d_sort = nullptr; uint64_t sort_bytes = 0;
   unsigned long long* d_sent = nullptr;
+  uint8_t* d_succ = nullptr; uint64_t succ_cap = 0;   // sliced build: per-frontier-state "has a successor" flags
   std::string err;
   uint32_t* d_scratch = nullptr; uint64_t scratch_words = 0; uint8_t* d_flags = nullptr; uint64_t flags_cap = 0;
 };
@@ -175,6 +178,191 @@ __device__ __forceinline__ void report_min(unsigned long long* slot, unsigned lo
   atomicMin(slot, key);
 }
 
+// ------------------------------------------------------------------ sliced native build
+// (tla_rust_b200/compile/sliced.py)  One kernel per slice of the model's program: k_sl_inv_<i> evaluates invariant i,
+// k_sl_next_<j> one disjunct of Next, each over the whole frontier, one thread per state.  All warps of a launch run
+// the same few KB of straight-line code (the whole-program compiled form of round 1 lost to the interpreter on
+// instruction-cache misses: 354 KB of code, every warp somewhere else); divergence inside a slice is the hardware's
+// (compiler-placed reconvergence) instead of a min-pc election per block; a successor is packed, fingerprinted and
+// inserted where it is produced, with opportunistic warp aggregation of the tail-counter atomics.
+#ifdef TLAG_SLICED_INC
+struct tlag_sl_cx {
+  const DevParams* p;
+  unsigned long long idx;
+  const uint32_t* src;              // packed words of the state being expanded (EMITD re-packs over a copy)
+  unsigned long long gen;
+  unsigned nsucc;
+  int phase;                        // 0 = invariant slice, 1 = slice of Next
+};
+
+#ifndef TLAG_SL_BLOCK
+#define TLAG_SL_BLOCK 256
+#endif
+#ifndef TLAG_SL_OCC
+#define TLAG_SL_OCC 4               /* resident CTAs per SM the slice kernels are compiled for (register cap) */
+#endif
+
+static __device__ __noinline__ void sl_emit_words(tlag_sl_cx* cx, int aid, const uint32_t* o);
+static __device__ __noinline__ void sl_emit_frame(tlag_sl_cx* cx, const int32_t* f, int aid, int dirty);
+#define TLAG_SL_EMIT(aid, dirty) sl_emit_frame(cx, f, (aid), (dirty))
+#define TLAG_SL_EMITW(aid, o) sl_emit_words(cx, (aid), (o))
+#define TLAG_SL_GEN() do { cx->nsucc++; cx->gen++; } while (0)
+#define TLAG_SL_ASSERT(id) report_min(&cx->p->ctr->viol_assert, (cx->idx << 20) | (unsigned)((id) & 0xFFFFF))
+#define TLAG_SL_INVF(i) do { if (cx->phase == 0) report_min(&cx->p->ctr->viol_inv, (cx->idx << 20) | (unsigned)((i) & 0xFFFFF)); } while (0)
+#define TLAG_SL_TRAP(code, line) do { report_min(&cx->p->ctr->viol_trap, (cx->idx << 20) | ((unsigned long long)((code) & 15) << 16) | (unsigned)((line) & 0xFFFF)); cx->nsucc++; } while (0)
+#define TLAG_SL_SUBQ static __device__ __noinline__
+#define TLAG_SL_SEGQ static __device__ __forceinline__
+#include TLAG_SLICED_INC
+
+// successor already packed: fingerprint -> seen-set (or owner's send region) -> store
+static __device__ __noinline__ void sl_emit_words(tlag_sl_cx* cx, int aid, const uint32_t* o) {
+  const DevParams& p = *cx->p;
+  constexpr int W = TLAG_SL_W;
+  cx->nsucc++; cx->gen++;
+  uint32_t w[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) w[i] = o[i];
+  const unsigned long long fp = tlag_fingerprint(w, W);
+  const unsigned lane = threadIdx.x & 31;
+  if (!p.route) {
+    int ins = seen_insert(p.table, p.mask, fp);
+    if (ins < 0) { atomicExch(&p.ctr->table_full, 1ULL); ins = 0; }
+    if (ins > 0) {
+      // warp-aggregated tail allocation over whichever lanes arrived here together
+      const unsigned am = __activemask();
+      const int leader = __ffs((int)am) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(&p.ctr->n_states, (unsigned long long)__popc(am));
+      base = __shfl_sync(am, base, leader);
+      const unsigned long long pos = base + (unsigned long long)__popc(am & lanemask_lt());
+      if (pos < p.cap_states) {
+        uint32_t* dst = p.states + pos * (unsigned long long)W;
+#pragma unroll
+        for (int i = 0; i < W; ++i) dst[i] = w[i];
+        p.parent[pos] = (uint32_t)cx->idx;
+        p.meta[pos] = ((uint32_t)aid << 8) | (uint32_t)(p.rank & 0xFF);
+      } else {
+        atomicExch(&p.ctr->store_overflow, 1ULL);
+      }
+    }
+  } else {
+    // A successor whose fingerprint this rank has already routed is known to its owner (direct-mapped exact-compare
+    // cache).  The slot is written only once the record is in the send region, so a chunk that is re-run after a
+    // region overflow loses nothing.
+    unsigned long long* cslot = p.sent_cache ? p.sent_cache + (fp & p.sent_mask) : nullptr;
+    if (cslot && __ldcv(cslot) == fp) return;
+    const int owner = (int)tlag_owner(w, W, (uint32_t)p.n_ranks);
+    const unsigned am = __activemask();
+    const unsigned peers = __match_any_sync(am, owner);
+    const int leader = __ffs((int)peers) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(&p.ctr->send_count[owner], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const unsigned long long pos = base + (unsigned long long)__popc(peers & lanemask_lt());
+    if (pos < p.region_cap) {
+      uint32_t* dst = p.send + ((unsigned long long)owner * p.region_cap + pos) * (unsigned long long)(W + 2);
+#pragma unroll
+      for (int i = 0; i < W; ++i) dst[i] = w[i];
+      dst[W] = (uint32_t)cx->idx;
+      dst[W + 1] = ((uint32_t)aid << 8) | (uint32_t)(p.rank & 0xFF);
+      if (cslot) *cslot = fp;
+    } else {
+      atomicExch(&p.ctr->route_overflow, 1ULL);
+    }
+  }
+}
+
+// array form: pack the primed frame (all slots, or the dirty ranges over a copy of the parent) first
+static __device__ __noinline__ void sl_emit_frame(tlag_sl_cx* cx, const int32_t* f, int aid, int dirty) {
+  const DevParams& p = *cx->p;
+  constexpr int W = TLAG_SL_W;
+  uint32_t succ[W];
+  int ov;
+  if (dirty > 0) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) succ[i] = cx->src[i];
+    ov = tlag_pack_ranges(p.layout, p.cpool, dirty, f + TLAG_SL_USZ, succ);
+  } else {
+    ov = tlag_pack(p.layout, p.n_slots, f + TLAG_SL_USZ, succ, W);
+  }
+  if (ov) {
+    cx->nsucc++; cx->gen++;
+    report_min(&p.ctr->viol_trap, (cx->idx << 20) | (2ULL << 16) | (unsigned)((ov - 1) & 0xFFFF));
+    return;
+  }
+  sl_emit_words(cx, aid, succ);
+}
+
+
+// One thread per frontier state (grid-stride).  FN: the slice function of this kernel.
+template <int PHASE, typename FN>
+__device__ __forceinline__ void sl_run(const DevParams& p, unsigned long long lo, unsigned long long hi, FN fn) {
+  constexpr int W = TLAG_SL_W;
+  tlag_sl_cx cxs;
+  tlag_sl_cx* cx = &cxs;
+  cx->p = &p; cx->gen = 0; cx->phase = PHASE;
+#if !TLAG_SL_SCALAR
+  int32_t f[TLAG_SL_FRAME];
+#endif
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < hi; idx += stride) {
+    const uint32_t* src = p.states + idx * (unsigned long long)W;
+    cx->idx = idx; cx->src = src; cx->nsucc = 0;
+#if TLAG_SL_SCALAR
+    uint32_t in_[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) in_[i] = src[i];
+    fn(p.cpool, in_, cx);
+#else
+    {
+      uint32_t in_[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) in_[i] = src[i];
+      tlag_unpack(p.layout, p.n_slots, in_, f);
+    }
+    fn(p.cpool, f, cx);
+#endif
+    if (PHASE == 1 && cx->nsucc && p.succ_flag) p.succ_flag[idx - lo] = 1;
+  }
+  // generated counter: warp reduce, one atomic per warp
+  unsigned long long g = cx->gen;
+  if (PHASE == 1) {
+    for (int o = 16; o > 0; o >>= 1) g += __shfl_down_sync(0xffffffffu, g, o);
+    if ((threadIdx.x & 31) == 0 && g) atomicAdd(&p.ctr->generated, g);
+  }
+}
+
+#if TLAG_SL_SCALAR
+#define TLAG_SL_FARG const uint32_t*
+#else
+#define TLAG_SL_FARG int32_t*
+#endif
+#define TLAG_SL_KERNEL_INV(j)                                                                                     \
+  __global__ void __launch_bounds__(TLAG_SL_BLOCK, TLAG_SL_OCC) k_sl_inv_##j(const __grid_constant__ DevParams p, \
+                                                                            unsigned long long lo, unsigned long long hi) { \
+    sl_run<0>(p, lo, hi, [](const int32_t* cp, TLAG_SL_FARG f, tlag_sl_cx* cx) { tlag_sl_inv_##j(cp, f, cx); });  \
+  }
+#define TLAG_SL_KERNEL_NEXT(j)                                                                                     \
+  __global__ void __launch_bounds__(TLAG_SL_BLOCK, TLAG_SL_OCC) k_sl_next_##j(const __grid_constant__ DevParams p, \
+                                                                             unsigned long long lo, unsigned long long hi) { \
+    sl_run<1>(p, lo, hi, [](const int32_t* cp, TLAG_SL_FARG f, tlag_sl_cx* cx) { tlag_sl_next_##j(cp, f, cx); });  \
+  }
+TLAG_SL_INV_LIST(TLAG_SL_KERNEL_INV)
+TLAG_SL_NEXT_LIST(TLAG_SL_KERNEL_NEXT)
+typedef void (*sl_kernel_t)(DevParams, unsigned long long, unsigned long long);
+#define TLAG_SL_ADDR_INV(j) k_sl_inv_##j,
+#define TLAG_SL_ADDR_NEXT(j) k_sl_next_##j,
+static const sl_kernel_t kSlInv[] = { TLAG_SL_INV_LIST(TLAG_SL_ADDR_INV) nullptr };
+static const sl_kernel_t kSlNext[] = { TLAG_SL_NEXT_LIST(TLAG_SL_ADDR_NEXT) nullptr };
+
+// deadlock = a frontier state for which no slice of Next produced a successor
+__global__ void k_sl_deadlock(DevParams p, unsigned long long lo, unsigned long long hi) {
+  const unsigned long long i = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < hi && !p.succ_flag[i - lo]) report_min(&p.ctr->viol_deadlock, i << 20);
+}
+#endif  // TLAG_SLICED_INC
+
+#ifndef TLAG_SLICED_INC
 // ------------------------------------------------------------------ wave kernel
 // Warp-scheduled interpreter.  A SIMT interpreter that lets every lane follow its own pc pays a
 // divergent fetch/decode/dispatch per distinct opcode per step.  Here the warp executes, at every
@@ -345,10 +533,10 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
         // route: owner = high bits of the fingerprint scaled to n_ranks (hash-range partition).
         // A successor whose fingerprint this rank has already routed is known to its owner: drop it
         // here (direct-mapped, exact-compare cache: misses only cost a redundant record).
-        if (has && p.sent_cache) {
-          unsigned long long* cslot = p.sent_cache + (fp & p.sent_mask);
-          if (__ldcv(cslot) == fp) has = false; else *cslot = fp;
-        }
+        // (the slot is written only once the record is in the send region: a chunk re-run after a region overflow
+        // must find none of its own dropped records in the cache)
+        unsigned long long* cslot = (has && p.sent_cache) ? p.sent_cache + (fp & p.sent_mask) : nullptr;
+        if (cslot && __ldcv(cslot) == fp) { has = false; cslot = nullptr; }
         int owner = has ? (int)tlag_owner(succ, W, (uint32_t)p.n_ranks) : -1;
         const unsigned peers = __match_any_sync(0xffffffffu, owner);
         if (has) {
@@ -362,6 +550,7 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
             for (int i = 0; i < W; ++i) dst[i] = succ[i];
             dst[W] = (uint32_t)idx;
             dst[W + 1] = ((uint32_t)act << 8) | (uint32_t)(p.rank & 0xFF);
+            if (cslot) *cslot = fp;
           } else {
             atomicExch(&p.ctr->route_overflow, 1ULL);
           }
@@ -377,6 +566,8 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
   for (int o = 16; o > 0; o >>= 1) gen_local += __shfl_down_sync(0xffffffffu, gen_local, o);
   if (lane == 0 && gen_local) atomicAdd(&p.ctr->generated, gen_local);
 }
+
+#endif  // !TLAG_SLICED_INC
 
 // ------------------------------------------------------------------ K1 alone: fingerprint + probe/insert
 // One thread per candidate state; W words loaded with the widest aligned vector the layout allows.
@@ -570,6 +761,37 @@ __global__ void k_rehash(DevParams p, unsigned long long n) {
 // ------------------------------------------------------------------ host side
 static const int kFrameClasses[] = {64, 128, 256, 512, 1024, 2048, 4096, 8192};
 
+#ifdef TLAG_SLICED_INC
+// One BFS level (or one chunk of it, route mode) = the invariant kernels, the kernels of the slices of Next, and the
+// deadlock scan, back to back on the engine's stream.
+template <int MODE>
+static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
+  const uint64_t n = hi - lo;
+  if (n == 0) return cudaSuccess;
+  const bool dl = (e->p.flags & TLAG_F_DEADLOCK_CHECK) != 0;
+  if (dl) {
+    if (n > e->succ_cap) {
+      cudaFree(e->d_succ); e->d_succ = nullptr; e->succ_cap = 0;
+      uint64_t cap = n + n / 2 + 4096;
+      cudaError_t r = cudaMalloc(&e->d_succ, cap);
+      if (r != cudaSuccess) return r;
+      e->succ_cap = cap;
+    }
+    cudaError_t r = cudaMemsetAsync(e->d_succ, 0, n, e->stream);
+    if (r != cudaSuccess) return r;
+  }
+  e->p.succ_flag = dl ? e->d_succ : nullptr;
+  e->p.route = MODE;
+  uint64_t blocks = (n + TLAG_SL_BLOCK - 1) / TLAG_SL_BLOCK;
+  const uint64_t maxb = (uint64_t)e->sm_count * 64;
+  if (blocks > maxb) blocks = maxb;
+  if (e->p.n_inv > 0)
+    for (int j = 0; kSlInv[j]; ++j) { kSlInv[j]<<<(unsigned)blocks, TLAG_SL_BLOCK, 0, e->stream>>>(e->p, lo, hi); e->launches++; }
+  for (int j = 0; kSlNext[j]; ++j) { kSlNext[j]<<<(unsigned)blocks, TLAG_SL_BLOCK, 0, e->stream>>>(e->p, lo, hi); e->launches++; }
+  if (dl) { k_sl_deadlock<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->p, lo, hi); e->launches++; }
+  return cudaGetLastError();
+}
+#else
 template <int MODE>
 static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   const uint64_t n = hi - lo;
@@ -613,6 +835,8 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   e->launches++;
   return cudaGetLastError();
 }
+
+#endif
 
 static int alloc_table(tlag_engine* e, unsigned log2) {
   if (e->d_table) cudaFree(e->d_table);
@@ -719,7 +943,9 @@ static int cluster_slice(tlag_engine* e, uint64_t first, uint64_t count) {
   return TLAG_OK;
 }
 
-#ifdef TLAG_NATIVE_INC
+#if defined(TLAG_SLICED_INC)
+extern "C" const char* tlag_version(void) { return "tlag 0.2 (sm_100a) native sliced"; }
+#elif defined(TLAG_NATIVE_INC)
 extern "C" const char* tlag_version(void) { return "tlag 0.1 (sm_100a) native"; }
 #else
 extern "C" const char* tlag_version(void) { return "tlag 0.1 (sm_100a)"; }
@@ -737,7 +963,10 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   e->m = *m;
   if (m->words_per_state == 0 || m->words_per_state > TLAG_MAXW) { e->err = "words_per_state out of range (1..128)"; return TLAG_EINVAL; }
   if (m->frame_words > 8192) { e->err = "frame_words > 8192 not supported"; return TLAG_EINVAL; }
-#ifdef TLAG_NATIVE_INC
+#if defined(TLAG_SLICED_INC)
+#define TLAG_NATIVE_FRAME TLAG_SL_FRAME
+#endif
+#if defined(TLAG_NATIVE_INC) || defined(TLAG_SLICED_INC)
   {
     uint64_t h = 0xcbf29ce484222325ULL;
     for (uint32_t i = 0; i < m->code_len; ++i) h = (h ^ m->code[i]) * 0x100000001b3ULL;
@@ -816,7 +1045,7 @@ extern "C" void tlag_destroy(tlag_engine* e) {
   if (!e) return;
   cudaFree(e->d_code); cudaFree(e->d_cpool); cudaFree(e->d_layout); cudaFree(e->d_states);
   cudaFree(e->d_parent); cudaFree(e->d_meta); cudaFree(e->d_table); cudaFree(e->d_ctr);
-  cudaFree(e->d_scratch); cudaFree(e->d_flags); cudaFree(e->d_sort); cudaFree(e->d_sent);
+  cudaFree(e->d_scratch); cudaFree(e->d_flags); cudaFree(e->d_sort); cudaFree(e->d_sent); cudaFree(e->d_succ);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);

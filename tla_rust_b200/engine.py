@@ -155,6 +155,76 @@ def build_native_library(cm, force=False, verbose=False):
     return so
 
 
+def _sliced_tag(cm, scalar):
+    import hashlib
+    from .compile.native import model_key
+    h = hashlib.sha256()
+    for rel in ("csrc/tlag_engine.cu", "csrc/tlag_vm.h", "csrc/tlag_vm_exec.inc", "compile/sliced.py", "../include/tlag.h"):
+        with open(os.path.join(_HERE, rel), "rb") as f:
+            h.update(f.read())
+    h.update(repr((getattr(cm, "segments", None), os.environ.get("TLAG_SL_OCC", ""), os.environ.get("TLAG_SL_BLOCK", ""))).encode())
+    return f"sl_{model_key(cm)}_{h.hexdigest()[:8]}{'_s' if scalar else ''}"
+
+
+def sliced_form(cm):
+    """scalar form (frame words as C locals) when the model allows it, else the array form; TLAG_SL_FORM overrides."""
+    from .compile.sliced import Emitter, SliceError
+    want = os.environ.get("TLAG_SL_FORM", "auto")
+    if want == "array":
+        return False
+    try:
+        Emitter(cm, scalar=True)
+        return True
+    except SliceError:
+        if want == "scalar":
+            raise
+        return False
+
+
+def sliced_library_path(cm, scalar=None):
+    if scalar is None:
+        scalar = sliced_form(cm)
+    return os.path.join(NATIVE_DIR, f"libtlag_{_sliced_tag(cm, scalar)}.so")
+
+
+def build_sliced_library(cm, force=False, verbose=False, scalar=None):
+    """Model-specialised engine library, sliced form (compile/sliced.py): one kernel per invariant and per disjunct of
+    Next, same engine source and C ABI.  Built in-tree (csrc/native/) so that it travels with the repo snapshot."""
+    from .compile.sliced import emit_sliced
+    if scalar is None:
+        scalar = sliced_form(cm)
+    os.makedirs(NATIVE_DIR, exist_ok=True)
+    tag = _sliced_tag(cm, scalar)
+    inc = os.path.join(NATIVE_DIR, f"{tag}.inc")
+    so = os.path.join(NATIVE_DIR, f"libtlag_{tag}.so")
+    if os.path.exists(so) and not force:
+        return so
+    with open(inc, "w") as f:
+        f.write(emit_sliced(cm, scalar=scalar))
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+           f'-DTLAG_SLICED_INC="{inc}"', "-shared", "-o", so + ".tmp", os.path.join(_HERE, "csrc", "tlag_engine.cu")]
+    for k in ("TLAG_SL_OCC", "TLAG_SL_BLOCK"):
+        if os.environ.get(k):
+            cmd.insert(-4, f"-D{k}={int(os.environ[k])}")
+    p = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if p.returncode != 0:
+        raise EngineError(f"nvcc failed for the sliced build of model {tag}: {(p.stderr or '')[-3000:]}")
+    os.replace(so + ".tmp", so)
+    return so
+
+
+def load_sliced_library(cm, build=True):
+    so = sliced_library_path(cm)
+    if so not in _NATIVE_LIBS:
+        if not os.path.exists(so):
+            if not build:
+                raise EngineUnavailable(f"{so} is missing (sliced native build of this model)")
+            build_sliced_library(cm)
+        _NATIVE_LIBS[so] = _bind(so)
+    return _NATIVE_LIBS[so]
+
+
 def load_native_library(cm, build=True):
     so = native_library_path(cm)
     if so not in _NATIVE_LIBS:
@@ -170,12 +240,17 @@ class Engine:
     """One BFS engine instance on one GPU (mirrors tlag_engine)."""
 
     def __init__(self, cm, deadlock=True, device=0, table_log2=0, max_states=0, keep_going=False, native=None):
-        """native=True: use (build if needed) the model-specialised library instead of the bytecode interpreter;
-        None: follow the environment variable TLAG_NATIVE (1 = on)."""
+        """native="sliced": the model-specialised sliced build (one kernel per slice of the program; built on demand);
+        native=True: the round-1 whole-program compiled form (kept for comparison); False: the bytecode interpreter;
+        None: follow the environment variable TLAG_NATIVE (sliced / 1 / 0)."""
         if native is None:
-            native = os.environ.get("TLAG_NATIVE", "0") == "1"
-        self.native = bool(native)
-        self.L = load_native_library(cm) if self.native else load_library()
+            env = os.environ.get("TLAG_NATIVE", "0")
+            native = "sliced" if env == "sliced" else (env == "1")
+        self.native = native if native == "sliced" else bool(native)
+        if self.native == "sliced":         # one kernel per invariant / disjunct of Next (compile/sliced.py)
+            self.L = load_sliced_library(cm)
+        else:
+            self.L = load_native_library(cm) if self.native else load_library()
         self.cm = cm
         self._code = np.ascontiguousarray(cm.code, dtype=np.uint64)
         self._cpool = np.ascontiguousarray(cm.cpool, dtype=np.int32)
