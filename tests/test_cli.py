@@ -62,7 +62,7 @@ class _CpuShimEngine:
     """Stand-in for tla_rust_b200.engine.Engine backed by the CPU bytecode oracle: lets the CPU suite drive the
     whole `tlc` control flow (compile, report formatting, capacity retry).  Test infrastructure only."""
 
-    def __init__(self, cm, deadlock=True, device=0):
+    def __init__(self, cm, deadlock=True, device=0, native=False):
         self.cm, self.deadlock, self.r = cm, deadlock, None
 
     def seed(self, iw):
@@ -71,7 +71,7 @@ class _CpuShimEngine:
     def result(self):
         import numpy as np
         if self.r is None:
-            return {"distinct": int(len(np.unique(self.iw, axis=0)))}
+            return {"distinct": int(len(np.unique(self.iw, axis=0))), "depth": 1}
         return self.r
 
     def step(self):

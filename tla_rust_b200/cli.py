@@ -13,9 +13,13 @@ from .front.parser import ParseError
 from .front.lexer import LexError
 from .front.values import EvalError
 from .front.pcal import translate_file, PcalError
-from .front.report import format_result, OK
+from .front.report import format_result, OK, CheckResult, PROPERTY
 from .compile.lower import CompileError
 from .compile.types import TypeErr
+
+# `tlc -engine auto`: programs of at least this many bytecode instructions are compiled to sliced kernels (about 10 s of
+# nvcc per thousand instructions, cached per model); smaller ones run on the interpreter kernel at once.
+AUTO_SLICED_MIN_CODE = int(os.environ.get("TLAG_AUTO_SLICED_MIN_CODE", "1500"))
 
 
 def pcal2tla_main(argv=None):
@@ -41,7 +45,11 @@ def pcal2tla_main(argv=None):
     return rc
 
 
-def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq_cap=None, verbose=True, lib_dirs=()):
+def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq_cap=None, verbose=True, lib_dirs=(),
+               engine="auto", max_depth=0):
+    """engine: "interp" = bytecode interpreter kernel, "sliced" = the model compiled to one CUDA kernel per slice of its
+    program (nvcc at run time, cached in csrc/native/), "auto" = sliced for programs big enough to repay the compile.
+    max_depth = L: stop after level L exists (levels 1..L-1 expanded) and report the prefix."""
     from .checker import compile_model, encode_states, result_from_engine
     from .engine import Engine
     t0 = time.time()
@@ -59,7 +67,6 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
     for st in init:      # Init => Init2 of each refinement PROPERTY (the step obligation is checked on the device)
         pbad = m.check_refinement_init(st)
         if pbad is not None:
-            from .report import CheckResult, PROPERTY
             res = CheckResult()
             res.verdict, res.invariant, res.trace = PROPERTY, pbad, [(st, None)]
             res.generated = res.distinct = res.init_states = len(init)
@@ -75,12 +82,18 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
             for w in cm.warnings:
                 print(f"Warning: {w}", file=out)
             iw = encode_states(cm, init)
-            e = Engine(cm, deadlock=deadlock and m.check_deadlock, device=device)
+            native = "sliced" if (engine == "sliced" or (engine == "auto" and len(cm.code) >= AUTO_SLICED_MIN_CODE)) else False
+            if native == "sliced" and verbose:
+                print("Compiling the model to sm_100a kernels (one per invariant / disjunct of Next) ...", file=out)
+            e = Engine(cm, deadlock=deadlock and m.check_deadlock, device=device, native=native)
             e.seed(iw)
             r0 = e.result()
             print(f"Finished computing initial states: {r0['distinct']} distinct state"
                   f"{'s' if r0['distinct'] != 1 else ''} generated.", file=out)
             while True:
+                if max_depth and e.result()["depth"] >= max_depth:
+                    print(f"Depth bound {max_depth} reached: the states of the last level were not expanded.", file=out)
+                    break
                 ws = e.step()
                 if ws["verdict"] != 5:
                     break
@@ -113,7 +126,7 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
 
 def tlc_main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
-    files, deadlock, cfg, dev, libs, seq_cap = [], True, None, 0, [], None
+    files, deadlock, cfg, dev, libs, seq_cap, engine, depth = [], True, None, 0, [], None, "auto", 0
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -128,7 +141,13 @@ def tlc_main(argv=None):
         elif a == "-seqcap":                # capacity of Seq(S)-typed variables (bounded by the model's CONSTRAINT)
             i += 1
             seq_cap = int(argv[i])
-        elif a in ("-workers", "-gpus", "-device", "-fpmem", "-depth", "-coverage", "-checkpoint"):
+        elif a == "-engine":                # interp | sliced | auto
+            i += 1
+            engine = argv[i]
+        elif a == "-depth":                 # depth-bounded prefix of the breadth-first search
+            i += 1
+            depth = int(argv[i])
+        elif a in ("-workers", "-gpus", "-device", "-fpmem", "-coverage", "-checkpoint"):
             i += 1
             if a == "-device":
                 dev = int(argv[i])
@@ -138,7 +157,7 @@ def tlc_main(argv=None):
             files.append(a)
         i += 1
     if not files:
-        print("usage: tlc [-deadlock] [-config FILE.cfg] [-I DIR] [-seqcap N] FILE.tla ...", file=sys.stderr)
+        print("usage: tlc [-deadlock] [-config FILE.cfg] [-I DIR] [-seqcap N] [-engine interp|sliced|auto] [-depth N] FILE.tla ...", file=sys.stderr)
         return 2
     rc = 0
     for f in files:
@@ -146,7 +165,8 @@ def tlc_main(argv=None):
             f += ".tla"
         print(f"Parsing file {os.path.abspath(f)}")
         try:
-            r = check_file(f, deadlock=deadlock, cfg_path=cfg, device=dev, lib_dirs=libs, seq_cap=seq_cap)
+            r = check_file(f, deadlock=deadlock, cfg_path=cfg, device=dev, lib_dirs=libs, seq_cap=seq_cap,
+                           engine=engine, max_depth=depth)
         except (SpecError, ParseError, LexError, EvalError, CompileError, TypeErr) as ex:
             print(f"Error: {type(ex).__name__}: {ex}")
             r = 150

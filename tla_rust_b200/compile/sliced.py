@@ -279,8 +279,8 @@ class Emitter:
             return goto(I)
         if op == "LI":
             return f"{R(a)} = {I};"
-        if op == "LIW":
-            return f"{R(a)} = tlag_cp(cpool, {I});"
+        if op == "LIW":           # the constant pool belongs to this model: its words are literals here
+            return f"{R(a)} = {self.cpool[I]};"
         if op == "MOV":
             return f"{R(a)} = {R(b)};"
         if op == "MOVN":
@@ -295,8 +295,8 @@ class Emitter:
                 return " ".join(f"{R(a + j)} = 0;" for j in range(b))
             return f"for (uint32_t i_ = 0; i_ < {b}u; ++i_) f[{a} + i_] = 0;"
         if op == "LDC":
-            if self.scalar:
-                return " ".join(f"{R(a + j)} = tlag_cp(cpool, {I + j});" for j in range(d))
+            if self.scalar or d <= 4:
+                return " ".join(f"{R(a + j)} = {self.cpool[I + j]};" for j in range(d))
             return f"for (uint32_t i_ = 0; i_ < {d}u; ++i_) f[{a} + i_] = tlag_cp(cpool, {I} + (int32_t)i_);"
         if op == "NEG":
             return f"{R(a)} = -{R(b)};"

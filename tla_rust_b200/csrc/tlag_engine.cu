@@ -144,6 +144,9 @@ struct tlag_engine {
   void* d_sort = nullptr; uint64_t sort_bytes = 0;
   unsigned long long* d_sent = nullptr;
   uint8_t* d_succ = nullptr; uint64_t succ_cap = 0;   // sliced build: per-frontier-state "has a successor" flags
+  unsigned long long* d_dig = nullptr;                // tlag_digest accumulators (XOR, SUM)
+  // TLAG_F_KEEP_GOING: the first violation is remembered, the search goes on to the fixpoint
+  int kg_verdict = 0, kg_detail = 0, kg_detail2 = 0; uint64_t kg_idx = 0;
   std::string err;
   uint32_t* d_scratch = nullptr; uint64_t scratch_words = 0; uint8_t* d_flags = nullptr; uint64_t flags_cap = 0;
 };
@@ -211,7 +214,13 @@ static __device__ __noinline__ void sl_emit_frame(tlag_sl_cx* cx, const int32_t*
 #define TLAG_SL_INVF(i) do { if (cx->phase == 0) report_min(&cx->p->ctr->viol_inv, (cx->idx << 20) | (unsigned)((i) & 0xFFFFF)); } while (0)
 #define TLAG_SL_TRAP(code, line) do { report_min(&cx->p->ctr->viol_trap, (cx->idx << 20) | ((unsigned long long)((code) & 15) << 16) | (unsigned)((line) & 0xFFFF)); cx->nsucc++; } while (0)
 #define TLAG_SL_SUBQ static __device__ __noinline__
+// Array form with a big frame (container models): the slice is a function of its own that receives the frame as a
+// pointer -- inlined, cicc tries scalar replacement of a 2 K-word array over a goto graph and takes many minutes (raft).
+#if defined(TLAG_SL_SEG_NOINLINE)
+#define TLAG_SL_SEGQ static __device__ __noinline__
+#else
 #define TLAG_SL_SEGQ static __device__ __forceinline__
+#endif
 #include TLAG_SLICED_INC
 
 // successor already packed: fingerprint -> seen-set (or owner's send region) -> store
@@ -874,6 +883,9 @@ static int grow_store_if_needed(tlag_engine* e, uint64_t need) {
   uint64_t ncap = e->cap_states;
   while (ncap < need) ncap *= 2;
   if (e->m.max_states && ncap > e->m.max_states) ncap = e->m.max_states;
+  // parent links are 32-bit indices into this rank's store and 0xFFFFFFFF marks an initial state: a store never holds
+  // more than 2^32 - 2 states per GPU (beyond that the wave reports a store overflow instead of wrapping a link)
+  if (ncap > 0xFFFFFFFEull) ncap = 0xFFFFFFFEull;
   if (ncap <= e->cap_states) return TLAG_OK;   // at the configured limit; overflow is detected by the kernel
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
@@ -1045,7 +1057,7 @@ extern "C" void tlag_destroy(tlag_engine* e) {
   if (!e) return;
   cudaFree(e->d_code); cudaFree(e->d_cpool); cudaFree(e->d_layout); cudaFree(e->d_states);
   cudaFree(e->d_parent); cudaFree(e->d_meta); cudaFree(e->d_table); cudaFree(e->d_ctr);
-  cudaFree(e->d_scratch); cudaFree(e->d_flags); cudaFree(e->d_sort); cudaFree(e->d_sent); cudaFree(e->d_succ);
+  cudaFree(e->d_scratch); cudaFree(e->d_flags); cudaFree(e->d_sort); cudaFree(e->d_sent); cudaFree(e->d_succ); cudaFree(e->d_dig);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1169,6 +1181,7 @@ extern "C" int tlag_restart(tlag_engine* e) {
   CK(cudaStreamSynchronize(e->stream));
   e->lo = e->hi = 0; e->level = 0; e->init_states = 0; e->generated = 0; e->depth = 0;
   e->verdict = TLAG_V_RUNNING; e->detail = e->detail2 = 0; e->viol_idx = 0; e->dev_seconds = 0;
+  e->kg_verdict = 0;
   e->restarting = true;
   const uint64_t W = e->m.words_per_state;
   int r = tlag_seed(e, e->h_init.data(), e->h_init.size() / W);
@@ -1207,35 +1220,87 @@ static void collect_violations(tlag_engine* e, const Counters& hc) {
   else if (kind == TLAG_V_INVARIANT) e->detail = (int)(hc.viol_inv & 0xFFFFF);
 }
 
+// Undo a wave that ran out of store or table space: the states it appended are dropped (n_states back to `hi`), the
+// seen-set is rebuilt from the store (it holds fingerprints of the dropped states), counters and violation slots are
+// cleared -- the level is then expanded again from scratch with more room.
+static int rollback_wave(tlag_engine* e, uint64_t hi, uint64_t want_states) {
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  hc.n_states = hi; hc.generated = 0; hc.work = 0; hc.store_overflow = 0; hc.table_full = 0;
+  hc.viol_inv = hc.viol_assert = hc.viol_trap = hc.viol_deadlock = ~0ULL;
+  CK(cudaMemcpy(e->d_ctr, &hc, sizeof(hc), cudaMemcpyHostToDevice));
+  int r = grow_store_if_needed(e, want_states + 4096);
+  if (r) return r;
+  unsigned log2 = e->table_log2;
+  while ((1ULL << log2) < want_states * 2 && log2 < 40) ++log2;
+  r = alloc_table(e, log2);
+  if (r) return r;
+  if (hi) {
+    k_rehash<<<(unsigned)((hi + 255) / 256), 256, 0, e->stream>>>(e->p, hi);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return TLAG_OK;
+}
+
 extern "C" int tlag_step(tlag_engine* e, tlag_wave_stats* out) {
   if (!e) return TLAG_EINVAL;
   if (out) memset(out, 0, sizeof(*out));
   if (e->level == 0) { e->level = 1; e->lo = 0; e->depth = e->hi > 0 ? 1 : 0; }
   if (e->verdict != TLAG_V_RUNNING) { if (out) out->verdict = e->verdict; return TLAG_OK; }
   const uint64_t lo = e->lo, hi = e->hi;
-  if (lo >= hi) { e->verdict = TLAG_V_OK; if (out) out->verdict = e->verdict; return TLAG_OK; }
+  if (lo >= hi) {
+    e->verdict = e->kg_verdict ? e->kg_verdict : TLAG_V_OK;
+    if (e->kg_verdict) { e->detail = e->kg_detail; e->detail2 = e->kg_detail2; e->viol_idx = e->kg_idx; }
+    if (out) out->verdict = e->verdict;
+    return TLAG_OK;
+  }
   int r = grow_store_if_needed(e, hi + (uint64_t)((double)(hi - lo) * e->growth_hint) + 4096);
   if (r) return r;
-  r = grow_table_if_needed(e, hi + (hi - lo) * 2);
+  r = grow_table_if_needed(e, hi + (uint64_t)((double)(hi - lo) * (e->growth_hint > 4.0 ? e->growth_hint * 0.5 : 2.0)));
   if (r) return r;
-  CK(cudaMemsetAsync(&e->d_ctr->work, 0, 8, e->stream));
-  CK(cudaEventRecord(e->ev0, e->stream));
-  cudaError_t ce = launch_wave<0>(e, lo, hi);
-  if (ce != cudaSuccess) { e->err = std::string("k_wave launch: ") + cudaGetErrorString(ce); return TLAG_ECUDA; }
-  CK(cudaEventRecord(e->ev1, e->stream));
   Counters hc;
-  CK(cudaMemcpyAsync(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
   float ms = 0;
-  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  for (int attempt = 0;; ++attempt) {
+    CK(cudaMemsetAsync(&e->d_ctr->work, 0, 8, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    cudaError_t ce = launch_wave<0>(e, lo, hi);
+    if (ce != cudaSuccess) { e->err = std::string("wave launch: ") + cudaGetErrorString(ce); return TLAG_ECUDA; }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaMemcpyAsync(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    float ms1 = 0;
+    CK(cudaEventElapsedTime(&ms1, e->ev0, e->ev1));
+    ms += ms1;
+    if (!hc.store_overflow && !hc.table_full) break;
+    // The head-room heuristics were too tight for this level (its discovered / expanded ratio jumped): n_states kept
+    // counting past the capacity, so it says how much room the level needs.  Redo the level with that much, twice over.
+    const uint64_t need = hc.n_states > hi ? hc.n_states : hi;
+    const uint64_t want = hi + (need - hi) * 2 + 4096;
+    if (attempt >= 3 || (e->m.max_states && need > e->m.max_states) || need > 0xFFFFFFFEull) {
+      e->err = hc.store_overflow ? "state store overflow: raise max_states (or the model needs more than 2^32 - 2 states per GPU)"
+                                 : "seen-set table full";
+      return TLAG_ENOMEM;
+    }
+    r = rollback_wave(e, hi, want);
+    if (r) return r;
+    if (e->cap_states < need + 1024) { e->err = "state store overflow: not enough device memory for this level"; return TLAG_ENOMEM; }
+  }
   e->dev_seconds += ms * 1e-3;
-  if (hc.store_overflow) { e->err = "state store overflow: raise max_states"; return TLAG_ENOMEM; }
-  if (hc.table_full) { e->err = "seen-set table full"; return TLAG_ENOMEM; }
   const uint64_t gen_wave = hc.generated;
   e->generated += gen_wave;
   CK(cudaMemsetAsync(&e->d_ctr->generated, 0, 8, e->stream));
   const uint64_t n_states = hc.n_states;
   collect_violations(e, hc);
+  if (e->verdict != TLAG_V_RUNNING && (e->m.flags & TLAG_F_KEEP_GOING)) {
+    // keep exploring: remember the first violation (lowest level, lowest index in it), clear the device slots
+    if (!e->kg_verdict) { e->kg_verdict = e->verdict; e->kg_detail = e->detail; e->kg_detail2 = e->detail2; e->kg_idx = e->viol_idx; }
+    e->verdict = TLAG_V_RUNNING;
+    const unsigned long long ones[4] = {~0ULL, ~0ULL, ~0ULL, ~0ULL};
+    CK(cudaMemcpyAsync(&e->d_ctr->viol_inv, ones, sizeof(ones), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
   if (out) {
     out->level = e->level; out->expanded = hi - lo; out->generated = gen_wave;
     out->discovered = n_states - hi; out->distinct_total = n_states; out->generated_total = e->generated;
@@ -1251,9 +1316,9 @@ extern "C" int tlag_step(tlag_engine* e, tlag_wave_stats* out) {
     e->growth_hint = ratio * 2.0 > 4.0 ? ratio * 2.0 : 4.0;
   }
   e->lo = hi; e->hi = n_states; e->level += 1;
-  if (e->verdict == TLAG_V_RUNNING && e->lo >= e->hi) e->verdict = TLAG_V_OK;
-  if (e->verdict != TLAG_V_RUNNING && e->verdict != TLAG_V_OK && (e->m.flags & TLAG_F_KEEP_GOING)) {
-    // keep exploring: remember the first violation only
+  if (e->verdict == TLAG_V_RUNNING && e->lo >= e->hi) {
+    e->verdict = e->kg_verdict ? e->kg_verdict : TLAG_V_OK;
+    if (e->kg_verdict) { e->detail = e->kg_detail; e->detail2 = e->kg_detail2; e->viol_idx = e->kg_idx; }
   }
   if (out) out->verdict = e->verdict;
   return TLAG_OK;
@@ -1292,8 +1357,8 @@ extern "C" int tlag_digest(tlag_engine* e, uint64_t* xor_out, uint64_t* sum_out)
   if (!e || !xor_out || !sum_out) return TLAG_EINVAL;
   Counters hc;
   CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
-  unsigned long long* d2 = nullptr;
-  CK(cudaMalloc(&d2, 16));
+  if (!e->d_dig) CK(cudaMalloc(&e->d_dig, 16));
+  unsigned long long* d2 = e->d_dig;
   CK(cudaMemsetAsync(d2, 0, 16, e->stream));
   if (hc.n_states) {
     k_digest<<<e->sm_count * 8, 256, 0, e->stream>>>(e->p, hc.n_states, d2);
@@ -1303,7 +1368,6 @@ extern "C" int tlag_digest(tlag_engine* e, uint64_t* xor_out, uint64_t* sum_out)
   unsigned long long h2[2];
   CK(cudaMemcpyAsync(h2, d2, 16, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  cudaFree(d2);
   *xor_out = h2[0]; *sum_out = h2[1];
   return TLAG_OK;
 }
@@ -1319,8 +1383,9 @@ extern "C" int tlag_trace(tlag_engine* e, uint64_t state_idx, uint32_t* states_o
   uint64_t cur = state_idx;
   for (;;) {
     uint32_t par = 0, meta = 0;
-    CK(cudaMemcpy(&par, e->d_parent + cur, 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(&meta, e->d_meta + cur, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(&par, e->d_parent + cur, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&meta, e->d_meta + cur, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     chain.push_back(cur);
     acts.push_back(par == 0xFFFFFFFFu ? -1 : (int32_t)(meta >> 8));
     if (par == 0xFFFFFFFFu) break;

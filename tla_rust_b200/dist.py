@@ -51,6 +51,21 @@ class DistributedBFS:
         self.e.seed(mine)
         self.n_init_total = len(init_words)
 
+    def global_digest(self):
+        """XOR / SUM (mod 2^64) of the fingerprints of every state stored on any rank: the checksum of checksums the
+        single-GPU run and the oracle are compared with (bit-exact state SET across ranks, not only its size)."""
+        x, s_ = self.e.digest()
+        t = torch.tensor([x - (1 << 64) if x >= (1 << 63) else x, s_ - (1 << 64) if s_ >= (1 << 63) else s_],
+                         dtype=torch.int64, device=self.device)
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t)
+        gx, gs = 0, 0
+        for p_ in parts:
+            a, b = (int(v) & 0xFFFFFFFFFFFFFFFF for v in p_.tolist())
+            gx ^= a
+            gs = (gs + b) & 0xFFFFFFFFFFFFFFFF
+        return gx, gs
+
     def _exchange_chunk(self, first, count, on_gpu, ev):
         e, world, rw = self.e, self.world, self.rec_words
         while True:

@@ -204,6 +204,8 @@ def build_sliced_library(cm, force=False, verbose=False, scalar=None):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
            f'-DTLAG_SLICED_INC="{inc}"', "-shared", "-o", so + ".tmp", os.path.join(_HERE, "csrc", "tlag_engine.cu")]
+    if not scalar and cm.frame_words > 512:
+        cmd.insert(-4, "-DTLAG_SL_SEG_NOINLINE")
     for k in ("TLAG_SL_OCC", "TLAG_SL_BLOCK"):
         if os.environ.get(k):
             cmd.insert(-4, f"-D{k}={int(os.environ[k])}")
@@ -215,6 +217,8 @@ def build_sliced_library(cm, force=False, verbose=False, scalar=None):
 
 
 def load_sliced_library(cm, build=True):
+    if os.environ.get("TLAG_NO_BUILD") == "1":      # GPU sessions: never spend box time in nvcc
+        build = False
     so = sliced_library_path(cm)
     if so not in _NATIVE_LIBS:
         if not os.path.exists(so):
