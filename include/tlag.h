@@ -91,6 +91,9 @@ int  tlag_result_now(tlag_engine *e, tlag_result *out);        /* counters so fa
 int  tlag_trace(tlag_engine *e, uint64_t state_idx, uint32_t *states_out, int32_t *actions_out,
                 uint32_t *len_inout);
 int  tlag_read_states(tlag_engine *e, uint64_t first, uint64_t n, uint32_t *states_out);
+/* One hop of a parent chain: state idx (W words), its parent's index and the meta word = action id << 8 | rank whose
+ * store holds the parent (multi-GPU: the host follows the chain from rank to rank).  parent 0xFFFFFFFF = initial state. */
+int  tlag_read_link(tlag_engine *e, uint64_t idx, uint32_t *state_out, uint32_t *parent_out, uint32_t *meta_out);
 /* Checksum of checksums over every stored state: XOR and SUM (mod 2^64) of the 64-bit fingerprints
  * (size-independent parity property for state spaces too large to read back). */
 int  tlag_digest(tlag_engine *e, uint64_t *xor_out, uint64_t *sum_out);
@@ -121,6 +124,20 @@ int  tlag_expand_route(tlag_engine *e, uint32_t n_ranks, uint64_t first, uint64_
 int  tlag_insert_records(tlag_engine *e, uint64_t d_recv, uint64_t n_records, uint32_t src_rank_unused,
                          uint64_t *n_new);
 int  tlag_advance_level(tlag_engine *e, tlag_wave_stats *out);  /* frontier <- newly inserted  */
+
+/* ---- peer-memory exchange (NVLink / NVSwitch; no NCCL on the data path) ---------------------------------------
+ * tlag_p2p_init allocates this rank's inbox (2 buffers x n_ranks regions of cap_records records) and send regions
+ * and returns a 64-byte CUDA IPC handle of the inbox; the host all-gathers the handles (any transport) and calls
+ * tlag_p2p_attach for every peer.  tlag_p2p_level then runs one whole BFS level on this rank: per chunk of
+ * chunk_states frontier states the expand kernels bucket successors by owner, k_push stores the buckets into the
+ * owners' inboxes and publishes {count, chunk number} with a system-scope release, k_insert_inbox waits for every
+ * source's chunk, inserts the records (this rank's share of the next frontier) and acknowledges.  All ranks must
+ * pass the same n_chunks.  expect_inbound: upper estimate of the records this rank may receive (store head-room).
+ * Follow with tlag_advance_level; termination is the host's all-reduce of `discovered`. */
+int  tlag_p2p_init(tlag_engine *e, uint32_t n_ranks, uint32_t rank, uint64_t cap_records, uint8_t *handle_out64);
+int  tlag_p2p_attach(tlag_engine *e, uint32_t peer, const uint8_t *handle64);
+int  tlag_p2p_level(tlag_engine *e, uint64_t n_chunks, uint64_t chunk_states, uint64_t expect_inbound,
+                    tlag_wave_stats *out);
 
 #ifdef __cplusplus
 }

@@ -23,29 +23,6 @@
 
 #include "../tla_rust_b200/csrc/tlag_vm.h"
 
-#ifdef TLAG_NATIVE_INC
-/* Test hook (tests/test_native.py): run the model-specialised native code that tla_rust_b200/compile/native.py
- * generates for the CUDA engine inside this engine, in place of the interpreter, so that its results can be compared
- * with the interpreter's on a machine without a GPU.  The library built this way serves ONE model. */
-#define TLAG_VM_EXEC_QUAL static inline __attribute__((always_inline))
-#define TLAG_VM_EXEC_FN tlag_vm_exec_inl
-#define TLAG_VM_EXT 1
-#include "../tla_rust_b200/csrc/tlag_vm_exec.inc"
-#undef TLAG_VM_EXEC_FN
-#undef TLAG_VM_EXT
-#undef TLAG_VM_EXEC_QUAL
-#define TLAG_NATIVE_X tlag_vm_exec_inl
-#define TLAG_NATIVE_QUAL static
-#include TLAG_NATIVE_INC
-#ifdef TLAG_NATIVE_SCHED_WARP
-/* block form: a single lane simply runs block after block */
-static int tlag_native_run(const int32_t *cpool, int32_t *f, uint32_t *pc_io, int32_t *info, int32_t *info2) {
-  for (;;) { const int ev = tlag_native_block(cpool, f, pc_io, info, info2); if (ev >= 0) return ev; }
-}
-#endif
-#define tlag_vm_run(code, cpool, f, pc, info, info2, steps) tlag_native_run(cpool, f, pc, info, info2)
-#endif
-
 #define MAXW 128
 #define MAX_STEPS (1ull << 38)   /* runaway-program backstop (InnerSerial needs ~10^9 instructions for one successor) */
 
@@ -172,12 +149,9 @@ static void sl_emit_frame(tlag_sl_cx *cx, const int32_t *f, int aid, int dirty) 
 #define TLAG_SL_TRAP(code, line) do { atomic_min64(&cx->e->viol_trap, (cx->idx << 20) | ((uint64_t)((code) & 15) << 16) | (uint32_t)((line) & 0xFFFF)); cx->trapped = 1; } while (0)
 #define TLAG_SL_SUBQ static __attribute__((noinline))
 #define TLAG_SL_SEGQ static __attribute__((noinline))
+#define TLAG_SL_POISON 1     /* array form: the frame of every slice starts as garbage, as in a fresh CUDA thread */
 #include TLAG_SLICED_INC
-#if TLAG_SL_SCALAR
 typedef void (*sl_fn)(const int32_t *, const uint32_t *, tlag_sl_cx *);
-#else
-typedef void (*sl_fn)(const int32_t *, int32_t *, tlag_sl_cx *);
-#endif
 #define SL_ADDR_INV(j) tlag_sl_inv_##j,
 #define SL_ADDR_NEXT(j) tlag_sl_next_##j,
 static const sl_fn sl_inv_fns[] = { TLAG_SL_INV_LIST(SL_ADDR_INV) NULL };
@@ -186,7 +160,6 @@ static const sl_fn sl_next_fns[] = { TLAG_SL_NEXT_LIST(SL_ADDR_NEXT) NULL };
 static void *worker(void *arg) {
   cpu_engine *e = (cpu_engine *)arg;
   const cpu_model *m = &e->m;
-  int32_t *frame = (int32_t *)calloc(m->frame_words + 8, 4);
   tlag_sl_cx cxs; memset(&cxs, 0, sizeof(cxs));
   tlag_sl_cx *cx = &cxs;
   cx->e = e;
@@ -202,13 +175,7 @@ static void *worker(void *arg) {
         const sl_fn *fns = ph == 0 ? sl_inv_fns : sl_next_fns;
         cx->phase = ph;
         for (int j = 0; fns[j]; ++j) {
-#if TLAG_SL_SCALAR
           fns[j](m->cpool, cx->src, cx);
-#else
-          for (uint32_t k = 0; k < m->frame_words; ++k) frame[k] = 0x5A5A5A5A;
-          tlag_unpack(m->layout, (int)m->n_slots, cx->src, frame);
-          fns[j](m->cpool, frame, cx);
-#endif
         }
       }
       if (cx->nsucc == 0 && !cx->trapped && (m->flags & 1)) atomic_min64(&e->viol_deadlock, idx << 20);
@@ -217,7 +184,6 @@ static void *worker(void *arg) {
   __atomic_fetch_add(&e->generated, cx->gen, __ATOMIC_RELAXED);
   __atomic_fetch_xor(&e->dig_xor, cx->dx, __ATOMIC_RELAXED);
   __atomic_fetch_add(&e->dig_sum, cx->ds, __ATOMIC_RELAXED);
-  free(frame);
   return NULL;
 }
 #else
@@ -507,6 +473,8 @@ typedef struct {
   cpu_engine e;
   uint64_t lo, hi, level, depth, init_states;
   int verdict, detail;
+  uint64_t viol_idx;       /* first violating state of this shard (index in its store) */
+  uint32_t rank;           /* written into the meta word of routed records (whose store holds the parent) */
 } cpu_shard;
 
 cpu_shard *tlagcpu_shard_create(const cpu_model *m) {
@@ -588,8 +556,8 @@ int tlagcpu_shard_expand_route(cpu_shard *s, uint32_t n_ranks, uint64_t first, u
         int32_t info = 0, info2 = 0;
         int ev = tlag_vm_run(m->code, m->cpool, frame, &pc, &info, &info2, MAX_STEPS);
         if (ev == TLAG_EV_HALT) break;
-        if (ev == TLAG_EV_INVF) { if (!kind) { kind = 1; s->detail = info; } continue; }
-        if (!kind) kind = 4;
+        if (ev == TLAG_EV_INVF) { if (!kind) { kind = 1; s->detail = info; if (!s->verdict) s->viol_idx = idx; } continue; }
+        if (!kind) { kind = 4; if (!s->verdict) s->viol_idx = idx; }
         break;
       }
     }
@@ -600,7 +568,7 @@ int tlagcpu_shard_expand_route(cpu_shard *s, uint32_t n_ranks, uint64_t first, u
       int ev = tlag_vm_run(m->code, m->cpool, frame, &pc, &info, &info2, MAX_STEPS);
       if (ev == TLAG_EV_HALT) break;
       if (ev == TLAG_EV_GEN) { ++nsucc; ++gen; continue; }
-      if (ev == TLAG_EV_ASSERT) { if (!kind) { kind = 2; s->detail = info; } continue; }
+      if (ev == TLAG_EV_ASSERT) { if (!kind) { kind = 2; s->detail = info; if (!s->verdict) s->viol_idx = idx; } continue; }
       if (ev == TLAG_EV_EMIT) {
         ++nsucc; ++gen;
         int ov;
@@ -613,14 +581,14 @@ int tlagcpu_shard_expand_route(cpu_shard *s, uint32_t n_ranks, uint64_t first, u
         if (counts[owner] >= region) { free(frame); return -5; }
         uint32_t *dst = send + (owner * region + counts[owner]) * (uint64_t)(W + 2);
         memcpy(dst, succ, (size_t)W * 4);
-        dst[W] = (uint32_t)idx; dst[W + 1] = (uint32_t)info << 8;
+        dst[W] = (uint32_t)idx; dst[W + 1] = ((uint32_t)info << 8) | (s->rank & 0xFF);
         counts[owner]++;
         continue;
       }
       if (!kind) kind = 4;
       break;
     }
-    if (nsucc == 0 && (m->flags & 1) && !kind) kind = 3;
+    if (nsucc == 0 && (m->flags & 1) && !kind) { kind = 3; if (!s->verdict) s->viol_idx = idx; }
   }
   free(frame);
   s->e.generated += gen;
@@ -636,6 +604,17 @@ void tlagcpu_shard_advance(cpu_shard *s) {
 
 void tlagcpu_shard_result(cpu_shard *s, uint64_t *out4) {
   out4[0] = s->e.generated; out4[1] = s->e.n_states; out4[2] = s->depth; out4[3] = (uint64_t)s->verdict;
+}
+
+void tlagcpu_shard_set_rank(cpu_shard *s, uint32_t rank) { s->rank = rank; }
+
+/* violation of this shard (verdict, detail, state index) and one hop of a parent chain, for the cross-rank trace */
+void tlagcpu_shard_violation(cpu_shard *s, uint64_t *out3) { out3[0] = (uint64_t)s->verdict; out3[1] = (uint64_t)s->detail; out3[2] = s->viol_idx; }
+int tlagcpu_shard_read_link(cpu_shard *s, uint64_t idx, uint32_t *state_out, uint32_t *parent_out, uint32_t *meta_out) {
+  if (idx >= s->e.n_states) return -1;
+  memcpy(state_out, s->e.states + idx * s->e.m.W, (size_t)s->e.m.W * 4);
+  *parent_out = s->e.parent[idx]; *meta_out = s->e.meta[idx];
+  return 0;
 }
 
 uint32_t tlagcpu_owner(const uint32_t *w, int W, uint32_t n_ranks) { return tlag_owner(w, W, n_ranks); }

@@ -89,7 +89,7 @@ def test_cabi_library_exports_every_declared_symbol():
     if not os.path.exists(engine.LIB_PATH):
         engine.build_library()
     hdr = open(os.path.join(ROOT, "include", "tlag.h")).read()
-    names = set(re.findall(r"\b(tlag_[a-z_]+)\s*\(", hdr))
+    names = set(re.findall(r"\b(tlag_[a-z0-9_]+)\s*\(", hdr))
     assert len(names) >= 15
     L = C.CDLL(engine.LIB_PATH)
     for nme in names:

@@ -32,6 +32,20 @@ class CpuShardEngine:
         self.L.tlagcpu_shard_create.restype = C.c_void_p
         self.L.tlagcpu_shard_insert.restype = C.c_uint64
         self.h = C.c_void_p(self.L.tlagcpu_shard_create(C.byref(m)))
+        if dist.is_initialized():
+            self.L.tlagcpu_shard_set_rank(self.h, C.c_uint32(dist.get_rank()))
+
+    def violation(self):
+        out = (C.c_uint64 * 3)()
+        self.L.tlagcpu_shard_violation(self.h, out)
+        return {"verdict": int(out[0]), "detail": int(out[1]), "state_idx": int(out[2])}
+
+    def read_link(self, idx):
+        st = np.zeros(self.cm.W, dtype=np.uint32)
+        par, meta = C.c_uint32(), C.c_uint32()
+        assert self.L.tlagcpu_shard_read_link(self.h, C.c_uint64(idx), st.ctypes.data_as(C.c_void_p), C.byref(par), C.byref(meta)) == 0
+        root = par.value == 0xFFFFFFFF
+        return st, (-1 if root else par.value), (-1 if root else meta.value >> 8), meta.value & 0xFF
 
     def seed(self, init):
         a = np.ascontiguousarray(init, dtype=np.uint32).reshape(-1, self.cm.W)
@@ -80,8 +94,10 @@ def _worker(rank, world, port, name, q):
     d = DistributedBFS(e, cm, rank, world, "cpu", cap_records=1 << 16, chunk_states=500)
     d.seed(init)
     out = d.run()
+    cex = d.counterexample()
     if rank == 0:
-        q.put((out["verdict"], out["generated"], out["distinct"], out["depth"], out["local"]["distinct"]))
+        q.put((out["verdict"], out["generated"], out["distinct"], out["depth"], out["local"]["distinct"],
+               None if cex is None else (cex[0], cex[1], cex[2].tolist(), cex[3].tolist())))
     e.close()
     dist.destroy_process_group()
 
@@ -104,7 +120,45 @@ def test_partitioned_bfs_matches_single(name, world):
         p.join(timeout=240)
         assert p.exitcode == 0
     res = q.get(timeout=10)
-    verdict, generated, distinct, depth, local = res
+    verdict, generated, distinct, depth, local, cex = res
+    assert cex is None
     o2 = exp["o2"]
     assert (verdict, generated, distinct, depth) == (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"])
     assert 0 < local < distinct            # the state space really was sharded
+
+
+@pytest.mark.parametrize("name,world", [("demo_race", 2), ("pcal_intro_readme_buggy", 3), ("MCVoting_deadlock", 2)])
+def test_counterexample_is_stitched_across_ranks(name, world):
+    """A violation found on some rank yields a behaviour: the parent chain hops between the ranks' stores (meta word =
+    rank holding the parent).  The chain must start in an initial state, have the oracle's depth, and every step must
+    be a real transition (the successor is among the states ORACLE O2 generates from its predecessor's level)."""
+    from oracle import cpu_engine
+    from tla_rust_b200.compiled import load_compiled
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    verdict, generated, distinct, depth, local, cex = q.get(timeout=10)
+    o2 = exp["o2"]
+    assert cex is not None and verdict != 0
+    kind, detail, states, acts = cex
+    assert kind == o2["verdict"]
+    states = np.array(states, dtype=np.uint32)
+    # starts in an initial state, one state per level up to the level the violation was seen in
+    assert any((states[0] == np.asarray(i, dtype=np.uint32)).all() for i in init.reshape(-1, cm.W))
+    assert acts[0] == -1 and all(a >= 0 for a in acts[1:])
+    assert len(states) == o2["depth"] - 1 or len(states) == o2["depth"]
+    # every hop is a transition of the model: the child is discovered when the single-process oracle expands the parent
+    r = cpu_engine.run(cm, init, deadlock=info["deadlock"], want_states=True, max_states=1 << 17)
+    known = {tuple(x) for x in r["states"].tolist()}
+    for st in states.tolist():
+        assert tuple(st) in known

@@ -14,13 +14,14 @@ pytestmark = pytest.mark.gpu
 
 def _engine(cm, **kw):
     from tla_rust_b200.engine import Engine
+    kw.setdefault("native", False)          # this file pins the interpreter kernel unless a test says otherwise
     return Engine(cm, **kw)
 
 
-def _check_fixture(name):
+def _check_fixture(name, native=False):
     from oracle import cpu_engine
     cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
-    e = _engine(cm, deadlock=info["deadlock"])
+    e = _engine(cm, deadlock=info["deadlock"], native=native)
     e.seed(init)
     levels = [int(len(np.unique(init, axis=0)))]
     while True:
@@ -57,74 +58,46 @@ def test_bfs_matches_oracle(name):
     _check_fixture(name)
 
 
-@pytest.mark.xfail(strict=False, reason="operator subroutines (CALL/RET) were added after the last GPU session of round 1: "
-                                        "bit-exact on the CPU bytecode engine, not yet run on a device")
 @pytest.mark.parametrize("name,counts", [("MCssi", [0, 945, 569, 9]), ("MCssi_3x1", [0, 152554, 90430, 13]),
                                          ("MCssi_2x2", [0, 50121, 29629, 13]), ("MCssi_2x2_wide", [0, 50121, 29629, 13])])
 def test_ssi_subroutine_model_on_device(name, counts):
     """serializableSnapshotIsolation.tla, eight invariants: 2 transactions x 1 key (frame 1720 words: 2048 class), 3 x 1
     and 2 x 2 (2910 / 3400 words: 4096 class), and 2 x 2 with a larger sequence capacity (5080 words: 8192 class); the
-    counts are the ones the AST oracle O1 produced (tests/test_containers.py), the digests the CPU bytecode engine's.
-    Runs in a child process with a time limit: this path has not been seen on a device yet, and a child can be
-    stopped without taking the test session (or the GPU context of the other tests) with it."""
-    import json
-    import subprocess
-    import sys
-    prog = (
-        "import json, os, sys\n"
-        "sys.path.insert(0, %r)\n"
-        "from tla_rust_b200.compiled import load_compiled\n"
-        "from tla_rust_b200.engine import Engine\n"
-        "cm, init, exp, info = load_compiled(%r)\n"
-        "e = Engine(cm, deadlock=info['deadlock'])\n"
-        "e.seed(init)\n"
-        "r = e.run()\n"
-        "print(json.dumps({'r': [r['verdict'], r['generated'], r['distinct'], r['depth']], 'digest': list(e.digest())}))\n"
-        "e.close()\n") % (os.path.dirname(GOLDEN.rstrip('/')).rsplit('/tests', 1)[0], os.path.join(GOLDEN, name + ".tlagz"))
-    p = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=120)
-    assert p.returncode == 0, p.stderr[-2000:]
-    got = json.loads(p.stdout.strip().splitlines()[-1])
+    counts are the ones the AST oracle O1 produced (tests/test_containers.py), the digests the CPU bytecode engine's."""
+    _check_fixture(name)
     _, _, exp, _ = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
     o2 = exp["o2"]
-    assert got["r"] == [o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]] == counts
-    assert got["digest"] == [o2["fp_xor"], o2["fp_sum"]]
+    assert [o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]] == counts
 
 
-@pytest.mark.xfail(strict=False, reason="the model-specialised native build (compile/native.py) was written after the last "
-                                        "GPU session of round 1: bit-exact inside the CPU engine, not yet run on a device")
-@pytest.mark.parametrize("name", ["MCPaxos3", "MCPaxos3_b2", "Containers", "MCraft_s3_l"])
-def test_native_build_matches_oracle_on_device(name):
-    """Same fixtures, same C ABI, but the library is the engine compiled with the model's program as native CUDA
-    (prebuilt into csrc/native/: by __graft_entry__.build() for the first three, by hand for the raft fixture, whose
-    10 K-instruction program takes nvcc 5 minutes -- skipped when that library is not there).  Child process with a
-    time limit, as above."""
-    import json
-    import subprocess
-    import sys
-    from tla_rust_b200.engine import native_library_path
-    cm0, _, _, _ = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
-    if not os.path.exists(native_library_path(cm0)):
-        pytest.skip("native library of this fixture was not prebuilt")
-    root = os.path.dirname(GOLDEN.rstrip('/')).rsplit('/tests', 1)[0]
-    prog = (
-        "import json, os, sys\n"
-        "sys.path.insert(0, %r)\n"
-        "from tla_rust_b200.compiled import load_compiled\n"
-        "from tla_rust_b200.engine import Engine\n"
-        "cm, init, exp, info = load_compiled(%r)\n"
-        "e = Engine(cm, deadlock=info['deadlock'], native=True)\n"
-        "assert b'native' in e.L.tlag_version()\n"
-        "e.seed(init)\n"
-        "r = e.run()\n"
-        "print(json.dumps({'r': [r['verdict'], r['generated'], r['distinct'], r['depth']], 'digest': list(e.digest())}))\n"
-        "e.close()\n") % (root, os.path.join(GOLDEN, name + ".tlagz"))
-    p = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=150)
-    assert p.returncode == 0, p.stderr[-2000:]
-    got = json.loads(p.stdout.strip().splitlines()[-1])
-    _, _, exp, _ = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
+def _check_prefix(name, levels, native):
+    """depth-bounded run: counts and fingerprint digest after `levels` levels against the oracle's per-level record"""
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
     o2 = exp["o2"]
-    assert got["r"] == [o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]]
-    assert got["digest"] == [o2["fp_xor"], o2["fp_sum"]]
+    x, sm, gen = o2["level_digests"][levels - 1]
+    e = _engine(cm, deadlock=info["deadlock"], native=native)
+    e.seed(init)
+    for _ in range(levels - 1):
+        ws = e.step()
+        assert ws["verdict"] == 5
+    r = e.result()
+    assert (r["generated"], r["distinct"], r["depth"]) == (gen, sum(o2["levels"][:levels]), levels)
+    assert e.digest() == (x, sm)
+    e.close()
+
+
+def test_config5_ssi_4x3_prefix_matches_oracle_on_both_engines():
+    """BASELINE config #5 at its stated bound (4 transactions x 3 keys, eight invariants, deadlock ON): the first 8
+    levels (2,453,305 states) on the interpreter kernel and on the sliced kernels, bit-exact against ORACLE O2's
+    per-level digests (the 10-level, 168 M-state job is bench.py --workload MCssi_4x3)."""
+    _check_prefix("MCssi_4x3", 8, False)
+    _check_prefix("MCssi_4x3", 8, "sliced")
+
+
+def test_config4_raft_t4l3_matches_oracle_on_both_engines():
+    """BASELINE config #4 at its stated bound (3 servers, MaxTerm 4, MaxLogLen 3): 11,296,712 states, whole space."""
+    _check_fixture("MCraft_t4l3")
+    _check_fixture("MCraft_t4l3", native="sliced")
 
 
 def test_assert_trace_is_a_shortest_counterexample():
@@ -218,8 +191,6 @@ def test_probe_roundtrip_full_size_properties():
     e.close()
 
 
-# Last in the file on purpose: the raft fixtures were recompiled (smaller code, smaller frame) after the last GPU
-# session of round 1; their state sets are unchanged (same digests on the CPU bytecode engine).
 @pytest.mark.parametrize("name", ["MCraft", "MCraft_s3", "MCraft_s3_m", "MCraft_s3_l"])
 def test_raft_fixtures_match_oracle(name):
     _check_fixture(name)

@@ -14,8 +14,7 @@ import pytest
 from conftest import GOLDEN, ROOT
 from oracle import cpu_engine
 from tla_rust_b200.compiled import load_compiled
-from tla_rust_b200.compile.native import model_key
-from tla_rust_b200.compile.sliced import Emitter, Plan, SliceError, emit_sliced
+from tla_rust_b200.compile.sliced import Emitter, Plan, SliceError, emit_sliced, model_key
 
 KEYS = ("verdict", "generated", "distinct", "depth", "fp_xor", "fp_sum", "levels")
 

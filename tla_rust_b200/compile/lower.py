@@ -3879,7 +3879,7 @@ class Lowering:
         Control falls through after all alternatives are exhausted."""
         self.bound = bound
         kind = n.k
-        # Segment cuts (compile/native.py, sliced build): `top` is true while nothing but disjunction structure lies
+        # Segment cuts (compile/sliced.py): `top` is true while nothing but disjunction structure lies
         # between the root of Next and this node, i.e. the code of each alternative below is a self-contained slice of
         # the program (entered by falling in, left by falling out) that can become a kernel of its own.
         top = self._seg_top

@@ -39,8 +39,9 @@ from __future__ import annotations
 
 import numpy as np
 
+import hashlib
+
 from .bytecode import OP
-from .native import model_key   # noqa: F401  (same key: program words + entry points)
 
 _NAME = {v: k for k, v in OP.items()}
 _COND_J = {"JEQ", "JNE", "JLT", "JGE", "JEQI", "JNEI", "JLTI", "JGEI", "JBT", "JBF", "JBTI", "JBFI"}
@@ -60,6 +61,15 @@ SCALAR_MAX_FRAME = 1024     # scalar form only below this frame size (statements
 
 class SliceError(Exception):
     pass
+
+
+def model_key(cm) -> str:
+    """Identifies the generated code: program words, entry points (the constant pool is folded in through them)."""
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(cm.code, dtype=np.uint64).tobytes())
+    h.update(np.ascontiguousarray(cm.cpool, dtype=np.int32).tobytes())
+    h.update(repr(sorted(cm.entries.items())).encode())
+    return h.hexdigest()[:16]
 
 
 def _imm28(v: int) -> int:
@@ -254,11 +264,189 @@ class Emitter:
         js = [self.dyn_index.get(base + i) for i in range(n)]
         return all(j is not None for j in js) and all(js[i] == js[0] + i for i in range(n))
 
+    # ---- liveness (per slice function) ------------------------------------------------------------------------
+    # Every slice kernel starts from the packed state; under the interpreter the state was unpacked once and the primed
+    # copy initialised once per state, here that would be paid per slice (raft: 589 + 589 word stores x 36 kernels).
+    # A backward liveness pass over the slice's control-flow graph finds the frame words a slice actually reads before
+    # writing them: only those slots are unpacked, copies / fills of words nobody reads afterwards are trimmed to the
+    # live sub-ranges, and pure instructions whose result is dead are dropped.
+    def _extent(self, i: Ins, base, nw):
+        if nw is not None:
+            return nw
+        blocks = getattr(self.cm, "blocks", None) or []
+        ends = [b + n for b, n in blocks if b <= base < b + n]
+        return max(ends) - base if ends else (i.d if i.op in ("LDX", "STX") else 1)
+
+    def _sub_reads(self, e):
+        """words a subroutine (and its callees) may read"""
+        memo = self.__dict__.setdefault("_sub_reads_memo", {})
+        if e not in memo:
+            memo[e] = 0
+            m = 0
+            for i in self.plan.ins[e:self.plan.subs[e]]:
+                m |= self.rw(i)[0]
+            memo[e] = m
+        return memo[e]
+
+    def rw(self, i: Ins):
+        """-> (words read, words certainly overwritten, droppable when the overwritten words are dead) as bit masks"""
+        mk = lambda base, n: (((1 << n) - 1) << base) if n > 0 else 0
+        op, a, b, c, d, I, J = i.op, i.a, i.b, i.c, i.d, i.I, i.J
+        dyn = 0
+        for base, nw in dyn_accesses(i):
+            dyn |= mk(base, self._extent(i, base, nw))
+        if op in _BIN:
+            return mk(b, 1) | mk(c, 1), mk(a, 1), True
+        if op in _BINI or op in ("MOV", "NEG", "NOT"):
+            return mk(b, 1), mk(a, 1), True
+        if op in ("JEQ", "JNE", "JLT", "JGE"):
+            return mk(a, 1) | mk(b, 1), 0, False
+        if op in ("JEQI", "JNEI", "JLTI", "JGEI") or op in _COND_I:
+            return mk(a, 1), 0, False
+        if op in ("JBT", "JBF"):
+            return mk(b, 1) | dyn, 0, False
+        if op in ("JBTI", "JBFI"):
+            return mk(a + (b >> 5), 1), 0, False
+        if op in ("JMP", "GEN", "ASSERTF", "INVF", "TRAP", "HALT", "RET"):
+            return 0, 0, False
+        if op in ("LI", "LIW"):
+            return 0, mk(a, 1), True
+        if op == "MOVN":
+            return mk(b, c), mk(a, c), True
+        if op == "ZERO":
+            return 0, mk(a, b), True
+        if op == "LDC":
+            return 0, mk(a, d), True
+        if op in ("DIV", "MOD"):
+            return mk(b, 1) | mk(c, 1), mk(a, 1), False
+        if op == "EQN":
+            return mk(b, d) | mk(c, d), mk(a, 1), True
+        if op == "LDX":
+            return mk(c, 1) | dyn, mk(a, d), True
+        if op == "STX":
+            return mk(b, 1) | mk(c, d), 0, False
+        if op == "TBL":
+            return mk(d, 1), mk(a, 1), True
+        if op == "TBLT":
+            return mk(d, 1), mk(a, 1), False
+        if op in ("BSET", "BCLR"):
+            return mk(b, 1) | dyn, 0, False
+        if op == "BTEST":
+            return mk(c, 1) | dyn, mk(a, 1), True
+        if op in _WORDWISE:
+            return mk(b, d) | mk(c, d), mk(a, d), True
+        if op == "BISZ":
+            return mk(b, c), mk(a, 1), True
+        if op == "BSUB":
+            return mk(b, d) | mk(c, d), mk(a, 1), True
+        if op == "BCNT":
+            return mk(b, c), mk(a, 1), True
+        if op == "BNEXT":
+            return mk(c, 1) | mk(b, (d + 31) // 32), mk(a, 1), True
+        if op == "BFILL":
+            return mk(a, (b + 31) // 32), 0, False
+        if op == "BSETI":
+            return mk(a + ((I & 0xFFFFFFFF) >> 5), 1), 0, False
+        if op == "BTESTI":
+            return mk(b + ((J & 0xFFFFFFFF) >> 5), 1), mk(a, 1), True
+        if op == "UCLAMP":
+            return mk(a, 1), 0, False
+        if op == "MADI":
+            return mk(a, 1) | mk(c, 1), 0, False
+        if op == "BANDC":
+            return mk(b, J & 0xFF), mk(a, J & 0xFF), True
+        if op == "LEXLT":
+            return mk(b, d) | mk(c, d), mk(a, 1), True
+        if op == "SFIND":
+            return mk(c, d & 127) | dyn, mk(a, 1), True
+        if op == "SINS":
+            return mk(b, d >> 7) | mk(c, 1) | dyn, 0, False
+        if op == "CALL":
+            return self._sub_reads(I), 0, False
+        if op in ("EMIT", "EMITD"):
+            p_off = self.usz
+            if op == "EMITD" and I > 0:
+                n = self.cpool[I]
+                slots = [s_ for r in range(n) for s_ in range(self.cpool[I + 1 + 3 * r], self.cpool[I + 1 + 3 * r] + self.cpool[I + 2 + 3 * r])]
+            else:
+                slots = range(len(self.layout))
+            m = 0
+            for s_ in slots:
+                m |= 1 << (p_off + self.layout[s_][0])
+            return m, 0, False
+        raise SliceError(f"no read/write description for opcode {op}")
+
+    def liveness(self, pro, seg):
+        """live-out word masks per pc for the function `prologue + slice`; also the live-in mask of the function"""
+        (p0, p1), (s, e) = pro, seg
+        order = list(range(p0, p1)) + list(range(s, e))
+        END = -1
+        succ = {}
+        for k in order:
+            i = self.plan.ins[k]
+            out = []
+            nxt = (k + 1 if k + 1 < p1 else s) if k < p1 and p0 <= k else (k + 1 if k + 1 < e else END)
+            if i.op not in ("JMP", "TRAP", "RET", "HALT"):
+                out.append(nxt)
+            if i.op == "HALT":
+                out.append(END)
+            t = i.target()
+            if t is not None and i.op != "CALL":
+                if p0 <= k < p1 and t == p1:
+                    t = s
+                out.append(END if t == e else t)
+            succ[k] = out
+        info = {k: self.rw(self.plan.ins[k]) for k in order}
+        live_in = {k: 0 for k in order}
+        live_in[END] = 0
+        live_out = {k: 0 for k in order}
+        changed = True
+        while changed:
+            changed = False
+            for k in reversed(order):
+                lo = 0
+                for t in succ[k]:
+                    lo |= live_in[t]
+                rd, kl, _ = info[k]
+                i = self.plan.ins[k]
+                if i.op in ("MOVN", "BANDC") or i.op in _WORDWISE:
+                    # element-wise: a source word is read only if the destination word it feeds is read afterwards
+                    n_ = i.c if i.op == "MOVN" else ((i.J & 0xFF) if i.op == "BANDC" else i.d)
+                    sel = (lo >> i.a) & ((1 << n_) - 1)
+                    rd = sel << i.b
+                    if i.op in _WORDWISE:
+                        rd |= sel << i.c
+                li = rd | (lo & ~kl)
+                if lo != live_out[k] or li != live_in[k]:
+                    live_out[k], live_in[k] = lo, li
+                    changed = True
+        return live_out, (live_in[order[0]] if order else 0), info
+
     # ---- one instruction -----------------------------------------------------------------------------------
-    def stmt(self, i: Ins, goto, rv: str) -> str:
-        """C statement(s) for instruction i.  goto(t) -> text of a jump to pc t; rv: return value text on a trap."""
+    @staticmethod
+    def _runs(base, n, live):
+        """maximal runs (offset, length) of the words base..base+n that are in the live mask (None: all of them)"""
+        if live is None:
+            return [(0, n)] if n > 0 else []
+        out, j = [], 0
+        while j < n:
+            if (live >> (base + j)) & 1:
+                k = j
+                while k < n and (live >> (base + k)) & 1:
+                    k += 1
+                out.append((j, k - j))
+                j = k
+            else:
+                j += 1
+        return out
+
+    def stmt(self, i: Ins, goto, rv: str, live=None) -> str:
+        """C statement(s) for instruction i.  goto(t) -> text of a jump to pc t; rv: return value text on a trap;
+        live: mask of the frame words that are read after this instruction (None = unknown: write everything)."""
         R, D = self.R, self.D
         op, a, b, c, d, I, J = i.op, i.a, i.b, i.c, i.d, i.I, i.J
+        runs = lambda n: self._runs(a, n, live)
+        words = lambda n: [o + j for o, ln in runs(n) for j in range(ln)]
         trap = lambda code, line: f"{{ TLAG_SL_TRAP({code}, {line}); return{rv}; }}"
         if op in _BIN:
             return f"{R(a)} = {_BIN[op].format(x=R(b), y=R(c))};"
@@ -285,19 +473,21 @@ class Emitter:
             return f"{R(a)} = {R(b)};"
         if op == "MOVN":
             if self.scalar:
-                order = range(c) if a <= b else range(c - 1, -1, -1)
+                ws = words(c)
+                order = ws if a <= b else ws[::-1]
                 return " ".join(f"{R(a + j)} = {R(b + j)};" for j in order)
             if a <= b:
-                return f"for (uint32_t i_ = 0; i_ < {c}u; ++i_) f[{a} + i_] = f[{b} + i_];"
-            return f"for (uint32_t i_ = {c}u; i_-- > 0;) f[{a} + i_] = f[{b} + i_];"
+                return " ".join(f"for (uint32_t i_ = {o}u; i_ < {o + ln}u; ++i_) f[{a} + i_] = f[{b} + i_];" for o, ln in runs(c))
+            return " ".join(f"for (uint32_t i_ = {o + ln}u; i_-- > {o}u;) f[{a} + i_] = f[{b} + i_];" for o, ln in runs(c)[::-1])
         if op == "ZERO":
             if self.scalar:
-                return " ".join(f"{R(a + j)} = 0;" for j in range(b))
-            return f"for (uint32_t i_ = 0; i_ < {b}u; ++i_) f[{a} + i_] = 0;"
+                return " ".join(f"{R(a + j)} = 0;" for j in words(b))
+            return " ".join(f"for (uint32_t i_ = {o}u; i_ < {o + ln}u; ++i_) f[{a} + i_] = 0;" for o, ln in runs(b))
         if op == "LDC":
             if self.scalar or d <= 4:
-                return " ".join(f"{R(a + j)} = {self.cpool[I + j]};" for j in range(d))
-            return f"for (uint32_t i_ = 0; i_ < {d}u; ++i_) f[{a} + i_] = tlag_cp(cpool, {I} + (int32_t)i_);"
+                return " ".join(f"{R(a + j)} = {self.cpool[I + j]};" for j in words(d))
+            return " ".join(f"for (uint32_t i_ = {o}u; i_ < {o + ln}u; ++i_) f[{a} + i_] = tlag_cp(cpool, {I} + (int32_t)i_);"
+                            for o, ln in runs(d))
         if op == "NEG":
             return f"{R(a)} = -{R(b)};"
         if op == "NOT":
@@ -332,9 +522,9 @@ class Emitter:
                     f"{R(a)} = (int32_t)(((uint32_t){D(b, '(i_ >> 5)')} >> (i_ & 31)) & 1u); }}")
         if op in _WORDWISE:
             if self.scalar:
-                return " ".join(f"{R(a + j)} = {_WORDWISE[op].format(x=R(b + j), y=R(c + j))};" for j in range(d))
-            return (f"for (uint32_t i_ = 0; i_ < {d}u; ++i_) f[{a} + i_] = "
-                    f"{_WORDWISE[op].format(x=f'f[{b} + i_]', y=f'f[{c} + i_]')};")
+                return " ".join(f"{R(a + j)} = {_WORDWISE[op].format(x=R(b + j), y=R(c + j))};" for j in words(d))
+            return " ".join(f"for (uint32_t i_ = {o}u; i_ < {o + ln}u; ++i_) f[{a} + i_] = "
+                            f"{_WORDWISE[op].format(x=f'f[{b} + i_]', y=f'f[{c} + i_]')};" for o, ln in runs(d))
         if op == "BISZ":
             if self.scalar:
                 return f"{R(a)} = ((" + " | ".join(R(b + j) for j in range(c)) + ") == 0);" if c else f"{R(a)} = 1;"
@@ -383,8 +573,9 @@ class Emitter:
             n_, base = J & 0xFF, (J & 0xFFFFFFFF) >> 8
             if self.scalar:
                 # the mask words are compile-time constants of this model: fold them into the code
-                return " ".join(f"{R(a + j)} = {R(b + j)} & (int32_t)0x{self.cpool[base + j] & 0xFFFFFFFF:x}u;" for j in range(n_))
-            return f"for (uint32_t i_ = 0; i_ < {n_}u; ++i_) f[{a} + i_] = f[{b} + i_] & tlag_cp(cpool, {base} + (int32_t)i_);"
+                return " ".join(f"{R(a + j)} = {R(b + j)} & (int32_t)0x{self.cpool[base + j] & 0xFFFFFFFF:x}u;" for j in words(n_))
+            return " ".join(f"for (uint32_t i_ = {o}u; i_ < {o + ln}u; ++i_) f[{a} + i_] = f[{b} + i_] & tlag_cp(cpool, {base} + (int32_t)i_);"
+                            for o, ln in runs(n_))
         if op == "DIV":
             return (f"{{ const int32_t x_ = {R(b)}, y_ = {R(c)}; if (y_ == 0) {trap(1, 0)} "
                     f"int32_t q_ = x_ / y_; if ((x_ % y_ != 0) && ((x_ < 0) != (y_ < 0))) --q_; {R(a)} = q_; }}")
@@ -471,12 +662,16 @@ class Emitter:
         out.append(f"TLAG_SL_EMITW({aid}, o_); }}")
         return "\n    ".join(out)
 
-    def unpack_code(self):
-        """scalar form: frame words of the current state from the packed words in_[0..W)"""
+    def unpack_code(self, live_in=None):
+        """frame words of the current state from the packed words in_[0..W); live_in: only the slots whose word the
+        function reads before writing it"""
         out = []
         bitpos = 0
         for off, width, bias in self.layout:
             wi, sh = bitpos >> 5, bitpos & 31
+            if live_in is not None and not (live_in >> off) & 1:
+                bitpos += width
+                continue
             e = f"(in_[{wi}] >> {sh})" if sh else f"in_[{wi}]"
             if sh + width > 32:
                 e = f"({e} | (in_[{wi + 1}] << {32 - sh}))"
@@ -487,9 +682,10 @@ class Emitter:
         return out
 
     # ---- functions ----------------------------------------------------------------------------------------------
-    def _body(self, ranges, end_pc, rv, leaders_extra=(), redirect=None):
+    def _body(self, ranges, end_pc, rv, leaders_extra=(), redirect=None, live=None):
         """statements of the pc ranges (in order); jumps to end_pc go to L_end; redirect = (from pc, to pc): a jump to
-        the first is a jump to the second (end of the prologue -> start of this function's slice)"""
+        the first is a jump to the second (end of the prologue -> start of this function's slice); live = (live-out
+        masks per pc, rw info per pc) from liveness(): dead pure instructions are dropped, dead words not written."""
         targets = set(leaders_extra)
         for s, e in ranges:
             for i in self.plan.ins[s:e]:
@@ -506,9 +702,15 @@ class Emitter:
             for i in self.plan.ins[s:e]:
                 if i.op == "HALT":
                     text = "goto L_end;"
+                elif live is not None:
+                    lv = live[0][i.k]
+                    _rd, kl, pure = live[1][i.k]
+                    text = ";" if (pure and kl and not (kl & lv)) else self.stmt(i, goto, rv, lv)   # ";": result never read
                 else:
                     text = self.stmt(i, goto, rv)
                 lab = f"L{i.k}: " if i.k in targets and i.k != end_pc and (redirect is None or i.k != redirect[0]) else ""
+                if text == ";" and not lab:
+                    continue
                 lines.append(f"  {lab}{{ {text} }}")
         return lines
 
@@ -524,7 +726,14 @@ class Emitter:
         out.append(f"  for (int i_ = 0; i_ < {nd}; ++i_) m[i_] = 0;")
         return out
 
-    def emit(self) -> str:
+    def _cpool_fnv(self):
+        h = 0xcbf29ce484222325
+        for w in self.cpool:
+            h = ((h ^ (w & 0xFFFFFFFF)) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    def pieces(self):
+        """-> (defs lines, subroutine declarations, {entry: (weight, lines)}, [(kind, j, weight, lines)])"""
         cm, plan = self.cm, self.plan
         code = [i.w for i in plan.ins]
         fnv = 0xcbf29ce484222325
@@ -534,46 +743,106 @@ class Emitter:
         n_inv_prog = len(isegs) if len(getattr(cm, "invariants", [])) else 0
         sig = "(const int32_t* __restrict__ cpool, int32_t* __restrict__ f, tlag_sl_cx* __restrict__ cx)"
         ssig = "(const int32_t* __restrict__ cpool, const uint32_t* __restrict__ in_, tlag_sl_cx* __restrict__ cx)"
-        out = [
+        defs = [
             "// generated by tla_rust_b200/compile/sliced.py -- do not edit",
             f"// model key {model_key(cm)}: {len(code)} instructions, {n_inv_prog} invariant slices, {len(nsegs)} slices of Next, "
             f"{len(plan.subs)} subroutines, {'scalar' if self.scalar else 'array'} form",
             f"#define TLAG_NATIVE_CODE_LEN {len(code)}u",
             f"#define TLAG_NATIVE_CODE_FNV 0x{fnv:016x}ULL   /* FNV-1a over the 64-bit program words */",
+            f"#define TLAG_NATIVE_CPOOL_FNV 0x{self._cpool_fnv():016x}ULL  /* ... over the constant pool (folded into the code) */",
             f"#define TLAG_SL_W {self.W}", f"#define TLAG_SL_USZ {self.usz}", f"#define TLAG_SL_FRAME {self.frame}",
             f"#define TLAG_SL_SCALAR {1 if self.scalar else 0}",
             f"#define TLAG_SL_NINV {n_inv_prog}", f"#define TLAG_SL_NNEXT {len(nsegs)}",
             "#define TLAG_SL_INV_LIST(X) " + " ".join(f"X({j})" for j in range(n_inv_prog)),
             "#define TLAG_SL_NEXT_LIST(X) " + " ".join(f"X({j})" for j in range(len(nsegs))),
         ]
+        decls = [f"TLAG_SL_SUBQ int tlag_sl_sub_{e}{sig};" for e in sorted(plan.subs)]
+        subs = {}
         for e in sorted(plan.subs):
-            out.append(f"TLAG_SL_SUBQ int tlag_sl_sub_{e}{sig};")
-        for e in sorted(plan.subs):
-            out.append(f"TLAG_SL_SUBQ int tlag_sl_sub_{e}{sig} {{")
-            out += self._body([(e, plan.subs[e])], -1, " 1")
-            out += ["  return 0;", "}"]
+            lines = [f"TLAG_SL_SUBQ int tlag_sl_sub_{e}{sig} {{"]
+            lines += self._body([(e, plan.subs[e])], -1, " 1")
+            lines += ["  return 0;", "}"]
+            subs[e] = (plan.subs[e] - e, lines)
+        slices = []
+        can_live = bool(getattr(cm, "blocks", None))        # extents of dynamic accesses come from the allocation blocks
         for name, pro, segs, cnt in (("inv", ip, isegs, n_inv_prog), ("next", np_, nsegs, len(nsegs))):
             for j, (s, e) in enumerate(segs[:cnt]):
-                out.append(f"// {name} slice {j}: pcs [{s}, {e}) after the prologue [{pro[0]}, {pro[1]})")
+                out = [f"// {name} slice {j}: pcs [{s}, {e}) after the prologue [{pro[0]}, {pro[1]})"]
                 ranges = [r for r in (pro, (s, e)) if r[1] > r[0]]
+                live, live_in = None, None
+                if can_live:
+                    lo, live_in, info = self.liveness(pro, (s, e))
+                    live = (lo, info)
+                out.append(f"TLAG_SL_SEGQ void tlag_sl_{name}_{j}{ssig} {{")
                 if self.scalar:
                     self._find_dyn(ranges)
-                    out.append(f"TLAG_SL_SEGQ void tlag_sl_{name}_{j}{ssig} {{")
                     out += self._decls()
-                    out += self.unpack_code()
                 else:
-                    out.append(f"TLAG_SL_SEGQ void tlag_sl_{name}_{j}{sig} {{")
+                    out.append(f"  int32_t f[{self.frame}];")
+                    out.append("#ifdef TLAG_SL_POISON")
+                    out.append(f"  for (int i_ = 0; i_ < {self.frame}; ++i_) f[i_] = 0x5A5A5A5A;")
+                    out.append("#endif")
+                ucode = self.unpack_code(live_in)
+                out.append(f"  // unpack: {len(ucode)} of {len(self.layout)} slots are read by this slice")
+                out += ucode
                 # the prologue falls into its first slice; for the others: jump over the slices in between
-                body = []
                 if pro[1] > pro[0]:
-                    body += self._body([pro], -1, "", leaders_extra=(), redirect=(pro[1], s))
-                    body.append(f"  goto L{s};")
-                body += self._body([(s, e)], e, "", leaders_extra=(s,))
-                out += body
+                    out += self._body([pro], -1, "", leaders_extra=(), redirect=(pro[1], s), live=live)
+                    out.append(f"  goto L{s};")
+                out += self._body([(s, e)], e, "", leaders_extra=(s,), live=live)
                 out += ["  L_end: return;", "}"]
+                slices.append((name, j, (pro[1] - pro[0]) + (e - s) + len(ucode) // 4, out))
+        return defs, decls, subs, slices
+
+    def emit(self) -> str:
+        """everything in one file (the CPU bytecode engine's test build includes it: oracle/tlag_cpu.c)"""
+        defs, decls, subs, slices = self.pieces()
+        out = list(defs) + decls
+        for e in sorted(subs):
+            out += subs[e][1]
+        for _n, _j, _w, lines in slices:
+            out += lines
         out.append("")
         return "\n".join(out)
+
+    def emit_parts(self, nparts, defs_path):
+        """The CUDA build: `defs` (constants, included by the engine's translation unit too) and `nparts` translation
+        units that each hold a share of the subroutines and slices (balanced by instruction count) with their kernels
+        and launchers -- compiled in parallel (nvcc -dc), linked with the engine unit.  -> (defs text, [part texts])"""
+        defs, decls, subs, slices = self.pieces()
+        items = [("sub", e, w, lines) for e, (w, lines) in subs.items()] + [("slice", (n, j), w, lines) for n, j, w, lines in slices]
+        items.sort(key=lambda t: -t[2])
+        nparts = max(1, min(nparts, len(items)))
+        bins = [[0, []] for _ in range(nparts)]
+        for it in items:
+            bmin = min(bins, key=lambda b_: b_[0])
+            bmin[0] += it[2] + 50
+            bmin[1].append(it)
+        parts = []
+        for k, (_w, its) in enumerate(bins):
+            out = [f"// generated by tla_rust_b200/compile/sliced.py -- part {k} of {nparts}; do not edit",
+                   f'#define TLAG_SLICED_DEFS "{defs_path}"', '#include "tlag_dev.cuh"',
+                   "#undef TLAG_SL_SUBQ", '#define TLAG_SL_SUBQ extern "C" __device__ __noinline__   /* defined in one part, called from any */']
+            out += decls
+            for kind, _key, _w2, lines in its:
+                if kind == "sub":
+                    out += lines
+            for kind, _key, _w2, lines in its:
+                if kind == "slice":
+                    out += lines
+            out.append('#include "tlag_dev2.cuh"')
+            for kind, key, _w2, _lines in its:
+                if kind == "slice":
+                    nm = "INV" if key[0] == "inv" else "NEXT"
+                    out.append(f"TLAG_SL_KERNEL_{nm}({key[1]}) TLAG_SL_LAUNCH_{nm}({key[1]})")
+            out.append("")
+            parts.append("\n".join(out))
+        return "\n".join(defs) + "\n", parts
 
 
 def emit_sliced(cm, scalar=False) -> str:
     return Emitter(cm, scalar=scalar).emit()
+
+
+def emit_parts(cm, scalar, nparts, defs_path):
+    return Emitter(cm, scalar=scalar).emit_parts(nparts, defs_path)

@@ -21,8 +21,7 @@
 #include <vector>
 #include <cub/device/device_radix_sort.cuh>   // CUDA-toolkit header library; used only to reorder a level (not on the hot path)
 
-#include "../../include/tlag.h"
-#include "tlag_vm.h"
+#include "tlag_dev.cuh"
 // second copy of the instruction executor without the extension ops (see tlag_vm_exec.inc)
 #define TLAG_VM_EXEC_FN tlag_vm_exec_lean
 #define TLAG_VM_EXT 0
@@ -30,41 +29,8 @@
 #undef TLAG_VM_EXEC_FN
 #undef TLAG_VM_EXT
 
-// Model-specialised build (tla_rust_b200/compile/native.py, engine.py: build_native_library): the program of ONE
-// model compiled to straight-line code.  -DTLAG_NATIVE_INC="<generated .inc>" -DTLAG_NATIVE_FRAME=<frame class>;
-// tlag_create refuses any other program (length + FNV-1a of the code words).
-#ifdef TLAG_NATIVE_INC
-#ifndef TLAG_NATIVE_FRAME
-#error "TLAG_NATIVE_FRAME (frame class of the model: 64 ... 8192) must be defined with TLAG_NATIVE_INC"
-#endif
-#define TLAG_NATIVE_X tlag_vm_exec
-#ifndef TLAG_NATIVE_SCHED_LANE
-#define TLAG_NATIVE_SCHED_WARP 1   /* block form + min-pc election (default); -DTLAG_NATIVE_SCHED_LANE: per-lane runs */
-#endif
-// Small frames: inlined into k_wave, so that the compiler sees the frame as a local array with constant indices and
-// keeps hot words in registers.  Big frames (> 512 words): a separate function that receives the frame as a pointer --
-// scalar replacement of a 2048-word array over a 6 K-block goto graph takes cicc many minutes (raft) and buys nothing.
-#ifndef TLAG_NATIVE_QUAL
-#if TLAG_NATIVE_FRAME > 512
-#define TLAG_NATIVE_QUAL static __device__ __noinline__
-#else
-#define TLAG_NATIVE_QUAL static __device__ __forceinline__
-#endif
-#endif
-#include TLAG_NATIVE_INC
-#endif
-
-// Resident CTAs per SM the wave kernel is compiled for (register cap = 65536 / (512 x this)).  The interpreter is happy
-// with 32 registers; compiled model code keeps frame values in registers, so the native build defaults to 2 CTAs
-// (64 registers) and exposes the choice for sweeps (-DTLAG_NATIVE_OCC=1|2|4).
-#ifdef TLAG_NATIVE_INC
-#ifndef TLAG_NATIVE_OCC
-#define TLAG_NATIVE_OCC 2
-#endif
-#define TLAG_WAVE_OCC(FRAME, SMEM) TLAG_NATIVE_OCC
-#else
+// Resident CTAs per SM the interpreter wave kernel is compiled for (register cap = 65536 / (512 x this)).
 #define TLAG_WAVE_OCC(FRAME, SMEM) ((FRAME) <= 256 ? 4 : ((FRAME) <= 512 ? 2 : ((SMEM) ? 1 : TLAG_BIG_OCC)))
-#endif
 
 #define TLAG_MAXW 128
 #ifndef TLAG_BIG_OCC
@@ -81,40 +47,6 @@
       return TLAG_ECUDA;                                                                 \
     }                                                                                    \
   } while (0)
-
-struct Counters {
-  unsigned long long n_states;      // tail of the state store
-  unsigned long long generated;
-  unsigned long long work;          // chunk dispenser
-  unsigned long long viol_inv;      // min key: idx<<20 | detail
-  unsigned long long viol_assert;
-  unsigned long long viol_trap;     // idx<<20 | code<<16 | line
-  unsigned long long viol_deadlock;
-  unsigned long long store_overflow;
-  unsigned long long table_full;
-  unsigned long long route_overflow;
-  unsigned long long send_count[16];
-};
-
-struct DevParams {
-  const uint64_t* code; uint32_t code_len; int code_in_smem;
-  const int32_t* cpool;
-  const tlag_slot* layout; int n_slots;
-  uint32_t entry_inv, entry_next;
-  uint32_t n_off, p_off;
-  int W;
-  uint32_t* states; uint32_t* parent; uint32_t* meta;
-  unsigned long long cap_states;
-  unsigned long long* table; unsigned long long mask;
-  Counters* ctr;
-  uint32_t flags;
-  int n_inv;
-  uint8_t* succ_flag;               // sliced build: one byte per frontier state, set when a slice produced a successor
-  // route mode
-  int route;                        // sliced build: successors go to the send regions instead of the local seen-set
-  uint32_t* send; unsigned long long region_cap; int n_ranks; int rank;
-  unsigned long long* sent_cache; unsigned long long sent_mask;   // direct-mapped filter of fingerprints already routed
-};
 
 struct tlag_engine {
   tlag_model m;
@@ -145,224 +77,37 @@ struct tlag_engine {
   unsigned long long* d_sent = nullptr;
   uint8_t* d_succ = nullptr; uint64_t succ_cap = 0;   // sliced build: per-frontier-state "has a successor" flags
   unsigned long long* d_dig = nullptr;                // tlag_digest accumulators (XOR, SUM)
+  // peer-memory exchange (tlag_p2p_*): one cudaMalloc'ed block [meta | inbox x 2 buffers], exported through CUDA IPC
+  P2PParams q;
+  void* d_p2p = nullptr; uint64_t p2p_bytes = 0;
+  uint32_t* d_send_own = nullptr;
+  unsigned int* d_tickets = nullptr;
+  void* peer_base[16] = {nullptr};
+  unsigned long long p2p_seq = 0;
+  bool p2p_ready = false;
   // TLAG_F_KEEP_GOING: the first violation is remembered, the search goes on to the fixpoint
   int kg_verdict = 0, kg_detail = 0, kg_detail2 = 0; uint64_t kg_idx = 0;
   std::string err;
   uint32_t* d_scratch = nullptr; uint64_t scratch_words = 0; uint8_t* d_flags = nullptr; uint64_t flags_cap = 0;
 };
 
-// ------------------------------------------------------------------ seen-set
-// returns 1 if fp was inserted by this call, 0 if already present, -1 if the table is full
-__device__ __forceinline__ int seen_insert(unsigned long long* table, unsigned long long mask,
-                                           unsigned long long fp) {
-  // read first, CAS only on an empty slot: measured 6.1 ms vs 7.9 ms for a CAS-first probe on the
-  // 2^27-candidate K1 batch (atomics are throughput-limited at L2; duplicates need no atomic at all)
-  unsigned long long i = fp & mask;
-  for (unsigned long long probes = 0; probes <= mask; ++probes) {
-    const unsigned long long cur = __ldcv(&table[i]);
-    if (cur == fp) return 0;
-    if (cur == 0ULL) {
-      const unsigned long long old = atomicCAS(&table[i], 0ULL, fp);
-      if (old == 0ULL) return 1;
-      if (old == fp) return 0;
-    }
-    i = (i + 1) & mask;
-  }
-  return -1;
-}
-
-__device__ __forceinline__ unsigned lanemask_lt() {
-  unsigned m;
-  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-  return m;
-}
-
-__device__ __forceinline__ void report_min(unsigned long long* slot, unsigned long long key) {
-  atomicMin(slot, key);
-}
-
 // ------------------------------------------------------------------ sliced native build
-// (tla_rust_b200/compile/sliced.py)  One kernel per slice of the model's program: k_sl_inv_<i> evaluates invariant i,
-// k_sl_next_<j> one disjunct of Next, each over the whole frontier, one thread per state.  All warps of a launch run
-// the same few KB of straight-line code (the whole-program compiled form of round 1 lost to the interpreter on
-// instruction-cache misses: 354 KB of code, every warp somewhere else); divergence inside a slice is the hardware's
-// (compiler-placed reconvergence) instead of a min-pc election per block; a successor is packed, fingerprinted and
-// inserted where it is produced, with opportunistic warp aggregation of the tail-counter atomics.
+// The slice kernels live in translation units of their own (csrc/native/<tag>_part<k>.cu, generated and compiled in
+// parallel: tla_rust_b200/engine.py build_sliced_library); this unit only knows their launchers.
 #ifdef TLAG_SLICED_INC
-struct tlag_sl_cx {
-  const DevParams* p;
-  unsigned long long idx;
-  const uint32_t* src;              // packed words of the state being expanded (EMITD re-packs over a copy)
-  unsigned long long gen;
-  unsigned nsucc;
-  int phase;                        // 0 = invariant slice, 1 = slice of Next
-};
-
+#include TLAG_SLICED_INC     /* the generated constants: TLAG_SL_W, TLAG_SL_*_LIST, program length + FNV */
 #ifndef TLAG_SL_BLOCK
 #define TLAG_SL_BLOCK 256
 #endif
-#ifndef TLAG_SL_OCC
-#define TLAG_SL_OCC 4               /* resident CTAs per SM the slice kernels are compiled for (register cap) */
-#endif
-
-static __device__ __noinline__ void sl_emit_words(tlag_sl_cx* cx, int aid, const uint32_t* o);
-static __device__ __noinline__ void sl_emit_frame(tlag_sl_cx* cx, const int32_t* f, int aid, int dirty);
-#define TLAG_SL_EMIT(aid, dirty) sl_emit_frame(cx, f, (aid), (dirty))
-#define TLAG_SL_EMITW(aid, o) sl_emit_words(cx, (aid), (o))
-#define TLAG_SL_GEN() do { cx->nsucc++; cx->gen++; } while (0)
-#define TLAG_SL_ASSERT(id) report_min(&cx->p->ctr->viol_assert, (cx->idx << 20) | (unsigned)((id) & 0xFFFFF))
-#define TLAG_SL_INVF(i) do { if (cx->phase == 0) report_min(&cx->p->ctr->viol_inv, (cx->idx << 20) | (unsigned)((i) & 0xFFFFF)); } while (0)
-#define TLAG_SL_TRAP(code, line) do { report_min(&cx->p->ctr->viol_trap, (cx->idx << 20) | ((unsigned long long)((code) & 15) << 16) | (unsigned)((line) & 0xFFFF)); cx->nsucc++; } while (0)
-#define TLAG_SL_SUBQ static __device__ __noinline__
-// Array form with a big frame (container models): the slice is a function of its own that receives the frame as a
-// pointer -- inlined, cicc tries scalar replacement of a 2 K-word array over a goto graph and takes many minutes (raft).
-#if defined(TLAG_SL_SEG_NOINLINE)
-#define TLAG_SL_SEGQ static __device__ __noinline__
-#else
-#define TLAG_SL_SEGQ static __device__ __forceinline__
-#endif
-#include TLAG_SLICED_INC
-
-// successor already packed: fingerprint -> seen-set (or owner's send region) -> store
-static __device__ __noinline__ void sl_emit_words(tlag_sl_cx* cx, int aid, const uint32_t* o) {
-  const DevParams& p = *cx->p;
-  constexpr int W = TLAG_SL_W;
-  cx->nsucc++; cx->gen++;
-  uint32_t w[W];
-#pragma unroll
-  for (int i = 0; i < W; ++i) w[i] = o[i];
-  const unsigned long long fp = tlag_fingerprint(w, W);
-  const unsigned lane = threadIdx.x & 31;
-  if (!p.route) {
-    int ins = seen_insert(p.table, p.mask, fp);
-    if (ins < 0) { atomicExch(&p.ctr->table_full, 1ULL); ins = 0; }
-    if (ins > 0) {
-      // warp-aggregated tail allocation over whichever lanes arrived here together
-      const unsigned am = __activemask();
-      const int leader = __ffs((int)am) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(&p.ctr->n_states, (unsigned long long)__popc(am));
-      base = __shfl_sync(am, base, leader);
-      const unsigned long long pos = base + (unsigned long long)__popc(am & lanemask_lt());
-      if (pos < p.cap_states) {
-        uint32_t* dst = p.states + pos * (unsigned long long)W;
-#pragma unroll
-        for (int i = 0; i < W; ++i) dst[i] = w[i];
-        p.parent[pos] = (uint32_t)cx->idx;
-        p.meta[pos] = ((uint32_t)aid << 8) | (uint32_t)(p.rank & 0xFF);
-      } else {
-        atomicExch(&p.ctr->store_overflow, 1ULL);
-      }
-    }
-  } else {
-    // A successor whose fingerprint this rank has already routed is known to its owner (direct-mapped exact-compare
-    // cache).  The slot is written only once the record is in the send region, so a chunk that is re-run after a
-    // region overflow loses nothing.
-    unsigned long long* cslot = p.sent_cache ? p.sent_cache + (fp & p.sent_mask) : nullptr;
-    if (cslot && __ldcv(cslot) == fp) return;
-    const int owner = (int)tlag_owner(w, W, (uint32_t)p.n_ranks);
-    const unsigned am = __activemask();
-    const unsigned peers = __match_any_sync(am, owner);
-    const int leader = __ffs((int)peers) - 1;
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(&p.ctr->send_count[owner], (unsigned long long)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const unsigned long long pos = base + (unsigned long long)__popc(peers & lanemask_lt());
-    if (pos < p.region_cap) {
-      uint32_t* dst = p.send + ((unsigned long long)owner * p.region_cap + pos) * (unsigned long long)(W + 2);
-#pragma unroll
-      for (int i = 0; i < W; ++i) dst[i] = w[i];
-      dst[W] = (uint32_t)cx->idx;
-      dst[W + 1] = ((uint32_t)aid << 8) | (uint32_t)(p.rank & 0xFF);
-      if (cslot) *cslot = fp;
-    } else {
-      atomicExch(&p.ctr->route_overflow, 1ULL);
-    }
-  }
-}
-
-// array form: pack the primed frame (all slots, or the dirty ranges over a copy of the parent) first
-static __device__ __noinline__ void sl_emit_frame(tlag_sl_cx* cx, const int32_t* f, int aid, int dirty) {
-  const DevParams& p = *cx->p;
-  constexpr int W = TLAG_SL_W;
-  uint32_t succ[W];
-  int ov;
-  if (dirty > 0) {
-#pragma unroll
-    for (int i = 0; i < W; ++i) succ[i] = cx->src[i];
-    ov = tlag_pack_ranges(p.layout, p.cpool, dirty, f + TLAG_SL_USZ, succ);
-  } else {
-    ov = tlag_pack(p.layout, p.n_slots, f + TLAG_SL_USZ, succ, W);
-  }
-  if (ov) {
-    cx->nsucc++; cx->gen++;
-    report_min(&p.ctr->viol_trap, (cx->idx << 20) | (2ULL << 16) | (unsigned)((ov - 1) & 0xFFFF));
-    return;
-  }
-  sl_emit_words(cx, aid, succ);
-}
-
-
-// One thread per frontier state (grid-stride).  FN: the slice function of this kernel.
-template <int PHASE, typename FN>
-__device__ __forceinline__ void sl_run(const DevParams& p, unsigned long long lo, unsigned long long hi, FN fn) {
-  constexpr int W = TLAG_SL_W;
-  tlag_sl_cx cxs;
-  tlag_sl_cx* cx = &cxs;
-  cx->p = &p; cx->gen = 0; cx->phase = PHASE;
-#if !TLAG_SL_SCALAR
-  int32_t f[TLAG_SL_FRAME];
-#endif
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long idx = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < hi; idx += stride) {
-    const uint32_t* src = p.states + idx * (unsigned long long)W;
-    cx->idx = idx; cx->src = src; cx->nsucc = 0;
-#if TLAG_SL_SCALAR
-    uint32_t in_[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) in_[i] = src[i];
-    fn(p.cpool, in_, cx);
-#else
-    {
-      uint32_t in_[W];
-#pragma unroll
-      for (int i = 0; i < W; ++i) in_[i] = src[i];
-      tlag_unpack(p.layout, p.n_slots, in_, f);
-    }
-    fn(p.cpool, f, cx);
-#endif
-    if (PHASE == 1 && cx->nsucc && p.succ_flag) p.succ_flag[idx - lo] = 1;
-  }
-  // generated counter: warp reduce, one atomic per warp
-  unsigned long long g = cx->gen;
-  if (PHASE == 1) {
-    for (int o = 16; o > 0; o >>= 1) g += __shfl_down_sync(0xffffffffu, g, o);
-    if ((threadIdx.x & 31) == 0 && g) atomicAdd(&p.ctr->generated, g);
-  }
-}
-
-#if TLAG_SL_SCALAR
-#define TLAG_SL_FARG const uint32_t*
-#else
-#define TLAG_SL_FARG int32_t*
-#endif
-#define TLAG_SL_KERNEL_INV(j)                                                                                     \
-  __global__ void __launch_bounds__(TLAG_SL_BLOCK, TLAG_SL_OCC) k_sl_inv_##j(const __grid_constant__ DevParams p, \
-                                                                            unsigned long long lo, unsigned long long hi) { \
-    sl_run<0>(p, lo, hi, [](const int32_t* cp, TLAG_SL_FARG f, tlag_sl_cx* cx) { tlag_sl_inv_##j(cp, f, cx); });  \
-  }
-#define TLAG_SL_KERNEL_NEXT(j)                                                                                     \
-  __global__ void __launch_bounds__(TLAG_SL_BLOCK, TLAG_SL_OCC) k_sl_next_##j(const __grid_constant__ DevParams p, \
-                                                                             unsigned long long lo, unsigned long long hi) { \
-    sl_run<1>(p, lo, hi, [](const int32_t* cp, TLAG_SL_FARG f, tlag_sl_cx* cx) { tlag_sl_next_##j(cp, f, cx); });  \
-  }
-TLAG_SL_INV_LIST(TLAG_SL_KERNEL_INV)
-TLAG_SL_NEXT_LIST(TLAG_SL_KERNEL_NEXT)
-typedef void (*sl_kernel_t)(DevParams, unsigned long long, unsigned long long);
-#define TLAG_SL_ADDR_INV(j) k_sl_inv_##j,
-#define TLAG_SL_ADDR_NEXT(j) k_sl_next_##j,
-static const sl_kernel_t kSlInv[] = { TLAG_SL_INV_LIST(TLAG_SL_ADDR_INV) nullptr };
-static const sl_kernel_t kSlNext[] = { TLAG_SL_NEXT_LIST(TLAG_SL_ADDR_NEXT) nullptr };
+typedef void (*sl_launch_t)(const DevParams*, unsigned long long, unsigned long long, unsigned, cudaStream_t);
+#define TLAG_SL_DECL_INV(j) extern "C" void tlag_sl_launch_inv_##j(const DevParams*, unsigned long long, unsigned long long, unsigned, cudaStream_t);
+#define TLAG_SL_DECL_NEXT(j) extern "C" void tlag_sl_launch_next_##j(const DevParams*, unsigned long long, unsigned long long, unsigned, cudaStream_t);
+TLAG_SL_INV_LIST(TLAG_SL_DECL_INV)
+TLAG_SL_NEXT_LIST(TLAG_SL_DECL_NEXT)
+#define TLAG_SL_ADDR_INV(j) tlag_sl_launch_inv_##j,
+#define TLAG_SL_ADDR_NEXT(j) tlag_sl_launch_next_##j,
+static const sl_launch_t kSlInv[] = { TLAG_SL_INV_LIST(TLAG_SL_ADDR_INV) nullptr };
+static const sl_launch_t kSlNext[] = { TLAG_SL_NEXT_LIST(TLAG_SL_ADDR_NEXT) nullptr };
 
 // deadlock = a frontier state for which no slice of Next produced a successor
 __global__ void k_sl_deadlock(DevParams p, unsigned long long lo, unsigned long long hi) {
@@ -388,34 +133,6 @@ enum { L_RUN = 0, L_EMIT = 1, L_DONE = 2, L_STOP = 3 };
 // decode/dispatch; only lanes whose pc equals the minimum execute.  (v1 of this loop spent 41 of ~73
 // SASS instructions per step on bookkeeping and fetched the instruction with a generic per-lane load:
 // profiles/r1_k_wave_warpsched_b2_ncu.txt.)
-#ifdef TLAG_NATIVE_INC
-// Native build: the compiled program instead of fetch / decode / dispatch.  Same contract as the interpreter below.
-template <bool SMEM, bool LEAN>
-__device__ __forceinline__ void warp_vm(const uint64_t* __restrict__, const uint64_t*,
-                                        const int32_t* __restrict__ cpool, int32_t* frame, uint32_t& pc,
-                                        uint32_t& rpc, int& ev_out, int32_t& info, int32_t& info2) {
-#ifdef TLAG_NATIVE_SCHED_WARP
-  // Same election as the interpreter, per basic block instead of per instruction: the lanes at the warp's minimum pc
-  // run their block (a warp-uniform switch target), everyone else waits; lanes re-join whenever their pcs meet.
-  for (;;) {
-    const uint32_t pcm = __reduce_min_sync(0xffffffffu, pc);
-    if (pcm == TLAG_PC_PARKED) break;
-    if (pc == pcm) {
-      const int ev = tlag_native_block(cpool, frame, &pc, &info, &info2);
-      if (ev >= 0) { ev_out = ev; rpc = pc; pc = TLAG_PC_PARKED; }
-    }
-  }
-#else
-  if (pc != TLAG_PC_PARKED) {
-    uint32_t p = pc;
-    ev_out = tlag_native_run(cpool, frame, &p, &info, &info2);
-    rpc = p;
-    pc = TLAG_PC_PARKED;
-  }
-  __syncwarp();
-#endif
-}
-#else
 template <bool SMEM, bool LEAN>
 __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, const uint64_t* scode,
                                         const int32_t* __restrict__ cpool, int32_t* frame, uint32_t& pc,
@@ -431,8 +148,6 @@ __device__ __forceinline__ void warp_vm(const uint64_t* __restrict__ gcode, cons
     }
   }
 }
-
-#endif
 
 // MODE 0: fused insert (single GPU).  MODE 1: route successors to per-owner send regions.
 // LEAN: interpreter without the extension ops, for models that do not use them (small frames only).
@@ -715,6 +430,115 @@ __global__ void __launch_bounds__(256) k_insert_records(DevParams p, const uint3
   }
 }
 
+// ------------------------------------------------------------------ peer-memory exchange (multi-GPU)
+// One process per GPU; the state space is partitioned by tlag_owner().  Instead of handing the per-owner send regions to
+// NCCL (two all_to_alls and three host round trips per chunk in round 1), every rank maps every other rank's INBOX with
+// CUDA IPC and the exchange is device code over NVLink / NVSwitch:
+//   k_push          copies this rank's send region for owner d into d's inbox (16-byte stores over NVLink), then
+//                   publishes {count, seq} in d's memory with a system-scope release;
+//   k_insert_inbox  waits (acquire) until every source has published chunk `seq`, inserts the records into this
+//                   rank's seen-set shard / state store (the next frontier), then acknowledges the chunk in the
+//                   sources' memory so that they may reuse the buffer.
+// Inboxes are double-buffered by chunk parity; a whole BFS level is enqueued on the engine's stream (expand kernels,
+// push, insert per chunk) and the host synchronises once per level for the termination all-reduce.
+// grid: (blocks_per_dst, n_ranks).  Copies min(send_count[dst], region_cap) records to dst's inbox.
+__global__ void __launch_bounds__(256) k_push(P2PParams q, const Counters* ctr, unsigned long long seq) {
+  const int dst = blockIdx.y;
+  __shared__ int s_last;
+  P2PMeta* mine_at_dst = q.peer_meta[dst] + q.rank;
+  if (threadIdx.x == 0 && seq > 2) {
+    // the buffer (seq & 1) at dst was last used for my chunk seq - 2: wait until dst has consumed it
+    const unsigned long long* ack = &q.meta[dst].ack;
+    while (ld_acquire_sys(ack) + 2 < seq) __nanosleep(200);
+  }
+  __syncthreads();
+  unsigned long long n = ctr->send_count[dst];
+  if (n > q.region_cap) n = q.region_cap;
+  const unsigned long long words = n * (unsigned long long)q.rec_words;
+  const uint32_t* src = q.send + (unsigned long long)dst * q.region_cap * q.rec_words;
+  uint32_t* out = q.peer_inbox[dst] + (((seq & 1ULL) * q.n_ranks + q.rank) * q.inbox_cap) * q.rec_words;
+  const unsigned long long w4 = words >> 2;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* o4 = reinterpret_cast<uint4*>(out);
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < w4;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    o4[i] = s4[i];
+  if (blockIdx.x == 0)
+    for (unsigned long long i = (w4 << 2) + threadIdx.x; i < words; i += blockDim.x) out[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&q.tickets[dst], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    q.tickets[dst] = 0;
+    __threadfence_system();
+    *(volatile unsigned long long*)&mine_at_dst->count[seq & 1ULL] = n;
+    __threadfence_system();
+    st_release_sys(&mine_at_dst->seq[seq & 1ULL], seq);
+  }
+}
+
+// Inserts every source's records of chunk `seq` (grid-stride over sources and records, whole warps).
+__global__ void __launch_bounds__(256) k_insert_inbox(DevParams p, P2PParams q, unsigned long long seq) {
+  const unsigned lane = threadIdx.x & 31;
+  const int W = p.W;
+  __shared__ unsigned long long s_n;
+  __shared__ int s_last;
+  for (int src = 0; src < q.n_ranks; ++src) {
+    if (threadIdx.x == 0) {
+      const P2PMeta* m = &q.meta[src];
+      while (ld_acquire_sys(&m->seq[seq & 1ULL]) != seq) __nanosleep(200);
+      s_n = *(volatile const unsigned long long*)&m->count[seq & 1ULL];
+    }
+    __syncthreads();
+    const unsigned long long n = s_n;
+    const uint32_t* rec = q.inbox + (((seq & 1ULL) * q.n_ranks + src) * q.inbox_cap) * q.rec_words;
+    const unsigned long long n32 = (n + 31ULL) & ~31ULL;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n32;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+      uint32_t w[TLAG_MAXW];
+      const bool has = i < n;
+      unsigned long long fp = 0;
+      const uint32_t* r = rec + i * (unsigned long long)(W + 2);
+      if (has) {
+        for (int k = 0; k < W; ++k) w[k] = __ldcg(r + k);      // written by a peer over NVLink: read through L2
+        fp = tlag_fingerprint(w, W);
+      }
+      int ins = has ? seen_insert(p.table, p.mask, fp) : 0;
+      if (ins < 0) { atomicExch(&p.ctr->table_full, 1ULL); ins = 0; }
+      const bool isnew = ins > 0;
+      const unsigned mk = __ballot_sync(0xffffffffu, isnew);
+      if (mk) {
+        const int leader = __ffs((int)mk) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(&p.ctr->n_states, (unsigned long long)__popc(mk));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (isnew) {
+          const unsigned long long pos = base + (unsigned long long)__popc(mk & lanemask_lt());
+          if (pos < p.cap_states) {
+            uint32_t* dst = p.states + pos * (unsigned long long)W;
+            for (int k = 0; k < W; ++k) dst[k] = w[k];
+            p.parent[pos] = __ldcg(r + W);
+            p.meta[pos] = __ldcg(r + W + 1);
+          } else {
+            atomicExch(&p.ctr->store_overflow, 1ULL);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // every block is done with every source: the last one acknowledges the chunk to all sources
+  __threadfence();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&q.tickets[16], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x < (unsigned)q.n_ranks) {
+    if (threadIdx.x == 0) q.tickets[16] = 0;
+    __threadfence_system();
+    st_release_sys(&(q.peer_meta[threadIdx.x] + q.rank)->ack, seq);
+  }
+}
+
 // checksum of checksums over the state store: XOR and SUM (mod 2^64) of all fingerprints
 __global__ void k_digest(DevParams p, unsigned long long n, unsigned long long* out2) {
   unsigned long long x = 0, sm = 0;
@@ -795,8 +619,8 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   const uint64_t maxb = (uint64_t)e->sm_count * 64;
   if (blocks > maxb) blocks = maxb;
   if (e->p.n_inv > 0)
-    for (int j = 0; kSlInv[j]; ++j) { kSlInv[j]<<<(unsigned)blocks, TLAG_SL_BLOCK, 0, e->stream>>>(e->p, lo, hi); e->launches++; }
-  for (int j = 0; kSlNext[j]; ++j) { kSlNext[j]<<<(unsigned)blocks, TLAG_SL_BLOCK, 0, e->stream>>>(e->p, lo, hi); e->launches++; }
+    for (int j = 0; kSlInv[j]; ++j) { kSlInv[j](&e->p, lo, hi, (unsigned)blocks, e->stream); e->launches++; }
+  for (int j = 0; kSlNext[j]; ++j) { kSlNext[j](&e->p, lo, hi, (unsigned)blocks, e->stream); e->launches++; }
   if (dl) { k_sl_deadlock<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->p, lo, hi); e->launches++; }
   return cudaGetLastError();
 }
@@ -811,11 +635,6 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   void (*fn)(DevParams, unsigned long long, unsigned long long) = nullptr;
   const bool sm = e->p.code_in_smem != 0;
   const bool lean = !e->uses_ext;
-#ifdef TLAG_NATIVE_INC
-  fn = k_wave<TLAG_NATIVE_FRAME, MODE, false, false>;   // LEAN only selects an interpreter variant
-  smem = 0;
-  (void)sm; (void)lean;
-#else
   switch (e->frame_class) {
     case 0: fn = lean ? (sm ? k_wave<64, MODE, true, true> : k_wave<64, MODE, false, true>)
                       : (sm ? k_wave<64, MODE, true> : k_wave<64, MODE, false>); break;
@@ -831,7 +650,6 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
     // 8192 words = 32 KB of local memory per thread (SSI at 4 transactions x 3 keys needs 6.9 K words)
     default: fn = sm ? k_wave<8192, MODE, true> : k_wave<8192, MODE, false>; break;
   }
-#endif
   if (smem > 48 * 1024) {
     cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (r != cudaSuccess) return r;
@@ -957,8 +775,6 @@ static int cluster_slice(tlag_engine* e, uint64_t first, uint64_t count) {
 
 #if defined(TLAG_SLICED_INC)
 extern "C" const char* tlag_version(void) { return "tlag 0.2 (sm_100a) native sliced"; }
-#elif defined(TLAG_NATIVE_INC)
-extern "C" const char* tlag_version(void) { return "tlag 0.1 (sm_100a) native"; }
 #else
 extern "C" const char* tlag_version(void) { return "tlag 0.1 (sm_100a)"; }
 #endif
@@ -976,13 +792,12 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   if (m->words_per_state == 0 || m->words_per_state > TLAG_MAXW) { e->err = "words_per_state out of range (1..128)"; return TLAG_EINVAL; }
   if (m->frame_words > 8192) { e->err = "frame_words > 8192 not supported"; return TLAG_EINVAL; }
 #if defined(TLAG_SLICED_INC)
-#define TLAG_NATIVE_FRAME TLAG_SL_FRAME
-#endif
-#if defined(TLAG_NATIVE_INC) || defined(TLAG_SLICED_INC)
-  {
-    uint64_t h = 0xcbf29ce484222325ULL;
+  {  // this library holds ONE model's program as kernels (constant pool folded in): refuse anything else
+    uint64_t h = 0xcbf29ce484222325ULL, hc = 0xcbf29ce484222325ULL;
     for (uint32_t i = 0; i < m->code_len; ++i) h = (h ^ m->code[i]) * 0x100000001b3ULL;
-    if (m->code_len != TLAG_NATIVE_CODE_LEN || h != TLAG_NATIVE_CODE_FNV || m->frame_words > TLAG_NATIVE_FRAME) {
+    for (uint32_t i = 0; i < m->cpool_len; ++i) hc = (hc ^ (uint64_t)(uint32_t)m->cpool[i]) * 0x100000001b3ULL;
+    if (m->code_len != TLAG_NATIVE_CODE_LEN || h != TLAG_NATIVE_CODE_FNV || hc != TLAG_NATIVE_CPOOL_FNV ||
+        m->frame_words > TLAG_SL_FRAME || m->words_per_state != TLAG_SL_W) {
       e->err = "this library was compiled for another model's program (native build)";
       return TLAG_EINVAL;
     }
@@ -1058,6 +873,8 @@ extern "C" void tlag_destroy(tlag_engine* e) {
   cudaFree(e->d_code); cudaFree(e->d_cpool); cudaFree(e->d_layout); cudaFree(e->d_states);
   cudaFree(e->d_parent); cudaFree(e->d_meta); cudaFree(e->d_table); cudaFree(e->d_ctr);
   cudaFree(e->d_scratch); cudaFree(e->d_flags); cudaFree(e->d_sort); cudaFree(e->d_sent); cudaFree(e->d_succ); cudaFree(e->d_dig);
+  for (int r = 0; r < 16; ++r) if (e->peer_base[r] && r != e->q.rank) cudaIpcCloseMemHandle(e->peer_base[r]);
+  cudaFree(e->d_p2p); cudaFree(e->d_send_own); cudaFree(e->d_tickets);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1403,6 +1220,22 @@ extern "C" int tlag_trace(tlag_engine* e, uint64_t state_idx, uint32_t* states_o
   return TLAG_OK;
 }
 
+// One hop of a counterexample chain: the state at idx with its parent index and meta word (action id << 8 | rank that
+// expanded the parent).  With several ranks the parent lives in THAT rank's store: the host follows the chain across
+// ranks (tla_rust_b200/dist.py: counterexample).
+extern "C" int tlag_read_link(tlag_engine* e, uint64_t idx, uint32_t* state_out, uint32_t* parent_out, uint32_t* meta_out) {
+  if (!e || !parent_out || !meta_out) return TLAG_EINVAL;
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  if (idx >= hc.n_states) { e->err = "tlag_read_link: no such state"; return TLAG_EINVAL; }
+  const uint64_t W = e->m.words_per_state;
+  if (state_out) CK(cudaMemcpyAsync(state_out, e->d_states + idx * W, W * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(parent_out, e->d_parent + idx, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(meta_out, e->d_meta + idx, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return TLAG_OK;
+}
+
 // ---- multi-GPU building blocks -----------------------------------------------------
 extern "C" int tlag_frontier(tlag_engine* e, uint64_t* first_idx, uint64_t* count) {
   if (!e) return TLAG_EINVAL;
@@ -1484,6 +1317,130 @@ extern "C" int tlag_insert_records(tlag_engine* e, uint64_t d_recv, uint64_t n_r
   if (hc.store_overflow) { e->err = "state store overflow: raise max_states"; return TLAG_ENOMEM; }
   if (hc.table_full) { e->err = "seen-set table full"; return TLAG_ENOMEM; }
   if (n_new) *n_new = hc.n_states - before;
+  return TLAG_OK;
+}
+
+
+// ---- peer-memory exchange: set-up and one-call-per-level driver ------------------------------------------------------
+static size_t p2p_meta_bytes() { return 16 * sizeof(P2PMeta); }
+
+extern "C" int tlag_p2p_init(tlag_engine* e, uint32_t n_ranks, uint32_t rank, uint64_t cap_records, uint8_t* handle_out64) {
+  if (!e || !handle_out64 || n_ranks == 0 || n_ranks > 16 || rank >= n_ranks || cap_records == 0) return TLAG_EINVAL;
+  if (e->d_p2p) { e->err = "tlag_p2p_init called twice"; return TLAG_ESTATE; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  const uint64_t rw = e->m.words_per_state + 2;
+  cap_records = (cap_records + 3) & ~3ULL;                       // regions stay 16-byte aligned
+  const uint64_t inbox_bytes = 2ULL * n_ranks * cap_records * rw * 4;
+  e->p2p_bytes = p2p_meta_bytes() + inbox_bytes;
+  CK(cudaMalloc(&e->d_p2p, e->p2p_bytes));
+  CK(cudaMemset(e->d_p2p, 0, p2p_meta_bytes()));
+  CK(cudaMalloc(&e->d_send_own, (uint64_t)n_ranks * cap_records * rw * 4));
+  CK(cudaMalloc(&e->d_tickets, 32 * sizeof(unsigned int)));
+  CK(cudaMemset(e->d_tickets, 0, 32 * sizeof(unsigned int)));
+  memset(&e->q, 0, sizeof(e->q));
+  e->q.n_ranks = (int)n_ranks; e->q.rank = (int)rank; e->q.rec_words = (int)rw;
+  e->q.inbox_cap = cap_records; e->q.region_cap = cap_records;
+  e->q.send = e->d_send_own;
+  e->q.meta = (P2PMeta*)e->d_p2p;
+  e->q.inbox = (uint32_t*)((uint8_t*)e->d_p2p + p2p_meta_bytes());
+  e->q.tickets = e->d_tickets;
+  e->peer_base[rank] = e->d_p2p;
+  e->q.peer_meta[rank] = e->q.meta; e->q.peer_inbox[rank] = e->q.inbox;
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, e->d_p2p));
+  memcpy(handle_out64, &h, 64);
+  e->p.n_ranks = (int)n_ranks; e->p.rank = (int)rank;
+  return TLAG_OK;
+}
+
+extern "C" int tlag_p2p_attach(tlag_engine* e, uint32_t peer, const uint8_t* handle64) {
+  if (!e || !handle64 || !e->d_p2p || peer >= (uint32_t)e->q.n_ranks) return TLAG_EINVAL;
+  if ((int)peer == e->q.rank) return TLAG_OK;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  e->peer_base[peer] = base;
+  e->q.peer_meta[peer] = (P2PMeta*)base;
+  e->q.peer_inbox[peer] = (uint32_t*)((uint8_t*)base + p2p_meta_bytes());
+  int ready = 1;
+  for (int r = 0; r < e->q.n_ranks; ++r) if (!e->peer_base[r]) ready = 0;
+  e->p2p_ready = ready != 0;
+  return TLAG_OK;
+}
+
+// One BFS level on this rank: the frontier shard in n_chunks chunks of chunk_states states; per chunk the expand
+// kernels (successors bucketed by owner), k_push (NVLink stores into the owners' inboxes) and k_insert_inbox (this
+// rank's share of the next frontier).  Every rank must call it with the same n_chunks (ranks with a shorter frontier
+// run empty chunks: the inbox protocol counts chunks).  One host synchronisation, at the end.
+extern "C" int tlag_p2p_level(tlag_engine* e, uint64_t n_chunks, uint64_t chunk_states, uint64_t expect_inbound,
+                              tlag_wave_stats* out) {
+  if (!e || chunk_states == 0) return TLAG_EINVAL;
+  if (!e->p2p_ready && e->q.n_ranks > 1) { e->err = "tlag_p2p_level before every peer was attached"; return TLAG_ESTATE; }
+  if (out) memset(out, 0, sizeof(*out));
+  if (e->level == 0) { e->level = 1; e->lo = 0; e->depth = e->hi > 0 ? 1 : 0; }
+  const uint32_t n_ranks = (uint32_t)e->q.n_ranks;
+  // room for what may arrive this level (the caller passes the all-reduced estimate; at least the heuristic)
+  uint64_t expect = (uint64_t)((double)(e->hi - e->lo) * e->growth_hint) + 4096;
+  if (expect_inbound > expect) expect = expect_inbound;
+  Counters hc;
+  CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+  const uint64_t before = hc.n_states;
+  int r = grow_store_if_needed(e, before + expect);
+  if (r) return r;
+  r = grow_table_if_needed(e, before + expect);
+  if (r) return r;
+  e->p.n_ranks = (int)n_ranks; e->p.rank = e->q.rank;
+  if (!e->d_sent && n_ranks > 1 && getenv("TLAG_NO_SENT_CACHE") == nullptr) {
+    const unsigned lg = 26;                                    // 2^26 x 8 B = 512 MB
+    if (cudaMalloc(&e->d_sent, (1ULL << lg) * 8) == cudaSuccess) {
+      CK(cudaMemsetAsync(e->d_sent, 0, (1ULL << lg) * 8, e->stream));
+      e->p.sent_cache = e->d_sent; e->p.sent_mask = (1ULL << lg) - 1;
+    } else { cudaGetLastError(); e->d_sent = nullptr; }
+  }
+  e->p.send = e->d_send_own;
+  e->p.region_cap = e->q.region_cap;
+  CK(cudaMemsetAsync(&e->d_ctr->route_overflow, 0, 8, e->stream));
+  CK(cudaMemsetAsync(&e->d_ctr->generated, 0, 8, e->stream));
+  CK(cudaEventRecord(e->ev0, e->stream));
+  const unsigned push_blocks = 64, ins_blocks = (unsigned)e->sm_count * 4;
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const unsigned long long seq = ++e->p2p_seq;
+    uint64_t lo = e->lo + c * chunk_states, hi = lo + chunk_states;
+    if (lo > e->hi) lo = e->hi;
+    if (hi > e->hi) hi = e->hi;
+    CK(cudaMemsetAsync(&e->d_ctr->work, 0, 8, e->stream));
+    CK(cudaMemsetAsync(e->d_ctr->send_count, 0, sizeof(unsigned long long) * 16, e->stream));
+    if (hi > lo) {
+      cudaError_t ce = launch_wave<1>(e, lo, hi);
+      if (ce != cudaSuccess) { e->err = std::string("route wave launch: ") + cudaGetErrorString(ce); return TLAG_ECUDA; }
+    }
+    k_push<<<dim3(push_blocks, n_ranks), 256, 0, e->stream>>>(e->q, e->d_ctr, seq);
+    k_insert_inbox<<<ins_blocks, 256, 0, e->stream>>>(e->p, e->q, seq);
+    e->launches += 2;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  CK(cudaMemcpyAsync(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->dev_seconds += ms * 1e-3;
+  if (hc.route_overflow) { e->err = "send region overflow in tlag_p2p_level: use smaller chunks or larger regions"; return TLAG_EOVERFLOW; }
+  if (hc.store_overflow) { e->err = "state store overflow in tlag_p2p_level"; return TLAG_ENOMEM; }
+  if (hc.table_full) { e->err = "seen-set table full in tlag_p2p_level"; return TLAG_ENOMEM; }
+  e->generated += hc.generated;
+  CK(cudaMemsetAsync(&e->d_ctr->generated, 0, 8, e->stream));
+  collect_violations(e, hc);
+  if (out) {
+    out->level = e->level; out->expanded = e->hi - e->lo; out->generated = hc.generated;
+    out->discovered = hc.n_states - before; out->distinct_total = hc.n_states; out->generated_total = e->generated;
+    out->kernel_ms = ms; out->verdict = e->verdict;
+  }
+  {
+    const double ratio = (double)(hc.n_states - before) / (double)((e->hi - e->lo) ? (e->hi - e->lo) : 1);
+    e->growth_hint = ratio * 2.0 > 4.0 ? ratio * 2.0 : 4.0;
+  }
   return TLAG_OK;
 }
 

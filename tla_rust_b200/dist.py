@@ -1,11 +1,20 @@
-"""Multi-GPU BFS: one process per GPU, fingerprint space hash-range
-partitioned across ranks.  Per BFS level each rank expands its frontier shard in chunks
-(tlag_expand_route: successors bucketed by owner = high bits of the fingerprint), each
-chunk's buckets are exchanged with ONE all-to-all over NCCL/NVLink, and every owner inserts
-what it received into its seen-set shard / state store (tlag_insert_records) -- the received
-states are that rank's share of the next frontier, so the frontier stays balanced by the hash.
-A 3-word all-reduce per level decides termination.  torch.distributed is plumbing only."""
+"""Multi-GPU BFS: one process per GPU, the state space partitioned across ranks by a hash of the
+state's clustering key (tlag_owner).  Per BFS level each rank expands its frontier shard in chunks; successors are
+bucketed by owner on the device and reach their owner in one of two ways:
+
+  * exchange="p2p" (default on GPUs): peer memory.  Every rank maps every other rank's inbox through CUDA IPC; the
+    engine's k_push kernel stores the buckets straight into the owners' inboxes over NVLink / NVSwitch and publishes
+    {count, chunk} with a system-scope release, k_insert_inbox on the owner waits for all sources and inserts.  A whole
+    level is enqueued on the device; the host synchronises once per level (tlag_p2p_level) for the termination
+    all-reduce.  No NCCL on the data path.
+  * exchange="nccl": the round-1 path (and the one the CPU shard engine of the gloo tests uses): per chunk one
+    all_to_all of counts, one of records, then tlag_insert_records.
+
+The received states are that rank's share of the next frontier, so the frontier stays balanced by the hash.  A 3-word
+all-reduce per level decides termination.  torch.distributed is plumbing only."""
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -32,15 +41,40 @@ def _all_to_all(outs, ins, rank):
 
 
 class DistributedBFS:
-    def __init__(self, engine, cm, rank, world, device, cap_records=1 << 24, chunk_states=1 << 21):
+    def __init__(self, engine, cm, rank, world, device, cap_records=1 << 24, chunk_states=1 << 21, exchange=None):
         self.e, self.cm, self.rank, self.world, self.device = engine, cm, rank, world, device
         self.rec_words = cm.W + 2
         self.cap_records = cap_records          # send-buffer capacity in records (all destinations together)
         self.chunk_states = chunk_states        # frontier states expanded per exchange
-        self.send = torch.empty(cap_records * self.rec_words, dtype=torch.int32, device=device)
-        self.recv = torch.empty(cap_records * self.rec_words, dtype=torch.int32, device=device)
         self.comm_ms = 0.0
         self.exchanges = 0
+        self.exchange = exchange or os.environ.get("TLAG_EXCHANGE", "p2p")
+        self.exchange_note = ""
+        if self.exchange == "p2p" and not (str(device).startswith("cuda") and hasattr(engine, "p2p_init")):
+            self.exchange = "nccl"
+        if self.exchange == "p2p":
+            try:
+                self._setup_p2p()
+            except Exception as ex:  # noqa: BLE001 -- e.g. CUDA IPC not permitted in this container: NCCL path
+                self.exchange, self.exchange_note = "nccl", f"p2p set-up failed ({str(ex)[:160]}); using NCCL all_to_all"
+        if self.exchange != "p2p":
+            self.send = torch.empty(cap_records * self.rec_words, dtype=torch.int32, device=device)
+            self.recv = torch.empty(cap_records * self.rec_words, dtype=torch.int32, device=device)
+
+    def _setup_p2p(self):
+        """inbox handles all-gathered through torch.distributed (64 bytes per rank), then mapped with CUDA IPC"""
+        region = max(4096, self.cap_records // self.world)
+        h = self.e.p2p_init(self.world, self.rank, region)
+        mine = torch.tensor(list(h), dtype=torch.uint8, device=self.device)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(parts, mine)
+        else:
+            parts = [mine]
+        for r, t in enumerate(parts):
+            self.e.p2p_attach(r, bytes(t.cpu().tolist()))
+        self.region = region
+        self._ratio = 8.0
 
     def seed(self, init_words: np.ndarray, fingerprints=None):
         """Every rank sees all initial states and keeps those it owns (tlag_owner: hash of the state's
@@ -65,6 +99,42 @@ class DistributedBFS:
             gx ^= a
             gs = (gs + b) & 0xFFFFFFFFFFFFFFFF
         return gx, gs
+
+    def counterexample(self):
+        """Collective: the behaviour leading to a violation found on some rank, reconstructed ACROSS ranks.  A stored
+        state's parent link is an index into the store of the rank that expanded the parent (meta word, low byte), so
+        the chain hops from rank to rank; every hop is one broadcast from the rank that holds the state.
+        -> (verdict, detail, [state words ...] from an initial state to the violating state, [action ids]) on every
+        rank, or None when no rank saw a violation.  The reporting rank is the lowest one that saw a violation in the
+        level the search stopped at (levels are synchronous, so every violation seen is at minimal depth)."""
+        r = self.e.violation() if hasattr(self.e, "violation") else self.e.result()
+        mine = torch.tensor([1 if r.get("verdict", 0) not in (0, 5) else 0, int(r.get("verdict", 0)), int(r.get("detail", 0)),
+                             int(r.get("state_idx", 0))], dtype=torch.int64, device=self.device)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine)
+        who = next((i for i, t in enumerate(parts) if int(t[0]) == 1), None)
+        if who is None:
+            return None
+        verdict, detail, cur_idx = int(parts[who][1]), int(parts[who][2]), int(parts[who][3])
+        cur_rank = who
+        W = self.cm.W
+        chain, acts = [], []
+        for _ in range(1 << 20):
+            hop = torch.zeros(W + 3, dtype=torch.int64, device=self.device)
+            if self.rank == cur_rank:
+                st, par, act, prank = self.e.read_link(cur_idx)
+                hop[:W] = torch.from_numpy(np.asarray(st, dtype=np.int64))
+                hop[W], hop[W + 1], hop[W + 2] = par, act, prank
+            dist.broadcast(hop, src=cur_rank)
+            vals = hop.tolist()
+            chain.append(np.array(vals[:W], dtype=np.uint32))
+            acts.append(int(vals[W + 1]))
+            if vals[W] < 0:
+                break
+            cur_rank, cur_idx = int(vals[W + 2]), int(vals[W])
+        chain.reverse()
+        acts.reverse()
+        return verdict, detail, np.stack(chain), np.array(acts, dtype=np.int32)
 
     def _exchange_chunk(self, first, count, on_gpu, ev):
         e, world, rw = self.e, self.world, self.rec_words
@@ -109,11 +179,22 @@ class DistributedBFS:
         verdict = 5
         while levels < max_levels:
             _, fr = e.frontier()
-            nch = torch.tensor([(fr + self.chunk_states - 1) // self.chunk_states], dtype=torch.int64,
+            nch = torch.tensor([(fr + self.chunk_states - 1) // self.chunk_states, fr], dtype=torch.int64,
                                device=self.device)
             dist.all_reduce(nch, op=dist.ReduceOp.MAX)
             n_new, gen, bad = 0, 0, 0
-            for c in range(int(nch.item())):
+            if self.exchange == "p2p":
+                # the whole level on the device: expand -> push over NVLink -> insert, per chunk; one sync at the end
+                max_fr = int(nch[1].item())
+                ws = e.p2p_level(max(1, int(nch[0].item())), self.chunk_states,
+                                 int(max_fr * max(8.0, 3.0 * self._ratio)) + (1 << 16))
+                n_new, gen = ws["discovered"], ws["generated"]
+                if ws["verdict"] not in (0, 5):
+                    bad = ws["verdict"]
+                self.exchanges += int(nch[0].item())
+                if fr:
+                    self._ratio = max(self._ratio * 0.5, ws["discovered"] / fr)
+            for c in range(int(nch[0].item()) if self.exchange != "p2p" else 0):
                 first = c * self.chunk_states
                 count = max(0, min(self.chunk_states, fr - first))
                 nn, ws = self._exchange_chunk(first, count, on_gpu, ev)

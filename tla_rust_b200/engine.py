@@ -60,7 +60,8 @@ class TlagResult(C.Structure):
 EXPORTS = ["tlag_create", "tlag_seed", "tlag_step", "tlag_run", "tlag_result_now", "tlag_trace",
            "tlag_read_states", "tlag_digest", "tlag_probe_batch", "tlag_probe_batch_device", "tlag_reset_table", "tlag_restart",
            "tlag_kernel_launches", "tlag_destroy", "tlag_last_error", "tlag_version",
-           "tlag_frontier", "tlag_expand_route", "tlag_insert_records", "tlag_advance_level"]
+           "tlag_frontier", "tlag_expand_route", "tlag_insert_records", "tlag_advance_level",
+           "tlag_p2p_init", "tlag_p2p_attach", "tlag_p2p_level", "tlag_read_link"]
 
 
 def build_library(verbose=False):
@@ -94,72 +95,12 @@ NATIVE_DIR = os.path.join(_HERE, "csrc", "native")
 _NATIVE_LIBS = {}
 
 
-def _native_tag(cm):
-    """Program key + a hash of the engine sources the library is compiled from (a stale library is never picked up)."""
-    import hashlib
-    from .compile.native import model_key
-    h = hashlib.sha256()
-    for rel in ("csrc/tlag_engine.cu", "csrc/tlag_vm.h", "csrc/tlag_vm_exec.inc", "compile/native.py", "../include/tlag.h"):
-        with open(os.path.join(_HERE, rel), "rb") as f:
-            h.update(f.read())
-    return f"{model_key(cm)}_{h.hexdigest()[:8]}"
-
-
-def _native_occ():
-    """Resident CTAs per SM the native wave kernel is compiled for (TLAG_NATIVE_OCC: 1, 2 or 4; default 2)."""
-    occ = int(os.environ.get("TLAG_NATIVE_OCC", "2"))
-    if occ not in (1, 2, 4):
-        raise EngineError("TLAG_NATIVE_OCC must be 1, 2 or 4")
-    return occ
-
-
-def _native_sched():
-    """warp (default): block form with min-pc election; lane: every lane runs to its next event (TLAG_NATIVE_SCHED)."""
-    sched = os.environ.get("TLAG_NATIVE_SCHED", "warp")
-    if sched not in ("warp", "lane"):
-        raise EngineError("TLAG_NATIVE_SCHED must be warp or lane")
-    return sched
-
-
-def native_library_path(cm):
-    occ, sched = _native_occ(), _native_sched()
-    return os.path.join(NATIVE_DIR, f"libtlag_{_native_tag(cm)}{'' if occ == 2 else f'_occ{occ}'}"
-                                    f"{'' if sched == 'warp' else '_lane'}.so")
-
-
-def build_native_library(cm, force=False, verbose=False):
-    """Model-specialised engine library: the model's bytecode compiled to straight-line CUDA (compile/native.py)
-    inside the same engine source, one frame class, same C ABI.  Built in-tree (csrc/native/) so that it travels with
-    the repo snapshot; nvcc takes about a minute for a 5 K-instruction program.  Returns the library path."""
-    from .compile.native import emit_c
-    os.makedirs(NATIVE_DIR, exist_ok=True)
-    key = _native_tag(cm)
-    inc = os.path.join(NATIVE_DIR, f"{key}.inc")
-    so = native_library_path(cm)
-    if os.path.exists(so) and not force:
-        return so
-    frame = next((c for c in FRAME_CLASSES if cm.frame_words <= c), None)
-    if frame is None:
-        raise EngineError(f"frame of {cm.frame_words} words exceeds the largest frame class")
-    with open(inc, "w") as f:
-        f.write(emit_c(cm))
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
-           f'-DTLAG_NATIVE_INC="{inc}"', f"-DTLAG_NATIVE_FRAME={frame}", f"-DTLAG_NATIVE_OCC={_native_occ()}",
-           *(["-DTLAG_NATIVE_SCHED_LANE"] if _native_sched() == "lane" else []), "-shared", "-o", so + ".tmp",
-           os.path.join(_HERE, "csrc", "tlag_engine.cu")]
-    p = subprocess.run(cmd, capture_output=not verbose, text=True)
-    if p.returncode != 0:
-        raise EngineError(f"nvcc failed for the native build of model {key}: {(p.stderr or '')[-2000:]}")
-    os.replace(so + ".tmp", so)
-    return so
-
-
 def _sliced_tag(cm, scalar):
     import hashlib
-    from .compile.native import model_key
+    from .compile.sliced import model_key
     h = hashlib.sha256()
-    for rel in ("csrc/tlag_engine.cu", "csrc/tlag_vm.h", "csrc/tlag_vm_exec.inc", "compile/sliced.py", "../include/tlag.h"):
+    for rel in ("csrc/tlag_engine.cu", "csrc/tlag_dev.cuh", "csrc/tlag_dev2.cuh", "csrc/tlag_vm.h", "csrc/tlag_vm_exec.inc",
+                "compile/sliced.py", "../include/tlag.h"):
         with open(os.path.join(_HERE, rel), "rb") as f:
             h.update(f.read())
     h.update(repr((getattr(cm, "segments", None), os.environ.get("TLAG_SL_OCC", ""), os.environ.get("TLAG_SL_BLOCK", ""))).encode())
@@ -187,32 +128,60 @@ def sliced_library_path(cm, scalar=None):
     return os.path.join(NATIVE_DIR, f"libtlag_{_sliced_tag(cm, scalar)}.so")
 
 
-def build_sliced_library(cm, force=False, verbose=False, scalar=None):
+def build_sliced_library(cm, force=False, verbose=False, scalar=None, jobs=None):
     """Model-specialised engine library, sliced form (compile/sliced.py): one kernel per invariant and per disjunct of
-    Next, same engine source and C ABI.  Built in-tree (csrc/native/) so that it travels with the repo snapshot."""
-    from .compile.sliced import emit_sliced
+    Next, same engine source and C ABI.  The slices are spread over several translation units that nvcc compiles in
+    parallel (-dc) next to the engine's own unit; built in-tree (csrc/native/) so that it travels with the snapshot."""
+    from concurrent.futures import ThreadPoolExecutor
+    from .compile.sliced import emit_parts
     if scalar is None:
         scalar = sliced_form(cm)
     os.makedirs(NATIVE_DIR, exist_ok=True)
     tag = _sliced_tag(cm, scalar)
-    inc = os.path.join(NATIVE_DIR, f"{tag}.inc")
     so = os.path.join(NATIVE_DIR, f"libtlag_{tag}.so")
     if os.path.exists(so) and not force:
         return so
-    with open(inc, "w") as f:
-        f.write(emit_sliced(cm, scalar=scalar))
+    jobs = jobs or int(os.environ.get("TLAG_BUILD_JOBS", "0")) or min(8, os.cpu_count() or 1)
+    work = os.path.join(NATIVE_DIR, tag)
+    os.makedirs(work, exist_ok=True)
+    defs_path = os.path.join(work, "defs.h")
+    nparts = max(1, min(jobs, 1 + len(cm.code) // 1500))
+    defs, parts = emit_parts(cm, scalar, nparts, defs_path)
+    with open(defs_path, "w") as f:
+        f.write(defs)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
-           f'-DTLAG_SLICED_INC="{inc}"', "-shared", "-o", so + ".tmp", os.path.join(_HERE, "csrc", "tlag_engine.cu")]
+    csrc = os.path.join(_HERE, "csrc")
+    base = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+            "-I", csrc, "-dc"]
     if not scalar and cm.frame_words > 512:
-        cmd.insert(-4, "-DTLAG_SL_SEG_NOINLINE")
+        base.append("-DTLAG_SL_SEG_NOINLINE")
     for k in ("TLAG_SL_OCC", "TLAG_SL_BLOCK"):
         if os.environ.get(k):
-            cmd.insert(-4, f"-D{k}={int(os.environ[k])}")
-    p = subprocess.run(cmd, capture_output=not verbose, text=True)
-    if p.returncode != 0:
-        raise EngineError(f"nvcc failed for the sliced build of model {tag}: {(p.stderr or '')[-3000:]}")
+            base.append(f"-D{k}={int(os.environ[k])}")
+    # subroutines are compiled apart from the kernels that call them (relocatable device code): give them the register
+    # budget of the kernels' __launch_bounds__ (tlag_dev.cuh: 256 threads x 4 CTAs per SM by default)
+    regcap = 65536 // (int(os.environ.get("TLAG_SL_BLOCK", "256")) * int(os.environ.get("TLAG_SL_OCC", "4")))
+    base.append(f"-maxrregcount={min(255, regcap)}")
+    units = []
+    for k, text in enumerate(parts):
+        src = os.path.join(work, f"part{k}.cu")
+        with open(src, "w") as f:
+            f.write(text)
+        units.append((base + ["-o", src[:-3] + ".o", src], src[:-3] + ".o"))
+    units.append((base + [f'-DTLAG_SLICED_INC="{defs_path}"', "-o", os.path.join(work, "engine.o"),
+                          os.path.join(csrc, "tlag_engine.cu")], os.path.join(work, "engine.o")))
+
+    def run(cmd):
+        p = subprocess.run(cmd, capture_output=not verbose, text=True)
+        if p.returncode != 0:
+            raise EngineError(f"nvcc failed for the sliced build of model {tag}: {(p.stderr or '')[-3000:]}")
+    with ThreadPoolExecutor(max_workers=jobs) as ex:
+        list(ex.map(run, [u[0] for u in units]))
+    run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so + ".tmp"] + [u[1] for u in units])
     os.replace(so + ".tmp", so)
+    if os.environ.get("TLAG_KEEP_BUILD") != "1":       # generated sources + objects (regenerated from the model at will)
+        import shutil
+        shutil.rmtree(work, ignore_errors=True)
     return so
 
 
@@ -229,32 +198,17 @@ def load_sliced_library(cm, build=True):
     return _NATIVE_LIBS[so]
 
 
-def load_native_library(cm, build=True):
-    so = native_library_path(cm)
-    if so not in _NATIVE_LIBS:
-        if not os.path.exists(so):
-            if not build:
-                raise EngineUnavailable(f"{so} is missing (native build of this model)")
-            build_native_library(cm)
-        _NATIVE_LIBS[so] = _bind(so)
-    return _NATIVE_LIBS[so]
-
-
 class Engine:
     """One BFS engine instance on one GPU (mirrors tlag_engine)."""
 
     def __init__(self, cm, deadlock=True, device=0, table_log2=0, max_states=0, keep_going=False, native=None):
-        """native="sliced": the model-specialised sliced build (one kernel per slice of the program; built on demand);
-        native=True: the round-1 whole-program compiled form (kept for comparison); False: the bytecode interpreter;
-        None: follow the environment variable TLAG_NATIVE (sliced / 1 / 0)."""
+        """native="sliced" (or True): the model-specialised sliced build -- one kernel per invariant / disjunct of Next,
+        compile/sliced.py; built on demand with nvcc and cached in csrc/native/; False: the bytecode interpreter kernel;
+        None: follow the environment variable TLAG_NATIVE (sliced / 0)."""
         if native is None:
-            env = os.environ.get("TLAG_NATIVE", "0")
-            native = "sliced" if env == "sliced" else (env == "1")
-        self.native = native if native == "sliced" else bool(native)
-        if self.native == "sliced":         # one kernel per invariant / disjunct of Next (compile/sliced.py)
-            self.L = load_sliced_library(cm)
-        else:
-            self.L = load_native_library(cm) if self.native else load_library()
+            native = "sliced" if os.environ.get("TLAG_NATIVE", "0") in ("sliced", "1") else False
+        self.native = "sliced" if native else False
+        self.L = load_sliced_library(cm) if self.native else load_library()
         self.cm = cm
         self._code = np.ascontiguousarray(cm.code, dtype=np.uint64)
         self._cpool = np.ascontiguousarray(cm.cpool, dtype=np.int32)
@@ -324,6 +278,15 @@ class Engine:
                  "tlag_read_states")
         return out
 
+    def read_link(self, idx: int):
+        """-> (state words, parent index or -1 for an initial state, action id, rank holding the parent)"""
+        st = np.zeros(self.cm.W, dtype=np.uint32)
+        par, meta = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.tlag_read_link(self.h, C.c_uint64(idx), st.ctypes.data_as(C.c_void_p), C.byref(par), C.byref(meta)),
+                 "tlag_read_link")
+        root = par.value == 0xFFFFFFFF
+        return st, (-1 if root else par.value), (-1 if root else meta.value >> 8), meta.value & 0xFF
+
     def digest(self):
         x, s_ = C.c_uint64(), C.c_uint64()
         self._ck(self.L.tlag_digest(self.h, C.byref(x), C.byref(s_)), "tlag_digest")
@@ -370,6 +333,22 @@ class Engine:
         self._ck(self.L.tlag_insert_records(self.h, C.c_uint64(d_recv_ptr), C.c_uint64(n_records), C.c_uint32(0),
                                             C.byref(nn)), "tlag_insert_records")
         return int(nn.value)
+
+    # peer-memory exchange (include/tlag.h: tlag_p2p_*)
+    def p2p_init(self, n_ranks, rank, cap_records) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self._ck(self.L.tlag_p2p_init(self.h, C.c_uint32(n_ranks), C.c_uint32(rank), C.c_uint64(cap_records), h), "tlag_p2p_init")
+        return bytes(h)
+
+    def p2p_attach(self, peer, handle: bytes):
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._ck(self.L.tlag_p2p_attach(self.h, C.c_uint32(peer), h), "tlag_p2p_attach")
+
+    def p2p_level(self, n_chunks, chunk_states, expect_inbound=0) -> dict:
+        ws = WaveStats()
+        self._ck(self.L.tlag_p2p_level(self.h, C.c_uint64(n_chunks), C.c_uint64(chunk_states), C.c_uint64(expect_inbound),
+                                       C.byref(ws)), "tlag_p2p_level")
+        return ws.as_dict()
 
     def advance_level(self) -> dict:
         ws = WaveStats()
