@@ -316,7 +316,7 @@ def main():
     else:
         from tla_rust_b200.dist import DistributedBFS
         e = Engine(cm, deadlock=info["deadlock"], device=local_rank, native=native)
-        d = DistributedBFS(e, cm, rank, world, dev, cap_records=1 << 26, chunk_states=1 << 22)
+        d = DistributedBFS(e, cm, rank, world, dev, cap_records=1 << 26, chunk_states=1 << 21)
         d.seed(init)
         first = [True]
 
@@ -355,7 +355,7 @@ def main():
         t1 = time.perf_counter()
         for _ in range(args.steps):
             e2 = Engine(cm, deadlock=info["deadlock"], device=local_rank, native=native)
-            d2 = DistributedBFS(e2, cm, rank, world, dev, cap_records=1 << 26, chunk_states=1 << 22)
+            d2 = DistributedBFS(e2, cm, rank, world, dev, cap_records=1 << 26, chunk_states=1 << 21)
             d2.seed(init)
             out2 = d2.run(max_levels=(levels - 1) if levels else 1 << 20)
             e2.close()

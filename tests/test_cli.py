@@ -132,3 +132,34 @@ def test_demo_specs_through_tlc_flow_on_cpu_shim(monkeypatch):
     out = io.StringIO()
     assert check_file(os.path.join(d, "race.tla"), out=out, verbose=False) == 12
     assert "Invariant Correct is violated" in out.getvalue()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Makefile"), reason="the reference checkout only exists in the build container")
+def test_config1_as_written_reference_makefile_and_specs(monkeypatch, capfd):
+    """BASELINE config #1 literally: the reference's own Makefile, pcal_intro.{tla,cfg} and atomic_add.tla copied to a
+    scratch directory (pcal2tla rewrites in place; /root/reference is read-only) with this repo's bin/ on PATH.
+    `make transpile` runs as real processes (the translator is host code); `tlc *tla` then runs in-process with the CPU
+    shim standing in for the GPU engine (this container has no GPU; the same two models run on the device as the
+    compiled fixtures pcal_intro / atomic_add in tests/test_gpu_parity.py)."""
+    import glob
+    import tla_rust_b200.engine as eng
+    from tla_rust_b200.cli import tlc_main
+    d = tempfile.mkdtemp(prefix="tlag_ref_")
+    for f in ("Makefile", "pcal_intro.tla", "pcal_intro.cfg", "atomic_add.tla"):
+        shutil.copy(os.path.join("/root/reference", f), d)
+    env = dict(os.environ)
+    env["PATH"] = os.path.join(ROOT, "bin") + os.pathsep + os.path.dirname(sys.executable) + os.pathsep + env["PATH"]
+    p = subprocess.run(["make", "transpile"], cwd=d, env=env, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert os.path.exists(os.path.join(d, "atomic_add.cfg")) and os.path.exists(os.path.join(d, "pcal_intro.old"))
+    assert "BEGIN TRANSLATION" in open(os.path.join(d, "atomic_add.tla")).read()
+    # what `make test` would run: tlc *tla (glob order), stopping at the first failing module
+    monkeypatch.setattr(eng, "Engine", _CpuShimEngine)
+    monkeypatch.chdir(d)
+    rc = tlc_main(sorted(glob.glob("*tla")))
+    sys.stdout.flush()
+    out = capfd.readouterr().out
+    assert rc == 0, out
+    assert out.count("Model checking completed. No error has been found.") == 2
+    assert "7 states generated, 5 distinct states found, 0 states left on queue." in out           # atomic_add
+    assert "5850 states generated, 3800 distinct states found, 0 states left on queue." in out     # pcal_intro (README.md:349-352)

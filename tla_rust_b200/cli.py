@@ -45,7 +45,7 @@ def pcal2tla_main(argv=None):
     return rc
 
 
-def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq_cap=None, verbose=True, lib_dirs=(),
+def check_file(path, deadlock=True, cfg_path=None, out=None, device=0, seq_cap=None, verbose=True, lib_dirs=(),
                engine="auto", max_depth=0):
     """engine: "interp" = bytecode interpreter kernel, "sliced" = the model compiled to one CUDA kernel per slice of its
     program (nvcc at run time, cached in csrc/native/), "auto" = sliced for programs big enough to repay the compile.
@@ -53,6 +53,8 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
     from .checker import compile_model, encode_states, result_from_engine
     from .engine import Engine
     t0 = time.time()
+    if out is None:
+        out = sys.stdout
     lib_dirs = list(lib_dirs) + [d for d in os.environ.get("TLA_LIBRARY", "").split(os.pathsep) if d]
     m = Model(path, cfg_path=cfg_path, extra_dirs=lib_dirs)
     m.ev.out = out
@@ -74,6 +76,12 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
             res.error_text = f"Property {pbad} is violated by the initial state"
             print(format_result(res, m.vars, m.module_name), file=out)
             return 12
+    # CONSTRAINT on initial states (TLC, ORACLE O1 oracle/tlc_oracle.py:158): an initial state outside the constraint is
+    # generated and counted but never explored -- it is not handed to the engine, the counts are adjusted below
+    init_all = init
+    if m.constraints:
+        init = [st for st in init_all if m.in_model(st)]
+    n_out = len(init_all) - len(init)
     from .compile import types as _types
     base_sparse = _types.SPARSE_CAP
     try:
@@ -85,6 +93,15 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
             native = "sliced" if (engine == "sliced" or (engine == "auto" and len(cm.code) >= AUTO_SLICED_MIN_CODE)) else False
             if native == "sliced" and verbose:
                 print("Compiling the model to sm_100a kernels (one per invariant / disjunct of Next) ...", file=out)
+            world = int(os.environ.get("WORLD_SIZE", "1"))
+            if world > 1:                   # `tlc -gpus N`: this process is one rank of N (see tlc_main)
+                r, trace, e = _check_distributed(cm, iw, deadlock and m.check_deadlock, native, max_depth, out)
+                if r["verdict"] == 4 and r["detail"] == 2 and attempt < 3:
+                    _types.SPARSE_CAP *= 2
+                    seq_cap = 2 * (seq_cap or getattr(cm, "seq_cap", None) or 4)
+                    e.close()
+                    continue
+                break
             e = Engine(cm, deadlock=deadlock and m.check_deadlock, device=device, native=native)
             e.seed(iw)
             r0 = e.result()
@@ -113,9 +130,12 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
             break
     finally:
         _types.SPARSE_CAP = base_sparse
-    trace = None
-    if r["verdict"] != 0:
-        trace = e.trace(r["state_idx"])
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        trace = None
+        if r["verdict"] != 0:
+            trace = e.trace(r["state_idx"])
+    if n_out:
+        r = dict(r, generated=r["generated"] + n_out, distinct=r["distinct"] + n_out, init_states=r.get("init_states", 0) + n_out)
     res = result_from_engine(cm, r, trace)
     print(format_result(res, m.vars, m.module_name), file=out)
     print(f"Finished in {time.time() - t0:.2f}s ({r['device_seconds']:.4f}s in GPU wave kernels, "
@@ -124,9 +144,53 @@ def check_file(path, deadlock=True, cfg_path=None, out=sys.stdout, device=0, seq
     return 0 if res.verdict == OK else 12
 
 
+def _check_distributed(cm, iw, deadlock, native, max_depth, out):
+    """One rank of `tlc -gpus N` (torchrun environment): the state space is partitioned over the N GPUs
+    (tla_rust_b200/dist.py); every rank computes, rank 0 reports.  -> (result dict, trace or None, engine)"""
+    import torch
+    import torch.distributed as dist
+    from .dist import DistributedBFS
+    from .engine import Engine
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if native:                              # one rank compiles the model's kernels, the others wait for the library
+        if rank == 0:
+            from .engine import build_sliced_library
+            build_sliced_library(cm)
+        dist.barrier()
+    e = Engine(cm, deadlock=deadlock, device=local, native=native)
+    d = DistributedBFS(e, cm, rank, world, f"cuda:{local}", cap_records=1 << 24, chunk_states=1 << 21)
+    d.seed(iw)
+    import numpy as np
+    n_init = int(len(np.unique(np.asarray(iw).reshape(-1, cm.W), axis=0)))
+    print(f"Finished computing initial states: {n_init} distinct state{'s' if n_init != 1 else ''} generated "
+          f"({world} GPUs, exchange: {d.exchange}).", file=out)
+    res = d.run(max_levels=(max_depth - 1) if max_depth else 1 << 20)
+    cex = d.counterexample()
+    r = dict(verdict=res["verdict"] if res["verdict"] != 5 else 0, detail=0, detail2=0, generated=res["generated"],
+             distinct=res["distinct"], depth=res["depth"], queue_left=0, init_states=n_init, state_idx=0,
+             device_seconds=res["local"]["device_seconds"])
+    trace = None
+    if cex is not None:
+        r["verdict"], r["detail"] = cex[0], cex[1]
+        trace = (cex[2], cex[3])
+    return r, trace, e
+
+
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
 def tlc_main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
-    files, deadlock, cfg, dev, libs, seq_cap, engine, depth = [], True, None, 0, [], None, "auto", 0
+    files, deadlock, cfg, dev, libs, seq_cap, engine, depth, gpus = [], True, None, 0, [], None, "auto", 0, 1
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -147,7 +211,10 @@ def tlc_main(argv=None):
         elif a == "-depth":                 # depth-bounded prefix of the breadth-first search
             i += 1
             depth = int(argv[i])
-        elif a in ("-workers", "-gpus", "-device", "-fpmem", "-coverage", "-checkpoint"):
+        elif a == "-gpus":                  # partition the state space over N GPUs of this box (one process per GPU)
+            i += 1
+            gpus = int(argv[i])
+        elif a in ("-workers", "-device", "-fpmem", "-coverage", "-checkpoint"):
             i += 1
             if a == "-device":
                 dev = int(argv[i])
@@ -157,8 +224,19 @@ def tlc_main(argv=None):
             files.append(a)
         i += 1
     if not files:
-        print("usage: tlc [-deadlock] [-config FILE.cfg] [-I DIR] [-seqcap N] [-engine interp|sliced|auto] [-depth N] FILE.tla ...", file=sys.stderr)
+        print("usage: tlc [-deadlock] [-config FILE.cfg] [-I DIR] [-seqcap N] [-engine interp|sliced|auto] [-depth N] [-gpus N] FILE.tla ...", file=sys.stderr)
         return 2
+    if gpus > 1 and "RANK" not in os.environ:
+        # re-run this command as N ranks (torch.distributed.run is plumbing: rendezvous + one process per GPU)
+        import subprocess
+        return subprocess.call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={gpus}",
+                                "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), "-m", "tla_rust_b200.cli"]
+                               + argv, env=dict(os.environ, PYTHONPATH=os.pathsep.join(
+                                   [os.path.dirname(os.path.dirname(os.path.abspath(__file__)))] +
+                                   [x for x in os.environ.get("PYTHONPATH", "").split(os.pathsep) if x])))
+    quiet = int(os.environ.get("RANK", "0")) != 0
+    if quiet:                               # ranks other than 0 compute but do not report
+        sys.stdout = open(os.devnull, "w")
     rc = 0
     for f in files:
         if not f.endswith(".tla"):

@@ -98,6 +98,9 @@ class Ins:
         return None
 
 
+STATIC_WORDS = 16    # scalar form: run-time indexed regions up to this many words are addressed through select chains
+
+
 def dyn_accesses(ins: Ins):
     """[(base, nwords or None)] of the frame regions instruction `ins` addresses with a run-time index."""
     op = ins.op
@@ -110,11 +113,15 @@ def dyn_accesses(ins: Ins):
     return []
 
 
+MIN_SLICE = 256      # adjacent slices are merged into one kernel until it holds at least this many bytecode instructions
+
+
 class Plan:
     """Slices of a compiled model: prologues, slice ranges (closed under their jumps), subroutine regions."""
 
-    def __init__(self, cm):
+    def __init__(self, cm, min_slice=None):
         self.cm = cm
+        self.min_slice = MIN_SLICE if min_slice is None else int(min_slice)
         self.ins = [Ins(k, int(w)) for k, w in enumerate(np.ascontiguousarray(cm.code, dtype=np.uint64))]
         n = len(self.ins)
         halts = [i.k for i in self.ins if i.op == "HALT"]
@@ -128,7 +135,25 @@ class Plan:
             cuts = sorted(set(c for c in (segs.get(name) or []) if entry <= c <= halt))
             if not cuts:
                 cuts = [entry]
-            self.progs[name] = self._close(entry, cuts, halt)
+            pro, closed = self._close(entry, cuts, halt)
+            # Every kernel re-reads the packed frontier (Paxos b4: 15.5 GB per launch at the peak levels) and pays a
+            # launch + tail: tiny slices (Phase1a(b): 7 instructions) are merged with their neighbours.  Adjacent
+            # slices are consecutive code whose only exit is falling into the next one, so a group is just a coarser cut.
+            merged, cur = [], None
+            for s_, e_ in closed:
+                if cur is None:
+                    cur = [s_, e_]
+                else:
+                    cur[1] = e_
+                if cur[1] - cur[0] >= self.min_slice:
+                    merged.append(tuple(cur))
+                    cur = None
+            if cur is not None:
+                if merged and cur[1] - cur[0] < self.min_slice // 2:
+                    merged[-1] = (merged[-1][0], cur[1])
+                else:
+                    merged.append(tuple(cur))
+            self.progs[name] = (pro, merged)
 
     def _subroutines(self, lo, hi):
         entries = sorted(set(i.I for i in self.ins if i.op == "CALL"))
@@ -204,9 +229,9 @@ class Plan:
 
 
 class Emitter:
-    def __init__(self, cm, scalar=False):
+    def __init__(self, cm, scalar=False, min_slice=None):
         self.cm = cm
-        self.plan = Plan(cm)
+        self.plan = Plan(cm, min_slice)
         self.usz = int(cm.state_words_unpacked)
         self.frame = int(cm.frame_words)
         self.layout = [tuple(int(x) for x in r) for r in np.asarray(cm.layout).reshape(-1, 3)]
@@ -222,11 +247,22 @@ class Emitter:
             self._find_dyn()
 
     # ---- scalar form: which words stay in memory ---------------------------------------------------------------
+    def _static_ok(self, i: Ins, base, nw) -> bool:
+        """scalar form: can this run-time indexed access be written with compile-time word names (a select chain over
+        the region's words)?  Then the region needs no memory at all."""
+        n = self._extent(i, base, nw)
+        if i.op in ("LDX", "STX"):
+            return n <= 4 * STATIC_WORDS and n // max(1, i.d) <= STATIC_WORDS
+        if i.op in ("SFIND", "SINS"):
+            return False
+        return n <= STATIC_WORDS
+
     def _find_dyn(self, ranges=None):
         """Frame words that some instruction of the given pc ranges (default: the whole program) addresses with a
-        run-time index, widened to the allocation blocks they lie in.  Computed per slice function: temporaries are
-        stack-allocated by the lowering, so a word that is a bitset under scan in one slice is a plain scalar in the
-        others."""
+        run-time index in a way that needs memory, widened to the allocation blocks they lie in.  Computed per slice
+        function: temporaries are stack-allocated by the lowering, so a word that is a bitset under scan in one slice
+        is a plain scalar in the others.  Small regions (<= STATIC_WORDS words) are not in here: their accesses are
+        written as select chains over the words' C locals (_static_ok)."""
         blocks = getattr(self.cm, "blocks", None)
         if not blocks:
             raise SliceError("scalar form needs the allocation blocks of the lowering (cm.blocks)")
@@ -236,12 +272,9 @@ class Emitter:
             if i.op in ("SFIND", "SINS"):
                 raise SliceError("scalar form: sparse containers")
             for base, nw in dyn_accesses(i):
-                if nw is None:
-                    ends = [b + n for b, n in blocks if b <= base < b + n]
-                    # blocks are recorded for multi-word allocations and every variable: anything else is one value of
-                    # one word (or one element of an indexed load/store)
-                    nw = max(ends) - base if ends else (i.d if i.op in ("LDX", "STX") else 1)
-                dyn.update(range(base, base + nw))
+                if self._static_ok(i, base, nw):
+                    continue
+                dyn.update(range(base, base + self._extent(i, base, nw)))
         self.dyn_index = {w: j for j, w in enumerate(sorted(dyn))}
 
     def R(self, k: int) -> str:
@@ -250,6 +283,20 @@ class Emitter:
             return f"f[{k}]"
         j = self.dyn_index.get(k)
         return f"r{k}" if j is None else f"m[{j}]"
+
+    def SEL(self, base: int, n: int, idx: str) -> str:
+        """C rvalue of frame word base + idx for a run-time idx in 0..n-1, as a select chain over the n words"""
+        e = self.R(base + n - 1)
+        for j in range(n - 2, -1, -1):
+            e = f"({idx} == {j}u ? {self.R(base + j)} : {e})"
+        return e
+
+    def SEL2(self, base: int, cnt: int, d: int, j: int, idx: str) -> str:
+        """word j of element idx (0..cnt-1) of an array of d-word elements at base, as a select chain"""
+        e = self.R(base + (cnt - 1) * d + j)
+        for k in range(cnt - 2, -1, -1):
+            e = f"({idx} == {k}u ? {self.R(base + k * d + j)} : {e})"
+        return e
 
     def D(self, base: int, idx: str) -> str:
         """C lvalue of frame word base + idx (run-time idx): the region is in memory in both forms"""
@@ -458,6 +505,38 @@ class Emitter:
             return f"if ({R(a)} {_CMP[op]} ({_k14(b)})) {goto(J)}"
         if op in _COND_I:
             return f"if ({R(a)} {_CMP[op]} 0) {goto(I)}"
+        st_ = self.scalar and bool(dyn_accesses(i)) and all(self._static_ok(i, bb, nn) for bb, nn in dyn_accesses(i))
+        if st_:
+            base_, nw_ = dyn_accesses(i)[0]
+            nw_ = self._extent(i, base_, nw_)
+            if op in ("JBT", "JBF"):
+                return (f"{{ const uint32_t i_ = (uint32_t){R(b)}; const uint32_t w_ = (uint32_t){self.SEL(a, nw_, '(i_ >> 5)')}; "
+                        f"if ((((w_ >> (i_ & 31)) & 1u) != 0) == {1 if op == 'JBT' else 0}) {goto(J)} }}")
+            if op == "BTEST":
+                return (f"{{ const uint32_t i_ = (uint32_t){R(c)}; const uint32_t w_ = (uint32_t){self.SEL(b, nw_, '(i_ >> 5)')}; "
+                        f"{R(a)} = (int32_t)((w_ >> (i_ & 31)) & 1u); }}")
+            if op in ("BSET", "BCLR"):
+                upd = "|= (int32_t)m_" if op == "BSET" else "&= ~(int32_t)m_"
+                return (f"{{ const uint32_t i_ = (uint32_t){R(b)}, w_ = i_ >> 5, m_ = 1u << (i_ & 31); "
+                        + " ".join(f"if (w_ == {j}u) {R(a + j)} {upd};" for j in range(nw_)) + " }")
+            if op == "BNEXT":
+                out_ = [f"{{ int32_t cur_ = {R(c)} + 1; int32_t res_ = -1; int done_ = 0;"]
+                for j in range(nw_):
+                    out_.append(f"if (!done_ && cur_ < {32 * (j + 1)}) {{ const uint32_t sh_ = cur_ > {32 * j} ? (uint32_t)(cur_ - {32 * j}) : 0u; "
+                                f"const uint32_t word_ = (uint32_t){R(b + j)} >> sh_; "
+                                f"if (word_) {{ const int32_t cand_ = {32 * j} + (int32_t)sh_ + tlag_ffs(word_) - 1; "
+                                f"if ((uint32_t)cand_ < {d}u) res_ = cand_; done_ = 1; }} else cur_ = {32 * (j + 1)}; }}")
+                out_.append(f"{R(a)} = res_; }}")
+                return " ".join(out_)
+            if op == "LDX":
+                cnt_ = max(1, nw_ // max(1, d))
+                return (f"{{ const uint32_t x_ = (uint32_t){R(c)}; "
+                        + " ".join(f"{R(a + j)} = {self.SEL2(b, cnt_, d, j, 'x_')};" for j in range(d)) + " }")
+            if op == "STX":
+                cnt_ = max(1, nw_ // max(1, d))
+                return (f"{{ const uint32_t x_ = (uint32_t){R(b)}; "
+                        + " ".join(f"if (x_ == {k_}u) {{ " + " ".join(f"{R(a + k_ * d + j)} = {R(c + j)};" for j in range(d)) + " }"
+                                   for k_ in range(cnt_)) + " }")
         if op in ("JBT", "JBF"):
             return (f"{{ const uint32_t i_ = (uint32_t){R(b)}; if (((((uint32_t){D(a, '(i_ >> 5)')} >> (i_ & 31)) & 1u) != 0) == "
                     f"{1 if op == 'JBT' else 0}) {goto(J)} }}")
@@ -721,9 +800,10 @@ class Emitter:
         out = []
         for j in range(0, len(words), 16):
             out.append("  int32_t " + ", ".join(f"r{k} = 0" for k in words[j:j + 16]) + ";")
-        nd = max(1, len(self.dyn_index))
-        out.append(f"  int32_t m[{nd}];")
-        out.append(f"  for (int i_ = 0; i_ < {nd}; ++i_) m[i_] = 0;")
+        nd = len(self.dyn_index)
+        if nd:
+            out.append(f"  int32_t m[{nd}];")
+            out.append(f"  for (int i_ = 0; i_ < {nd}; ++i_) m[i_] = 0;")
         return out
 
     def _cpool_fnv(self):
@@ -840,9 +920,9 @@ class Emitter:
         return "\n".join(defs) + "\n", parts
 
 
-def emit_sliced(cm, scalar=False) -> str:
-    return Emitter(cm, scalar=scalar).emit()
+def emit_sliced(cm, scalar=False, min_slice=None) -> str:
+    return Emitter(cm, scalar=scalar, min_slice=min_slice).emit()
 
 
-def emit_parts(cm, scalar, nparts, defs_path):
-    return Emitter(cm, scalar=scalar).emit_parts(nparts, defs_path)
+def emit_parts(cm, scalar, nparts, defs_path, min_slice=None):
+    return Emitter(cm, scalar=scalar, min_slice=min_slice).emit_parts(nparts, defs_path)

@@ -97,7 +97,7 @@ __device__ __forceinline__ void sl_run(const DevParams& p, unsigned long long lo
     uint32_t in_[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) in_[i] = src[i];
-    cx->src = in_;
+    cx->src = src;                 // (the global row: taking the address of in_ would force it out of registers)
     fn(p.cpool, in_, cx);
     if (PHASE == 1 && cx->nsucc && p.succ_flag) p.succ_flag[idx - lo] = 1;
   }

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_probe(const uint32_t* __restrict__ stat
 // exactly once; ncu on the strided v0 showed 2.4x DRAM read amplification from L1 thrash), staged in
 // shared memory with an odd row stride (W|1 words -> conflict-free), then each thread fingerprints its
 // own row and probes the table.
-#define TLAG_PROBE_ROWS 1   /* rows per thread: two independent probes in flight per thread */
+#define TLAG_PROBE_ROWS 1   /* rows per thread of the staged form */
 __global__ void __launch_bounds__(256) k_probe_staged(const uint32_t* __restrict__ states, unsigned long long n, int W,
                                                       unsigned long long* table, unsigned long long mask,
                                                       uint8_t* __restrict__ is_new, Counters* ctr) {
@@ -390,6 +390,108 @@ __global__ void __launch_bounds__(256) k_probe_staged(const uint32_t* __restrict
     }
     if (ins < 0) { atomicExch(&ctr->table_full, 1ULL); ins = 0; }
     is_new[base + threadIdx.x + 256u * q] = (uint8_t)ins;
+  }
+}
+
+// K1, Blackwell form (W a multiple of 4 with W/4 odd: W = 4, 12, 20 ...).  A persistent CTA streams its tiles of
+// 512 rows through a 2-stage shared-memory ring filled by 1-D bulk copies of the TMA engine (cp.async.bulk ...
+// mbarrier::complete_tx::bytes -- UBLKCP in SASS): one elected thread arms the stage's mbarrier with the byte count and
+// issues the copy, the copy of tile k+1 is in flight while tile k is hashed and probed, and no thread spends issue
+// slots on LDG -> STS staging.  Rows are dense in shared memory (pitch = 4 W bytes, no padding) and read back with
+// 128-bit LDS: for W/4 odd the 8 rows of a quarter-warp fall into 8 distinct 4-bank groups, so the loads are
+// conflict-free.  Every thread owns TWO rows per tile: both fingerprints are computed first, both home-slot loads are
+// issued back to back (two independent DRAM round trips in flight per thread), then resolved.
+#define TLAG_TMA_ROWS 2
+#define TLAG_TMA_STAGES 2
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+__global__ void __launch_bounds__(256) k_probe_tma(const uint32_t* __restrict__ states, unsigned long long n, int W,
+                                                   unsigned long long* table, unsigned long long mask,
+                                                   uint8_t* __restrict__ is_new, Counters* ctr) {
+  extern __shared__ __align__(128) uint8_t s_ring[];
+  __shared__ __align__(8) uint64_t s_full[TLAG_TMA_STAGES];
+  constexpr unsigned ROWS = 256 * TLAG_TMA_ROWS;
+  const unsigned row_bytes = (unsigned)W * 4u;
+  const unsigned tile_bytes = ROWS * row_bytes;
+  const unsigned long long n_tiles = (n + ROWS - 1) / ROWS;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TLAG_TMA_STAGES; ++s) mbar_init(&s_full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](unsigned long long tile, int stage) {
+    const unsigned long long first = tile * ROWS;
+    const unsigned rows = (unsigned)((n - first) < (unsigned long long)ROWS ? (n - first) : (unsigned long long)ROWS);
+    const unsigned bytes = rows * row_bytes;
+    mbar_expect_tx(&s_full[stage], bytes);
+    bulk_g2s(s_ring + (size_t)stage * tile_bytes, states + first * (unsigned long long)W, bytes, &s_full[stage]);
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < TLAG_TMA_STAGES; ++s) {
+      const unsigned long long t = blockIdx.x + (unsigned long long)s * gridDim.x;
+      if (t < n_tiles) issue(t, s);
+    }
+  unsigned long long k = 0;
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+    const int stage = (int)(k % TLAG_TMA_STAGES);
+    mbar_wait(&s_full[stage], (unsigned)((k / TLAG_TMA_STAGES) & 1));
+    const unsigned long long first = tile * ROWS;
+    const unsigned nst = (unsigned)((n - first) < (unsigned long long)ROWS ? (n - first) : (unsigned long long)ROWS);
+    const uint8_t* base = s_ring + (size_t)stage * tile_bytes;
+    unsigned long long fp[TLAG_TMA_ROWS], slot[TLAG_TMA_ROWS], cur[TLAG_TMA_ROWS];
+    bool live[TLAG_TMA_ROWS];
+#pragma unroll
+    for (int q = 0; q < TLAG_TMA_ROWS; ++q) {
+      const unsigned row = threadIdx.x + 256u * q;
+      live[q] = row < nst;
+      const uint4* r4 = reinterpret_cast<const uint4*>(base + (size_t)(live[q] ? row : 0) * row_bytes);
+      uint64_t h = tlag_fp_init(W);
+      for (int j = 0; j < W / 4; ++j) {
+        const uint4 v = r4[j];
+        h = tlag_fp_pair(h, v.x, v.y);
+        h = tlag_fp_pair(h, v.z, v.w);
+      }
+      fp[q] = tlag_fp_final(h, W);
+      slot[q] = fp[q] & mask;
+    }
+#pragma unroll
+    for (int q = 0; q < TLAG_TMA_ROWS; ++q) cur[q] = live[q] ? __ldcv(&table[slot[q]]) : 0ULL;
+    __syncthreads();                                   // every row of this stage has been read: refill it
+    if (threadIdx.x == 0) {
+      const unsigned long long nt = tile + (unsigned long long)TLAG_TMA_STAGES * gridDim.x;
+      if (nt < n_tiles) issue(nt, stage);
+    }
+#pragma unroll
+    for (int q = 0; q < TLAG_TMA_ROWS; ++q) {
+      if (!live[q]) continue;
+      int ins;
+      if (cur[q] == fp[q]) ins = 0;
+      else if (cur[q] == 0ULL) {
+        const unsigned long long old = atomicCAS(&table[slot[q]], 0ULL, fp[q]);
+        ins = (old == 0ULL) ? 1 : (old == fp[q] ? 0 : seen_insert(table, mask, fp[q]));
+      } else {
+        ins = seen_insert(table, mask, fp[q]);
+      }
+      if (ins < 0) { atomicExch(&ctr->table_full, 1ULL); ins = 0; }
+      is_new[first + threadIdx.x + 256u * q] = (uint8_t)ins;
+    }
   }
 }
 
@@ -900,7 +1002,17 @@ static int launch_probe(tlag_engine* e, const uint32_t* d_states, uint64_t n, ui
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (n == 0) return TLAG_OK;
   const bool a16 = ((uintptr_t)d_states % 16) == 0, a8 = ((uintptr_t)d_states % 8) == 0;
-  if (a16 && W >= 2) {
+  static const bool no_tma = getenv("TLAG_K1_STAGED") != nullptr;       // knob: the LDG -> STS staged form
+  if (a16 && W % 4 == 0 && ((W / 4) & 1) && !no_tma) {
+    const size_t smem = (size_t)TLAG_TMA_STAGES * 256 * TLAG_TMA_ROWS * (size_t)W * 4;
+    CK(cudaFuncSetAttribute(k_probe_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_probe_tma, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+    const uint64_t tiles = (n + 256 * TLAG_TMA_ROWS - 1) / (256 * TLAG_TMA_ROWS);
+    uint64_t grid = (uint64_t)e->sm_count * (uint64_t)occ;                // persistent: one resident wave of CTAs
+    if (grid > tiles) grid = tiles;
+    k_probe_tma<<<(unsigned)grid, 256, smem, e->stream>>>(d_states, n, W, e->d_table, e->p.mask, d_is_new, e->d_ctr);
+  } else if (a16 && W >= 2) {
     const size_t smem = (size_t)256 * TLAG_PROBE_ROWS * (size_t)(W | 1) * 4;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_probe_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned sblocks = (unsigned)((n + 256 * TLAG_PROBE_ROWS - 1) / (256 * TLAG_PROBE_ROWS));

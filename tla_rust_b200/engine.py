@@ -103,7 +103,8 @@ def _sliced_tag(cm, scalar):
                 "compile/sliced.py", "../include/tlag.h"):
         with open(os.path.join(_HERE, rel), "rb") as f:
             h.update(f.read())
-    h.update(repr((getattr(cm, "segments", None), os.environ.get("TLAG_SL_OCC", ""), os.environ.get("TLAG_SL_BLOCK", ""))).encode())
+    h.update(repr((getattr(cm, "segments", None), os.environ.get("TLAG_SL_OCC", ""), os.environ.get("TLAG_SL_BLOCK", ""),
+                   os.environ.get("TLAG_SL_MIN_SLICE", ""))).encode())
     return f"sl_{model_key(cm)}_{h.hexdigest()[:8]}{'_s' if scalar else ''}"
 
 
@@ -146,7 +147,8 @@ def build_sliced_library(cm, force=False, verbose=False, scalar=None, jobs=None)
     os.makedirs(work, exist_ok=True)
     defs_path = os.path.join(work, "defs.h")
     nparts = max(1, min(jobs, 1 + len(cm.code) // 1500))
-    defs, parts = emit_parts(cm, scalar, nparts, defs_path)
+    ms = os.environ.get("TLAG_SL_MIN_SLICE")
+    defs, parts = emit_parts(cm, scalar, nparts, defs_path, min_slice=int(ms) if ms else None)
     with open(defs_path, "w") as f:
         f.write(defs)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -284,6 +284,10 @@ class Model:
                 cfg_text = ""
         self.cfg = parse_cfg(cfg_text)
         self.warnings = []
+        if self.cfg.view:
+            # TLC would fingerprint the VIEW expression instead of the whole state; here every state is distinguished by
+            # all of its variables (a superset of the view's classes: sound, possibly more states)
+            self.warnings.append(f"cfg: VIEW {self.cfg.view} is not applied -- states are identified by all variables")
         self._apply_cfg()
         self._assemble()
 
@@ -430,6 +434,14 @@ class Model:
             acc["live"] = True
             return
         acc["init"].append((n, ctx))
+
+    def in_model(self, st) -> bool:
+        """CONSTRAINTs on a state (host side: used for the initial states; on successors the device evaluates them)"""
+        from .eval import Fr
+        for _nm, node, c in self.constraints:
+            if self.ev.eval(node, {}, Fr(c, st, None)) is not True:
+                return False
+        return True
 
     def check_refinement_init(self, st):
         """Init => Init2 for every refinement PROPERTY; returns the name of a violated property or None."""
