@@ -315,9 +315,14 @@ def main():
         stats = dict(kern_s=kern_s)
     else:
         from tla_rust_b200.dist import DistributedBFS
+        # exchange buffers: ~4 GB of send regions per rank (the inbox is twice that), chunks sized so that a chunk's
+        # records fit its regions at up to 20 successors per state (an overflow rolls the level back and halves the chunk)
+        cap_rec = min(1 << 27, int(4e9 // ((cm.W + 2) * 4)))
+        chunk_st = max(1 << 16, min(1 << 22, cap_rec // 20))
         e = Engine(cm, deadlock=info["deadlock"], device=local_rank, native=native)
-        d = DistributedBFS(e, cm, rank, world, dev, cap_records=1 << 26, chunk_states=1 << 21)
+        d = DistributedBFS(e, cm, rank, world, dev, cap_records=cap_rec, chunk_states=chunk_st)
         d.seed(init)
+        exch, exch_note = d.exchange, d.exchange_note
         first = [True]
 
         def one():
@@ -355,7 +360,7 @@ def main():
         t1 = time.perf_counter()
         for _ in range(args.steps):
             e2 = Engine(cm, deadlock=info["deadlock"], device=local_rank, native=native)
-            d2 = DistributedBFS(e2, cm, rank, world, dev, cap_records=1 << 26, chunk_states=1 << 21)
+            d2 = DistributedBFS(e2, cm, rank, world, dev, cap_records=cap_rec, chunk_states=chunk_st)
             d2.seed(init)
             out2 = d2.run(max_levels=(levels - 1) if levels else 1 << 20)
             e2.close()
@@ -366,7 +371,7 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dt_e2e = float(tmax.item())
         assert out2["distinct"] == distinct
-        stats = dict(kern_s=kern_s, comm_ms=comm_ms)
+        stats = dict(kern_s=kern_s, comm_ms=comm_ms, exchange=exch, exchange_note=exch_note)
 
     if sampler:
         sampler.stop_flag = True
@@ -432,6 +437,10 @@ def main():
             "parity": {"counts_match_oracle": True, "digest_matches_oracle": True},
             "other_workloads": others}
     if multi:
+        # p2p: the exchange is device code inside the level (k_push / k_insert_inbox), no separate communication time;
+        # nccl: time between the expand kernel and the end of the payload all_to_all
+        line["exchange"] = ("peer memory over NVLink (CUDA IPC inboxes, k_push / k_insert_inbox)" if stats["exchange"] == "p2p"
+                            else "NCCL all_to_all" + (f" ({stats['exchange_note']})" if stats["exchange_note"] else ""))
         line["comm_ms_per_step"] = round(stats["comm_ms"] / args.steps, 3)
         dist.destroy_process_group()
     print(json.dumps(line))

@@ -138,6 +138,10 @@ int  tlag_p2p_init(tlag_engine *e, uint32_t n_ranks, uint32_t rank, uint64_t cap
 int  tlag_p2p_attach(tlag_engine *e, uint32_t peer, const uint8_t *handle64);
 int  tlag_p2p_level(tlag_engine *e, uint64_t n_chunks, uint64_t chunk_states, uint64_t expect_inbound,
                     tlag_wave_stats *out);
+/* TLAG_EOVERFLOW from tlag_p2p_level on ANY rank (a send region was too small for a chunk): every rank calls
+ * tlag_p2p_rollback -- the level's appended states are dropped, the seen-set rebuilt -- and the level is run again
+ * with smaller chunks. */
+int  tlag_p2p_rollback(tlag_engine *e);
 
 #ifdef __cplusplus
 }

@@ -163,3 +163,22 @@ def test_config1_as_written_reference_makefile_and_specs(monkeypatch, capfd):
     assert out.count("Model checking completed. No error has been found.") == 2
     assert "7 states generated, 5 distinct states found, 0 states left on queue." in out           # atomic_add
     assert "5850 states generated, 3800 distinct states found, 0 states left on queue." in out     # pcal_intro (README.md:349-352)
+
+
+def test_constraint_on_initial_states_and_view_warning(monkeypatch, capfd):
+    """Initial states outside the CONSTRAINT are generated and counted, not explored (as TLC and ORACLE O1 do); a cfg
+    VIEW is reported as not applied instead of being dropped silently."""
+    import tla_rust_b200.engine as eng
+    from tla_rust_b200.cli import check_file
+    from tla_rust_b200.front.spec import Model
+    from oracle.tlc_oracle import Oracle
+    spec = os.path.join(ROOT, "tests", "specs", "Cinit.tla")
+    m = Model(spec)
+    o1 = Oracle(m).run()
+    monkeypatch.setattr(eng, "Engine", _CpuShimEngine)
+    rc = check_file(spec, verbose=False, engine="interp")
+    sys.stdout.flush()
+    out = capfd.readouterr().out
+    assert rc == 0, out
+    assert "VIEW x is not applied" in out
+    assert f"{o1.generated} states generated, {o1.distinct} distinct states found, 0 states left on queue." in out

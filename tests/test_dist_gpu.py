@@ -62,6 +62,18 @@ def test_send_region_overflow_retry_loses_no_state(engine):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
+def test_p2p_region_overflow_rolls_the_level_back():
+    """Peer-memory path with send regions of 8 K records: a chunk overflows them, every rank rolls the level back
+    (tlag_p2p_rollback: appended states dropped, seen-set rebuilt) and re-runs it with halved chunks -- same state set."""
+    _, _, exp, _ = load_compiled(os.path.join(GOLDEN, "MCPaxos3_b2.tlagz"))
+    o2 = exp["o2"]
+    r = _run(2, "MCPaxos3_b2", "p2p", "sliced", 16384, 1 << 16)
+    assert r["exchange"] == "p2p" and r["retries"] >= 1 and r["chunk_states"] < (1 << 16)
+    assert (r["verdict"], r["generated"], r["distinct"], r["depth"]) == (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"])
+    assert r["digest"] == [o2["fp_xor"], o2["fp_sum"]]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 def test_violation_on_two_gpus_has_a_behaviour(exchange):
     cm, init, exp, info = load_compiled(os.path.join(GOLDEN, "demo_race.tlagz"))

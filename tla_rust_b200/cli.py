@@ -229,11 +229,23 @@ def tlc_main(argv=None):
     if gpus > 1 and "RANK" not in os.environ:
         # re-run this command as N ranks (torch.distributed.run is plumbing: rendezvous + one process per GPU)
         import subprocess
-        return subprocess.call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={gpus}",
-                                "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), "-m", "tla_rust_b200.cli"]
-                               + argv, env=dict(os.environ, PYTHONPATH=os.pathsep.join(
-                                   [os.path.dirname(os.path.dirname(os.path.abspath(__file__)))] +
-                                   [x for x in os.environ.get("PYTHONPATH", "").split(os.pathsep) if x])))
+        import tempfile
+        # the ranks leave the exit status (0 / 12 violation / 150 spec error ...) in a file and exit 0 themselves: a
+        # non-zero rank makes the launcher print a failure report of its own on top of the TLC-format one
+        with tempfile.NamedTemporaryFile(prefix="tlag_rc_", delete=False) as tf:
+            rc_file = tf.name
+        launcher = subprocess.call(
+            [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={gpus}", "--master-addr", "127.0.0.1",
+             "--master-port", str(_free_port()), "-m", "tla_rust_b200.cli"] + argv,
+            env=dict(os.environ, TLAG_RC_FILE=rc_file, PYTHONPATH=os.pathsep.join(
+                [os.path.dirname(os.path.dirname(os.path.abspath(__file__)))] +
+                [x for x in os.environ.get("PYTHONPATH", "").split(os.pathsep) if x])))
+        try:
+            txt = open(rc_file).read().strip()
+            os.remove(rc_file)
+        except OSError:
+            txt = ""
+        return int(txt) if txt else (launcher or 255)
     quiet = int(os.environ.get("RANK", "0")) != 0
     if quiet:                               # ranks other than 0 compute but do not report
         sys.stdout = open(os.devnull, "w")
@@ -254,6 +266,17 @@ def tlc_main(argv=None):
         if r != 0:
             rc = r
             break      # `make` semantics: TLC exits non-zero at the first failing module
+    if "RANK" in os.environ and os.environ.get("TLAG_RC_FILE"):
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
+        if not quiet:
+            with open(os.environ["TLAG_RC_FILE"], "w") as f:
+                f.write(str(rc))
+        return 0
     return rc
 
 

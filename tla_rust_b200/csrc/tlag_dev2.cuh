@@ -12,7 +12,9 @@ static __device__ __noinline__ void sl_emit_words(tlag_sl_cx* cx, int aid, const
   for (int i = 0; i < W; ++i) w[i] = o[i];
   const unsigned long long fp = tlag_fingerprint(w, W);
   const unsigned lane = threadIdx.x & 31;
-  if (!p.route) {
+  // route mode: a successor this rank owns itself never leaves the GPU (1/N of the records)
+  const int owner = p.route ? (int)tlag_owner(w, W, (uint32_t)p.n_ranks) : p.rank;
+  if (!p.route || owner == p.rank) {
     int ins = seen_insert(p.table, p.mask, fp);
     if (ins < 0) { atomicExch(&p.ctr->table_full, 1ULL); ins = 0; }
     if (ins > 0) {
@@ -39,7 +41,6 @@ static __device__ __noinline__ void sl_emit_words(tlag_sl_cx* cx, int aid, const
     // region overflow loses nothing.
     unsigned long long* cslot = p.sent_cache ? p.sent_cache + (fp & p.sent_mask) : nullptr;
     if (cslot && __ldcv(cslot) == fp) return;
-    const int owner = (int)tlag_owner(w, W, (uint32_t)p.n_ranks);
     const unsigned am = __activemask();
     const unsigned peers = __match_any_sync(am, owner);
     const int leader = __ffs((int)peers) - 1;

@@ -85,6 +85,7 @@ struct tlag_engine {
   void* peer_base[16] = {nullptr};
   unsigned long long p2p_seq = 0;
   bool p2p_ready = false;
+  uint64_t p2p_level_start = 0, p2p_level_generated = 0;   // for tlag_p2p_rollback: store tail before the level, what it added
   // TLAG_F_KEEP_GOING: the first violation is remembered, the search goes on to the fixpoint
   int kg_verdict = 0, kg_detail = 0, kg_detail2 = 0; uint64_t kg_idx = 0;
   std::string err;
@@ -1002,8 +1003,11 @@ static int launch_probe(tlag_engine* e, const uint32_t* d_states, uint64_t n, ui
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (n == 0) return TLAG_OK;
   const bool a16 = ((uintptr_t)d_states % 16) == 0, a8 = ((uintptr_t)d_states % 8) == 0;
-  static const bool no_tma = getenv("TLAG_K1_STAGED") != nullptr;       // knob: the LDG -> STS staged form
-  if (a16 && W % 4 == 0 && ((W / 4) & 1) && !no_tma) {
+  // TLAG_K1_TMA=1 selects the TMA-ring form.  Measured (profiles/r2_s3_session.log, 2^27 candidates, W = 20): 7.30 ms
+  // against 6.10 ms for the staged form -- the ring's shared memory (2 x 40 KB per CTA) halves the resident threads, and
+  // K1 is bound by the latency of the random table probes, not by the row copies the TMA engine takes over.
+  static const bool use_tma = getenv("TLAG_K1_TMA") != nullptr;
+  if (a16 && W % 4 == 0 && ((W / 4) & 1) && use_tma) {
     const size_t smem = (size_t)TLAG_TMA_STAGES * 256 * TLAG_TMA_ROWS * (size_t)W * 4;
     CK(cudaFuncSetAttribute(k_probe_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
@@ -1391,7 +1395,15 @@ extern "C" int tlag_expand_route(tlag_engine* e, uint32_t n_ranks, uint64_t firs
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->dev_seconds += ms * 1e-3;
-  if (hc.route_overflow) { e->err = "send buffer overflow in tlag_expand_route"; return TLAG_EOVERFLOW; }
+  if (hc.route_overflow) {
+    // The caller re-runs this chunk with larger regions and throws this attempt's buffer away -- including the records
+    // that did fit, whose fingerprints are now in the routed-fingerprint cache.  Forget them all (the cache is only a
+    // filter: an empty one costs redundant records, a stale one loses states).
+    if (e->d_sent) CK(cudaMemsetAsync(e->d_sent, 0, (e->p.sent_mask + 1) * 8, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->err = "send buffer overflow in tlag_expand_route";
+    return TLAG_EOVERFLOW;
+  }
   e->generated += hc.generated;
   CK(cudaMemsetAsync(&e->d_ctr->generated, 0, 8, e->stream));
   for (uint32_t r = 0; r < n_ranks; ++r) counts[r] = hc.send_count[r];
@@ -1498,6 +1510,7 @@ extern "C" int tlag_p2p_level(tlag_engine* e, uint64_t n_chunks, uint64_t chunk_
   Counters hc;
   CK(cudaMemcpy(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
   const uint64_t before = hc.n_states;
+  e->p2p_level_start = before; e->p2p_level_generated = 0;
   int r = grow_store_if_needed(e, before + expect);
   if (r) return r;
   r = grow_table_if_needed(e, before + expect);
@@ -1542,6 +1555,7 @@ extern "C" int tlag_p2p_level(tlag_engine* e, uint64_t n_chunks, uint64_t chunk_
   if (hc.store_overflow) { e->err = "state store overflow in tlag_p2p_level"; return TLAG_ENOMEM; }
   if (hc.table_full) { e->err = "seen-set table full in tlag_p2p_level"; return TLAG_ENOMEM; }
   e->generated += hc.generated;
+  e->p2p_level_generated = hc.generated;
   CK(cudaMemsetAsync(&e->d_ctr->generated, 0, 8, e->stream));
   collect_violations(e, hc);
   if (out) {
@@ -1553,6 +1567,23 @@ extern "C" int tlag_p2p_level(tlag_engine* e, uint64_t n_chunks, uint64_t chunk_
     const double ratio = (double)(hc.n_states - before) / (double)((e->hi - e->lo) ? (e->hi - e->lo) : 1);
     e->growth_hint = ratio * 2.0 > 4.0 ? ratio * 2.0 : 4.0;
   }
+  return TLAG_OK;
+}
+
+// Undo the level tlag_p2p_level just ran on this rank (some rank's send regions overflowed: every rank rolls back and
+// the host re-runs the level with smaller chunks).  The states the level appended are dropped, the seen-set is rebuilt
+// from the store, the routed-fingerprint cache is emptied; the inbox chunk numbering simply continues.
+extern "C" int tlag_p2p_rollback(tlag_engine* e) {
+  if (!e || !e->d_p2p) return TLAG_EINVAL;
+  CK(cudaStreamSynchronize(e->stream));
+  int r = rollback_wave(e, e->p2p_level_start, e->p2p_level_start + 4096);
+  if (r) return r;
+  if (e->d_sent) CK(cudaMemsetAsync(e->d_sent, 0, (e->p.sent_mask + 1) * 8, e->stream));
+  CK(cudaMemsetAsync(&e->d_ctr->route_overflow, 0, 8, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->generated -= e->p2p_level_generated;
+  e->p2p_level_generated = 0;
+  e->verdict = TLAG_V_RUNNING; e->detail = e->detail2 = 0; e->viol_idx = 0;
   return TLAG_OK;
 }
 

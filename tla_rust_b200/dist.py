@@ -186,12 +186,23 @@ class DistributedBFS:
             if self.exchange == "p2p":
                 # the whole level on the device: expand -> push over NVLink -> insert, per chunk; one sync at the end
                 max_fr = int(nch[1].item())
-                ws = e.p2p_level(max(1, int(nch[0].item())), self.chunk_states,
-                                 int(max_fr * max(8.0, 3.0 * self._ratio)) + (1 << 16))
+                while True:
+                    n_chunks = max(1, (max_fr + self.chunk_states - 1) // self.chunk_states)
+                    ws = e.p2p_level(n_chunks, self.chunk_states, int(max_fr * max(8.0, 3.0 * self._ratio)) + (1 << 16))
+                    over = torch.tensor([1 if ws is None else 0], dtype=torch.int64, device=self.device)
+                    dist.all_reduce(over, op=dist.ReduceOp.MAX)
+                    if int(over.item()) == 0:
+                        break
+                    # some rank's send region was too small for a chunk: every rank undoes the level, smaller chunks
+                    e.p2p_rollback()
+                    if self.chunk_states <= 1024:
+                        raise RuntimeError("peer-memory exchange: send regions too small even for 1 K-state chunks")
+                    self.chunk_states //= 2
+                    self.retries = getattr(self, "retries", 0) + 1
                 n_new, gen = ws["discovered"], ws["generated"]
                 if ws["verdict"] not in (0, 5):
                     bad = ws["verdict"]
-                self.exchanges += int(nch[0].item())
+                self.exchanges += n_chunks
                 if fr:
                     self._ratio = max(self._ratio * 0.5, ws["discovered"] / fr)
             for c in range(int(nch[0].item()) if self.exchange != "p2p" else 0):

@@ -61,7 +61,7 @@ EXPORTS = ["tlag_create", "tlag_seed", "tlag_step", "tlag_run", "tlag_result_now
            "tlag_read_states", "tlag_digest", "tlag_probe_batch", "tlag_probe_batch_device", "tlag_reset_table", "tlag_restart",
            "tlag_kernel_launches", "tlag_destroy", "tlag_last_error", "tlag_version",
            "tlag_frontier", "tlag_expand_route", "tlag_insert_records", "tlag_advance_level",
-           "tlag_p2p_init", "tlag_p2p_attach", "tlag_p2p_level", "tlag_read_link"]
+           "tlag_p2p_init", "tlag_p2p_attach", "tlag_p2p_level", "tlag_p2p_rollback", "tlag_read_link"]
 
 
 def build_library(verbose=False):
@@ -346,11 +346,18 @@ class Engine:
         h = (C.c_uint8 * 64).from_buffer_copy(handle)
         self._ck(self.L.tlag_p2p_attach(self.h, C.c_uint32(peer), h), "tlag_p2p_attach")
 
-    def p2p_level(self, n_chunks, chunk_states, expect_inbound=0) -> dict:
+    def p2p_level(self, n_chunks, chunk_states, expect_inbound=0):
+        """-> wave stats dict, or None when one of this rank's send regions overflowed (see p2p_rollback)"""
         ws = WaveStats()
-        self._ck(self.L.tlag_p2p_level(self.h, C.c_uint64(n_chunks), C.c_uint64(chunk_states), C.c_uint64(expect_inbound),
-                                       C.byref(ws)), "tlag_p2p_level")
+        rc = self.L.tlag_p2p_level(self.h, C.c_uint64(n_chunks), C.c_uint64(chunk_states), C.c_uint64(expect_inbound),
+                                   C.byref(ws))
+        if rc == -5:            # TLAG_EOVERFLOW
+            return None
+        self._ck(rc, "tlag_p2p_level")
         return ws.as_dict()
+
+    def p2p_rollback(self):
+        self._ck(self.L.tlag_p2p_rollback(self.h), "tlag_p2p_rollback")
 
     def advance_level(self) -> dict:
         ws = WaveStats()
