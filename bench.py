@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--workload", default="MCPaxos3_b4")
     ap.add_argument("--engine", default=os.environ.get("TLAG_BENCH_ENGINE", "sliced"), choices=["sliced", "interp"])
     ap.add_argument("--no-k1", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU arm (multi-GPU sessions: the other ranks' boxes idle meanwhile)")
     args = ap.parse_args()
     if os.environ.get("TLAG_BENCH_WATCHDOG"):
         import faulthandler
@@ -411,8 +412,11 @@ def main():
             k1["peak_source"] = peak_src
         except Exception as ex:  # noqa: BLE001
             k1 = {"error": str(ex)}
-    cpu_r, cpu_v, cpu_spread = cpu_arm(cm, init, info, threads, want, levels, repeats=3 if not multi else 1, exp=exp,
-                                       workload=args.workload)
+    if args.no_cpu:
+        cpu_r, cpu_v, cpu_spread = {"sample": "skipped (--no-cpu)"}, 0.0, {}
+    else:
+        cpu_r, cpu_v, cpu_spread = cpu_arm(cm, init, info, threads, want, levels, repeats=3 if not multi else 1, exp=exp,
+                                           workload=args.workload)
     others = []
     if not multi and not args.no_k1:
         for name, label, tmo in (

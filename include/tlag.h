@@ -34,7 +34,12 @@ enum { TLAG_V_OK = 0, TLAG_V_INVARIANT = 1, TLAG_V_ASSERT = 2, TLAG_V_DEADLOCK =
        TLAG_V_EVAL_ERROR = 4, TLAG_V_RUNNING = 5 };
 
 enum { TLAG_F_DEADLOCK_CHECK = 1u,   /* report states without successors            */
-       TLAG_F_KEEP_GOING     = 2u }; /* do not stop a run at the first violation    */
+       TLAG_F_KEEP_GOING     = 2u,   /* do not stop a run at the first violation    */
+       TLAG_F_EXACT          = 4u }; /* TLC-exact replay: the search runs as ONE sequential worker on the device (states
+                                      * dequeued in FIFO order, successors in program order) and stops AT the first
+                                      * Assert failure / deadlock, so the counts at that moment, the state reported and
+                                      * its parent chain are the ones TLC's single worker prints (README.md:267-321).
+                                      * Interpreter kernel only; meant for re-running a small model after an error. */
 
 typedef struct {
   uint32_t words_per_state;      /* W: packed state vector width in u32 words (1..128)        */
@@ -117,6 +122,9 @@ const char *tlag_version(void);
  * index + action id, record = W+2 u32) are bucketed by owner rank = fingerprint >> (64-log2 R)
  * ... into d_send (device, capacity cap_records), counts[r] records per rank (host out). */
 int  tlag_frontier(tlag_engine *e, uint64_t *first_idx, uint64_t *count);   /* current frontier slice */
+/* Which shard this engine holds (before the first tlag_expand_route of a multi-rank run): successors the rank owns
+ * itself are inserted in place, and the rank is recorded in the meta word of the states whose parent it expands. */
+int  tlag_set_rank(tlag_engine *e, uint32_t n_ranks, uint32_t rank);
 /* `first`/`count` select a sub-range of the frontier (chunked exchange with bounded buffers). */
 int  tlag_expand_route(tlag_engine *e, uint32_t n_ranks, uint64_t first, uint64_t count, uint64_t d_send,
                        uint64_t cap_records, uint64_t *counts, tlag_wave_stats *out);

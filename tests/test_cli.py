@@ -62,8 +62,8 @@ class _CpuShimEngine:
     """Stand-in for tla_rust_b200.engine.Engine backed by the CPU bytecode oracle: lets the CPU suite drive the
     whole `tlc` control flow (compile, report formatting, capacity retry).  Test infrastructure only."""
 
-    def __init__(self, cm, deadlock=True, device=0, native=False):
-        self.cm, self.deadlock, self.r = cm, deadlock, None
+    def __init__(self, cm, deadlock=True, device=0, native=False, exact=False):
+        self.cm, self.deadlock, self.r, self.exact = cm, deadlock, None, exact
 
     def seed(self, iw):
         self.iw = iw
@@ -76,15 +76,19 @@ class _CpuShimEngine:
 
     def step(self):
         from oracle import cpu_engine
-        r = cpu_engine.run(self.cm, self.iw, deadlock=self.deadlock, want_states=True, max_states=1 << 17)
+        r = cpu_engine.run(self.cm, self.iw, deadlock=self.deadlock, want_states=True, max_states=1 << 17, exact=self.exact)
         self.states = r.pop("states")
-        r.update(queue_left=0, device_seconds=r["seconds"])
+        r.update(queue_left=r.get("queue", 0), device_seconds=r["seconds"])
         self.r = r
         return {"verdict": r["verdict"], "expanded": 0}
 
+    def run(self):
+        self.step()
+        return self.r
+
     def trace(self, idx):
         import numpy as np
-        return self.states[idx:idx + 1], np.array([-1])
+        return self.states[idx:idx + 1], np.array([-1])       # (the shim keeps no parent links: one-state "trace")
 
     def launches(self):
         return 0
@@ -182,3 +186,31 @@ def test_constraint_on_initial_states_and_view_warning(monkeypatch, capfd):
     assert rc == 0, out
     assert "VIEW x is not applied" in out
     assert f"{o1.generated} states generated, {o1.distinct} distinct states found, 0 states left on queue." in out
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/pcal_intro.tla"), reason="the reference checkout only exists in the build container")
+def test_error_is_replayed_sequentially_for_tlc_exact_counts(monkeypatch, capfd):
+    """README.md:232-236 + 267-321: with labels A: and B: inserted, TLC's single worker stops at the failed assert with
+    9097 states generated, 6164 distinct, 999 left on queue, depth 7.  `tlc` finds the error with the parallel search
+    (whole-level counts), then replays the model as ONE sequential worker (TLAG_F_EXACT on the device; ORACLE O2's
+    sequential mode behind the CPU shim here) and reports that run."""
+    import tla_rust_b200.engine as eng
+    from tla_rust_b200.cli import check_file
+    from tla_rust_b200.front.pcal import translate_file
+    from test_frontend import README_BUGGY
+    d = tempfile.mkdtemp(prefix="tlag_readme_")
+    src = open("/root/reference/pcal_intro.tla").read()
+    for a, b in README_BUGGY:
+        src = src.replace(a, b)
+    p = os.path.join(d, "pcal_intro.tla")
+    open(p, "w").write(src)
+    open(os.path.join(d, "pcal_intro.cfg"), "w").write("SPECIFICATION Spec\n")
+    translate_file(p)
+    monkeypatch.setattr(eng, "Engine", _CpuShimEngine)
+    rc = check_file(p, verbose=False, engine="interp")
+    sys.stdout.flush()
+    out = capfd.readouterr().out
+    assert rc == 12
+    assert "Failure of assertion at line 16, column 4." in out
+    assert "9097 states generated, 6164 distinct states found, 999 states left on queue." in out
+    assert "The depth of the complete state graph search is 7." in out

@@ -56,7 +56,7 @@ def test_send_region_overflow_retry_loses_no_state(engine):
     _, _, exp, _ = load_compiled(os.path.join(GOLDEN, "MCPaxos3_b2.tlagz"))
     o2 = exp["o2"]
     r = _run(2, "MCPaxos3_b2", "nccl", engine, 2048, 1 << 16)
-    assert r["cap_records"] > 2048                         # the retry really happened
+    assert r["retries_max"] >= 1                           # on some rank the retry really happened
     assert (r["generated"], r["distinct"]) == (o2["generated"], o2["distinct"])
     assert r["digest"] == [o2["fp_xor"], o2["fp_sum"]]
 
@@ -81,7 +81,7 @@ def test_violation_on_two_gpus_has_a_behaviour(exchange):
     assert r["verdict"] == 1 and r["cex"] is not None
     states = np.array(r["cex"]["states"], dtype=np.uint32)
     assert any((states[0] == i).all() for i in init.reshape(-1, cm.W))
-    assert r["cex"]["actions"][0] == -1 and len(states) == exp["o2"]["depth"] - 1
+    assert r["cex"]["actions"][0] == -1 and len(states) == 5          # initial state + 4 steps: the shortest lost update
     from tla_rust_b200.checker import decode_state
     last = decode_state(cm, states[-1])
     assert last["pc"] == ("Done", "Done") and last["counter"] == 1      # the lost update

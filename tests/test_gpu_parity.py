@@ -118,6 +118,44 @@ def test_assert_trace_is_a_shortest_counterexample():
     e.close()
 
 
+def test_exact_replay_reproduces_the_readme_transcript_on_the_device():
+    """README.md:267-321, the reference's only known-answer transcript for this path, on the GPU: TLAG_F_EXACT runs the
+    search as one sequential worker (one warp, one state at a time, FIFO order, stop AT the failed assert) -- the counts
+    TLC printed (9097 generated / 6164 distinct / 999 on queue / depth 7) and the 6-state trace it printed."""
+    from tla_rust_b200.front.report import format_result
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, "pcal_intro_readme_buggy.tlagz"))
+    e = _engine(cm, exact=True)
+    e.seed(init)
+    r = e.run()
+    assert r["verdict"] == 2
+    assert (r["generated"], r["distinct"], r["queue_left"], r["depth"]) == (9097, 6164, 999, 7)       # README.md:319-320
+    res = result_from_engine(cm, r, e.trace(r["state_idx"]))
+    want = [dict(bob_account=10, money=(1, 10), alice_account=10, pc=("Transfer", "Transfer"), account_total=20),
+            dict(bob_account=10, money=(1, 10), alice_account=10, pc=("A", "Transfer"), account_total=20),
+            dict(bob_account=10, money=(1, 10), alice_account=10, pc=("A", "A"), account_total=20),
+            dict(bob_account=10, money=(1, 10), alice_account=9, pc=("B", "A"), account_total=20),
+            dict(bob_account=11, money=(1, 10), alice_account=9, pc=("C", "A"), account_total=20),
+            dict(bob_account=11, money=(1, 10), alice_account=-1, pc=("C", "B"), account_total=20)]
+    assert [st for st, _ in res.trace] == want                                                          # README.md:271-311
+    assert [None if a is None else a[2] for _, a in res.trace] == [None, (35, 19, 40, 42), (35, 19, 40, 42), (42, 12, 45, 63),
+                                                                   (47, 12, 50, 65), (42, 12, 45, 63)]   # README.md:278-306
+    txt = format_result(res, cm.vars, "pcal_intro")
+    assert "Failure of assertion at line 16, column 4." in txt
+    assert "9097 states generated, 6164 distinct states found, 999 states left on queue." in txt
+    assert txt.rstrip().endswith("The depth of the complete state graph search is 7.")
+    e.close()
+    # the same flag on a deadlocking model: stops at the first state without successors, in FIFO order
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, "MCVoting_deadlock.tlagz"))
+    from oracle import cpu_engine
+    o = cpu_engine.run(cm, init, deadlock=True, exact=True)
+    e = _engine(cm, deadlock=True, exact=True)
+    e.seed(init)
+    r = e.run()
+    assert (r["verdict"], r["generated"], r["distinct"], r["queue_left"], r["state_idx"]) == (
+        3, o["generated"], o["distinct"], o["queue"], o["state_idx"])
+    e.close()
+
+
 def test_invariant_and_deadlock_traces_are_valid_counterexamples():
     """Verdict kinds other than ok: the reported state really is an error state and the parent chain is a
     behaviour of minimal length starting in an initial state (level-synchronous BFS => shortest)."""

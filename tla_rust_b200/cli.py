@@ -20,6 +20,8 @@ from .compile.types import TypeErr
 # `tlc -engine auto`: programs of at least this many bytecode instructions are compiled to sliced kernels (about 10 s of
 # nvcc per thousand instructions, cached per model); smaller ones run on the interpreter kernel at once.
 AUTO_SLICED_MIN_CODE = int(os.environ.get("TLAG_AUTO_SLICED_MIN_CODE", "1500"))
+# an Assert failure / deadlock found within this many states is replayed sequentially for TLC-exact counts and trace
+EXACT_REPLAY_MAX_STATES = int(os.environ.get("TLAG_EXACT_REPLAY_MAX_STATES", "200000"))
 
 
 def pcal2tla_main(argv=None):
@@ -131,6 +133,15 @@ def check_file(path, deadlock=True, cfg_path=None, out=None, device=0, seq_cap=N
     finally:
         _types.SPARSE_CAP = base_sparse
     if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        # The parallel search reports an error with the counts of the whole level it was found in, and with whichever of
+        # several shortest behaviours won the race.  TLC's single worker stops AT the first Assert failure / deadlock
+        # (README.md:319: 9097 generated / 6164 distinct / 999 on queue).  For a model small enough, replay the search as
+        # one sequential worker on the device (TLAG_F_EXACT) and report that run: TLC's counts and TLC's trace.
+        if r["verdict"] in (2, 3) and r["distinct"] <= EXACT_REPLAY_MAX_STATES and not max_depth:
+            e.close()
+            e = Engine(cm, deadlock=deadlock and m.check_deadlock, device=device, native=False, exact=True)
+            e.seed(iw)
+            r = e.run()
         trace = None
         if r["verdict"] != 0:
             trace = e.trace(r["state_idx"])

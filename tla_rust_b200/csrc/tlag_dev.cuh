@@ -19,6 +19,7 @@ struct Counters {
   unsigned long long table_full;
   unsigned long long route_overflow;
   unsigned long long send_count[16];
+  unsigned long long stop;          // TLAG_F_EXACT: an error was found, no further state is dequeued
 };
 
 struct DevParams {

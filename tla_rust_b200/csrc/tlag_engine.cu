@@ -166,15 +166,19 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
   const unsigned lane = threadIdx.x & 31;
   const int W = p.W;
   unsigned long long gen_local = 0;
+  // TLAG_F_EXACT (launched as ONE warp): lane 0 dequeues one state at a time, in index = FIFO order, and the search
+  // stops at the first Assert failure / deadlock -- TLC's single worker, on the device
+  const bool exact = MODE == 0 && (p.flags & TLAG_F_EXACT) != 0;
 
   for (;;) {
+    if (exact && *(volatile unsigned long long*)&p.ctr->stop) break;
     unsigned long long chunk = 0;
     if (lane == 0) chunk = atomicAdd(&p.ctr->work, 1ULL);
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    const unsigned long long first = lo + chunk * 32ULL;
+    const unsigned long long first = lo + chunk * (exact ? 1ULL : 32ULL);
     if (first >= hi) break;
     const unsigned long long idx = first + lane;
-    const bool active = idx < hi;
+    const bool active = idx < hi && (!exact || lane == 0);
     if (active) {
       const uint32_t* src = p.states + idx * (unsigned long long)W;
       for (int i = 0; i < W; ++i) succ[i] = src[i];
@@ -205,7 +209,11 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
           if (phase == 0) report_min(&p.ctr->viol_inv, (idx << 20) | (unsigned)(info & 0xFFFFF));
           pc = rpc;
         }
-        else if (ev == TLAG_EV_ASSERT) { report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF)); pc = rpc; }
+        else if (ev == TLAG_EV_ASSERT) {
+          report_min(&p.ctr->viol_assert, (idx << 20) | (unsigned)(info & 0xFFFFF));
+          if (exact) { atomicExch(&p.ctr->stop, 1ULL); st = L_DONE; trapped = true; }   // stop here: nothing after it is generated
+          else pc = rpc;
+        }
         else {
           report_min(&p.ctr->viol_trap, (idx << 20) | ((unsigned long long)(info & 15) << 16) | (unsigned)(info2 & 0xFFFF));
           st = L_DONE; trapped = true;
@@ -285,6 +293,7 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
     }
     if (active && nsucc == 0 && !trapped && (p.flags & TLAG_F_DEADLOCK_CHECK)) {
       report_min(&p.ctr->viol_deadlock, idx << 20);
+      if (exact) atomicExch(&p.ctr->stop, 1ULL);
     }
   }
   // generated counter: warp reduce then one atomic
@@ -761,6 +770,11 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TLAG_BLOCK, smem) != cudaSuccess || occ < 1) occ = 1;
   const uint64_t maxb = (uint64_t)e->sm_count * (uint64_t)occ;   // persistent grid: one resident wave of CTAs
   if (blocks > maxb) blocks = maxb;
+  if (MODE == 0 && (e->p.flags & TLAG_F_EXACT)) {                 // sequential replay: one warp, one state at a time
+    fn<<<1, 32, smem, e->stream>>>(e->p, lo, hi);
+    e->launches++;
+    return cudaGetLastError();
+  }
   fn<<<(unsigned)blocks, TLAG_BLOCK, smem, e->stream>>>(e->p, lo, hi);
   e->launches++;
   return cudaGetLastError();
@@ -802,7 +816,7 @@ static int grow_table_if_needed(tlag_engine* e, uint64_t expected_states) {
 static int grow_store_if_needed(tlag_engine* e, uint64_t need) {
   if (need <= e->cap_states) return TLAG_OK;
   uint64_t ncap = e->cap_states;
-  while (ncap < need) ncap *= 2;
+  while (ncap < need) ncap *= (ncap < (1ULL << 25) ? 4 : 2);   // few re-allocations while the store is small
   if (e->m.max_states && ncap > e->m.max_states) ncap = e->m.max_states;
   // parent links are 32-bit indices into this rank's store and 0xFFFFFFFF marks an initial state: a store never holds
   // more than 2^32 - 2 states per GPU (beyond that the wave reports a store overflow instead of wrapping a link)
@@ -836,7 +850,7 @@ static int grow_store_if_needed(tlag_engine* e, uint64_t need) {
 
 static int cluster_slice(tlag_engine* e, uint64_t first, uint64_t count) {
   static const bool off = getenv("TLAG_NO_SORT") != nullptr;
-  if (off || count < 8192 || count > 0xFFFFFFFFull) return TLAG_OK;
+  if (off || count < 8192 || count > 0xFFFFFFFFull || (e->m.flags & TLAG_F_EXACT)) return TLAG_OK;   // exact: FIFO order is the point
   const uint64_t W = e->m.words_per_state;
   size_t cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
@@ -847,8 +861,13 @@ static int cluster_slice(tlag_engine* e, uint64_t first, uint64_t count) {
   const uint64_t bytes = count * 8 * 2 + count * 4 * 2 + cub_bytes + 256 + count * (W + 2) * 4;
   if (bytes > e->sort_bytes) {
     cudaFree(e->d_sort); e->d_sort = nullptr; e->sort_bytes = 0;
-    if (cudaMalloc(&e->d_sort, bytes) != cudaSuccess) { cudaGetLastError(); return TLAG_OK; }   // no memory: skip (optimisation only)
-    e->sort_bytes = bytes;
+    uint64_t want = bytes * 2;                                  // geometric: levels grow, a re-allocation per level is slow
+    if (cudaMalloc(&e->d_sort, want) != cudaSuccess) {
+      cudaGetLastError();
+      want = bytes;
+      if (cudaMalloc(&e->d_sort, want) != cudaSuccess) { cudaGetLastError(); return TLAG_OK; }   // no memory: skip (optimisation only)
+    }
+    e->sort_bytes = want;
   }
   uint8_t* b = (uint8_t*)e->d_sort;
   unsigned long long* k_in = (unsigned long long*)b; b += count * 8;
@@ -895,6 +914,7 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   if (m->words_per_state == 0 || m->words_per_state > TLAG_MAXW) { e->err = "words_per_state out of range (1..128)"; return TLAG_EINVAL; }
   if (m->frame_words > 8192) { e->err = "frame_words > 8192 not supported"; return TLAG_EINVAL; }
 #if defined(TLAG_SLICED_INC)
+  if (m->flags & TLAG_F_EXACT) { e->err = "TLAG_F_EXACT (sequential replay) runs on the interpreter kernel: use libtlag.so"; return TLAG_EINVAL; }
   {  // this library holds ONE model's program as kernels (constant pool folded in): refuse anything else
     uint64_t h = 0xcbf29ce484222325ULL, hc = 0xcbf29ce484222325ULL;
     for (uint32_t i = 0; i < m->code_len; ++i) h = (h ^ m->code[i]) * 0x100000001b3ULL;
@@ -1088,7 +1108,15 @@ extern "C" int tlag_seed(tlag_engine* e, const uint32_t* states, uint64_t n) {
     r = ensure_scratch(e, n * (W + 2), 0);
     if (r) return r;
     CK(cudaMemcpyAsync(e->d_scratch, rec.data(), rec.size() * 4, cudaMemcpyHostToDevice, e->stream));
-    k_insert_records<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->p, e->d_scratch, n);
+    if (e->m.flags & TLAG_F_EXACT) {
+      // store order = the caller's order (TLC enumerates the initial states in a fixed order): one warp at a time
+      for (uint64_t o = 0; o < n; o += 32) {
+        const uint64_t c = n - o < 32 ? n - o : 32;
+        k_insert_records<<<1, 32, 0, e->stream>>>(e->p, e->d_scratch + o * (W + 2), c);
+      }
+    } else {
+      k_insert_records<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->p, e->d_scratch, n);
+    }
     e->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
@@ -1131,6 +1159,8 @@ static void fill_result(tlag_engine* e, tlag_result* out, uint64_t n_states) {
   out->generated = e->generated;
   out->distinct = n_states;
   out->queue_left = (e->verdict == TLAG_V_OK) ? 0 : (n_states - e->hi) + 0;
+  if ((e->m.flags & TLAG_F_EXACT) && (e->verdict == TLAG_V_ASSERT || e->verdict == TLAG_V_DEADLOCK) && n_states > e->viol_idx)
+    out->queue_left = n_states - e->viol_idx - 1;      // discovered, not yet dequeued when the worker stopped
   out->depth = e->depth;
   out->init_states = e->init_states;
   const double n = (double)n_states, g = (double)e->generated;
@@ -1361,6 +1391,15 @@ extern "C" int tlag_frontier(tlag_engine* e, uint64_t* first_idx, uint64_t* coun
   return TLAG_OK;
 }
 
+// Which shard of the partitioned state space this engine holds (host-driven exchange: tlag_expand_route /
+// tlag_insert_records; tlag_p2p_init sets it for the peer-memory path).  The rank goes into the meta word of every
+// state this engine expands a parent of, and successors the rank owns itself are inserted in place.
+extern "C" int tlag_set_rank(tlag_engine* e, uint32_t n_ranks, uint32_t rank) {
+  if (!e || n_ranks == 0 || n_ranks > 16 || rank >= n_ranks) return TLAG_EINVAL;
+  e->p.n_ranks = (int)n_ranks; e->p.rank = (int)rank;
+  return TLAG_OK;
+}
+
 extern "C" int tlag_expand_route(tlag_engine* e, uint32_t n_ranks, uint64_t first, uint64_t count, uint64_t d_send,
                                  uint64_t cap_records, uint64_t* counts, tlag_wave_stats* out) {
   if (!e || !counts || n_ranks == 0 || n_ranks > 16) return TLAG_EINVAL;
@@ -1369,7 +1408,10 @@ extern "C" int tlag_expand_route(tlag_engine* e, uint32_t n_ranks, uint64_t firs
   uint64_t lo = e->lo + first, hi = lo + count;
   if (lo > e->hi) lo = e->hi;
   if (hi > e->hi) hi = e->hi;
-  e->p.n_ranks = (int)n_ranks;
+  if ((uint32_t)e->p.n_ranks != n_ranks) {
+    if (n_ranks > 1) { e->err = "tlag_expand_route: call tlag_set_rank(n_ranks, rank) first"; return TLAG_ESTATE; }
+    e->p.n_ranks = 1; e->p.rank = 0;
+  }
   if (!e->d_sent && n_ranks > 1 && getenv("TLAG_NO_SENT_CACHE") == nullptr) {
     const unsigned lg = 26;                                    // 2^26 x 8 B = 512 MB
     if (cudaMalloc(&e->d_sent, (1ULL << lg) * 8) == cudaSuccess) {

@@ -58,6 +58,8 @@ class DistributedBFS:
             except Exception as ex:  # noqa: BLE001 -- e.g. CUDA IPC not permitted in this container: NCCL path
                 self.exchange, self.exchange_note = "nccl", f"p2p set-up failed ({str(ex)[:160]}); using NCCL all_to_all"
         if self.exchange != "p2p":
+            if hasattr(engine, "set_rank"):
+                engine.set_rank(world, rank)
             self.send = torch.empty(cap_records * self.rec_words, dtype=torch.int32, device=device)
             self.recv = torch.empty(cap_records * self.rec_words, dtype=torch.int32, device=device)
 
@@ -146,6 +148,7 @@ class DistributedBFS:
                 if "overflow" not in str(ex) or self.cap_records >= (1 << 30):
                     raise
                 self.cap_records *= 2
+                self.retries = getattr(self, "retries", 0) + 1
                 self.send = torch.empty(self.cap_records * rw, dtype=torch.int32, device=self.device)
         region = self.cap_records // world
         cnt = torch.tensor(counts, dtype=torch.int64, device=self.device)

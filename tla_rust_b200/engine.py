@@ -16,6 +16,7 @@ _LIB = None
 
 F_DEADLOCK_CHECK = 1
 F_KEEP_GOING = 2
+F_EXACT = 4
 V_OK, V_INVARIANT, V_ASSERT, V_DEADLOCK, V_EVAL_ERROR, V_RUNNING = 0, 1, 2, 3, 4, 5
 
 
@@ -61,7 +62,7 @@ EXPORTS = ["tlag_create", "tlag_seed", "tlag_step", "tlag_run", "tlag_result_now
            "tlag_read_states", "tlag_digest", "tlag_probe_batch", "tlag_probe_batch_device", "tlag_reset_table", "tlag_restart",
            "tlag_kernel_launches", "tlag_destroy", "tlag_last_error", "tlag_version",
            "tlag_frontier", "tlag_expand_route", "tlag_insert_records", "tlag_advance_level",
-           "tlag_p2p_init", "tlag_p2p_attach", "tlag_p2p_level", "tlag_p2p_rollback", "tlag_read_link"]
+           "tlag_p2p_init", "tlag_p2p_attach", "tlag_p2p_level", "tlag_p2p_rollback", "tlag_read_link", "tlag_set_rank"]
 
 
 def build_library(verbose=False):
@@ -203,19 +204,21 @@ def load_sliced_library(cm, build=True):
 class Engine:
     """One BFS engine instance on one GPU (mirrors tlag_engine)."""
 
-    def __init__(self, cm, deadlock=True, device=0, table_log2=0, max_states=0, keep_going=False, native=None):
+    def __init__(self, cm, deadlock=True, device=0, table_log2=0, max_states=0, keep_going=False, native=None, exact=False):
         """native="sliced" (or True): the model-specialised sliced build -- one kernel per invariant / disjunct of Next,
         compile/sliced.py; built on demand with nvcc and cached in csrc/native/; False: the bytecode interpreter kernel;
         None: follow the environment variable TLAG_NATIVE (sliced / 0)."""
         if native is None:
             native = "sliced" if os.environ.get("TLAG_NATIVE", "0") in ("sliced", "1") else False
+        if exact:               # TLAG_F_EXACT: TLC's single worker replayed on the device (interpreter kernel, one warp)
+            native = False
         self.native = "sliced" if native else False
         self.L = load_sliced_library(cm) if self.native else load_library()
         self.cm = cm
         self._code = np.ascontiguousarray(cm.code, dtype=np.uint64)
         self._cpool = np.ascontiguousarray(cm.cpool, dtype=np.int32)
         self._layout = np.ascontiguousarray(cm.layout, dtype=np.int32)
-        flags = (F_DEADLOCK_CHECK if deadlock else 0) | (F_KEEP_GOING if keep_going else 0)
+        flags = (F_DEADLOCK_CHECK if deadlock else 0) | (F_KEEP_GOING if keep_going else 0) | (F_EXACT if exact else 0)
         m = TlagModel(cm.W, self._code.ctypes.data, len(self._code), cm.entries["inv"], cm.entries["next"],
                       self._cpool.ctypes.data, len(self._cpool), self._layout.ctypes.data, self._layout.shape[0],
                       cm.frame_words, cm.state_words_unpacked, len(cm.invariants), len(cm.actions),
@@ -321,6 +324,9 @@ class Engine:
         a, b = C.c_uint64(), C.c_uint64()
         self._ck(self.L.tlag_frontier(self.h, C.byref(a), C.byref(b)), "tlag_frontier")
         return int(a.value), int(b.value)
+
+    def set_rank(self, n_ranks, rank):
+        self._ck(self.L.tlag_set_rank(self.h, C.c_uint32(n_ranks), C.c_uint32(rank)), "tlag_set_rank")
 
     def expand_route(self, n_ranks, first, count, d_send_ptr, cap_records):
         counts = (C.c_uint64 * n_ranks)()

@@ -34,11 +34,13 @@ def main():
     out = d.run(max_levels=(max_levels - 1) if max_levels else 1 << 20)
     dig = d.global_digest()
     cex = d.counterexample()
+    rt = torch.tensor([getattr(d, "retries", 0)], dtype=torch.int64, device=f"cuda:{local}")
+    dist.all_reduce(rt, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"verdict": out["verdict"], "generated": out["generated"], "distinct": out["distinct"],
                           "depth": out["depth"], "local_distinct": out["local"]["distinct"], "digest": list(dig),
                           "exchange": d.exchange, "exchange_note": d.exchange_note, "exchanges": d.exchanges,
-                          "cap_records": d.cap_records, "retries": getattr(d, "retries", 0), "chunk_states": d.chunk_states,
+                          "cap_records": d.cap_records, "retries": getattr(d, "retries", 0), "retries_max": int(rt.item()), "chunk_states": d.chunk_states,
                           "cex": None if cex is None else {"verdict": cex[0], "detail": cex[1], "states": cex[2].tolist(),
                                                            "actions": cex[3].tolist()}}))
     e.close()
