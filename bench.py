@@ -171,7 +171,7 @@ def k1_microbench(dev, peak):
             traffic = tj["bytes_per_launch"]
     except Exception:
         pass
-    return {"kernel": "k_probe_tiled", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+    return {"kernel": "k_probe_staged", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
             "frac": round(ach / peak, 4), "traffic": traffic, "n": n, "W": W, "p_new": n_new / n,
             "ms_per_launch": round(med, 4), "candidates_per_s": round(n / (med * 1e-3), 1),
             "bytes_per_candidate": bytes_per}, launches

@@ -704,6 +704,24 @@ __global__ void k_rehash(DevParams p, unsigned long long n) {
 }
 
 // ------------------------------------------------------------------ host side
+// Big device buffers (state store, parent / meta, seen-set, sort scratch, routed-fingerprint cache, send regions) come
+// from the device's stream-ordered memory pool with its release threshold lifted: a buffer freed by a growth step or by
+// tlag_destroy stays in the pool, and the next allocation of that size -- the next growth step, the next engine of a
+// long-lived host process -- is served without going back to the driver.  cudaMalloc / cudaFree of multi-GB buffers
+// cost tens of milliseconds each, and a fresh engine performs a dozen of them while its store and table grow (the
+// end-to-end leg of bench.py creates and destroys an engine per job).  The peer-memory inbox stays on cudaMalloc: CUDA
+// IPC cannot export pool memory.
+static cudaError_t dmalloc(tlag_engine* e, void* pp, size_t bytes) {
+  static const bool plain = getenv("TLAG_NO_POOL") != nullptr;
+  return plain ? cudaMalloc((void**)pp, bytes) : cudaMallocAsync((void**)pp, bytes, e->stream);
+}
+static void dfree(tlag_engine* e, void* p) {
+  static const bool plain = getenv("TLAG_NO_POOL") != nullptr;
+  if (!p) return;
+  if (plain) cudaFree(p); else cudaFreeAsync(p, e->stream);
+}
+
+
 static const int kFrameClasses[] = {64, 128, 256, 512, 1024, 2048, 4096, 8192};
 
 #ifdef TLAG_SLICED_INC
@@ -716,9 +734,9 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
   const bool dl = (e->p.flags & TLAG_F_DEADLOCK_CHECK) != 0;
   if (dl) {
     if (n > e->succ_cap) {
-      cudaFree(e->d_succ); e->d_succ = nullptr; e->succ_cap = 0;
+      dfree(e, e->d_succ); e->d_succ = nullptr; e->succ_cap = 0;
       uint64_t cap = n + n / 2 + 4096;
-      cudaError_t r = cudaMalloc(&e->d_succ, cap);
+      cudaError_t r = dmalloc(e, &e->d_succ, cap);
       if (r != cudaSuccess) return r;
       e->succ_cap = cap;
     }
@@ -783,10 +801,10 @@ static cudaError_t launch_wave(tlag_engine* e, uint64_t lo, uint64_t hi) {
 #endif
 
 static int alloc_table(tlag_engine* e, unsigned log2) {
-  if (e->d_table) cudaFree(e->d_table);
+  if (e->d_table) dfree(e, e->d_table);
   e->d_table = nullptr;
   const uint64_t slots = 1ULL << log2;
-  CK(cudaMalloc(&e->d_table, slots * 8));
+  CK(dmalloc(e, &e->d_table, slots * 8));
   CK(cudaMemsetAsync(e->d_table, 0, slots * 8, e->stream));
   e->table_log2 = log2;
   e->p.table = e->d_table;
@@ -830,9 +848,9 @@ static int grow_store_if_needed(tlag_engine* e, uint64_t need) {
     if (ncap <= e->cap_states) return TLAG_OK;
   }
   uint32_t *ns = nullptr, *np = nullptr, *nm = nullptr;
-  CK(cudaMalloc(&ns, ncap * (uint64_t)e->m.words_per_state * 4));
-  CK(cudaMalloc(&np, ncap * 4));
-  CK(cudaMalloc(&nm, ncap * 4));
+  CK(dmalloc(e, &ns, ncap * (uint64_t)e->m.words_per_state * 4));
+  CK(dmalloc(e, &np, ncap * 4));
+  CK(dmalloc(e, &nm, ncap * 4));
   Counters hc;
   CK(cudaMemcpyAsync(&hc, e->d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -841,7 +859,7 @@ static int grow_store_if_needed(tlag_engine* e, uint64_t need) {
   CK(cudaMemcpyAsync(np, e->d_parent, n * 4, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(nm, e->d_meta, n * 4, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  cudaFree(e->d_states); cudaFree(e->d_parent); cudaFree(e->d_meta);
+  dfree(e, e->d_states); dfree(e, e->d_parent); dfree(e, e->d_meta);
   e->d_states = ns; e->d_parent = np; e->d_meta = nm;
   e->cap_states = ncap;
   e->p.states = ns; e->p.parent = np; e->p.meta = nm; e->p.cap_states = ncap;
@@ -860,12 +878,12 @@ static int cluster_slice(tlag_engine* e, uint64_t first, uint64_t count) {
   // one scratch allocation: keys in/out, idx in/out, cub temp, gathered slice
   const uint64_t bytes = count * 8 * 2 + count * 4 * 2 + cub_bytes + 256 + count * (W + 2) * 4;
   if (bytes > e->sort_bytes) {
-    cudaFree(e->d_sort); e->d_sort = nullptr; e->sort_bytes = 0;
+    dfree(e, e->d_sort); e->d_sort = nullptr; e->sort_bytes = 0;
     uint64_t want = bytes * 2;                                  // geometric: levels grow, a re-allocation per level is slow
-    if (cudaMalloc(&e->d_sort, want) != cudaSuccess) {
+    if (dmalloc(e, &e->d_sort, want) != cudaSuccess) {
       cudaGetLastError();
       want = bytes;
-      if (cudaMalloc(&e->d_sort, want) != cudaSuccess) { cudaGetLastError(); return TLAG_OK; }   // no memory: skip (optimisation only)
+      if (dmalloc(e, &e->d_sort, want) != cudaSuccess) { cudaGetLastError(); return TLAG_OK; }   // no memory: skip (optimisation only)
     }
     e->sort_bytes = want;
   }
@@ -936,6 +954,13 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   CK(cudaGetDeviceProperties(&prop, m->device));
   e->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, m->device) == cudaSuccess) {
+      uint64_t thr = ~0ULL;                       // keep freed buffers mapped (see dmalloc)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    } else cudaGetLastError();
+  }
   CK(cudaEventCreate(&e->ev0));
   CK(cudaEventCreate(&e->ev1));
   e->frame_class = 7;
@@ -963,9 +988,9 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   if (!m->max_states) cap = 1ULL << 20;
   else if (cap > (1ULL << 22)) cap = 1ULL << 22;   // start modest, grow on demand up to max_states
   e->cap_states = cap;
-  CK(cudaMalloc(&e->d_states, cap * (uint64_t)m->words_per_state * 4));
-  CK(cudaMalloc(&e->d_parent, cap * 4));
-  CK(cudaMalloc(&e->d_meta, cap * 4));
+  CK(dmalloc(e, &e->d_states, cap * (uint64_t)m->words_per_state * 4));
+  CK(dmalloc(e, &e->d_parent, cap * 4));
+  CK(dmalloc(e, &e->d_meta, cap * 4));
   memset(&e->p, 0, sizeof(e->p));
   e->p.code = e->d_code; e->p.code_len = m->code_len;
   {
@@ -993,11 +1018,15 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
 
 extern "C" void tlag_destroy(tlag_engine* e) {
   if (!e) return;
-  cudaFree(e->d_code); cudaFree(e->d_cpool); cudaFree(e->d_layout); cudaFree(e->d_states);
-  cudaFree(e->d_parent); cudaFree(e->d_meta); cudaFree(e->d_table); cudaFree(e->d_ctr);
-  cudaFree(e->d_scratch); cudaFree(e->d_flags); cudaFree(e->d_sort); cudaFree(e->d_sent); cudaFree(e->d_succ); cudaFree(e->d_dig);
+  cudaFree(e->d_code); cudaFree(e->d_cpool); cudaFree(e->d_layout); cudaFree(e->d_ctr); cudaFree(e->d_dig);
+  if (e->stream) {
+    dfree(e, e->d_states); dfree(e, e->d_parent); dfree(e, e->d_meta); dfree(e, e->d_table);
+    dfree(e, e->d_scratch); dfree(e, e->d_flags); dfree(e, e->d_sort); dfree(e, e->d_sent); dfree(e, e->d_succ);
+    dfree(e, e->d_send_own);
+    cudaStreamSynchronize(e->stream);
+  }
   for (int r = 0; r < 16; ++r) if (e->peer_base[r] && r != e->q.rank) cudaIpcCloseMemHandle(e->peer_base[r]);
-  cudaFree(e->d_p2p); cudaFree(e->d_send_own); cudaFree(e->d_tickets);
+  cudaFree(e->d_p2p); cudaFree(e->d_tickets);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1006,13 +1035,13 @@ extern "C" void tlag_destroy(tlag_engine* e) {
 
 static int ensure_scratch(tlag_engine* e, uint64_t words, uint64_t flags) {
   if (words > e->scratch_words) {
-    cudaFree(e->d_scratch); e->d_scratch = nullptr; e->scratch_words = 0;
-    CK(cudaMalloc(&e->d_scratch, words * 4));
+    dfree(e, e->d_scratch); e->d_scratch = nullptr; e->scratch_words = 0;
+    CK(dmalloc(e, &e->d_scratch, words * 4));
     e->scratch_words = words;
   }
   if (flags > e->flags_cap) {
-    cudaFree(e->d_flags); e->d_flags = nullptr; e->flags_cap = 0;
-    CK(cudaMalloc(&e->d_flags, flags));
+    dfree(e, e->d_flags); e->d_flags = nullptr; e->flags_cap = 0;
+    CK(dmalloc(e, &e->d_flags, flags));
     e->flags_cap = flags;
   }
   return TLAG_OK;
@@ -1414,7 +1443,7 @@ extern "C" int tlag_expand_route(tlag_engine* e, uint32_t n_ranks, uint64_t firs
   }
   if (!e->d_sent && n_ranks > 1 && getenv("TLAG_NO_SENT_CACHE") == nullptr) {
     const unsigned lg = 26;                                    // 2^26 x 8 B = 512 MB
-    if (cudaMalloc(&e->d_sent, (1ULL << lg) * 8) == cudaSuccess) {
+    if (dmalloc(e, &e->d_sent, (1ULL << lg) * 8) == cudaSuccess) {
       CK(cudaMemsetAsync(e->d_sent, 0, (1ULL << lg) * 8, e->stream));
       e->p.sent_cache = e->d_sent; e->p.sent_mask = (1ULL << lg) - 1;
     } else { cudaGetLastError(); e->d_sent = nullptr; }
@@ -1500,7 +1529,7 @@ extern "C" int tlag_p2p_init(tlag_engine* e, uint32_t n_ranks, uint32_t rank, ui
   e->p2p_bytes = p2p_meta_bytes() + inbox_bytes;
   CK(cudaMalloc(&e->d_p2p, e->p2p_bytes));
   CK(cudaMemset(e->d_p2p, 0, p2p_meta_bytes()));
-  CK(cudaMalloc(&e->d_send_own, (uint64_t)n_ranks * cap_records * rw * 4));
+  CK(dmalloc(e, &e->d_send_own, (uint64_t)n_ranks * cap_records * rw * 4));
   CK(cudaMalloc(&e->d_tickets, 32 * sizeof(unsigned int)));
   CK(cudaMemset(e->d_tickets, 0, 32 * sizeof(unsigned int)));
   memset(&e->q, 0, sizeof(e->q));
@@ -1560,7 +1589,7 @@ extern "C" int tlag_p2p_level(tlag_engine* e, uint64_t n_chunks, uint64_t chunk_
   e->p.n_ranks = (int)n_ranks; e->p.rank = e->q.rank;
   if (!e->d_sent && n_ranks > 1 && getenv("TLAG_NO_SENT_CACHE") == nullptr) {
     const unsigned lg = 26;                                    // 2^26 x 8 B = 512 MB
-    if (cudaMalloc(&e->d_sent, (1ULL << lg) * 8) == cudaSuccess) {
+    if (dmalloc(e, &e->d_sent, (1ULL << lg) * 8) == cudaSuccess) {
       CK(cudaMemsetAsync(e->d_sent, 0, (1ULL << lg) * 8, e->stream));
       e->p.sent_cache = e->d_sent; e->p.sent_mask = (1ULL << lg) - 1;
     } else { cudaGetLastError(); e->d_sent = nullptr; }

@@ -208,14 +208,18 @@ class DistributedBFS:
                 self.exchanges += n_chunks
                 if fr:
                     self._ratio = max(self._ratio * 0.5, ws["discovered"] / fr)
-            for c in range(int(nch[0].item()) if self.exchange != "p2p" else 0):
-                first = c * self.chunk_states
-                count = max(0, min(self.chunk_states, fr - first))
-                nn, ws = self._exchange_chunk(first, count, on_gpu, ev)
-                n_new += nn
-                gen += ws["generated"]
-                if ws["verdict"] not in (0, 5):
-                    bad = ws["verdict"]
+            if self.exchange != "p2p":
+                # what the level discovers on this rank = growth of its store: records received from the other ranks
+                # AND the successors it owns itself, which the expand kernels insert in place
+                d0 = e.result()["distinct"]
+                for c in range(int(nch[0].item())):
+                    first = c * self.chunk_states
+                    count = max(0, min(self.chunk_states, fr - first))
+                    _nn, ws = self._exchange_chunk(first, count, on_gpu, ev)
+                    gen += ws["generated"]
+                    if ws["verdict"] not in (0, 5):
+                        bad = ws["verdict"]
+                n_new = e.result()["distinct"] - d0
             e.advance_level()
             flag = torch.tensor([n_new, bad, gen], dtype=torch.int64, device=self.device)
             dist.all_reduce(flag, op=dist.ReduceOp.SUM)
