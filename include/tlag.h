@@ -125,6 +125,9 @@ int  tlag_frontier(tlag_engine *e, uint64_t *first_idx, uint64_t *count);   /* c
 /* Which shard this engine holds (before the first tlag_expand_route of a multi-rank run): successors the rank owns
  * itself are inserted in place, and the rank is recorded in the meta word of the states whose parent it expands. */
 int  tlag_set_rank(tlag_engine *e, uint32_t n_ranks, uint32_t rank);
+/* Trailing packed words the ownership hash covers (same on every rank, before anything is routed): 2 (default) keeps
+ * clusters of like states on one rank, words_per_state spreads models whose tail words carry little entropy. */
+int  tlag_set_owner_words(tlag_engine *e, uint32_t k);
 /* `first`/`count` select a sub-range of the frontier (chunked exchange with bounded buffers). */
 int  tlag_expand_route(tlag_engine *e, uint32_t n_ranks, uint64_t first, uint64_t count, uint64_t d_send,
                        uint64_t cap_records, uint64_t *counts, tlag_wave_stats *out);

@@ -181,6 +181,24 @@ def test_invariant_and_deadlock_traces_are_valid_counterexamples():
     e.close()
 
 
+def test_keep_going_explores_the_whole_space_and_reports_the_first_violation():
+    """TLAG_F_KEEP_GOING (TLC's -continue): the search does not stop at the violation; the verdict, the violating state
+    and its trace are those of the FIRST violation, the counts are those of the whole reachable space."""
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, "demo_race.tlagz"))
+    e = _engine(cm)
+    e.seed(init)
+    first = e.run()
+    e.close()
+    e = _engine(cm, keep_going=True)
+    e.seed(init)
+    r = e.run()
+    assert (r["verdict"], r["detail"], r["state_idx"]) == (first["verdict"], first["detail"], first["state_idx"]) and r["verdict"] == 1
+    assert r["distinct"] >= first["distinct"] and r["generated"] >= first["generated"] and r["queue_left"] == 0
+    res = result_from_engine(cm, r, e.trace(r["state_idx"]))
+    assert res.trace[-1][0]["counter"] == 1 and res.trace[-1][0]["pc"] == ("Done", "Done")
+    e.close()
+
+
 @pytest.mark.parametrize("W,n", [(1, 1000), (3, 5000), (4, 100000), (20, 200000), (7, 0), (64, 300)])
 def test_probe_batch_matches_cpu(W, n):
     """K1 alone through the C ABI: exactly one 'new' flag per distinct state, same set as the CPU oracle;

@@ -38,6 +38,7 @@ struct DevParams {
   uint8_t* succ_flag;               // sliced build: one byte per frontier state, set when a slice produced a successor
   // route mode
   int route;                        // sliced build: successors go to the send regions instead of the local seen-set
+  int owner_words;                  // trailing packed words the ownership hash covers (tlag_owner_k; 2 = clustering key)
   uint32_t* send; unsigned long long region_cap; int n_ranks; int rank;
   unsigned long long* sent_cache; unsigned long long sent_mask;   // direct-mapped filter of fingerprints already routed
 };

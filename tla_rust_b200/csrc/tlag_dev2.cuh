@@ -13,7 +13,7 @@ static __device__ __noinline__ void sl_emit_words(tlag_sl_cx* cx, int aid, const
   const unsigned long long fp = tlag_fingerprint(w, W);
   const unsigned lane = threadIdx.x & 31;
   // route mode: a successor this rank owns itself never leaves the GPU (1/N of the records)
-  const int owner = p.route ? (int)tlag_owner(w, W, (uint32_t)p.n_ranks) : p.rank;
+  const int owner = p.route ? (int)tlag_owner_k(w, W, (uint32_t)p.n_ranks, p.owner_words) : p.rank;
   if (!p.route || owner == p.rank) {
     int ins = seen_insert(p.table, p.mask, fp);
     if (ins < 0) { atomicExch(&p.ctr->table_full, 1ULL); ins = 0; }

@@ -84,6 +84,7 @@ struct tlag_engine {
   unsigned int* d_tickets = nullptr;
   void* peer_base[16] = {nullptr};
   unsigned long long p2p_seq = 0;
+  int p2p_slot = -1;                                   // entry of g_p2p_parked this engine's exchange buffers belong to
   bool p2p_ready = false;
   uint64_t p2p_level_start = 0, p2p_level_generated = 0;   // for tlag_p2p_rollback: store tail before the level, what it added
   // TLAG_F_KEEP_GOING: the first violation is remembered, the search goes on to the fixpoint
@@ -270,7 +271,7 @@ k_wave(DevParams p, unsigned long long lo, unsigned long long hi) {
         // must find none of its own dropped records in the cache)
         unsigned long long* cslot = (has && p.sent_cache) ? p.sent_cache + (fp & p.sent_mask) : nullptr;
         if (cslot && __ldcv(cslot) == fp) { has = false; cslot = nullptr; }
-        int owner = has ? (int)tlag_owner(succ, W, (uint32_t)p.n_ranks) : -1;
+        int owner = has ? (int)tlag_owner_k(succ, W, (uint32_t)p.n_ranks, p.owner_words) : -1;
         const unsigned peers = __match_any_sync(0xffffffffu, owner);
         if (has) {
           const int leader = __ffs((int)peers) - 1;
@@ -703,6 +704,19 @@ __global__ void k_rehash(DevParams p, unsigned long long n) {
   seen_insert(p.table, p.mask, tlag_fingerprint(w, p.W));
 }
 
+// Exchange buffers outlive the engine that created them: allocating an 8 GB inbox, exporting it and mapping seven peers'
+// inboxes costs seconds, and a host process that checks one model after another (bench.py's end-to-end leg does) would
+// pay it per job.  tlag_destroy parks the buffers of a p2p engine here; the next engine of the same shape (device, ranks,
+// record size, capacity) adopts them -- same IPC handle, peers' mappings still valid, chunk numbering continued (every
+// rank has run the same number of chunks, so the inbox protocol needs no reset).
+struct P2PParked {
+  int device, n_ranks, rank, rec_words; uint64_t cap;
+  void* d_p2p; uint64_t bytes; uint32_t* d_send; unsigned int* d_tickets;
+  void* peer_base[16]; uint8_t peer_handle[16][64]; bool peer_ok[16];
+  unsigned long long seq; bool in_use;
+};
+static std::vector<P2PParked> g_p2p_parked;
+
 // ------------------------------------------------------------------ host side
 // Big device buffers (state store, parent / meta, seen-set, sort scratch, routed-fingerprint cache, send regions) come
 // from the device's stream-ordered memory pool with its release threshold lifted: a buffer freed by a growth step or by
@@ -1008,7 +1022,7 @@ extern "C" int tlag_create(const tlag_model* m, tlag_engine** out) {
   e->p.n_off = 0; e->p.p_off = m->unpacked_words; e->p.W = (int)m->words_per_state;
   e->p.states = e->d_states; e->p.parent = e->d_parent; e->p.meta = e->d_meta; e->p.cap_states = cap;
   e->p.ctr = e->d_ctr; e->p.flags = m->flags; e->p.n_inv = (int)m->n_invariants;
-  e->p.n_ranks = 1; e->p.rank = 0;
+  e->p.n_ranks = 1; e->p.rank = 0; e->p.owner_words = 2;
   unsigned log2 = m->table_slots_log2 ? m->table_slots_log2 : 22;
   int r = alloc_table(e, log2);
   if (r) return r;
@@ -1022,11 +1036,13 @@ extern "C" void tlag_destroy(tlag_engine* e) {
   if (e->stream) {
     dfree(e, e->d_states); dfree(e, e->d_parent); dfree(e, e->d_meta); dfree(e, e->d_table);
     dfree(e, e->d_scratch); dfree(e, e->d_flags); dfree(e, e->d_sort); dfree(e, e->d_sent); dfree(e, e->d_succ);
-    dfree(e, e->d_send_own);
     cudaStreamSynchronize(e->stream);
   }
-  for (int r = 0; r < 16; ++r) if (e->peer_base[r] && r != e->q.rank) cudaIpcCloseMemHandle(e->peer_base[r]);
-  cudaFree(e->d_p2p); cudaFree(e->d_tickets);
+  if (e->p2p_slot >= 0) {                              // exchange buffers and peer mappings are parked, not released
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    g_p2p_parked[e->p2p_slot].seq = e->p2p_seq;
+    g_p2p_parked[e->p2p_slot].in_use = false;
+  }
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1423,6 +1439,14 @@ extern "C" int tlag_frontier(tlag_engine* e, uint64_t* first_idx, uint64_t* coun
 // Which shard of the partitioned state space this engine holds (host-driven exchange: tlag_expand_route /
 // tlag_insert_records; tlag_p2p_init sets it for the peer-memory path).  The rank goes into the meta word of every
 // state this engine expands a parent of, and successors the rank owns itself are inserted in place.
+// How many trailing packed words the ownership hash covers (every rank must use the same value; before any state is
+// routed).  2 keeps whole clusters of like states on one rank; W balances models whose tail words carry no entropy.
+extern "C" int tlag_set_owner_words(tlag_engine* e, uint32_t k) {
+  if (!e || k < 2) return TLAG_EINVAL;
+  e->p.owner_words = (int)(k > e->m.words_per_state ? e->m.words_per_state : k);
+  return TLAG_OK;
+}
+
 extern "C" int tlag_set_rank(tlag_engine* e, uint32_t n_ranks, uint32_t rank) {
   if (!e || n_ranks == 0 || n_ranks > 16 || rank >= n_ranks) return TLAG_EINVAL;
   e->p.n_ranks = (int)n_ranks; e->p.rank = (int)rank;
@@ -1525,13 +1549,43 @@ extern "C" int tlag_p2p_init(tlag_engine* e, uint32_t n_ranks, uint32_t rank, ui
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   const uint64_t rw = e->m.words_per_state + 2;
   cap_records = (cap_records + 3) & ~3ULL;                       // regions stay 16-byte aligned
+  for (size_t i = 0; i < g_p2p_parked.size(); ++i) {
+    P2PParked& c = g_p2p_parked[i];
+    if (c.in_use || c.device != e->m.device || c.n_ranks != (int)n_ranks || c.rank != (int)rank || c.rec_words != (int)rw ||
+        c.cap != cap_records) continue;
+    c.in_use = true;
+    e->p2p_slot = (int)i;
+    e->d_p2p = c.d_p2p; e->p2p_bytes = c.bytes; e->d_send_own = c.d_send; e->d_tickets = c.d_tickets; e->p2p_seq = c.seq;
+    memset(&e->q, 0, sizeof(e->q));
+    e->q.n_ranks = (int)n_ranks; e->q.rank = (int)rank; e->q.rec_words = (int)rw;
+    e->q.inbox_cap = cap_records; e->q.region_cap = cap_records;
+    e->q.send = e->d_send_own;
+    e->q.meta = (P2PMeta*)e->d_p2p;
+    e->q.inbox = (uint32_t*)((uint8_t*)e->d_p2p + p2p_meta_bytes());
+    e->q.tickets = e->d_tickets;
+    e->peer_base[rank] = e->d_p2p;
+    e->q.peer_meta[rank] = e->q.meta; e->q.peer_inbox[rank] = e->q.inbox;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->d_p2p));
+    memcpy(handle_out64, &h, 64);
+    e->p.n_ranks = (int)n_ranks; e->p.rank = (int)rank;
+    return TLAG_OK;
+  }
   const uint64_t inbox_bytes = 2ULL * n_ranks * cap_records * rw * 4;
   e->p2p_bytes = p2p_meta_bytes() + inbox_bytes;
   CK(cudaMalloc(&e->d_p2p, e->p2p_bytes));
   CK(cudaMemset(e->d_p2p, 0, p2p_meta_bytes()));
-  CK(dmalloc(e, &e->d_send_own, (uint64_t)n_ranks * cap_records * rw * 4));
+  CK(cudaMalloc(&e->d_send_own, (uint64_t)n_ranks * cap_records * rw * 4));
   CK(cudaMalloc(&e->d_tickets, 32 * sizeof(unsigned int)));
   CK(cudaMemset(e->d_tickets, 0, 32 * sizeof(unsigned int)));
+  {
+    P2PParked c;
+    memset(&c, 0, sizeof(c));
+    c.device = e->m.device; c.n_ranks = (int)n_ranks; c.rank = (int)rank; c.rec_words = (int)rw; c.cap = cap_records;
+    c.d_p2p = e->d_p2p; c.bytes = e->p2p_bytes; c.d_send = e->d_send_own; c.d_tickets = e->d_tickets; c.in_use = true;
+    g_p2p_parked.push_back(c);
+    e->p2p_slot = (int)g_p2p_parked.size() - 1;
+  }
   memset(&e->q, 0, sizeof(e->q));
   e->q.n_ranks = (int)n_ranks; e->q.rank = (int)rank; e->q.rec_words = (int)rw;
   e->q.inbox_cap = cap_records; e->q.region_cap = cap_records;
@@ -1554,7 +1608,14 @@ extern "C" int tlag_p2p_attach(tlag_engine* e, uint32_t peer, const uint8_t* han
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, 64);
   void* base = nullptr;
-  CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  P2PParked* c = e->p2p_slot >= 0 ? &g_p2p_parked[e->p2p_slot] : nullptr;
+  if (c && c->peer_ok[peer] && memcmp(c->peer_handle[peer], handle64, 64) == 0) {
+    base = c->peer_base[peer];                                  // the peer parked and re-adopted the same inbox
+  } else {
+    if (c && c->peer_ok[peer]) { cudaIpcCloseMemHandle(c->peer_base[peer]); c->peer_ok[peer] = false; }
+    CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    if (c) { c->peer_base[peer] = base; memcpy(c->peer_handle[peer], handle64, 64); c->peer_ok[peer] = true; }
+  }
   e->peer_base[peer] = base;
   e->q.peer_meta[peer] = (P2PMeta*)base;
   e->q.peer_inbox[peer] = (uint32_t*)((uint8_t*)base + p2p_meta_bytes());

@@ -186,9 +186,16 @@ TLAG_HD uint64_t tlag_fingerprint(const uint32_t* w, int W) {
 // scaled to n_ranks.  All states of one cluster therefore live on, and are expanded by, the same rank, so a
 // rank's level slices are as dense in like states as on a single GPU (hashing the whole state spread every
 // cluster over all ranks and cost ~25 % of the per-rank interpreter efficiency at N = 2).
-TLAG_HD uint32_t tlag_owner(const uint32_t* w, int W, uint32_t n_ranks) {
+// k = number of trailing packed words the hash covers: 2 = the clustering key (default); up to W = the whole state, for
+// models whose last two words carry too little entropy to balance the ranks (SSI: the zero tail of a half-empty
+// history sequence -- 278 distinct keys in 2.4 M states, one of 8 ranks would own 70 % of them).
+TLAG_HD uint32_t tlag_owner_k(const uint32_t* w, int W, uint32_t n_ranks, int k) {
   const uint64_t key = ((uint64_t)w[W - 1] << 32) | (uint64_t)(W >= 2 ? w[W - 2] : 0u);
-  const uint64_t h = tlag_fmix64(key * 0x9E3779B97F4A7C15ULL + 0x7F4A7C15ULL);
+  uint64_t h = tlag_fmix64(key * 0x9E3779B97F4A7C15ULL + 0x7F4A7C15ULL);
+  for (int i = W - 3, n = 2; i >= 0 && n < k; --i, ++n)
+    h = tlag_fmix64(h ^ ((uint64_t)w[i] * 0x9E3779B97F4A7C15ULL + (uint64_t)n));
   return (uint32_t)(((h >> 32) * (uint64_t)n_ranks) >> 32);
 }
+
+TLAG_HD uint32_t tlag_owner(const uint32_t* w, int W, uint32_t n_ranks) { return tlag_owner_k(w, W, n_ranks, 2); }
 

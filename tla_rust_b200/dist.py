@@ -78,11 +78,55 @@ class DistributedBFS:
         self.region = region
         self._ratio = 8.0
 
+    def _choose_owner_words(self, init_words):
+        """Ownership = hash of the last k packed words.  k = 2 (the clustering key) keeps clusters of like states on one
+        rank, which the per-level clustering sort thrives on -- unless those two words carry too little entropy to
+        balance the ranks (SSI 4 x 3: 278 distinct keys in 2.4 M states; one of 8 ranks would own 70 % of the states).
+        Probe: every rank runs the first levels of the search on its own GPU (a few ms, identical on all ranks), looks at
+        how k = 2 would spread those states, and the ranks switch to k = W together if the fullest rank would hold more
+        than 1.25 x its share."""
+        if self.world == 1 or not hasattr(self.e, "set_owner_words") or os.environ.get("TLAG_OWNER_WORDS"):
+            k = int(os.environ.get("TLAG_OWNER_WORDS", "2"))
+            if k != 2 and hasattr(self.e, "set_owner_words"):
+                self.e.set_owner_words(k)
+            return k
+        from .engine import Engine
+        probe = Engine(self.cm, deadlock=False, device=torch.device(self.device).index or 0, native=self.e.native)
+        probe.seed(init_words)
+        n = probe.result()["distinct"]
+        for _ in range(64):
+            if n >= (1 << 16):
+                break
+            ws = probe.step()
+            n = ws["distinct_total"] or n
+            if ws["verdict"] != 5:
+                break
+        st = probe.read_states(0, min(n, 1 << 18)).astype(np.uint64)
+        probe.close()
+        W = self.cm.W
+        key = (st[:, W - 1] << np.uint64(32)) | (st[:, W - 2] if W >= 2 else np.uint64(0))
+        x = key * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x7F4A7C15)
+        for mul in (0xff51afd7ed558ccd, 0xc4ceb9fe1a85ec53):
+            x ^= x >> np.uint64(33)
+            x *= np.uint64(mul)
+        x ^= x >> np.uint64(33)
+        own = ((x >> np.uint64(32)) * np.uint64(self.world)) >> np.uint64(32)
+        cnt = np.bincount(own.astype(np.int64), minlength=self.world)
+        skew = float(cnt.max()) / max(1.0, float(cnt.mean()))
+        dec = torch.tensor([1 if (len(st) >= 4096 and skew > 1.25) else 0], dtype=torch.int64, device=self.device)
+        dist.all_reduce(dec, op=dist.ReduceOp.MAX)
+        k = W if int(dec.item()) else 2
+        self.owner_skew = skew
+        if k != 2:
+            self.e.set_owner_words(k)
+        return k
+
     def seed(self, init_words: np.ndarray, fingerprints=None):
-        """Every rank sees all initial states and keeps those it owns (tlag_owner: hash of the state's
-        clustering key, so that whole clusters stay on one rank)."""
+        """Every rank sees all initial states and keeps those it owns (tlag_owner_k: hash of the state's last k packed
+        words; k = 2, the clustering key, unless that would not balance the ranks)."""
         from .fingerprint import owner_of_words
-        own = np.array([owner_of_words(w, self.world) for w in init_words], dtype=np.int64)
+        self.owner_words = self._choose_owner_words(np.ascontiguousarray(init_words, dtype=np.uint32).reshape(-1, self.cm.W))
+        own = np.array([owner_of_words(w, self.world, self.owner_words) for w in init_words], dtype=np.int64)
         mine = init_words[own == self.rank]
         self.e.seed(mine)
         self.n_init_total = len(init_words)

@@ -62,7 +62,7 @@ EXPORTS = ["tlag_create", "tlag_seed", "tlag_step", "tlag_run", "tlag_result_now
            "tlag_read_states", "tlag_digest", "tlag_probe_batch", "tlag_probe_batch_device", "tlag_reset_table", "tlag_restart",
            "tlag_kernel_launches", "tlag_destroy", "tlag_last_error", "tlag_version",
            "tlag_frontier", "tlag_expand_route", "tlag_insert_records", "tlag_advance_level",
-           "tlag_p2p_init", "tlag_p2p_attach", "tlag_p2p_level", "tlag_p2p_rollback", "tlag_read_link", "tlag_set_rank"]
+           "tlag_p2p_init", "tlag_p2p_attach", "tlag_p2p_level", "tlag_p2p_rollback", "tlag_read_link", "tlag_set_rank", "tlag_set_owner_words"]
 
 
 def build_library(verbose=False):
@@ -324,6 +324,9 @@ class Engine:
         a, b = C.c_uint64(), C.c_uint64()
         self._ck(self.L.tlag_frontier(self.h, C.byref(a), C.byref(b)), "tlag_frontier")
         return int(a.value), int(b.value)
+
+    def set_owner_words(self, k):
+        self._ck(self.L.tlag_set_owner_words(self.h, C.c_uint32(k)), "tlag_set_owner_words")
 
     def set_rank(self, n_ranks, rank):
         self._ck(self.L.tlag_set_rank(self.h, C.c_uint32(n_ranks), C.c_uint32(rank)), "tlag_set_rank")

@@ -43,9 +43,15 @@ def owner_rank(fp: int, world: int) -> int:
     return (fp * world) >> 64
 
 
-def owner_of_words(words, world: int) -> int:
-    """Mirror of tlag_owner (csrc/tlag_vm.h): owner = hash of the last two packed words, scaled to `world`."""
+def owner_of_words(words, world: int, k: int = 2) -> int:
+    """Mirror of tlag_owner_k (csrc/tlag_vm.h): owner = hash of the last k packed words, scaled to `world`."""
     w = [int(x) & 0xFFFFFFFF for x in words]
-    key = (w[-1] << 32) | (w[-2] if len(w) >= 2 else 0)
+    W = len(w)
+    key = (w[-1] << 32) | (w[-2] if W >= 2 else 0)
     h = _fmix((key * 0x9E3779B97F4A7C15 + 0x7F4A7C15) & M64)
+    i, n = W - 3, 2
+    while i >= 0 and n < k:
+        h = _fmix(h ^ ((w[i] * 0x9E3779B97F4A7C15 + n) & M64))
+        i -= 1
+        n += 1
     return ((h >> 32) * world) >> 32

@@ -40,7 +40,7 @@ def main():
         print(json.dumps({"verdict": out["verdict"], "generated": out["generated"], "distinct": out["distinct"],
                           "depth": out["depth"], "local_distinct": out["local"]["distinct"], "digest": list(dig),
                           "exchange": d.exchange, "exchange_note": d.exchange_note, "exchanges": d.exchanges,
-                          "cap_records": d.cap_records, "retries": getattr(d, "retries", 0), "retries_max": int(rt.item()), "chunk_states": d.chunk_states,
+                          "cap_records": d.cap_records, "owner_words": d.owner_words, "owner_skew_k2": getattr(d, "owner_skew", None), "retries": getattr(d, "retries", 0), "retries_max": int(rt.item()), "chunk_states": d.chunk_states,
                           "cex": None if cex is None else {"verdict": cex[0], "detail": cex[1], "states": cex[2].tolist(),
                                                            "actions": cex[3].tolist()}}))
     e.close()
