@@ -106,6 +106,8 @@ def _sliced_tag(cm, scalar):
             h.update(f.read())
     h.update(repr((getattr(cm, "segments", None), os.environ.get("TLAG_SL_OCC", ""), os.environ.get("TLAG_SL_BLOCK", ""),
                    os.environ.get("TLAG_SL_MIN_SLICE", ""))).encode())
+    if os.environ.get("TLAG_CSRC_DIR"):                 # experiments built from a modified copy of csrc/
+        h.update(os.environ["TLAG_CSRC_DIR"].encode())
     return f"sl_{model_key(cm)}_{h.hexdigest()[:8]}{'_s' if scalar else ''}"
 
 
@@ -153,7 +155,7 @@ def build_sliced_library(cm, force=False, verbose=False, scalar=None, jobs=None)
     with open(defs_path, "w") as f:
         f.write(defs)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    csrc = os.path.join(_HERE, "csrc")
+    csrc = os.environ.get("TLAG_CSRC_DIR") or os.path.join(_HERE, "csrc")      # (experiments: a modified copy of csrc/)
     base = [nvcc, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
             "-I", csrc, "-dc"]
     if not scalar and cm.frame_words > 512:
