@@ -162,3 +162,32 @@ def test_counterexample_is_stitched_across_ranks(name, world):
     known = {tuple(x) for x in r["states"].tolist()}
     for st in states.tolist():
         assert tuple(st) in known
+
+
+def test_ownership_probe_decision_on_the_baseline_workloads():
+    """DistributedBFS probes the first levels on the device and asks clustering_key_is_unbalanced() whether ownership by
+    the clustering key would balance the ranks.  Same question here on ORACLE O2's states of the same prefix: Paxos keeps
+    the clustering key at every rank count (its early skew at 8 ranks is an accident of 3 K keys, 1.04 over the whole
+    space), SSI 4 x 3 (154 keys, one rank would own 70 %) hashes the whole state."""
+    from oracle import cpu_engine
+    from tla_rust_b200.compiled import load_compiled
+    from tla_rust_b200.dist import clustering_key_is_unbalanced
+
+    def prefix(name):
+        cm, init, exp, info = load_compiled(os.path.join(GOLDEN, name + ".tlagz"))
+        tot, levels = 0, 0
+        for i, x in enumerate(exp["o2"]["levels"]):
+            tot, levels = tot + x, i + 1
+            if tot >= 65536:
+                break
+        r = cpu_engine.run(cm, init, n_threads=2, deadlock=False, max_states=1 << 20, max_levels=levels, want_states=True)
+        return cm.W, r["states"][:1 << 18]
+    W, st = prefix("MCPaxos3_b4")
+    assert [clustering_key_is_unbalanced(st, W, n)[0] for n in (2, 4, 8)] == [False, False, False]
+    W, st = prefix("MCssi_4x3")
+    dec = [clustering_key_is_unbalanced(st, W, n) for n in (2, 4, 8)]
+    assert [d[0] for d in dec] == [True, True, True] and dec[2][1] > 4.0
+    # whole-state ownership (k = W) does balance them: the host mirror of tlag_owner_k
+    from tla_rust_b200.fingerprint import owner_of_words
+    own = np.bincount([owner_of_words(w, 8, W) for w in st[:20000]], minlength=8)
+    assert own.max() / own.mean() < 1.1

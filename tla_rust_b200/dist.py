@@ -40,6 +40,27 @@ def _all_to_all(outs, ins, rank):
             w.wait()
 
 
+def clustering_key_is_unbalanced(states: np.ndarray, W: int, world: int):
+    """Would ownership by the clustering key (hash of the last two packed words, tlag_owner) leave the ranks unbalanced?
+    -> (decision, skew): skew = states of the fullest rank / mean; the decision also asks for FEW distinct keys (fewer
+    than 256 per rank), which is what makes the imbalance structural rather than an accident of the first levels (Paxos
+    b4's first 149 K states: skew 1.30 at 8 ranks over 3 298 keys -- 1.04 over the whole space; SSI 4 x 3: skew 6.2
+    over 154 keys, and it stays that way)."""
+    st = np.ascontiguousarray(states).astype(np.uint64).reshape(-1, W)
+    if len(st) < 4096:
+        return False, 1.0
+    key = (st[:, W - 1] << np.uint64(32)) | (st[:, W - 2] if W >= 2 else np.uint64(0))
+    x = key * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x7F4A7C15)
+    for mul in (0xff51afd7ed558ccd, 0xc4ceb9fe1a85ec53):
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(mul)
+    x ^= x >> np.uint64(33)
+    own = ((x >> np.uint64(32)) * np.uint64(world)) >> np.uint64(32)
+    cnt = np.bincount(own.astype(np.int64), minlength=world)
+    skew = float(cnt.max()) / max(1.0, float(cnt.mean()))
+    return bool(skew > 1.25 and len(np.unique(key)) < 256 * world), skew
+
+
 class DistributedBFS:
     def __init__(self, engine, cm, rank, world, device, cap_records=1 << 24, chunk_states=1 << 21, exchange=None):
         self.e, self.cm, self.rank, self.world, self.device = engine, cm, rank, world, device
@@ -84,7 +105,7 @@ class DistributedBFS:
         balance the ranks (SSI 4 x 3: 278 distinct keys in 2.4 M states; one of 8 ranks would own 70 % of the states).
         Probe: every rank runs the first levels of the search on its own GPU (a few ms, identical on all ranks), looks at
         how k = 2 would spread those states, and the ranks switch to k = W together if the fullest rank would hold more
-        than 1.25 x its share."""
+        than 1.25 x its share AND the states have few distinct keys (clustering_key_is_unbalanced)."""
         if self.world == 1 or not hasattr(self.e, "set_owner_words") or os.environ.get("TLAG_OWNER_WORDS"):
             k = int(os.environ.get("TLAG_OWNER_WORDS", "2"))
             if k != 2 and hasattr(self.e, "set_owner_words"):
@@ -104,16 +125,8 @@ class DistributedBFS:
         st = probe.read_states(0, min(n, 1 << 18)).astype(np.uint64)
         probe.close()
         W = self.cm.W
-        key = (st[:, W - 1] << np.uint64(32)) | (st[:, W - 2] if W >= 2 else np.uint64(0))
-        x = key * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x7F4A7C15)
-        for mul in (0xff51afd7ed558ccd, 0xc4ceb9fe1a85ec53):
-            x ^= x >> np.uint64(33)
-            x *= np.uint64(mul)
-        x ^= x >> np.uint64(33)
-        own = ((x >> np.uint64(32)) * np.uint64(self.world)) >> np.uint64(32)
-        cnt = np.bincount(own.astype(np.int64), minlength=self.world)
-        skew = float(cnt.max()) / max(1.0, float(cnt.mean()))
-        dec = torch.tensor([1 if (len(st) >= 4096 and skew > 1.25) else 0], dtype=torch.int64, device=self.device)
+        want_all, skew = clustering_key_is_unbalanced(st, W, self.world)
+        dec = torch.tensor([1 if want_all else 0], dtype=torch.int64, device=self.device)
         dist.all_reduce(dec, op=dist.ReduceOp.MAX)
         k = W if int(dec.item()) else 2
         self.owner_skew = skew
