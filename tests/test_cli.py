@@ -136,6 +136,11 @@ def test_demo_specs_through_tlc_flow_on_cpu_shim(monkeypatch):
     out = io.StringIO()
     assert check_file(os.path.join(d, "race.tla"), out=out, verbose=False) == 12
     assert "Invariant Correct is violated" in out.getvalue()
+    # ./states/ (reference .gitignore:2): the report of every run, and the behaviour leading to an error
+    assert "No error has been found" in open(os.path.join(d, "states", "lock.out")).read()
+    assert not os.path.exists(os.path.join(d, "states", "lock.trace"))
+    tr = open(os.path.join(d, "states", "race.trace")).read()
+    assert tr.startswith("State 1:") and "/\\ counter" in tr
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/Makefile"), reason="the reference checkout only exists in the build container")

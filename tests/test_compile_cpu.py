@@ -107,3 +107,22 @@ def test_engine_fails_loudly_without_gpu():
     cm, init, _, _ = load_compiled(os.path.join(GOLDEN, "atomic_add.tlagz"))
     with pytest.raises(engine.EngineUnavailable):
         engine.Engine(cm)
+
+
+def test_action_constraint_matches_the_ast_oracle():
+    """ACTION-CONSTRAINT (cfg keyword, TLC/ConfigFileGrammar.tla:8-12): lowered as a conjunct of the in-model test after
+    every completed successor; ORACLE O1 evaluates it on the AST (oracle/tlc_oracle.py: in_actions)."""
+    from tla_rust_b200.front.spec import Model
+    from tla_rust_b200.checker import compile_model, encode_states
+    from oracle.tlc_oracle import Oracle
+    spec = os.path.join(ROOT, "tests", "specs", "ActC.tla")
+    m = Model(spec)
+    assert [nm for nm, _, _ in m.action_constraints] == ["SmallStep"]
+    o1 = Oracle(m).run()
+    init = m.initial_states()
+    cm = compile_model(m, init)
+    o2 = cpu_engine.run(cm, encode_states(cm, init), deadlock=m.check_deadlock)
+    assert (o2["verdict"], o2["generated"], o2["distinct"], o2["depth"]) == (0, o1.generated, o1.distinct, o1.depth)
+    assert o1.distinct == 6 * 3                       # x stays in 0..5: the jumps to 6..8 are cut
+    free = Oracle(Model(spec, cfg_text="INIT Init\nNEXT Next\nINVARIANT TypeOK\nCHECK_DEADLOCK FALSE\n")).run()
+    assert free.distinct == 9 * 3 and free.generated > o1.generated

@@ -148,7 +148,28 @@ def check_file(path, deadlock=True, cfg_path=None, out=None, device=0, seq_cap=N
     if n_out:
         r = dict(r, generated=r["generated"] + n_out, distinct=r["distinct"] + n_out, init_states=r.get("init_states", 0) + n_out)
     res = result_from_engine(cm, r, trace)
-    print(format_result(res, m.vars, m.module_name), file=out)
+    text = format_result(res, m.vars, m.module_name)
+    print(text, file=out)
+    # TLC keeps its metadata (fingerprint set, trace file) under ./states/ (reference .gitignore:2); the state store of
+    # this checker lives in HBM, what is worth keeping on disk is the report: states/<module>.out, and the behaviour
+    # leading to an error as states/<module>.trace
+    if int(os.environ.get("RANK", "0")) == 0 and os.environ.get("TLAG_NO_STATES_DIR") != "1":
+        try:
+            sd = os.path.join(os.path.dirname(os.path.abspath(path)), "states")
+            os.makedirs(sd, exist_ok=True)
+            with open(os.path.join(sd, m.module_name + ".out"), "w") as f:
+                f.write(text + "\n")
+            tr = os.path.join(sd, m.module_name + ".trace")
+            lines = text.splitlines()
+            if res.trace and any(ln.startswith("State 1:") for ln in lines):
+                first = next(i for i, ln in enumerate(lines) if ln.startswith("State 1:"))
+                last = max(i for i, ln in enumerate(lines) if ln.startswith("/\\") or ln.startswith("State "))
+                with open(tr, "w") as f:
+                    f.write("\n".join(lines[first:last + 1]) + "\n")
+            elif os.path.exists(tr):
+                os.remove(tr)
+        except OSError:
+            pass
     print(f"Finished in {time.time() - t0:.2f}s ({r['device_seconds']:.4f}s in GPU wave kernels, "
           f"{e.launches()} kernel launches).", file=out)
     e.close()
