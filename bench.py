@@ -114,19 +114,17 @@ def cpu_reference(cm, init, info, threads, want, levels):
 
 
 def cpu_arm(cm, init, info, threads, want, levels, repeats, exp=None, workload=None):
-    """median + spread over `repeats` runs of the bounded sample"""
-    if workload in CPU_SAMPLE_LEVELS:
+    """median + spread over `repeats` runs of the bounded sample (depth-bounded workloads: a shorter prefix, sized
+    from the oracle's per-level record)"""
+    if workload in CPU_SAMPLE_LEVELS and exp is not None:
         levels = CPU_SAMPLE_LEVELS[workload]
-        want = dict(want, distinct=want["distinct"])      # capacity from the oracle record of the shorter prefix
-        if exp is not None:
-            want_cap = sum(exp["o2"]["levels"][:levels])
-            rs = [cpu_reference(cm, init, info, threads, dict(want, distinct=want_cap), levels) for _ in range(repeats)]
-            for r in rs:
-                r["sample"] = r["sample"].replace("the whole workload job once",
-                                                  f"BFS prefix: levels 1..{levels} of the workload ({r['distinct']} distinct states)")
-            return _summ(rs, repeats)
-    rs = [cpu_reference(cm, init, info, threads, want, levels) for _ in range(repeats)]
-    return _summ(rs, repeats)
+        want = dict(want, distinct=sum(exp["o2"]["levels"][:levels]))
+        rs = [cpu_reference(cm, init, info, threads, want, levels) for _ in range(repeats)]
+        for r in rs:
+            r["sample"] = r["sample"].replace("the whole workload job once",
+                                              f"BFS prefix: levels 1..{levels} of the workload ({r['distinct']} distinct states)")
+        return _summ(rs, repeats)
+    return _summ([cpu_reference(cm, init, info, threads, want, levels) for _ in range(repeats)], repeats)
 
 
 def _summ(rs, repeats):
