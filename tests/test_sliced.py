@@ -60,6 +60,22 @@ def test_sliced_code_reproduces_the_fixture_on_the_cpu_engine(tmp_path, name):
             assert r[k] == exp["o2"][k], (name, "scalar" if scalar else "array", k)
 
 
+def test_sliced_code_at_eight_million_states(tmp_path):
+    """Beyond the AST oracle's reach (~10^5 states) the interpreter-side check is VM against VM; the emitted C is a second
+    implementation of every opcode and of pack / unpack: MCPaxos3 with ballots 0..3 (8,220,065 states) through the scalar
+    form inside the CPU engine must land on the digest ORACLE O2's interpreter recorded."""
+    cm, init, exp, info = load_compiled(os.path.join(GOLDEN, "MCPaxos3_b3.tlagz"))
+    L = _cpu_sliced_lib(tmp_path, cm, True)
+    cpu_engine.lib()
+    saved, cpu_engine._LIB = cpu_engine._LIB, L
+    try:
+        r = cpu_engine.run(cm, init, n_threads=os.cpu_count() or 2, deadlock=info["deadlock"], max_states=1 << 24)
+    finally:
+        cpu_engine._LIB = saved
+    for k in KEYS:
+        assert r[k] == exp["o2"][k], k
+
+
 def test_subroutines_and_sparse_containers_in_sliced_code(tmp_path):
     """CALL -> a C function per subroutine, RET -> return; SFIND / SINS; raft and SSI at their smallest bounds."""
     for name in ("MCraft", "MCssi"):
